@@ -1,0 +1,293 @@
+/*
+ * qdiff_b200 -- C ABI of the B200-native quantized-diffusion UNet engine (libqdiff_b200.so).
+ *
+ * The reference (Xiuyu-Li/q-diffusion) has no FFI layer: its boundary is the Python class API of
+ * `qdiff` (QuantModel.forward, qdiff/quant_model.py:68-69) and every op underneath is a PyTorch
+ * library call.  This header is the boundary a maintainer binds (ctypes stub in INTEGRATION.md):
+ * each entry point names the reference code it replaces.  Plain pointers and sizes only; all
+ * pointers are DEVICE pointers unless stated; every call is asynchronous on the given stream;
+ * every function returns 0 on success or a negative qd_status.  No CPU fallback exists.
+ */
+#ifndef QDIFF_B200_H
+#define QDIFF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* qd_stream_t; /* cudaStream_t */
+
+enum qd_status {
+  QD_OK = 0,
+  QD_ERR_BAD_ARG = -1,
+  QD_ERR_UNSUPPORTED = -2,
+  QD_ERR_CUDA = -3,
+  QD_ERR_NOT_FINALIZED = -4
+};
+
+/* Activation quantizer parameters (UniformAffineQuantizer.forward, qdiff/quant_layer.py:82-88):
+ * code = clamp(rne(x / delta) + zero_point, qmin, qmax).  Symmetric 8 bit: [-128,127], zp = 0;
+ * asymmetric n bit: [0, 2^n-1].  Codes are stored as raw bytes (s8 if qmin < 0, else u8). */
+typedef struct qd_qparams {
+  float delta;
+  int32_t zero_point;
+  int32_t qmin;
+  int32_t qmax;
+} qd_qparams;
+
+/* ------------------------------------------------------------------------------------------
+ * qd_qgemm_i8 -- QuantModule.forward (qdiff/quant_layer.py:248-279) for Conv2d 3x3 (stride 1,
+ * pad 1), Conv2d 1x1, Conv1d k=1 and Linear, as INT8 tcgen05 GEMM with the de-quantisation fused
+ * into the epilogue:
+ *   y[m,n] = scale[n] * (sum_k a[m,k] * w[n,k] - corr[cls(m)][n]) + bias[n]
+ *            (+ rowvec[m / rows_per_batch][n]) (+ residual[m,n])
+ * a: activation codes, NHWC / token-major.  taps==1: [M, lda] bytes; taps==9: [B,H,W,C] dense.
+ * w: weight codes minus zero point (s8), [n_rows][taps*C], tap-major then channel (OHWI).
+ * corr: zx * sum_k w[n,k]; for taps==9 one row per border class (3x3 classes, row-major:
+ *       top/mid/bottom x left/mid/right) because the reference zero-pads after de-quantisation.
+ * Output: fp32 `out` and/or re-quantised codes `out_q` with the consumer's quantizer `oq`
+ *       (out_q_transposed: [M/rows_per_batch][N][rows_per_batch], used for attention V).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct qd_gemm_desc {
+  const void* a;
+  const void* w;
+  long long lda;        /* bytes between rows of a (taps==1) */
+  int32_t M, N, C, taps;
+  int32_t w_rows;       /* rows present in w (>= N; padded rows must be zero) */
+  int32_t B, H, W;      /* conv geometry (taps==9): M == B*H*W */
+  int32_t a_signed;     /* activation codes are s8 (symmetric) or u8 */
+  const float* scale;   /* [N] delta_x * delta_w[n] */
+  const float* bias;    /* [N] or NULL */
+  const int32_t* corr;  /* [9][N] (taps==9) / [N] (taps==1) or NULL when zx == 0 */
+  const float* rowvec;  /* [M/rows_per_batch][ld_rowvec] or NULL (timestep-embedding add) */
+  long long ld_rowvec;
+  int32_t rows_per_batch;
+  int32_t out_q_transposed;
+  const float* residual; /* [M, ldr] or NULL; may alias out */
+  long long ldr;
+  float* out;            /* [M, ldo] or NULL */
+  long long ldo;
+  void* out_q;           /* codes or NULL */
+  long long ldq;
+  qd_qparams oq;
+  int32_t bn_hint;       /* 0 = auto N-tile */
+  int32_t reserved;
+} qd_gemm_desc;
+
+int qd_qgemm_i8(const qd_gemm_desc* d, qd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * qd_quantize -- standalone activation fake-quant input side (qdiff/quant_layer.py:256-264)
+ * with the elementwise producer fused: dst = Q(f(src)).
+ *   act: 0 none, 1 SiLU (x*sigmoid(x): nonlinearity / nn.SiLU), 2 GEGLU (src has 2*C columns,
+ *        value = src[:, c] * gelu_erf(src[:, C + c]); ldm/modules/attention.py:42-44)
+ *   split > 0: columns [0,split) use q0, columns [split,C) use q1 (split-shortcut,
+ *        qdiff/quant_layer.py:257-261)
+ *   upsample2x: src is [B,H,W,C], dst [B,2H,2W,C] nearest (F.interpolate, openaimodel.py:116)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct qd_quantize_desc {
+  const float* src;
+  long long ld_src;
+  void* dst;
+  long long ld_dst;
+  int32_t M, C;
+  int32_t act;
+  int32_t split;
+  qd_qparams q0, q1;
+  int32_t upsample2x, B, H, W;
+} qd_quantize_desc;
+
+int qd_quantize(const qd_quantize_desc* d, qd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * qd_groupnorm_quant -- GroupNorm32 / Normalize (32 groups; ldm util.py:214-216 eps 1e-5,
+ * ddim diffusion.py:32-33 eps 1e-6) [+ scale-shift] [+ SiLU] + up to 3 consumer quantizers.
+ * x: fp32 NHWC [B, HW, C] (row pitch ld_x).  ws: workspace >= B*(nslab*C*2 + 64) floats.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct qd_groupnorm_desc {
+  const float* x;
+  long long ld_x;
+  int32_t B, HW, C, groups;
+  float eps;
+  int32_t silu;
+  const float* gamma;
+  const float* beta;
+  const float* ss_scale; /* [B, ld_ss] per-image (1+scale) operand or NULL (use_scale_shift_norm) */
+  const float* ss_shift;
+  long long ld_ss;
+  int32_t n_out;         /* number of quantized outputs (0..3) */
+  int32_t reserved;
+  void* out_q[3];
+  long long ld_q[3];
+  qd_qparams q[3];
+  float* out_f;          /* optional fp32 output (NULL if unused) */
+  long long ld_f;
+  float* ws;
+} qd_groupnorm_desc;
+
+int qd_groupnorm_quant(const qd_groupnorm_desc* d, qd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * qd_layernorm_quant -- nn.LayerNorm(C) (eps 1e-5) followed by the act quantizers of its
+ * consumers (to_q/to_k/to_v or ff.net.0.proj; qdiff/quant_block.py:268-270).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct qd_layernorm_desc {
+  const float* x;
+  long long ld_x;
+  int32_t M, C;
+  float eps;
+  int32_t n_out;
+  const float* gamma;
+  const float* beta;
+  void* out_q[3];
+  long long ld_q[3];
+  qd_qparams q[3];
+} qd_layernorm_desc;
+
+int qd_layernorm_quant(const qd_layernorm_desc* d, qd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * qd_im2col_i8 -- explicit patch gather for the convs the implicit-GEMM path does not take
+ * (stride-2 downsample convs: openaimodel.py:134-160 pad 1, ddim diffusion.py:55-74 pad (0,1,0,1);
+ * conv_in with C_in 3/4).  src: codes NHWC [B,H,W,C]; dst: [B*Ho*Wo, ld_dst], k = (ky*3+kx)*C + c,
+ * out-of-image taps = pad_code (the activation zero point == real 0), columns >= 9C zero.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct qd_im2col_desc {
+  const void* src;
+  void* dst;
+  long long ld_dst;
+  int32_t B, H, W, C;
+  int32_t Ho, Wo, stride, pad_top, pad_left;
+  int32_t pad_code;
+} qd_im2col_desc;
+
+int qd_im2col_i8(const qd_im2col_desc* d, qd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * qd_qattention -- quantised attention core:
+ *   CIFAR  QuantAttnBlock.forward            qdiff/quant_block.py:354-386
+ *   LDM    QuantQKMatMul/QuantSMVMatMul      qdiff/quant_block.py:123-157 (+ openaimodel.py:384-406)
+ *   SD     cross_attn_forward                qdiff/quant_block.py:190-221
+ * q,k: codes [B, Tq|Tk, *] with head h at columns q_off + h*head_stride (d codes each);
+ * vt: V codes TRANSPOSED [B, n_rows_v, Tk_pad] with head h at rows v_off + h*head_stride.
+ * S = sum_d (q-zq)(k-zk) * sim_scale (sim_scale = dq*dk*softmax scale), P = softmax_j(S) in fp32,
+ * Pq = clamp(rne(P/dw)+zw, 0.., 2^sm_bits-1) (sm_bits 8 or 16), out = dw*dv * sum_j (Pq-zw)(v-zv).
+ * out: fp32 [B, Tq, ld_out] at columns h*d.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct qd_attention_desc {
+  const void* q;
+  const void* k;
+  const void* vt;
+  long long ld_q, ld_k;      /* bytes per token row */
+  long long ld_vt;           /* bytes per V^T row (>= Tk, multiple of 16) */
+  long long v_batch_stride;  /* bytes between batches of V^T */
+  int32_t B, heads, d, Tq, Tk;
+  int32_t q_off, k_off, v_off, head_stride_q, head_stride_k, head_stride_v;
+  int32_t q_signed, k_signed, v_signed, p_signed;
+  int32_t zq, zk, zv, zw;
+  int32_t p_qmin, p_qmax, sm_bits;
+  float sim_scale;
+  float delta_w;             /* softmax quantizer step */
+  float out_scale;           /* delta_w * delta_v */
+  float* out;
+  long long ld_out;
+} qd_attention_desc;
+
+int qd_qattention(const qd_attention_desc* d, qd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Small fp32 helpers on the path.
+ *  qd_timestep_embedding: mode 0 = ldm timestep_embedding ([cos,sin], freq exp(-ln(1e4)*i/half),
+ *      ldm/modules/diffusionmodules/util.py:151-171); mode 1 = ddim get_timestep_embedding
+ *      ([sin,cos], divisor half-1, ddim/models/diffusion.py:6-24).
+ *  qd_copy2d: strided fp32 copy (torch.cat along channels, openaimodel.py:776).
+ *  qd_nchw_to_nhwc / qd_nhwc_to_nchw: UNet boundary layout change (latents are NCHW fp32).
+ *  qd_avgpool2x / qd_upsample2x_f32: Downsample(use_conv=False) / Upsample for resblock_updown.
+ * ------------------------------------------------------------------------------------------ */
+int qd_timestep_embedding(const float* t, int32_t B, int32_t dim, int32_t mode, float* out, qd_stream_t s);
+int qd_copy2d(const float* src, long long ld_src, float* dst, long long ld_dst, int32_t M, int32_t C, qd_stream_t s);
+int qd_nchw_to_nhwc(const float* src, float* dst, int32_t B, int32_t C, int32_t HW, qd_stream_t s);
+int qd_nhwc_to_nchw(const float* src, float* dst, int32_t B, int32_t C, int32_t HW, qd_stream_t s);
+int qd_avgpool2x(const float* src, float* dst, int32_t B, int32_t H, int32_t W, int32_t C, qd_stream_t s);
+int qd_upsample2x_f32(const float* src, float* dst, int32_t B, int32_t H, int32_t W, int32_t C, qd_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * qd_sampler_step -- closed-form latent update of the denoising loop, fused with the
+ * classifier-free-guidance combine (e_t = e_uc + s (e_c - e_uc), plms.py:185-190):
+ *   DDIM / generalized_steps (ddim/functions/denoising.py:23-29, ldm ddim.py:205-219) and the PLMS
+ *   Adams-Bashforth combine (plms.py:203-238).  All tensors fp32 NCHW, n = elements per tensor.
+ *   e_t' = c_e0*e + c_e1*old1 + c_e2*old2 + c_e3*old3   (PLMS order weights; DDIM: c_e0 = 1)
+ *   pred_x0 = (x - sqrt_one_minus_at * e_t') / sqrt(a_t)
+ *   x_prev = sqrt(a_prev) * pred_x0 + dir_coef * e_t' + sigma * noise
+ * ------------------------------------------------------------------------------------------ */
+typedef struct qd_sampler_desc {
+  const float* x;
+  const float* eps;       /* [n] or, with cfg_scale != 0, [2n]: uncond half then cond half */
+  const float* old1;
+  const float* old2;
+  const float* old3;
+  const float* noise;     /* NULL when sigma == 0 */
+  float* x_prev;
+  float* pred_x0;         /* optional */
+  float* eps_out;         /* optional: guided (combined) eps e_t before multistep weights */
+  long long n;
+  float cfg_scale;        /* 0 = no guidance (eps has n elements) */
+  float c_e0, c_e1, c_e2, c_e3;
+  float sqrt_at, sqrt_one_minus_at, sqrt_a_prev, dir_coef, sigma;
+} qd_sampler_desc;
+
+int qd_sampler_step(const qd_sampler_desc* d, qd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Engine: a recorded program of the ops above for one UNet (QuantModel.forward,
+ * qdiff/quant_model.py:68-69 -> UNetModel.forward openaimodel.py:745-782 / Model.forward
+ * ddim/models/diffusion.py:308-360).  The host graph builder (qdiff_b200/graph.py) records ops
+ * once; qd_engine_run replays them on a stream (optionally as one CUDA graph).  The engine owns
+ * only the recorded descriptors and TMA maps; buffers belong to the caller.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct qd_engine qd_engine;
+
+enum qd_op_kind {
+  QD_OP_GEMM = 1,
+  QD_OP_QUANTIZE = 2,
+  QD_OP_GROUPNORM = 3,
+  QD_OP_LAYERNORM = 4,
+  QD_OP_IM2COL = 5,
+  QD_OP_ATTENTION = 6,
+  QD_OP_TIMESTEP_EMB = 7,
+  QD_OP_COPY2D = 8,
+  QD_OP_NCHW_TO_NHWC = 9,
+  QD_OP_NHWC_TO_NCHW = 10,
+  QD_OP_AVGPOOL2X = 11,
+  QD_OP_UPSAMPLE2X = 12
+};
+
+/* generic argument block for the small helpers when recorded into an engine */
+typedef struct qd_misc_desc {
+  const float* src;
+  float* dst;
+  long long ld_src, ld_dst;
+  int32_t a, b, c, d;   /* meaning per op: see qd_engine_add_op */
+} qd_misc_desc;
+
+int qd_engine_create(int device, qd_engine** out);
+/* desc points at the matching qd_*_desc (qd_misc_desc for kinds >= 7); copied. */
+int qd_engine_add_op(qd_engine* e, int kind, const void* desc);
+int qd_engine_num_ops(const qd_engine* e);
+int qd_engine_finalize(qd_engine* e);
+int qd_engine_run(qd_engine* e, qd_stream_t stream);
+/* run ops [first, last) only (debug / per-layer parity) */
+int qd_engine_run_range(qd_engine* e, int first, int last, qd_stream_t stream);
+void qd_engine_destroy(qd_engine* e);
+
+const char* qd_last_error(void);
+int qd_num_sms(void);
+/* number of kernels this library launched since load (bench.py "gpu_launches") */
+long long qd_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QDIFF_B200_H */

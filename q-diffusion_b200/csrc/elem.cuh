@@ -1,0 +1,376 @@
+// Memory-bound fused kernels on the UNet path: activation quantizers with their elementwise
+// producers (SiLU / GEGLU / nearest-2x upsample / split-shortcut), GroupNorm(+SiLU)+quant,
+// LayerNorm+multi-consumer quant, im2col for the strided convs, layout changes, sampler update.
+// All are HBM-bound: 128-bit loads, channel-contiguous (NHWC) coalescing, grids sized in
+// multiples of the SM count with grid-stride loops.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/qdiff_b200.h"
+
+namespace qd {
+
+__device__ __forceinline__ uint32_t quant_code(float y, const qd_qparams& q) {
+  // UniformAffineQuantizer.forward, qdiff/quant_layer.py:82-87: rne(x/delta) + zp, clamp.
+  float t = rintf(__fdiv_rn(y, q.delta)) + (float)q.zero_point;
+  t = fminf(fmaxf(t, (float)q.qmin), (float)q.qmax);
+  return (uint32_t)(int)t & 0xFFu;
+}
+__device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  return a | (b << 8) | (c << 16) | (d << 24);
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// ------------------------------------------------------------------------------------ quantize
+// One thread = 4 consecutive channels of one row.
+__global__ void quantize_kernel(const qd_quantize_desc p) {
+  const int cq = p.C >> 2;
+  const long long rows_out = p.upsample2x ? (long long)p.B * (2 * p.H) * (2 * p.W) : (long long)p.M;
+  const long long total = rows_out * cq;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long ro = i / cq;
+    const int c = (int)(i - ro * cq) << 2;
+    long long rs = ro;
+    if (p.upsample2x) {
+      const int W2 = 2 * p.W, H2 = 2 * p.H;
+      const int w2 = (int)(ro % W2);
+      const long long t = ro / W2;
+      const int h2 = (int)(t % H2);
+      const long long b = t / H2;
+      rs = (b * p.H + (h2 >> 1)) * p.W + (w2 >> 1);
+    }
+    const float* s = p.src + rs * p.ld_src + c;
+    float4 v = *reinterpret_cast<const float4*>(s);
+    if (p.act == 1) {
+      v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
+    } else if (p.act == 2) {
+      const float4 g = *reinterpret_cast<const float4*>(s + p.C);
+      v.x *= gelu_erf_f(g.x); v.y *= gelu_erf_f(g.y); v.z *= gelu_erf_f(g.z); v.w *= gelu_erf_f(g.w);
+    }
+    uint32_t out;
+    if (p.split > 0 && c >= p.split) {
+      out = pack4(quant_code(v.x, p.q1), quant_code(v.y, p.q1), quant_code(v.z, p.q1), quant_code(v.w, p.q1));
+    } else {
+      out = pack4(quant_code(v.x, p.q0), quant_code(v.y, p.q0), quant_code(v.z, p.q0), quant_code(v.w, p.q0));
+    }
+    *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.dst) + ro * p.ld_dst + c) = out;
+  }
+}
+
+// scalar tail variant for C % 4 != 0 (conv_in with 3 input channels, etc.)
+__global__ void quantize_scalar_kernel(const qd_quantize_desc p) {
+  const long long total = (long long)p.M * p.C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / p.C;
+    const int c = (int)(i - r * p.C);
+    float v = p.src[r * p.ld_src + c];
+    if (p.act == 1) v = silu_f(v);
+    else if (p.act == 2) v *= gelu_erf_f(p.src[r * p.ld_src + p.C + c]);
+    const qd_qparams& q = (p.split > 0 && c >= p.split) ? p.q1 : p.q0;
+    reinterpret_cast<uint8_t*>(p.dst)[r * p.ld_dst + c] = (uint8_t)quant_code(v, q);
+  }
+}
+
+// ------------------------------------------------------------------------------------ groupnorm
+// Pass 1: per (image, slab of pixels) per-channel partial sums. block = (C/4 threads rounded to warp) x rows.
+constexpr int GN_SLAB = 64;  // pixels per partial-sum slab
+__global__ void gn_partial_kernel(const float* __restrict__ x, long long ld_x, int HW, int C, int nslab,
+                                  float* __restrict__ ws) {
+  // grid: (nslab, B); threads stride over channel quads
+  const int b = blockIdx.y, slab = blockIdx.x;
+  const int p0 = slab * GN_SLAB;
+  const int p1 = min(HW, p0 + GN_SLAB);
+  const int cq = C >> 2;
+  float* o = ws + ((long long)b * nslab + slab) * C * 2;
+  for (int q = threadIdx.x; q < cq; q += blockDim.x) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* base = x + ((long long)b * HW + p0) * ld_x + (q << 2);
+    for (int p = p0; p < p1; ++p) {
+      const float4 v = *reinterpret_cast<const float4*>(base);
+      base += ld_x;
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      ss.x += v.x * v.x; ss.y += v.y * v.y; ss.z += v.z * v.z; ss.w += v.w * v.w;
+    }
+    *reinterpret_cast<float4*>(o + (q << 2)) = s;
+    *reinterpret_cast<float4*>(o + C + (q << 2)) = ss;
+  }
+}
+// Pass 2: per (image, group): reduce slabs and channels in double -> mean, rstd.
+__global__ void gn_finalize_kernel(const float* __restrict__ ws, int HW, int C, int groups, int nslab, float eps,
+                                   float* __restrict__ stats) {
+  const int b = blockIdx.y, g = blockIdx.x;
+  const int cpg = C / groups;
+  double s = 0.0, ss = 0.0;
+  const int n = nslab * cpg;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int slab = i / cpg, c = g * cpg + (i - slab * cpg);
+    const float* o = ws + ((long long)b * nslab + slab) * C * 2;
+    s += (double)o[c];
+    ss += (double)o[C + c];
+  }
+  __shared__ double sh[2][32];
+  for (int off = 16; off > 0; off >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, off);
+    ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sh[0][w] = s; sh[1][w] = ss; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    s = l < nw ? sh[0][l] : 0.0;
+    ss = l < nw ? sh[1][l] : 0.0;
+    for (int off = 16; off > 0; off >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, off);
+      ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    }
+    if (l == 0) {
+      const double cnt = (double)HW * cpg;
+      const double mean = s / cnt;
+      double var = ss / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      stats[((long long)b * groups + g) * 2] = (float)mean;
+      stats[((long long)b * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  }
+}
+// Pass 3: normalise + affine (+scale-shift) (+SiLU) + quantise for each consumer.
+__global__ void gn_apply_kernel(const qd_groupnorm_desc p, const float* __restrict__ stats) {
+  const int cq = p.C >> 2;
+  const int cpg = p.C / p.groups;
+  const long long total = (long long)p.B * p.HW * cq;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cq;
+    const int c = (int)(i - r * cq) << 2;
+    const int b = (int)(r / p.HW);
+    const float4 v = *reinterpret_cast<const float4*>(p.x + r * p.ld_x + c);
+    float y[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ch = c + j;
+      const int g = ch / cpg;
+      const float mean = __ldg(stats + ((long long)b * p.groups + g) * 2);
+      const float rstd = __ldg(stats + ((long long)b * p.groups + g) * 2 + 1);
+      float t = (y[j] - mean) * rstd * __ldg(p.gamma + ch) + __ldg(p.beta + ch);
+      if (p.ss_scale)
+        t = t * (1.0f + __ldg(p.ss_scale + (long long)b * p.ld_ss + ch)) + __ldg(p.ss_shift + (long long)b * p.ld_ss + ch);
+      if (p.silu) t = silu_f(t);
+      y[j] = t;
+    }
+    if (p.out_f) *reinterpret_cast<float4*>(p.out_f + r * p.ld_f + c) = make_float4(y[0], y[1], y[2], y[3]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (k < p.n_out) {
+        const uint32_t o = pack4(quant_code(y[0], p.q[k]), quant_code(y[1], p.q[k]), quant_code(y[2], p.q[k]),
+                                 quant_code(y[3], p.q[k]));
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.out_q[k]) + r * p.ld_q[k] + c) = o;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ layernorm
+// One warp per row; row kept in registers (C <= 4096), two-pass mean / variance in fp32.
+constexpr int LN_MAX_VEC = 32;  // float4 per lane -> C <= 4096
+__global__ void layernorm_quant_kernel(const qd_layernorm_desc p) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cq = p.C >> 2;
+  for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < p.M;
+       row += (long long)gridDim.x * warps_per_block) {
+    const float* xr = p.x + row * p.ld_x;
+    float4 v[LN_MAX_VEC];
+    float s = 0.f;
+    int n = 0;
+    for (int q = lane; q < cq; q += 32, ++n) {
+      v[n] = *reinterpret_cast<const float4*>(xr + (q << 2));
+      s += (v[n].x + v[n].y) + (v[n].z + v[n].w);
+    }
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    const float mean = s / (float)p.C;
+    float ss = 0.f;
+    for (int k = 0; k < n; ++k) {
+      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+      ss += (a * a + b * b) + (c * c + d * d);
+    }
+    for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    const float rstd = 1.0f / sqrtf(ss / (float)p.C + p.eps);
+    n = 0;
+    for (int q = lane; q < cq; q += 32, ++n) {
+      const int c = q << 2;
+      const float4 g = *reinterpret_cast<const float4*>(p.gamma + c);
+      const float4 be = *reinterpret_cast<const float4*>(p.beta + c);
+      float y0 = (v[n].x - mean) * rstd * g.x + be.x;
+      float y1 = (v[n].y - mean) * rstd * g.y + be.y;
+      float y2 = (v[n].z - mean) * rstd * g.z + be.z;
+      float y3 = (v[n].w - mean) * rstd * g.w + be.w;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (k < p.n_out) {
+          const uint32_t o = pack4(quant_code(y0, p.q[k]), quant_code(y1, p.q[k]), quant_code(y2, p.q[k]),
+                                   quant_code(y3, p.q[k]));
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.out_q[k]) + row * p.ld_q[k] + c) = o;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ im2col
+__global__ void im2col_kernel(const qd_im2col_desc p) {
+  // one thread = one byte-quad where possible; generic byte path keeps it simple (small tensors).
+  const long long rows = (long long)p.B * p.Ho * p.Wo;
+  const int K = 9 * p.C;
+  const long long total = rows * p.ld_dst;
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(p.src);
+  uint8_t* dst = reinterpret_cast<uint8_t*>(p.dst);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / p.ld_dst;
+    const int k = (int)(i - r * p.ld_dst);
+    uint8_t val = 0;
+    if (k < K) {
+      const int tap = k / p.C, c = k - tap * p.C;
+      const int ky = tap / 3, kx = tap - ky * 3;
+      const int wo = (int)(r % p.Wo);
+      const long long t = r / p.Wo;
+      const int ho = (int)(t % p.Ho);
+      const long long b = t / p.Ho;
+      const int h = ho * p.stride - p.pad_top + ky;
+      const int w = wo * p.stride - p.pad_left + kx;
+      if (h >= 0 && h < p.H && w >= 0 && w < p.W)
+        val = src[((b * p.H + h) * p.W + w) * p.C + c];
+      else
+        val = (uint8_t)p.pad_code;
+    }
+    dst[i] = val;
+  }
+}
+
+// ------------------------------------------------------------------------------------ misc fp32
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, int dim, int mode,
+                                          float* __restrict__ out) {
+  const int half = dim / 2;
+  const int total = B * half;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / half, k = i - b * half;
+    // mode 0 (ldm util.py:162-166): freqs = exp(-log(10000) * k / half); emb = [cos, sin]
+    // mode 1 (ddim diffusion.py:16-21): freqs = exp(k * -(log(10000)/(half-1))); emb = [sin, cos]
+    float freq;
+    if (mode == 0) freq = expf(-9.210340371976184f * (float)k / (float)half);
+    else           freq = expf((float)k * -(9.210340371976184f / (float)(half - 1)));
+    const float a = t[b] * freq;
+    const float sv = sinf(a), cv = cosf(a);
+    float* o = out + (long long)b * dim;
+    if (mode == 0) { o[k] = cv; o[half + k] = sv; }
+    else           { o[k] = sv; o[half + k] = cv; }
+    if ((dim & 1) && k == 0) o[dim - 1] = 0.f;
+  }
+}
+
+__global__ void copy2d_kernel(const float* __restrict__ src, long long ld_src, float* __restrict__ dst,
+                              long long ld_dst, int M, int C) {
+  const int cq = C >> 2;
+  const long long total = (long long)M * cq;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cq;
+    const int c = (int)(i - r * cq) << 2;
+    *reinterpret_cast<float4*>(dst + r * ld_dst + c) = *reinterpret_cast<const float4*>(src + r * ld_src + c);
+  }
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int HW) {
+  const long long total = (long long)B * C * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    // i indexes dst (b, p, c)
+    const int c = (int)(i % C);
+    const long long t = i / C;
+    const int p = (int)(t % HW);
+    const long long b = t / HW;
+    dst[i] = src[(b * C + c) * HW + p];
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int HW) {
+  const long long total = (long long)B * C * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    // i indexes dst (b, c, p)
+    const int p = (int)(i % HW);
+    const long long t = i / HW;
+    const int c = (int)(t % C);
+    const long long b = t / C;
+    dst[i] = src[(b * HW + p) * C + c];
+  }
+}
+
+__global__ void avgpool2x_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, cq = C >> 2;
+  const long long total = (long long)B * Ho * Wo * cq;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cq) << 2;
+    long long t = i / cq;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const long long b = t / Ho;
+    const float* s = src + ((b * H + 2 * ho) * W + 2 * wo) * (long long)C + c;
+    const float4 a = *reinterpret_cast<const float4*>(s);
+    const float4 bq = *reinterpret_cast<const float4*>(s + C);
+    const float4 cc = *reinterpret_cast<const float4*>(s + (long long)W * C);
+    const float4 d = *reinterpret_cast<const float4*>(s + (long long)W * C + C);
+    float4 o;
+    o.x = (a.x + bq.x + cc.x + d.x) * 0.25f;
+    o.y = (a.y + bq.y + cc.y + d.y) * 0.25f;
+    o.z = (a.z + bq.z + cc.z + d.z) * 0.25f;
+    o.w = (a.w + bq.w + cc.w + d.w) * 0.25f;
+    *reinterpret_cast<float4*>(dst + ((b * Ho + ho) * Wo + wo) * (long long)C + c) = o;
+  }
+}
+__global__ void upsample2x_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int H, int W,
+                                      int C) {
+  const int H2 = 2 * H, W2 = 2 * W, cq = C >> 2;
+  const long long total = (long long)B * H2 * W2 * cq;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cq) << 2;
+    long long t = i / cq;
+    const int w2 = (int)(t % W2); t /= W2;
+    const int h2 = (int)(t % H2);
+    const long long b = t / H2;
+    *reinterpret_cast<float4*>(dst + ((b * H2 + h2) * W2 + w2) * (long long)C + c) =
+        *reinterpret_cast<const float4*>(src + ((b * H + (h2 >> 1)) * W + (w2 >> 1)) * (long long)C + c);
+  }
+}
+
+// ------------------------------------------------------------------------------------ sampler
+__global__ void sampler_step_kernel(const qd_sampler_desc p) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float e;
+    if (p.cfg_scale != 0.f) {
+      const float eu = p.eps[i], ec = p.eps[p.n + i];
+      e = eu + p.cfg_scale * (ec - eu);
+    } else {
+      e = p.eps[i];
+    }
+    if (p.eps_out) p.eps_out[i] = e;
+    float ep = p.c_e0 * e;
+    if (p.old1) ep += p.c_e1 * p.old1[i];
+    if (p.old2) ep += p.c_e2 * p.old2[i];
+    if (p.old3) ep += p.c_e3 * p.old3[i];
+    const float x = p.x[i];
+    const float x0 = (x - p.sqrt_one_minus_at * ep) / p.sqrt_at;
+    float xp = p.sqrt_a_prev * x0 + p.dir_coef * ep;
+    if (p.noise) xp += p.sigma * p.noise[i];
+    if (p.pred_x0) p.pred_x0[i] = x0;
+    p.x_prev[i] = xp;
+  }
+}
+
+}  // namespace qd

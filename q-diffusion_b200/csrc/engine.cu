@@ -1,0 +1,472 @@
+// C ABI of libqdiff_b200.so (see include/qdiff_b200.h): per-op launchers + recorded-program engine.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/qdiff_b200.h"
+#include "attention.cuh"
+#include "elem.cuh"
+#include "gemm_i8.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+int g_num_sms = 0;
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(QD_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return QD_OK;
+}
+
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+      fail(QD_ERR_CUDA, "no CUDA device: qdiff_b200 has no CPU fallback");
+      return 0;
+    }
+    g_num_sms = n;
+  }
+  return g_num_sms;
+}
+
+int grid_for(long long work_items, int threads, int per_sm = 8) {
+  const int sms = num_sms();
+  long long blocks = (work_items + threads - 1) / threads;
+  long long cap = (long long)sms * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ------------------------------------------------------------------ TMA descriptor encode
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+int encode_u8_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                  const cuuint32_t* box) {
+  auto enc = get_encode();
+  if (!enc) return fail(QD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(QD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return QD_OK;
+}
+
+// ------------------------------------------------------------------ GEMM plan
+struct GemmPlan {
+  CUtensorMap tmA, tmB;
+  qd::GemmArgs args;
+  int grid, smem;
+};
+
+int pick_bn(int N, int tiles_m, int sms, int hint) {
+  if (hint > 0) return hint;
+  int best = 16;
+  long long best_cost = -1;
+  const int n16 = (N + 15) / 16 * 16;
+  for (int bn = 16; bn <= 256; bn += 16) {
+    if (bn > n16) break;
+    const long long tiles = (long long)tiles_m * ((N + bn - 1) / bn);
+    const long long waves = (tiles + sms - 1) / sms;
+    const long long cost = waves * (bn + 24);
+    if (best_cost < 0 || cost < best_cost || (cost == best_cost && bn > best)) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
+  if (!d || !d->a || !d->w || !d->scale) return fail(QD_ERR_BAD_ARG, "gemm: null operand");
+  if (d->taps != 1 && d->taps != 9) return fail(QD_ERR_UNSUPPORTED, "gemm: taps must be 1 or 9 (got %d)", d->taps);
+  if (d->C <= 0 || (d->C % 32) != 0) return fail(QD_ERR_UNSUPPORTED, "gemm: C=%d must be a positive multiple of 32", d->C);
+  if (d->M <= 0 || d->N <= 0) return fail(QD_ERR_BAD_ARG, "gemm: bad M/N");
+  if (!d->out && !d->out_q) return fail(QD_ERR_BAD_ARG, "gemm: no output");
+  const int sms = num_sms();
+  if (!sms) return QD_ERR_CUDA;
+
+  qd::GemmArgs& a = pl->args;
+  memset(&a, 0, sizeof(a));
+  a.M = d->M; a.N = d->N; a.C = d->C; a.taps = d->taps;
+  a.tiles_m = (d->M + qd::GEMM_BM - 1) / qd::GEMM_BM;
+  a.BN = pick_bn(d->N, a.tiles_m, sms, d->bn_hint);
+  if (a.BN % 16 || a.BN < 16 || a.BN > 256) return fail(QD_ERR_BAD_ARG, "gemm: bad BN %d", a.BN);
+  a.tiles_n = (d->N + a.BN - 1) / a.BN;
+  a.a_signed = d->a_signed; a.b_signed = 1;
+
+  const int stage_bytes = qd::GEMM_A_STAGE_BYTES + a.BN * qd::GEMM_BK;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > qd::GEMM_MAX_STAGES) stages = qd::GEMM_MAX_STAGES;
+  if (stages < 2) stages = 2;
+  a.stages = stages;
+  pl->smem = qd::gemm_smem_layout(a.BN, stages).total;
+
+  // ---- A map (always rank 4)
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4];
+  if (d->taps == 1) {
+    if (d->lda % 16) return fail(QD_ERR_UNSUPPORTED, "gemm: lda=%lld must be a multiple of 16", d->lda);
+    if (d->lda < d->C) return fail(QD_ERR_BAD_ARG, "gemm: lda < C");
+    dims[0] = (cuuint64_t)d->C; dims[1] = (cuuint64_t)d->M; dims[2] = 1; dims[3] = 1;
+    strides[0] = (cuuint64_t)d->lda; strides[1] = (cuuint64_t)d->lda * d->M; strides[2] = strides[1];
+    box[0] = qd::GEMM_BK; box[1] = qd::GEMM_BM; box[2] = 1; box[3] = 1;
+  } else {
+    const int H = d->H, W = d->W, B = d->B;
+    if (H <= 0 || W <= 0 || B <= 0 || (long long)B * H * W != d->M) return fail(QD_ERR_BAD_ARG, "gemm: conv geometry");
+    const int hw = H * W;
+    int bh, bn;
+    if (hw >= 128) {
+      if (128 % W) return fail(QD_ERR_UNSUPPORTED, "gemm: conv W=%d must divide 128", W);
+      bh = 128 / W; bn = 1;
+      if (H % bh) return fail(QD_ERR_UNSUPPORTED, "gemm: conv H=%d not a multiple of %d", H, bh);
+    } else {
+      if (128 % hw) return fail(QD_ERR_UNSUPPORTED, "gemm: conv H*W=%d must divide 128", hw);
+      bh = H; bn = 128 / hw;
+    }
+    a.H = H; a.W = W; a.bh = bh; a.bn = bn;
+    dims[0] = (cuuint64_t)d->C; dims[1] = (cuuint64_t)W; dims[2] = (cuuint64_t)H; dims[3] = (cuuint64_t)B;
+    strides[0] = (cuuint64_t)d->C; strides[1] = (cuuint64_t)d->C * W; strides[2] = (cuuint64_t)d->C * W * H;
+    box[0] = qd::GEMM_BK; box[1] = (cuuint32_t)W; box[2] = (cuuint32_t)bh; box[3] = (cuuint32_t)bn;
+  }
+  int rc = encode_u8_map(&pl->tmA, d->a, 4, dims, strides, box);
+  if (rc) return rc;
+  // ---- B map: [w_rows][taps*C]
+  {
+    const int w_rows = d->w_rows > 0 ? d->w_rows : d->N;
+    cuuint64_t bd[2] = {(cuuint64_t)d->taps * d->C, (cuuint64_t)w_rows};
+    cuuint64_t bs[1] = {(cuuint64_t)d->taps * d->C};
+    cuuint32_t bb[2] = {qd::GEMM_BK, (cuuint32_t)a.BN};
+    rc = encode_u8_map(&pl->tmB, d->w, 2, bd, bs, bb);
+    if (rc) return rc;
+  }
+  a.out = d->out; a.ldo = d->ldo;
+  a.out_q = reinterpret_cast<int8_t*>(d->out_q); a.ldq = d->ldq;
+  a.out_q_transposed = d->out_q_transposed;
+  a.rows_per_batch = d->rows_per_batch;
+  if ((d->rowvec || d->out_q_transposed) && d->rows_per_batch <= 0) return fail(QD_ERR_BAD_ARG, "gemm: rows_per_batch required");
+  a.q_delta = d->oq.delta; a.q_zp = d->oq.zero_point; a.q_lo = d->oq.qmin; a.q_hi = d->oq.qmax;
+  a.scale = d->scale; a.bias = d->bias; a.corr = d->corr;
+  a.rowvec = d->rowvec; a.ld_rowvec = d->ld_rowvec;
+  a.residual = d->residual; a.ldr = d->ldr;
+  const int tiles = a.tiles_m * a.tiles_n;
+  pl->grid = tiles < sms ? tiles : sms;
+  return QD_OK;
+}
+
+int launch_gemm(const GemmPlan& pl, cudaStream_t s) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(qd::gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) return fail(QD_ERR_CUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  qd::gemm_i8_kernel<<<pl.grid, qd::GEMM_THREADS, pl.smem, s>>>(pl.tmA, pl.tmB, pl.args);
+  return check_launch("gemm_i8_kernel");
+}
+
+// ------------------------------------------------------------------ elementwise launchers
+int launch_quantize(const qd_quantize_desc& d, cudaStream_t s) {
+  if (!d.src || !d.dst || d.M <= 0 || d.C <= 0) return fail(QD_ERR_BAD_ARG, "quantize: bad args");
+  const bool vec = (d.C % 4 == 0) && (d.ld_src % 4 == 0) && (d.ld_dst % 4 == 0) && (d.split % 4 == 0);
+  if (d.upsample2x && !vec) return fail(QD_ERR_UNSUPPORTED, "quantize: upsample needs C %% 4 == 0");
+  if (vec) {
+    const long long rows = d.upsample2x ? (long long)d.B * 4 * d.H * d.W : d.M;
+    qd::quantize_kernel<<<grid_for(rows * (d.C / 4), 256), 256, 0, s>>>(d);
+  } else {
+    qd::quantize_scalar_kernel<<<grid_for((long long)d.M * d.C, 256), 256, 0, s>>>(d);
+  }
+  return check_launch("quantize_kernel");
+}
+
+int launch_groupnorm(const qd_groupnorm_desc& d, cudaStream_t s) {
+  if (!d.x || !d.ws || !d.gamma || !d.beta) return fail(QD_ERR_BAD_ARG, "groupnorm: null arg");
+  if (d.C % 4 || d.C % d.groups || d.ld_x % 4) return fail(QD_ERR_UNSUPPORTED, "groupnorm: C=%d groups=%d", d.C, d.groups);
+  if (d.n_out < 0 || d.n_out > 3) return fail(QD_ERR_BAD_ARG, "groupnorm: n_out");
+  const int nslab = (d.HW + qd::GN_SLAB - 1) / qd::GN_SLAB;
+  float* stats = d.ws + (long long)d.B * nslab * d.C * 2;
+  int threads = d.C / 4;
+  threads = (threads + 31) / 32 * 32;
+  if (threads > 256) threads = 256;
+  qd::gn_partial_kernel<<<dim3(nslab, d.B), threads, 0, s>>>(d.x, d.ld_x, d.HW, d.C, nslab, d.ws);
+  int rc = check_launch("gn_partial_kernel");
+  if (rc) return rc;
+  qd::gn_finalize_kernel<<<dim3(d.groups, d.B), 128, 0, s>>>(d.ws, d.HW, d.C, d.groups, nslab, d.eps, stats);
+  rc = check_launch("gn_finalize_kernel");
+  if (rc) return rc;
+  qd::gn_apply_kernel<<<grid_for((long long)d.B * d.HW * (d.C / 4), 256), 256, 0, s>>>(d, stats);
+  return check_launch("gn_apply_kernel");
+}
+
+int launch_layernorm(const qd_layernorm_desc& d, cudaStream_t s) {
+  if (!d.x || !d.gamma || !d.beta) return fail(QD_ERR_BAD_ARG, "layernorm: null arg");
+  if (d.C % 4 || d.C > 4 * 32 * qd::LN_MAX_VEC || d.ld_x % 4) return fail(QD_ERR_UNSUPPORTED, "layernorm: C=%d", d.C);
+  if (d.n_out < 1 || d.n_out > 3) return fail(QD_ERR_BAD_ARG, "layernorm: n_out");
+  const int wpb = 8;
+  qd::layernorm_quant_kernel<<<grid_for((long long)d.M * 32, wpb * 32, 4), wpb * 32, 0, s>>>(d);
+  return check_launch("layernorm_quant_kernel");
+}
+
+int launch_im2col(const qd_im2col_desc& d, cudaStream_t s) {
+  if (!d.src || !d.dst) return fail(QD_ERR_BAD_ARG, "im2col: null arg");
+  if (d.ld_dst < 9 * d.C) return fail(QD_ERR_BAD_ARG, "im2col: ld_dst too small");
+  const long long total = (long long)d.B * d.Ho * d.Wo * d.ld_dst;
+  qd::im2col_kernel<<<grid_for(total, 256), 256, 0, s>>>(d);
+  return check_launch("im2col_kernel");
+}
+
+template <int DQ, int DV>
+int launch_attention_t(const qd_attention_desc& d, cudaStream_t s) {
+  dim3 grid((d.Tq + qd::ATT_BM - 1) / qd::ATT_BM, d.B * d.heads);
+  const bool qs = d.q_signed != 0, vs = d.v_signed != 0, s16 = d.sm_bits > 8;
+#define QD_ATT(QS, VS, S16) qd::qattention_kernel<DQ, DV, QS, VS, S16><<<grid, qd::ATT_WARPS * 32, 0, s>>>(d)
+  if (qs && vs && s16) QD_ATT(true, true, true);
+  else if (qs && vs && !s16) QD_ATT(true, true, false);
+  else if (!qs && !vs && s16) QD_ATT(false, false, true);
+  else if (!qs && !vs && !s16) QD_ATT(false, false, false);
+  else return fail(QD_ERR_UNSUPPORTED, "attention: mixed signedness q=%d v=%d", d.q_signed, d.v_signed);
+#undef QD_ATT
+  return check_launch("qattention_kernel");
+}
+
+int launch_attention(const qd_attention_desc& d, cudaStream_t s) {
+  if (!d.q || !d.k || !d.vt || !d.out) return fail(QD_ERR_BAD_ARG, "attention: null arg");
+  if (d.q_signed != d.k_signed) return fail(QD_ERR_UNSUPPORTED, "attention: q/k signedness differ");
+  if (d.zw != 0) return fail(QD_ERR_UNSUPPORTED, "attention: softmax zero point must be 0 (got %d)", d.zw);
+  if (d.sm_bits != 8 && d.sm_bits != 16) return fail(QD_ERR_UNSUPPORTED, "attention: sm_bits %d", d.sm_bits);
+  if (d.ld_vt % 16 || d.ld_vt < d.Tk) return fail(QD_ERR_BAD_ARG, "attention: ld_vt");
+  if ((d.q_off | d.k_off | d.head_stride_q | d.head_stride_k | (int)d.ld_q | (int)d.ld_k) & 3) return fail(QD_ERR_UNSUPPORTED, "attention: 4-byte alignment");
+  if (d.ld_out % 2) return fail(QD_ERR_UNSUPPORTED, "attention: ld_out");
+  switch (d.d) {
+    case 24: return launch_attention_t<32, 24>(d, s);
+    case 32: return launch_attention_t<32, 32>(d, s);
+    case 40: return launch_attention_t<64, 40>(d, s);
+    case 48: return launch_attention_t<64, 48>(d, s);
+    case 64: return launch_attention_t<64, 64>(d, s);
+    case 80: return launch_attention_t<96, 80>(d, s);
+    case 96: return launch_attention_t<96, 96>(d, s);
+    case 160: return launch_attention_t<160, 160>(d, s);
+    case 256: return launch_attention_t<256, 256>(d, s);
+    default: return fail(QD_ERR_UNSUPPORTED, "attention: head dim %d not instantiated", d.d);
+  }
+}
+
+int launch_misc(int kind, const qd_misc_desc& m, cudaStream_t s) {
+  switch (kind) {
+    case QD_OP_TIMESTEP_EMB:
+      qd::timestep_embedding_kernel<<<grid_for((long long)m.a * (m.b / 2), 128), 128, 0, s>>>(m.src, m.a, m.b, m.c, m.dst);
+      return check_launch("timestep_embedding_kernel");
+    case QD_OP_COPY2D:
+      if (m.b % 4 || m.ld_src % 4 || m.ld_dst % 4) return fail(QD_ERR_UNSUPPORTED, "copy2d: alignment");
+      qd::copy2d_kernel<<<grid_for((long long)m.a * (m.b / 4), 256), 256, 0, s>>>(m.src, m.ld_src, m.dst, m.ld_dst, m.a, m.b);
+      return check_launch("copy2d_kernel");
+    case QD_OP_NCHW_TO_NHWC:
+      qd::nchw_to_nhwc_kernel<<<grid_for((long long)m.a * m.b * m.c, 256), 256, 0, s>>>(m.src, m.dst, m.a, m.b, m.c);
+      return check_launch("nchw_to_nhwc_kernel");
+    case QD_OP_NHWC_TO_NCHW:
+      qd::nhwc_to_nchw_kernel<<<grid_for((long long)m.a * m.b * m.c, 256), 256, 0, s>>>(m.src, m.dst, m.a, m.b, m.c);
+      return check_launch("nhwc_to_nchw_kernel");
+    case QD_OP_AVGPOOL2X:
+      if (m.d % 4) return fail(QD_ERR_UNSUPPORTED, "avgpool: C %% 4");
+      qd::avgpool2x_kernel<<<grid_for((long long)m.a * (m.b / 2) * (m.c / 2) * (m.d / 4), 256), 256, 0, s>>>(m.src, m.dst, m.a, m.b, m.c, m.d);
+      return check_launch("avgpool2x_kernel");
+    case QD_OP_UPSAMPLE2X:
+      if (m.d % 4) return fail(QD_ERR_UNSUPPORTED, "upsample: C %% 4");
+      qd::upsample2x_f32_kernel<<<grid_for((long long)m.a * m.b * m.c * m.d, 256), 256, 0, s>>>(m.src, m.dst, m.a, m.b, m.c, m.d);
+      return check_launch("upsample2x_f32_kernel");
+    default:
+      return fail(QD_ERR_BAD_ARG, "misc: unknown kind %d", kind);
+  }
+}
+
+struct Op {
+  int kind;
+  GemmPlan gemm;
+  union {
+    qd_quantize_desc quant;
+    qd_groupnorm_desc gn;
+    qd_layernorm_desc ln;
+    qd_im2col_desc im2col;
+    qd_attention_desc att;
+    qd_misc_desc misc;
+  };
+  Op() : kind(0) { memset(&gemm, 0, sizeof(gemm)); memset(&gn, 0, sizeof(gn)); }
+};
+
+int run_op(const Op& op, cudaStream_t s) {
+  switch (op.kind) {
+    case QD_OP_GEMM: return launch_gemm(op.gemm, s);
+    case QD_OP_QUANTIZE: return launch_quantize(op.quant, s);
+    case QD_OP_GROUPNORM: return launch_groupnorm(op.gn, s);
+    case QD_OP_LAYERNORM: return launch_layernorm(op.ln, s);
+    case QD_OP_IM2COL: return launch_im2col(op.im2col, s);
+    case QD_OP_ATTENTION: return launch_attention(op.att, s);
+    default: return launch_misc(op.kind, op.misc, s);
+  }
+}
+
+}  // namespace
+
+struct qd_engine {
+  int device;
+  bool finalized;
+  std::vector<Op> ops;
+};
+
+extern "C" {
+
+const char* qd_last_error(void) { return g_err; }
+int qd_num_sms(void) { return num_sms(); }
+long long qd_launch_count(void) { return g_launches.load(); }
+
+int qd_qgemm_i8(const qd_gemm_desc* d, qd_stream_t stream) {
+  GemmPlan pl;
+  int rc = plan_gemm(d, &pl);
+  if (rc) return rc;
+  return launch_gemm(pl, (cudaStream_t)stream);
+}
+int qd_quantize(const qd_quantize_desc* d, qd_stream_t s) {
+  if (!d) return fail(QD_ERR_BAD_ARG, "null desc");
+  return launch_quantize(*d, (cudaStream_t)s);
+}
+int qd_groupnorm_quant(const qd_groupnorm_desc* d, qd_stream_t s) {
+  if (!d) return fail(QD_ERR_BAD_ARG, "null desc");
+  return launch_groupnorm(*d, (cudaStream_t)s);
+}
+int qd_layernorm_quant(const qd_layernorm_desc* d, qd_stream_t s) {
+  if (!d) return fail(QD_ERR_BAD_ARG, "null desc");
+  return launch_layernorm(*d, (cudaStream_t)s);
+}
+int qd_im2col_i8(const qd_im2col_desc* d, qd_stream_t s) {
+  if (!d) return fail(QD_ERR_BAD_ARG, "null desc");
+  return launch_im2col(*d, (cudaStream_t)s);
+}
+int qd_qattention(const qd_attention_desc* d, qd_stream_t s) {
+  if (!d) return fail(QD_ERR_BAD_ARG, "null desc");
+  return launch_attention(*d, (cudaStream_t)s);
+}
+int qd_timestep_embedding(const float* t, int32_t B, int32_t dim, int32_t mode, float* out, qd_stream_t s) {
+  qd_misc_desc m{t, out, 0, 0, B, dim, mode, 0};
+  return launch_misc(QD_OP_TIMESTEP_EMB, m, (cudaStream_t)s);
+}
+int qd_copy2d(const float* src, long long ld_src, float* dst, long long ld_dst, int32_t M, int32_t C, qd_stream_t s) {
+  qd_misc_desc m{src, dst, ld_src, ld_dst, M, C, 0, 0};
+  return launch_misc(QD_OP_COPY2D, m, (cudaStream_t)s);
+}
+int qd_nchw_to_nhwc(const float* src, float* dst, int32_t B, int32_t C, int32_t HW, qd_stream_t s) {
+  qd_misc_desc m{src, dst, 0, 0, B, C, HW, 0};
+  return launch_misc(QD_OP_NCHW_TO_NHWC, m, (cudaStream_t)s);
+}
+int qd_nhwc_to_nchw(const float* src, float* dst, int32_t B, int32_t C, int32_t HW, qd_stream_t s) {
+  qd_misc_desc m{src, dst, 0, 0, B, C, HW, 0};
+  return launch_misc(QD_OP_NHWC_TO_NCHW, m, (cudaStream_t)s);
+}
+int qd_avgpool2x(const float* src, float* dst, int32_t B, int32_t H, int32_t W, int32_t C, qd_stream_t s) {
+  qd_misc_desc m{src, dst, 0, 0, B, H, W, C};
+  return launch_misc(QD_OP_AVGPOOL2X, m, (cudaStream_t)s);
+}
+int qd_upsample2x_f32(const float* src, float* dst, int32_t B, int32_t H, int32_t W, int32_t C, qd_stream_t s) {
+  qd_misc_desc m{src, dst, 0, 0, B, H, W, C};
+  return launch_misc(QD_OP_UPSAMPLE2X, m, (cudaStream_t)s);
+}
+int qd_sampler_step(const qd_sampler_desc* d, qd_stream_t s) {
+  if (!d || !d->x || !d->eps || !d->x_prev || d->n <= 0) return fail(QD_ERR_BAD_ARG, "sampler: bad args");
+  qd::sampler_step_kernel<<<grid_for(d->n, 256), 256, 0, (cudaStream_t)s>>>(*d);
+  return check_launch("sampler_step_kernel");
+}
+
+int qd_engine_create(int device, qd_engine** out) {
+  if (!out) return fail(QD_ERR_BAD_ARG, "null out");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(QD_ERR_CUDA, "cudaSetDevice(%d) failed: no CPU fallback", device);
+  if (!num_sms()) return QD_ERR_CUDA;
+  qd_engine* e = new (std::nothrow) qd_engine();
+  if (!e) return fail(QD_ERR_BAD_ARG, "out of host memory");
+  e->device = device;
+  e->finalized = false;
+  *out = e;
+  return QD_OK;
+}
+
+int qd_engine_add_op(qd_engine* e, int kind, const void* desc) {
+  if (!e || !desc) return fail(QD_ERR_BAD_ARG, "null arg");
+  Op op;
+  op.kind = kind;
+  switch (kind) {
+    case QD_OP_GEMM: {
+      int rc = plan_gemm(reinterpret_cast<const qd_gemm_desc*>(desc), &op.gemm);
+      if (rc) return rc;
+      break;
+    }
+    case QD_OP_QUANTIZE: op.quant = *reinterpret_cast<const qd_quantize_desc*>(desc); break;
+    case QD_OP_GROUPNORM: op.gn = *reinterpret_cast<const qd_groupnorm_desc*>(desc); break;
+    case QD_OP_LAYERNORM: op.ln = *reinterpret_cast<const qd_layernorm_desc*>(desc); break;
+    case QD_OP_IM2COL: op.im2col = *reinterpret_cast<const qd_im2col_desc*>(desc); break;
+    case QD_OP_ATTENTION: op.att = *reinterpret_cast<const qd_attention_desc*>(desc); break;
+    case QD_OP_TIMESTEP_EMB: case QD_OP_COPY2D: case QD_OP_NCHW_TO_NHWC: case QD_OP_NHWC_TO_NCHW:
+    case QD_OP_AVGPOOL2X: case QD_OP_UPSAMPLE2X:
+      op.misc = *reinterpret_cast<const qd_misc_desc*>(desc);
+      break;
+    default: return fail(QD_ERR_BAD_ARG, "unknown op kind %d", kind);
+  }
+  e->ops.push_back(op);
+  e->finalized = false;
+  return QD_OK;
+}
+
+int qd_engine_num_ops(const qd_engine* e) { return e ? (int)e->ops.size() : 0; }
+
+int qd_engine_finalize(qd_engine* e) {
+  if (!e) return fail(QD_ERR_BAD_ARG, "null engine");
+  e->finalized = true;
+  return QD_OK;
+}
+
+int qd_engine_run_range(qd_engine* e, int first, int last, qd_stream_t stream) {
+  if (!e) return fail(QD_ERR_BAD_ARG, "null engine");
+  if (!e->finalized) return fail(QD_ERR_NOT_FINALIZED, "engine not finalized");
+  if (first < 0 || last > (int)e->ops.size() || first > last) return fail(QD_ERR_BAD_ARG, "bad op range");
+  for (int i = first; i < last; ++i) {
+    int rc = run_op(e->ops[i], (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return QD_OK;
+}
+int qd_engine_run(qd_engine* e, qd_stream_t stream) {
+  if (!e) return fail(QD_ERR_BAD_ARG, "null engine");
+  return qd_engine_run_range(e, 0, (int)e->ops.size(), stream);
+}
+void qd_engine_destroy(qd_engine* e) { delete e; }
+
+}  // extern "C"

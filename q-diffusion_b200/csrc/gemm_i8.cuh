@@ -1,0 +1,310 @@
+// INT8 tcgen05 GEMM / implicit-GEMM conv3x3 for sm_100a.
+//
+// Realises the reference's QuantModule.forward (qdiff/quant_layer.py:248-279) as true integer
+// compute:   y[m,n] = scale[n] * (sum_k xq[m,k]*ws[n,k] - corr[cls(m)][n]) + bias[n] (+ fused adds)
+// where xq are the activation codes (u8 or s8), ws = wq - zw the zero-point-free weight codes (s8),
+// scale[n] = delta_x * delta_w[n] and corr = zx * sum_k ws[n,k] (per border class for padded convs,
+// because the reference pads with real zeros AFTER de-quantisation).
+//
+// Structure (one CTA per SM, persistent, warp-specialised):
+//   warp 0   : TMA producer  (A tile 128 x 128 B, B tile BN x 128 B, 128B swizzle, mbarrier ring)
+//   warp 1   : MMA issuer    (tcgen05.mma.kind::i8, M=128, N=BN, K=32 per instruction, int32 acc in TMEM)
+//   warp 2   : TMEM allocator (512 columns: two accumulator stages of up to 256 columns)
+//   warps 4-7: epilogue      (tcgen05.ld -> zero-point correction -> scale/bias/adds -> fp32 or requantised store)
+#pragma once
+#include "ptx.cuh"
+
+namespace qd {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 128;  // bytes == int8 elements per k-block (one 128B swizzle row)
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK;
+constexpr int GEMM_MAX_STAGES = 8;
+
+struct GemmArgs {
+  int M, N;            // logical output rows / columns (columns >= N are masked)
+  int C;               // reduction length per tap (multiple of 32)
+  int taps;            // 1 = plain GEMM, 9 = 3x3 conv (stride 1, pad 1)
+  int BN;              // N tile (multiple of 16, <= 256)
+  int tiles_m, tiles_n;
+  int stages;
+  // conv geometry (taps == 9): activations are NHWC, tile = bn images x bh rows x W columns = 128 pixels
+  int H, W, bh, bn;
+  int a_signed, b_signed;
+  // epilogue
+  float* out;          // fp32 [M, ldo] or nullptr
+  long long ldo;
+  int8_t* out_q;       // requantised output (codes), [M, ldq] or transposed [M/rows_per_batch][N][rows_per_batch]
+  long long ldq;
+  int out_q_transposed;
+  int rows_per_batch;  // rows (pixels/tokens) per image: rowvec index and transposed-store geometry
+  float q_delta;
+  int q_zp, q_lo, q_hi;
+  const float* scale;      // [N]
+  const float* bias;       // [N] or nullptr
+  const int32_t* corr;     // [ncls][N] or nullptr   (ncls = 9 for conv, 1 plain)
+  const float* rowvec;     // [M/rows_per_batch][ld_rowvec] per-image per-channel add (timestep embedding) or nullptr
+  long long ld_rowvec;
+  const float* residual;   // [M, ldr] or nullptr (may alias out)
+  long long ldr;
+};
+
+struct GemmSmemLayout {
+  int stage_bytes;
+  int bar_offset;
+  int total;
+};
+
+__host__ __device__ inline GemmSmemLayout gemm_smem_layout(int BN, int stages) {
+  GemmSmemLayout l;
+  l.stage_bytes = GEMM_A_STAGE_BYTES + BN * GEMM_BK;
+  l.bar_offset = l.stage_bytes * stages;
+  l.total = l.bar_offset + 256 + 1024;  // barriers + alignment slack
+  return l;
+}
+
+template <int NC>
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& p, const uint32_t (&acc)[NC], int m, int n0,
+                                                    int cls, int img) {
+  // One thread: row m, columns n0 .. n0+NC-1.
+  float y[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    int n = n0 + j;
+    int a = (int)acc[j];
+    if (n < p.N) {
+      if (p.corr) a -= __ldg(p.corr + (long long)cls * p.N + n);
+      float v = (float)a * __ldg(p.scale + n);
+      if (p.bias) v += __ldg(p.bias + n);
+      if (p.rowvec) v += __ldg(p.rowvec + (long long)img * p.ld_rowvec + n);
+      y[j] = v;
+    } else {
+      y[j] = 0.f;
+    }
+  }
+  if (p.residual) {
+    const float* r = p.residual + (long long)m * p.ldr + n0;
+    if ((n0 + NC <= p.N) && ((p.ldr & 3) == 0)) {
+#pragma unroll
+      for (int j = 0; j < NC; j += 4) {
+        float4 rv = *reinterpret_cast<const float4*>(r + j);
+        y[j] += rv.x; y[j + 1] += rv.y; y[j + 2] += rv.z; y[j + 3] += rv.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        if (n0 + j < p.N) y[j] += r[j];
+    }
+  }
+  if (p.out) {
+    float* o = p.out + (long long)m * p.ldo + n0;
+    if ((n0 + NC <= p.N) && ((p.ldo & 3) == 0)) {
+#pragma unroll
+      for (int j = 0; j < NC; j += 4)
+        *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        if (n0 + j < p.N) o[j] = y[j];
+    }
+  }
+  if (p.out_q) {
+    // consumer's activation quantizer (qdiff/quant_layer.py:82-88): rne(y/delta)+zp, clamp
+    uint8_t q[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      float t = rintf(__fdiv_rn(y[j], p.q_delta)) + (float)p.q_zp;
+      t = fminf(fmaxf(t, (float)p.q_lo), (float)p.q_hi);
+      q[j] = (uint8_t)(int)t;
+    }
+    if (!p.out_q_transposed) {
+      int8_t* o = p.out_q + (long long)m * p.ldq + n0;
+      if ((n0 + NC <= p.N) && ((p.ldq & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < NC; j += 16) {
+          uint4 v;
+          v.x = q[j] | (q[j + 1] << 8) | (q[j + 2] << 16) | ((uint32_t)q[j + 3] << 24);
+          v.y = q[j + 4] | (q[j + 5] << 8) | (q[j + 6] << 16) | ((uint32_t)q[j + 7] << 24);
+          v.z = q[j + 8] | (q[j + 9] << 8) | (q[j + 10] << 16) | ((uint32_t)q[j + 11] << 24);
+          v.w = q[j + 12] | (q[j + 13] << 8) | (q[j + 14] << 16) | ((uint32_t)q[j + 15] << 24);
+          *reinterpret_cast<uint4*>(o + j) = v;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NC; ++j)
+          if (n0 + j < p.N) o[j] = (int8_t)q[j];
+      }
+    } else {
+      // [img][n][t]: consecutive lanes = consecutive t -> byte-coalesced across the warp
+      int t_in = m - img * p.rows_per_batch;
+      int8_t* o = p.out_q + ((long long)img * p.ldq + n0) * p.rows_per_batch + t_in;
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        if (n0 + j < p.N) o[(long long)j * p.rows_per_batch] = (int8_t)q[j];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
+  uint8_t* smem = smem_raw + pad;
+
+  const GemmSmemLayout lay = gemm_smem_layout(p.BN, p.stages);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_offset);
+  uint64_t* full_bar = bars;                          // [stages]
+  uint64_t* empty_bar = bars + GEMM_MAX_STAGES;       // [stages]
+  uint64_t* tmem_full = bars + 2 * GEMM_MAX_STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;               // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int kb_per_tap = (p.C + GEMM_BK - 1) / GEMM_BK;
+  const int num_kb = kb_per_tap * p.taps;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = (uint32_t)lay.stage_bytes;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile / p.tiles_n;
+        const int tn = tile - tm * p.tiles_n;
+        const int m0 = tm * GEMM_BM;
+        const int n0 = tn * p.BN;
+        int b0 = 0, h0 = 0;
+        if (p.taps == 9) {
+          const int hw = p.H * p.W;
+          b0 = m0 / hw;
+          h0 = (m0 - b0 * hw) / p.W;
+        }
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int ky = tap / 3, kx = tap - ky * 3;
+          for (int kc = 0; kc < kb_per_tap; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + (size_t)stage * lay.stage_bytes;
+            uint8_t* sb = sa + GEMM_A_STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            if (p.taps == 9)
+              tma_load_4d(sa, &tmA, &full_bar[stage], kc * GEMM_BK, kx - 1, h0 + ky - 1, b0);
+            else
+              tma_load_4d(sa, &tmA, &full_bar[stage], kc * GEMM_BK, m0, 0, 0);
+            tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.C + kc * GEMM_BK, n0);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_i8(GEMM_BM, p.BN, p.a_signed, p.b_signed);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int kc = kb % kb_per_tap;
+          const int rem = p.C - kc * GEMM_BK;
+          const int nmma = rem >= GEMM_BK ? 4 : (rem >> 5);
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * lay.stage_bytes);
+          const uint64_t da = make_smem_desc_sw128(sa);
+          const uint64_t db = make_smem_desc_sw128(sa + GEMM_A_STAGE_BYTES);
+          for (int j = 0; j < nmma; ++j) {
+            // advance 32 bytes (one K=32 slice) inside the 128B swizzle row: +2 in 16-byte units
+            umma_i8(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (kb | j) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tm = tile / p.tiles_n;
+      const int tn = tile - tm * p.tiles_n;
+      const int m = tm * GEMM_BM + q * 32 + lane;
+      const int n_base = tn * p.BN;
+      int cls = 0, img = 0;
+      if (p.rows_per_batch > 0) img = m / p.rows_per_batch;
+      if (p.taps == 9) {
+        const int hw = p.H * p.W;
+        const int r = m % hw;
+        const int h = r / p.W, w = r - h * p.W;
+        const int rc = (h == 0) ? 0 : (h == p.H - 1 ? 2 : 1);
+        const int cc = (w == 0) ? 0 : (w == p.W - 1 ? 2 : 1);
+        cls = rc * 3 + cc;
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
+      int c = 0;
+      for (; c + 32 <= p.BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (m < p.M && n_base + c < p.N) gemm_epilogue_chunk<32>(p, v, m, n_base + c, cls, img);
+      }
+      if (c < p.BN) {
+        uint32_t v[16];
+        tmem_ld_32x16(t_row + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (m < p.M && n_base + c < p.N) gemm_epilogue_chunk<16>(p, v, m, n_base + c, cls, img);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace qd

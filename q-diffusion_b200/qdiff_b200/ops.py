@@ -1,0 +1,144 @@
+"""Thin torch-tensor front ends of the C-ABI ops (one call = one launch on the current stream).
+
+Used by the graph builder (descriptor construction) and by the per-op parity tests.  Tensors are
+only containers for device memory here; all arithmetic happens inside libqdiff_b200.so.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (AttentionDesc, GemmDesc, GroupNormDesc, Im2colDesc, LayerNormDesc, MiscDesc, QParams,
+                   QuantizeDesc, SamplerDesc, check, lib, ptr, stream_ptr)
+
+
+def qparams(delta, zero_point, qmin, qmax):
+    return QParams(float(delta), int(zero_point), int(qmin), int(qmax))
+
+
+def act_qparams(delta, zero_point, n_bits, symmetric):
+    """Clamp range of UniformAffineQuantizer (qdiff/quant_layer.py:54,83-87)."""
+    if symmetric:
+        n_lv = 2 ** (n_bits - 1) - 1
+        return qparams(delta, 0, -n_lv - 1, n_lv)
+    return qparams(delta, zero_point, 0, 2 ** n_bits - 1)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("qdiff_b200 ops need CUDA tensors: there is no CPU fallback")
+
+
+def gemm_desc(a, w, scale, *, M, N, C, taps=1, lda=None, conv_bhw=None, a_signed=True, bias=None, corr=None,
+              rowvec=None, ld_rowvec=0, rows_per_batch=0, residual=None, ldr=0, out=None, ldo=0, out_q=None, ldq=0,
+              oq=None, out_q_transposed=False, bn_hint=0, w_rows=None):
+    d = GemmDesc()
+    d.a, d.w = ptr(a), ptr(w)
+    d.lda = int(lda if lda is not None else C)
+    d.M, d.N, d.C, d.taps = int(M), int(N), int(C), int(taps)
+    d.w_rows = int(w_rows if w_rows is not None else w.shape[0])
+    if conv_bhw is not None:
+        d.B, d.H, d.W = [int(v) for v in conv_bhw]
+    d.a_signed = 1 if a_signed else 0
+    d.scale, d.bias, d.corr, d.rowvec = ptr(scale), ptr(bias), ptr(corr), ptr(rowvec)
+    d.ld_rowvec, d.rows_per_batch = int(ld_rowvec), int(rows_per_batch)
+    d.out_q_transposed = 1 if out_q_transposed else 0
+    d.residual, d.ldr = ptr(residual), int(ldr)
+    d.out, d.ldo = ptr(out), int(ldo)
+    d.out_q, d.ldq = ptr(out_q), int(ldq)
+    d.oq = oq if oq is not None else qparams(1.0, 0, 0, 0)
+    d.bn_hint = int(bn_hint)
+    return d
+
+
+def qgemm(desc):
+    check(lib().qd_qgemm_i8(C.byref(desc), stream_ptr()), "qd_qgemm_i8")
+
+
+def quantize_desc(src, dst, *, M, C_, ld_src, ld_dst, q0, q1=None, act=0, split=0, upsample=None):
+    d = QuantizeDesc()
+    d.src, d.ld_src, d.dst, d.ld_dst = ptr(src), int(ld_src), ptr(dst), int(ld_dst)
+    d.M, d.C, d.act, d.split = int(M), int(C_), int(act), int(split)
+    d.q0 = q0
+    d.q1 = q1 if q1 is not None else q0
+    if upsample is not None:
+        d.upsample2x = 1
+        d.B, d.H, d.W = [int(v) for v in upsample]
+    return d
+
+
+def quantize(desc):
+    check(lib().qd_quantize(C.byref(desc), stream_ptr()), "qd_quantize")
+
+
+def gn_workspace_floats(B, HW, C_):
+    nslab = (HW + 63) // 64
+    return B * (nslab * C_ * 2 + 64)
+
+
+def groupnorm_desc(x, gamma, beta, ws, *, B, HW, C_, ld_x, eps, silu, outs, groups=32, ss=None, out_f=None, ld_f=0):
+    """outs: list of (tensor, ld, QParams)."""
+    d = GroupNormDesc()
+    d.x, d.ld_x = ptr(x), int(ld_x)
+    d.B, d.HW, d.C, d.groups = int(B), int(HW), int(C_), int(groups)
+    d.eps, d.silu = float(eps), 1 if silu else 0
+    d.gamma, d.beta = ptr(gamma), ptr(beta)
+    if ss is not None:
+        d.ss_scale, d.ss_shift, d.ld_ss = ptr(ss[0]), ptr(ss[1]), int(ss[2])
+    d.n_out = len(outs)
+    for i, (t, ld, q) in enumerate(outs):
+        d.out_q[i] = t.data_ptr()
+        d.ld_q[i] = int(ld)
+        d.q[i] = q
+    d.out_f, d.ld_f = ptr(out_f), int(ld_f)
+    d.ws = ptr(ws)
+    return d
+
+
+def groupnorm_quant(desc):
+    check(lib().qd_groupnorm_quant(C.byref(desc), stream_ptr()), "qd_groupnorm_quant")
+
+
+def layernorm_desc(x, gamma, beta, *, M, C_, ld_x, eps, outs):
+    d = LayerNormDesc()
+    d.x, d.ld_x, d.M, d.C, d.eps = ptr(x), int(ld_x), int(M), int(C_), float(eps)
+    d.gamma, d.beta = ptr(gamma), ptr(beta)
+    d.n_out = len(outs)
+    for i, (t, ld, q) in enumerate(outs):
+        d.out_q[i] = t.data_ptr()
+        d.ld_q[i] = int(ld)
+        d.q[i] = q
+    return d
+
+
+def layernorm_quant(desc):
+    check(lib().qd_layernorm_quant(C.byref(desc), stream_ptr()), "qd_layernorm_quant")
+
+
+def im2col_desc(src, dst, *, B, H, W, C_, Ho, Wo, stride, pad_top, pad_left, pad_code, ld_dst):
+    d = Im2colDesc()
+    d.src, d.dst, d.ld_dst = ptr(src), ptr(dst), int(ld_dst)
+    d.B, d.H, d.W, d.C = int(B), int(H), int(W), int(C_)
+    d.Ho, d.Wo, d.stride, d.pad_top, d.pad_left = int(Ho), int(Wo), int(stride), int(pad_top), int(pad_left)
+    d.pad_code = int(pad_code)
+    return d
+
+
+def im2col(desc):
+    check(lib().qd_im2col_i8(C.byref(desc), stream_ptr()), "qd_im2col_i8")
+
+
+def attention(desc):
+    check(lib().qd_qattention(C.byref(desc), stream_ptr()), "qd_qattention")
+
+
+def sampler_step(desc):
+    check(lib().qd_sampler_step(C.byref(desc), stream_ptr()), "qd_sampler_step")
+
+
+def timestep_embedding(t, dim, mode):
+    _require_cuda(t)
+    out = torch.empty(t.shape[0], dim, device=t.device, dtype=torch.float32)
+    check(lib().qd_timestep_embedding(ptr(t), t.shape[0], dim, mode, ptr(out), stream_ptr()), "qd_timestep_embedding")
+    return out
