@@ -270,6 +270,7 @@ int launch_attention(const qd_attention_desc& d, cudaStream_t s) {
   if ((d.q_off | d.k_off | d.head_stride_q | d.head_stride_k | (int)d.ld_q | (int)d.ld_k) & 3) return fail(QD_ERR_UNSUPPORTED, "attention: 4-byte alignment");
   if (d.ld_out % 2) return fail(QD_ERR_UNSUPPORTED, "attention: ld_out");
   switch (d.d) {
+    case 16: return launch_attention_t<32, 16>(d, s);
     case 24: return launch_attention_t<32, 24>(d, s);
     case 32: return launch_attention_t<32, 32>(d, s);
     case 40: return launch_attention_t<64, 40>(d, s);

@@ -1,0 +1,65 @@
+"""Pin the CPU oracle against outputs of the reference itself (fixtures from tools/make_golden.py,
+which imports /root/reference).  CPU-only: runs in the build container and on the GPU box."""
+import os
+
+import pytest
+import torch
+
+from oracle import ops_oracle as O
+from oracle import unet_oracle as U
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ["ddim_w4a8_split", "ldm_legacy_w4a8", "ldm_updown_w4a8", "sd_tiny_w4a8_sm16"]
+
+
+def load_case(name):
+    g = torch.load(os.path.join(GOLD, name + ".pt"), map_location="cpu", weights_only=False)
+    g["ckpt"] = {k: (v.float() if k.endswith(".alpha") else v) for k, v in g["ckpt"].items()}
+    return g
+
+
+def oracle_forward(g, trace=None):
+    q = g["qcfg"]
+    qc = U.QuantCfg(q["weight_bit"], q["act_bit"], q["a_sym"], q["sm_abit"], q["quant_act"], adaround=True)
+    if g["family"] == "ddim":
+        p = g["params"]
+        cfg = dict(ch=p["ch"], ch_mult=p["ch_mult"], num_res_blocks=p["num_res_blocks"],
+                   attn_resolutions=p["attn_resolutions"], resolution=p["resolution"], resamp_with_conv=True,
+                   split_shortcut=p["split_shortcut"])
+        return U.ddim_unet_forward(g["ckpt"], cfg, qc, g["x"], g["t"], trace=trace)
+    arch = U.ldm_arch_from_params(split=g["params"].get("split", False), **g["params"]["unet"])
+    return U.ldm_unet_forward(g["ckpt"], arch, qc, g["x"], g["t"], g["context"], trace=trace)
+
+
+def test_quantizer_known_answers():
+    k = torch.load(os.path.join(GOLD, "quantizer_kats.pt"), map_location="cpu", weights_only=False)
+    for kat in k["act"]:
+        y = O.uaq_fake_quant(kat["x"], kat["delta"], kat["zero_point"], kat["n_bits"], kat["symmetric"])
+        assert torch.equal(y, kat["y"]), kat["n_bits"]
+    # init: the reference derived (delta, zp) from the tensor; so must the oracle
+    for kat in k["act"][:4]:
+        d, z = O.uaq_init_max(kat["x"], kat["n_bits"], kat["symmetric"], kat["always_zero"])
+        assert torch.equal(d, kat["delta"]) and float(z) == kat["zero_point"]
+    # ties and symmetric clamp
+    ties = k["act"][4]
+    assert ties["y"].tolist() == [0.0, 2.0, 2.0, 4.0, -128.0, -128.0, 126.0, 127.0, 127.0]
+    w = k["weight"]
+    d, z = O.weight_init_max(w["w"], 4)
+    assert torch.equal(d, w["delta"].flatten()) and torch.equal(z, w["zero_point"].flatten())
+    assert torch.equal(O.uaq_weight_fake_quant(w["w"], d, z, 4), w["y"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference(name):
+    g = load_case(name)
+    trace = {}
+    out = oracle_forward(g, trace)
+    ref = g["out"]
+    err = (out - ref).abs().max().item()
+    mse = ((out - ref) ** 2).mean().item()
+    # same fp32 torch ops in the same order -> expect (near) bit equality; allow reduction-order noise only
+    assert err <= 1e-5 * max(1.0, ref.abs().max().item()), (name, err, mse)
+    for key, t in g["traces"].items():
+        if key in trace:
+            e = (trace[key] - t).abs().max().item()
+            assert e <= 1e-5 * max(1.0, t.abs().max().item()), (name, key, e)
