@@ -48,7 +48,7 @@ typedef struct qd_qparams {
  * corr: zx * sum_k w[n,k]; for taps==9 one row per border class (3x3 classes, row-major:
  *       top/mid/bottom x left/mid/right) because the reference zero-pads after de-quantisation.
  * Output: fp32 `out` and/or re-quantised codes `out_q` with the consumer's quantizer `oq`
- *       (out_q_transposed: [M/rows_per_batch][N][rows_per_batch], used for attention V).
+ *       (out_q_transposed: [M/rows_per_batch][N][ldq] with ldq >= rows_per_batch, used for attention V^T).
  * ------------------------------------------------------------------------------------------ */
 typedef struct qd_gemm_desc {
   const void* a;

@@ -35,7 +35,7 @@ struct GemmArgs {
   // epilogue
   float* out;          // fp32 [M, ldo] or nullptr
   long long ldo;
-  int8_t* out_q;       // requantised output (codes), [M, ldq] or transposed [M/rows_per_batch][N][rows_per_batch]
+  int8_t* out_q;       // requantised output (codes), [M, ldq] or transposed [M/rows_per_batch][N][ldq]
   long long ldq;
   int out_q_transposed;
   int rows_per_batch;  // rows (pixels/tokens) per image: rowvec index and transposed-store geometry
@@ -136,12 +136,12 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& p, const uin
           if (n0 + j < p.N) o[j] = (int8_t)q[j];
       }
     } else {
-      // [img][n][t]: consecutive lanes = consecutive t -> byte-coalesced across the warp
+      // [img][n][ldq]: consecutive lanes = consecutive t -> byte-coalesced across the warp
       int t_in = m - img * p.rows_per_batch;
-      int8_t* o = p.out_q + ((long long)img * p.ldq + n0) * p.rows_per_batch + t_in;
+      int8_t* o = p.out_q + ((long long)img * p.N + n0) * p.ldq + t_in;
 #pragma unroll
       for (int j = 0; j < NC; ++j)
-        if (n0 + j < p.N) o[(long long)j * p.rows_per_batch] = (int8_t)q[j];
+        if (n0 + j < p.N) o[(long long)j * p.ldq] = (int8_t)q[j];
     }
   }
 }

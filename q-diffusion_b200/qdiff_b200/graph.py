@@ -1,0 +1,701 @@
+"""Lowering of a wrapped UNet (QuantModel) to an engine program: the host-side graph builder.
+
+Walks the module tree (class names + attributes: works on qdiff_b200.unet containers and on the
+reference's own ldm / ddim module objects), folds every calibrated quantizer into integer operands
+(fold.py) and records one C-ABI op per kernel launch into a qd_engine.  Activations flow
+pixel-major / token-major (NHWC == 'b (h w) c'): fp32 between blocks, u8/s8 codes into every GEMM.
+
+Reference graph being lowered:
+  UNetModel.forward  ldm/modules/diffusionmodules/openaimodel.py:745-782
+  Model.forward      ddim/models/diffusion.py:308-360
+with the Quant*Block forwards of qdiff/quant_block.py (cited at each lowering function).
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib, fold, ops
+from ._lib import AttentionDesc, MiscDesc, check, lib, ptr
+
+
+class Act:
+    """A device activation: rows x cols with a row pitch (elements), fp32 or 8-bit codes."""
+
+    def __init__(self, t, rows, cols, ld=None, signed=None):
+        self.t, self.rows, self.cols = t, rows, cols
+        self.ld = cols if ld is None else ld
+        self.signed = signed  # None for fp32
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr()
+
+
+class _Offset:
+    """Pointer arithmetic helper: a view `bytes` into a tensor, keeping the storage alive."""
+
+    def __init__(self, t, byte_offset):
+        self.t, self.off = t, byte_offset
+
+    def data_ptr(self):
+        return self.t.data_ptr() + self.off
+
+
+class Program:
+    def __init__(self, engine, keep, x_in, t_in, ctx_in, out, nops, traces, use_cuda_graph):
+        self.engine, self.keep = engine, keep
+        self.x_in, self.t_in, self.ctx_in, self.out = x_in, t_in, ctx_in, out
+        self.nops, self.traces = nops, traces
+        self.use_cuda_graph = use_cuda_graph
+        self.graph = None
+
+    def _launch(self):
+        check(lib().qd_engine_run(self.engine, _lib.stream_ptr()), "qd_engine_run")
+
+    def run(self, x, timesteps, context=None):
+        self.x_in.copy_(x.to(torch.float32))
+        self.t_in.copy_(timesteps.to(torch.float32))
+        if self.ctx_in is not None:
+            if context is None:
+                raise ValueError("this UNet was compiled with a cross-attention context")
+            self.ctx_in.copy_(context.to(torch.float32))
+        if not self.use_cuda_graph:
+            self._launch()
+        else:
+            if self.graph is None:
+                self._launch()  # warm-up outside capture (lazy module loading, attribute setup)
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch()
+                self.graph = g
+            self.graph.replay()
+        return self.out.clone()
+
+    def run_range(self, first, last):
+        check(lib().qd_engine_run_range(self.engine, first, last, _lib.stream_ptr()), "qd_engine_run_range")
+
+    def __del__(self):
+        try:
+            self.graph = None
+            lib().qd_engine_destroy(self.engine)
+        except Exception:
+            pass
+
+
+def _name(m):
+    return type(m).__name__
+
+
+_RES = ("ResBlock", "QuantResBlock")
+_ST = ("SpatialTransformer",)
+_ATTN = ("AttentionBlock", "QuantAttentionBlock")
+_DDIM_RES = ("ResnetBlock", "QuantResnetBlock")
+_DDIM_ATTN = ("AttnBlock", "QuantAttnBlock")
+
+
+class Builder:
+    def __init__(self, qnn, device, batch):
+        self.qnn, self.dev, self.B = qnn, device, batch
+        self.names = {id(m): n for n, m in qnn.named_modules()}
+        e = C.c_void_p()
+        check(lib().qd_engine_create(device.index or 0, C.byref(e)), "qd_engine_create")
+        self.engine = e
+        self.keep = []       # tensors referenced by recorded ops
+        self.nops = 0
+        self.traces = {}     # block name -> (Act, (B, H, W)) for parity debugging
+        self.op_names = []
+        self.aq = qnn.act_quant_params
+        self.wbits = qnn.weight_quant_params['n_bits']
+        self.gn_ws = None
+
+    # ------------------------------------------------------------------ helpers
+    def new(self, rows, cols, dtype):
+        t = torch.empty((rows, cols), dtype=dtype, device=self.dev)
+        self.keep.append(t)
+        return t
+
+    def new_f32(self, rows, cols):
+        return Act(self.new(rows, cols, torch.float32), rows, cols)
+
+    def new_codes(self, rows, cols, signed):
+        return Act(self.new(rows, cols, torch.int8 if signed else torch.uint8), rows, cols, signed=signed)
+
+    def dev_t(self, t, dtype):
+        t = t.detach().to(device=self.dev, dtype=dtype).contiguous()
+        self.keep.append(t)
+        return t
+
+    def add(self, kind, desc, label):
+        check(lib().qd_engine_add_op(self.engine, kind, C.byref(desc)), f"qd_engine_add_op[{label}]")
+        self.nops += 1
+        self.op_names.append(label)
+
+    def key(self, m):
+        return self.names[id(m)]
+
+    def qp(self, q):
+        """QParams of an activation quantizer object (delta, zero_point, clamp range)."""
+        if q.delta is None:
+            raise RuntimeError("activation quantizer has no calibrated delta: load a checkpoint with "
+                               "resume_cali_model(..., quant_act=True) first")
+        delta = float(q.delta.detach().reshape(-1)[0])
+        zp = q.zero_point
+        zp = int(zp.reshape(-1)[0].item()) if torch.is_tensor(zp) else int(zp)
+        lo, hi = q.clamp_range()
+        return ops.qparams(delta, zp, lo, hi), (lo < 0)
+
+    # ------------------------------------------------------------------ elementwise recorders
+    def quantize(self, src, q, label, act=0, out_cols=None, split=0, q1=None, upsample=None):
+        qp0, signed = self.qp(q)
+        qp1 = self.qp(q1)[0] if q1 is not None else None
+        cols = out_cols if out_cols is not None else src.cols
+        rows = src.rows * (4 if upsample is not None else 1)
+        dst = self.new_codes(rows, cols, signed)
+        d = ops.quantize_desc(src.t, dst.t, M=src.rows, C_=cols, ld_src=src.ld, ld_dst=dst.ld, q0=qp0, q1=qp1, act=act,
+                              split=split, upsample=upsample)
+        d.src = src.ptr
+        self.add(_lib.QD_OP_QUANTIZE, d, label)
+        dst.zp = (qp0.zero_point, qp1.zero_point if qp1 is not None else None)
+        dst.delta = (qp0.delta, qp1.delta if qp1 is not None else None)
+        return dst
+
+    def groupnorm(self, x, norm, hw, quantizers, silu, label, ss=None, want_f32=False):
+        """GroupNorm(32) [+scale-shift] [+SiLU] -> codes for each consumer quantizer (and/or fp32)."""
+        B = self.B
+        ws_need = ops.gn_workspace_floats(B, hw, x.cols)
+        if self.gn_ws is None or self.gn_ws.numel() < ws_need:
+            self.gn_ws = torch.empty(max(ws_need, 1 << 20), dtype=torch.float32, device=self.dev)
+            self.keep.append(self.gn_ws)
+        outs, acts = [], []
+        for q in quantizers:
+            qp_, signed = self.qp(q)
+            a = self.new_codes(x.rows, x.cols, signed)
+            a.zp, a.delta = (qp_.zero_point, None), (qp_.delta, None)
+            outs.append((a.t, a.ld, qp_))
+            acts.append(a)
+        out_f = self.new_f32(x.rows, x.cols) if want_f32 else None
+        d = ops.groupnorm_desc(x.t, self.dev_t(norm.weight, torch.float32), self.dev_t(norm.bias, torch.float32),
+                               self.gn_ws, B=B, HW=hw, C_=x.cols, ld_x=x.ld, eps=norm.eps, silu=silu, outs=outs,
+                               groups=norm.num_groups, ss=ss, out_f=out_f.t if out_f else None,
+                               ld_f=out_f.ld if out_f else 0)
+        d.x = x.ptr
+        self.add(_lib.QD_OP_GROUPNORM, d, label)
+        return acts, out_f
+
+    def layernorm(self, x, norm, quantizers, label):
+        outs, acts = [], []
+        for q in quantizers:
+            qp_, signed = self.qp(q)
+            a = self.new_codes(x.rows, x.cols, signed)
+            a.zp, a.delta = (qp_.zero_point, None), (qp_.delta, None)
+            outs.append((a.t, a.ld, qp_))
+            acts.append(a)
+        d = ops.layernorm_desc(x.t, self.dev_t(norm.weight, torch.float32), self.dev_t(norm.bias, torch.float32),
+                               M=x.rows, C_=x.cols, ld_x=x.ld, eps=norm.eps, outs=outs)
+        d.x = x.ptr
+        self.add(_lib.QD_OP_LAYERNORM, d, label)
+        return acts
+
+    def misc(self, kind, src, dst, a, b, c=0, d_=0, ld_src=0, ld_dst=0, label="misc"):
+        m = MiscDesc()
+        m.src, m.dst = src, dst
+        m.ld_src, m.ld_dst, m.a, m.b, m.c, m.d = ld_src, ld_dst, a, b, c, d_
+        self.add(kind, m, label)
+
+    def concat(self, a, b, label):
+        out = self.new_f32(a.rows, a.cols + b.cols)
+        self.misc(_lib.QD_OP_COPY2D, a.ptr, out.ptr, a.rows, a.cols, ld_src=a.ld, ld_dst=out.ld, label=label + ".cat0")
+        self.misc(_lib.QD_OP_COPY2D, b.ptr, out.ptr + 4 * a.cols, b.rows, b.cols, ld_src=b.ld, ld_dst=out.ld,
+                  label=label + ".cat1")
+        return out
+
+    # ------------------------------------------------------------------ QuantModule -> GEMM
+    def _fold(self, qm, cols=None, suffix=""):
+        """Integer weight codes (zero point removed), per-channel step, for the whole module or a
+        column range of its input channels (split-shortcut halves)."""
+        wq = getattr(qm, "weight_quantizer" + suffix)
+        w = qm.weight.detach().to(self.dev, torch.float32)
+        if cols is not None:
+            w = w[:, cols[0]:cols[1], ...]
+        if wq.delta is None:
+            raise RuntimeError(f"{self.key(qm)}: weight quantizer not calibrated (resume_cali_model first)")
+        delta = wq.delta.detach().to(self.dev, torch.float32).reshape(-1)
+        zp = wq.zero_point.detach().to(self.dev, torch.float32).reshape(-1)
+        alpha = getattr(wq, "alpha", None)
+        if alpha is not None:
+            alpha = alpha.detach().to(self.dev, torch.float32).reshape(w.shape)
+        codes = fold.weight_codes(w, delta, zp, wq.n_bits, alpha)
+        ws = codes - zp.reshape(-1, *([1] * (w.dim() - 1)))
+        if float(ws.abs().max()) > 127:
+            raise NotImplementedError(
+                f"{self.key(qm)}: {wq.n_bits}-bit weight codes minus zero point exceed s8; the W8 operand split "
+                "(SURVEY H3) is the next hot-path row, W4 is realised")
+        return ws, delta
+
+    def gemm(self, qm, a, label, *, conv_bhw=None, out=None, out_cols_offset=0, rowvec=None, residual=None,
+             out_q=None, out_scale=1.0, k_pad=None, cols=None, suffix="", zx=None, dx=None, accumulate_into=None,
+             rows_per_batch=0, use_bias=True):
+        """Record one INT8 GEMM for QuantModule `qm` on activation codes `a`.
+
+        cols/suffix select a split-shortcut half.  out_q = (quantizer, transposed) requantises in the
+        epilogue.  out_scale multiplies scale and bias (LDM legacy attention q*s, k*s)."""
+        ws, delta_w = self._fold(qm, cols, suffix)
+        N = ws.shape[0]
+        taps = 9 if (ws.dim() == 4 and ws.shape[-1] == 3 and conv_bhw is not None) else 1
+        if zx is None:
+            zx, dx = a.zp[0], a.delta[0]
+        wk = fold.to_k_major(ws) if ws.dim() > 2 else ws
+        Cred = wk.shape[1] // taps
+        if k_pad is not None and k_pad != wk.shape[1]:
+            wk = torch.nn.functional.pad(wk, (0, k_pad - wk.shape[1]))
+            Cred = k_pad
+        w_dev = wk.to(torch.int8).contiguous()
+        self.keep.append(w_dev)
+        scale = (delta_w.double() * float(dx) * out_scale).to(torch.float32).contiguous()
+        self.keep.append(scale)
+        corr = None
+        if zx != 0:
+            if taps == 9:
+                corr = fold.border_corr(ws, zx).to(self.dev).contiguous()
+            else:
+                corr = (ws.reshape(N, -1).double().sum(dim=1) * zx).to(torch.int32).contiguous()
+            self.keep.append(corr)
+        bias = None
+        if use_bias and qm.bias is not None:
+            bias = (qm.bias.detach().to(self.dev, torch.float64) * out_scale).to(torch.float32).contiguous()
+            self.keep.append(bias)
+        M = a.rows
+        o = None
+        if out_q is None:
+            o = accumulate_into if accumulate_into is not None else (out if out is not None else self.new_f32(M, N))
+        oq_params, oq_act, transposed = None, None, False
+        if out_q is not None:
+            quantizer, transposed = out_q
+            oq_params, signed = self.qp(quantizer)
+            if transposed:
+                T = rows_per_batch
+                t_pad = (T + 15) // 16 * 16
+                t = torch.zeros((M // T) * N * t_pad, dtype=torch.int8 if signed else torch.uint8, device=self.dev)
+                self.keep.append(t)
+                oq_act = Act(t, M // T * N, t_pad, signed=signed)
+                oq_act.t_pad = t_pad
+            else:
+                oq_act = self.new_codes(M, N, signed)
+            oq_act.zp, oq_act.delta = (oq_params.zero_point, None), (oq_params.delta, None)
+        res = accumulate_into if accumulate_into is not None else residual
+        d = ops.gemm_desc(a.t, w_dev, scale, M=M, N=N, C=Cred, taps=taps, lda=a.ld, conv_bhw=conv_bhw,
+                          a_signed=bool(a.signed), bias=bias, corr=corr,
+                          rowvec=rowvec.t if rowvec is not None else None,
+                          ld_rowvec=rowvec.ld if rowvec is not None else 0, rows_per_batch=rows_per_batch,
+                          residual=res.t if res is not None else None, ldr=res.ld if res is not None else 0,
+                          out=o.t if o is not None else None, ldo=o.ld if o is not None else 0,
+                          out_q=oq_act.t if oq_act is not None else None,
+                          ldq=(oq_act.t_pad if transposed else oq_act.ld) if oq_act is not None else 0,
+                          oq=oq_params, out_q_transposed=transposed)
+        d.a = a.ptr + (cols[0] if cols is not None else 0)
+        if rowvec is not None:
+            d.rowvec = rowvec.ptr
+        if res is not None:
+            d.residual = res.ptr
+        if o is not None:
+            d.out = o.ptr + 4 * out_cols_offset
+        self.add(_lib.QD_OP_GEMM, d, label)
+        return oq_act if out_q is not None else o
+
+    def qlinear(self, qm, x_f32, label, act=0, **kw):
+        """fp32 activation -> this module's input quantizer -> GEMM (QuantModule.forward, quant_layer.py:248-279)."""
+        cols = x_f32.cols // 2 if act == 2 else x_f32.cols
+        a = self.quantize(x_f32, qm.act_quantizer, label + ".q", act=act, out_cols=cols)
+        return self.gemm(qm, a, label, **kw)
+
+    def conv3x3_s1(self, qm, a, hw, label, **kw):
+        H, W = hw
+        return self.gemm(qm, a, label, conv_bhw=(self.B, H, W), rows_per_batch=H * W, **kw)
+
+    def conv_im2col(self, qm, a, hw, label, stride, pad_tl, out_hw, k_to, **kw):
+        """Explicit patch gather + plain GEMM (stride-2 convs, conv_in with 3/4 input channels)."""
+        H, W = hw
+        Ho, Wo = out_hw
+        Cin = a.cols
+        patches = self.new_codes(self.B * Ho * Wo, k_to, a.signed)
+        d = ops.im2col_desc(a.t, patches.t, B=self.B, H=H, W=W, C_=Cin, Ho=Ho, Wo=Wo, stride=stride,
+                            pad_top=pad_tl[0], pad_left=pad_tl[1], pad_code=a.zp[0] & 0xFF, ld_dst=k_to)
+        self.add(_lib.QD_OP_IM2COL, d, label + ".im2col")
+        patches.zp, patches.delta = a.zp, a.delta
+        return self.gemm(qm, patches, label, k_pad=k_to, **kw)
+
+    # ------------------------------------------------------------------ attention recorder
+    def attention(self, qc, kc, vt, *, heads, d, Tq, Tk, q_layout, k_layout, v_layout, sim_scale_extra, qw, label):
+        """qc/kc: code Acts [B*T, *]; vt: transposed codes.  *_layout = (col offset, head stride)."""
+        out = self.new_f32(self.B * Tq, heads * d)
+        qpw, _ = self.qp(qw)
+        a = AttentionDesc()
+        a.q, a.k, a.vt = qc.ptr, kc.ptr, vt.ptr
+        a.ld_q, a.ld_k = qc.ld, kc.ld
+        a.ld_vt = vt.t_pad
+        a.v_batch_stride = (vt.rows // self.B) * vt.t_pad
+        a.B, a.heads, a.d, a.Tq, a.Tk = self.B, heads, d, Tq, Tk
+        a.q_off, a.head_stride_q = q_layout
+        a.k_off, a.head_stride_k = k_layout
+        a.v_off, a.head_stride_v = v_layout
+        a.q_signed, a.k_signed, a.v_signed, a.p_signed = int(qc.signed), int(kc.signed), int(vt.signed), 0
+        a.zq, a.zk, a.zv, a.zw = qc.zp[0], kc.zp[0], vt.zp[0], qpw.zero_point
+        a.p_qmin, a.p_qmax = 0, qpw.qmax
+        a.sm_bits = 16 if qpw.qmax > 255 else 8
+        a.sim_scale = float(qc.delta[0]) * float(kc.delta[0]) * sim_scale_extra
+        a.delta_w = qpw.delta
+        a.out_scale = float(qpw.delta) * float(vt.delta[0])
+        a.out, a.ld_out = out.ptr, out.ld
+        self.add(_lib.QD_OP_ATTENTION, a, label)
+        return out
+
+    # ================================================================== LDM / SD family
+    def ldm_resblock(self, blk, x, emb, hw, split):
+        """QuantResBlock._forward, qdiff/quant_block.py:83-111."""
+        k = self.key(blk)
+        H, W = hw
+        norm1, conv1 = blk.in_layers[0], blk.in_layers[2]
+        norm2, conv2 = blk.out_layers[0], blk.out_layers[3]
+        lin = blk.emb_layers[1]
+        updown = None
+        if getattr(blk, "updown", False):
+            updown = "up" if _name(blk.h_upd) == "Upsample" else "down"
+        if updown is None:
+            (a1,), _ = self.groupnorm(x, norm1, H * W, [conv1.act_quantizer], True, k + ".in_layers.0")
+            oh, ow = H, W
+            x_res = x
+        else:
+            _, hf = self.groupnorm(x, norm1, H * W, [], True, k + ".in_layers.0", want_f32=True)
+            if updown == "up":
+                oh, ow = 2 * H, 2 * W
+                a1 = self.quantize(hf, conv1.act_quantizer, k + ".h_upd.q", upsample=(self.B, H, W))
+                x_res = self.new_f32(self.B * oh * ow, x.cols)
+                self.misc(_lib.QD_OP_UPSAMPLE2X, x.ptr, x_res.ptr, self.B, H, W, x.cols, label=k + ".x_upd")
+            else:
+                oh, ow = H // 2, W // 2
+                hp = self.new_f32(self.B * oh * ow, x.cols)
+                self.misc(_lib.QD_OP_AVGPOOL2X, hf.ptr, hp.ptr, self.B, H, W, x.cols, label=k + ".h_upd")
+                a1 = self.quantize(hp, conv1.act_quantizer, k + ".h_upd.q")
+                x_res = self.new_f32(self.B * oh * ow, x.cols)
+                self.misc(_lib.QD_OP_AVGPOOL2X, x.ptr, x_res.ptr, self.B, H, W, x.cols, label=k + ".x_upd")
+        emb_out = self.qlinear(lin, emb, k + ".emb_layers.1", act=1)
+        oc = conv2.weight.shape[0]
+        if getattr(blk, "use_scale_shift_norm", False):
+            h = self.conv3x3_s1(conv1, a1, (oh, ow), k + ".in_layers.2")
+            ss = (emb_out.t, _Offset(emb_out.t, 4 * oc), emb_out.ld)
+            (a2,), _ = self.groupnorm(h, norm2, oh * ow, [conv2.act_quantizer], True, k + ".out_layers.0", ss=ss)
+        else:
+            h = self.conv3x3_s1(conv1, a1, (oh, ow), k + ".in_layers.2", rowvec=emb_out)
+            (a2,), _ = self.groupnorm(h, norm2, oh * ow, [conv2.act_quantizer], True, k + ".out_layers.0")
+        skip = blk.skip_connection
+        if _name(skip) == "QuantModule":
+            if skip.weight.shape[-1] != 1:
+                raise NotImplementedError("3x3 skip_connection (use_conv=True) is not used by any reference config")
+            if split:
+                if skip.split == 0:
+                    raise RuntimeError(f"{k}.skip_connection: model.split is set but the checkpoint has no split quantizers")
+                a = self.quantize(x_res, skip.act_quantizer, k + ".skip.q", split=split, q1=skip.act_quantizer_0)
+                s = self.gemm(skip, a, k + ".skip.0", cols=(0, split), suffix="", zx=a.zp[0], dx=a.delta[0])
+                self.gemm(skip, a, k + ".skip.1", cols=(split, a.cols), suffix="_0", zx=a.zp[1], dx=a.delta[1],
+                          accumulate_into=s, use_bias=False)
+            else:
+                s = self.qlinear(skip, x_res, k + ".skip")
+        else:
+            s = x_res
+        out = self.conv3x3_s1(conv2, a2, (oh, ow), k + ".out_layers.3", residual=s)
+        return out, (oh, ow)
+
+    def sd_cross_attention(self, attn, x_codes_q, kv_codes, h_res, Tq, Tk, label):
+        """cross_attn_forward, qdiff/quant_block.py:190-221: to_q/to_k/to_v GEMMs requantise straight
+        into the attention operand layouts; softmax quantizer = act_quantizer_w (sm_abit, zero point 0)."""
+        heads = attn.heads
+        inner = attn.to_q.weight.shape[0]
+        d = inner // heads
+        qc = self.gemm(attn.to_q, x_codes_q, label + ".to_q", out_q=(attn.act_quantizer_q, False))
+        kc = self.gemm(attn.to_k, kv_codes[0], label + ".to_k", out_q=(attn.act_quantizer_k, False))
+        vt = self.gemm(attn.to_v, kv_codes[1], label + ".to_v", out_q=(attn.act_quantizer_v, True), rows_per_batch=Tk)
+        o = self.attention(qc, kc, vt, heads=heads, d=d, Tq=Tq, Tk=Tk, q_layout=(0, d), k_layout=(0, d),
+                           v_layout=(0, d), sim_scale_extra=float(attn.scale), qw=attn.act_quantizer_w,
+                           label=label + ".attn")
+        return self.qlinear(attn.to_out[0], o, label + ".to_out.0", residual=h_res)
+
+    def spatial_transformer(self, st, x, ctx, hw):
+        """SpatialTransformer.forward (ldm/modules/attention.py:276-287) + QuantBasicTransformerBlock._forward
+        (qdiff/quant_block.py:263-271)."""
+        k = self.key(st)
+        H, W = hw
+        T = H * W
+        (a,), _ = self.groupnorm(x, st.norm, T, [st.proj_in.act_quantizer], False, k + ".norm")
+        h = self.gemm(st.proj_in, a, k + ".proj_in")
+        for i, blk in enumerate(st.transformer_blocks):
+            bk = f"{k}.transformer_blocks.{i}"
+            a1, a2 = blk.attn1, blk.attn2
+            cq, ck, cv = self.layernorm(h, blk.norm1, [a1.to_q.act_quantizer, a1.to_k.act_quantizer,
+                                                       a1.to_v.act_quantizer], bk + ".norm1")
+            h = self.sd_cross_attention(a1, cq, (ck, cv), h, T, T, bk + ".attn1")
+            (cq2,) = self.layernorm(h, blk.norm2, [a2.to_q.act_quantizer], bk + ".norm2")
+            if ctx is None:
+                raise ValueError("SpatialTransformer needs a context tensor")
+            ctx_act, Tk = ctx
+            kk = self.quantize(ctx_act, a2.to_k.act_quantizer, bk + ".attn2.ctx_k.q")
+            kv = self.quantize(ctx_act, a2.to_v.act_quantizer, bk + ".attn2.ctx_v.q")
+            h = self.sd_cross_attention(a2, cq2, (kk, kv), h, T, Tk, bk + ".attn2")
+            proj, ff_out = blk.ff.net[0].proj, blk.ff.net[2]
+            (cf,) = self.layernorm(h, blk.norm3, [proj.act_quantizer], bk + ".norm3")
+            f = self.gemm(proj, cf, bk + ".ff.net.0.proj")
+            h = self.qlinear(ff_out, f, bk + ".ff.net.2", act=2, residual=h)
+        return self.qlinear(st.proj_out, h, k + ".proj_out", residual=x)
+
+    def ldm_attention_block(self, blk, x, hw):
+        """AttentionBlock._forward + QKVAttentionLegacy (openaimodel.py:321-327,384-406) with QuantQKMatMul /
+        QuantSMVMatMul (qdiff/quant_block.py:123-157).  The qkv Conv1d rows are regrouped into q / k / v GEMMs;
+        s = ch^-1/4 is folded into the q,k epilogue scale so the codes are those of q*s, k*s."""
+        k = self.key(blk)
+        T = hw[0] * hw[1]
+        C_ = x.cols
+        heads = blk.attention.n_heads
+        ch = C_ // heads
+        qk, smv = blk.attention.qkv_matmul, blk.attention.smv_matmul
+        if _name(qk) != "QuantQKMatMul":
+            raise NotImplementedError("weight-only (quant_act=False) LDM attention is not lowered yet")
+        (a,), _ = self.groupnorm(x, blk.norm, T, [blk.qkv.act_quantizer], False, k + ".norm")
+        s = 1.0 / math.sqrt(math.sqrt(ch))
+        idx = torch.arange(3 * C_, device=self.dev).reshape(heads, 3, ch)
+        parts = []
+        for j, (quantizer, transposed, sc) in enumerate(((qk.act_quantizer_q, False, s), (qk.act_quantizer_k, False, s),
+                                                         (smv.act_quantizer_v, True, 1.0))):
+            rows = idx[:, j, :].reshape(-1)
+            view = _RowView(blk.qkv, rows)
+            parts.append(self.gemm(view, a, f"{k}.qkv.{'qkv'[j]}", out_q=(quantizer, transposed), out_scale=sc,
+                                   rows_per_batch=T))
+        qc, kc, vt = parts
+        o = self.attention(qc, kc, vt, heads=heads, d=ch, Tq=T, Tk=T, q_layout=(0, ch), k_layout=(0, ch),
+                           v_layout=(0, ch), sim_scale_extra=1.0, qw=smv.act_quantizer_w, label=k + ".attention")
+        return self.qlinear(blk.proj_out, o, k + ".proj_out", residual=x)
+
+    def lower_ldm(self, model, x_shape, ctx_shape):
+        B, Cin, H, W = x_shape
+        x_in = torch.zeros(x_shape, dtype=torch.float32, device=self.dev)
+        t_in = torch.zeros(B, dtype=torch.float32, device=self.dev)
+        ctx_in = torch.zeros(ctx_shape, dtype=torch.float32, device=self.dev) if ctx_shape is not None else None
+        self.keep += [x_in, t_in] + ([ctx_in] if ctx_in is not None else [])
+        mc = model.model_channels
+        temb = self.new_f32(B, mc)
+        self.misc(_lib.QD_OP_TIMESTEP_EMB, t_in.data_ptr(), temb.ptr, B, mc, 0, label="timestep_embedding")
+        e = self.qlinear(model.time_embed[0], temb, "time_embed.0")
+        emb = self.qlinear(model.time_embed[2], e, "time_embed.2", act=1)
+        ctx = None
+        if ctx_in is not None:
+            ctx = (Act(ctx_in, ctx_shape[0] * ctx_shape[1], ctx_shape[2]), ctx_shape[1])
+        xh = self.new_f32(B * H * W, Cin)
+        self.misc(_lib.QD_OP_NCHW_TO_NHWC, x_in.data_ptr(), xh.ptr, B, Cin, H * W, label="x.nhwc")
+        h, hw = xh, (H, W)
+        hs = []
+
+        def run(seq, h, hw, split):
+            for layer in seq:
+                n = _name(layer)
+                if n == "QuantModule":                       # conv_in
+                    a = self.quantize(h, layer.act_quantizer, self.key(layer) + ".q")
+                    kt = (9 * h.cols + 31) // 32 * 32
+                    h = self.conv_im2col(layer, a, hw, self.key(layer), 1, (1, 1), hw, kt)
+                elif n in _RES:
+                    h, hw = self.ldm_resblock(layer, h, emb, hw, split)
+                elif n in _ST:
+                    h = self.spatial_transformer(layer, h, ctx, hw)
+                elif n in _ATTN:
+                    h = self.ldm_attention_block(layer, h, hw)
+                elif n == "Downsample":
+                    op = layer.op
+                    if _name(op) != "QuantModule":
+                        raise NotImplementedError("Downsample without conv")
+                    a = self.quantize(h, op.act_quantizer, self.key(op) + ".q")
+                    ohw = (hw[0] // 2, hw[1] // 2)
+                    h = self.conv_im2col(op, a, hw, self.key(op), 2, (1, 1), ohw, 9 * h.cols)
+                    hw = ohw
+                elif n == "Upsample":
+                    conv = layer.conv
+                    a = self.quantize(h, conv.act_quantizer, self.key(conv) + ".q", upsample=(B, hw[0], hw[1]))
+                    hw = (2 * hw[0], 2 * hw[1])
+                    h = self.conv3x3_s1(conv, a, hw, self.key(conv))
+                else:
+                    raise NotImplementedError(f"unhandled layer type {n} at {self.key(layer)}")
+            return h, hw
+
+        for i, blk in enumerate(model.input_blocks):
+            h, hw = run(blk, h, hw, 0)
+            hs.append((h, hw))
+            self.traces[f"input_blocks.{i}"] = (h, hw)
+        h, hw = run(model.middle_block, h, hw, 0)
+        self.traces["middle_block"] = (h, hw)
+        for i, blk in enumerate(model.output_blocks):
+            skip_t, _ = hs.pop()
+            split = h.cols if getattr(model, "split", False) else 0
+            h = self.concat(h, skip_t, f"output_blocks.{i}")
+            h, hw = run(blk, h, hw, split)
+            self.traces[f"output_blocks.{i}"] = (h, hw)
+        norm, conv = model.out[0], model.out[2]
+        (a,), _ = self.groupnorm(h, norm, hw[0] * hw[1], [conv.act_quantizer], True, "out.0")
+        o = self.conv3x3_s1(conv, a, hw, "out.2")
+        out = torch.zeros((B, o.cols, hw[0], hw[1]), dtype=torch.float32, device=self.dev)
+        self.keep.append(out)
+        self.misc(_lib.QD_OP_NHWC_TO_NCHW, o.ptr, out.data_ptr(), B, o.cols, hw[0] * hw[1], label="eps.nchw")
+        return x_in, t_in, ctx_in, out
+
+    # ================================================================== DDIM (CIFAR) family
+    def ddim_resnet(self, blk, x, temb, hw, split):
+        """QuantResnetBlock.forward, qdiff/quant_block.py:307-330."""
+        k = self.key(blk)
+        H, W = hw
+        (a1,), _ = self.groupnorm(x, blk.norm1, H * W, [blk.conv1.act_quantizer], True, k + ".norm1")
+        tp = self.qlinear(blk.temb_proj, temb, k + ".temb_proj", act=1)
+        h = self.conv3x3_s1(blk.conv1, a1, hw, k + ".conv1", rowvec=tp)
+        (a2,), _ = self.groupnorm(h, blk.norm2, H * W, [blk.conv2.act_quantizer], True, k + ".norm2")
+        s = x
+        if blk.in_channels != blk.out_channels:
+            if getattr(blk, "use_conv_shortcut", False):
+                raise NotImplementedError("conv_shortcut=True is not used by the reference configs")
+            nin = blk.nin_shortcut
+            if split:
+                if nin.split == 0:
+                    raise RuntimeError(f"{k}.nin_shortcut: split_shortcut is set but the checkpoint has no split quantizers")
+                a = self.quantize(x, nin.act_quantizer, k + ".nin.q", split=split, q1=nin.act_quantizer_0)
+                s = self.gemm(nin, a, k + ".nin.0", cols=(0, split), suffix="", zx=a.zp[0], dx=a.delta[0])
+                self.gemm(nin, a, k + ".nin.1", cols=(split, a.cols), suffix="_0", zx=a.zp[1], dx=a.delta[1],
+                          accumulate_into=s, use_bias=False)
+            else:
+                s = self.qlinear(nin, x, k + ".nin")
+        return self.conv3x3_s1(blk.conv2, a2, hw, k + ".conv2", residual=s)
+
+    def ddim_attn(self, blk, x, hw):
+        """QuantAttnBlock.forward, qdiff/quant_block.py:354-386 (single head, d = C, scale C^-1/2 after QK^T)."""
+        k = self.key(blk)
+        T = hw[0] * hw[1]
+        C_ = x.cols
+        aq, ak, av = self.groupnorm(x, blk.norm, T, [blk.q.act_quantizer, blk.k.act_quantizer, blk.v.act_quantizer],
+                                    False, k + ".norm")[0]
+        qc = self.gemm(blk.q, aq, k + ".q", out_q=(blk.act_quantizer_q, False))
+        kc = self.gemm(blk.k, ak, k + ".k", out_q=(blk.act_quantizer_k, False))
+        vt = self.gemm(blk.v, av, k + ".v", out_q=(blk.act_quantizer_v, True), rows_per_batch=T)
+        o = self.attention(qc, kc, vt, heads=1, d=C_, Tq=T, Tk=T, q_layout=(0, C_), k_layout=(0, C_), v_layout=(0, C_),
+                           sim_scale_extra=float(int(C_) ** (-0.5)), qw=blk.act_quantizer_w, label=k + ".attn")
+        return self.qlinear(blk.proj_out, o, k + ".proj_out", residual=x)
+
+    def lower_ddim(self, model, x_shape):
+        B, Cin, H, W = x_shape
+        x_in = torch.zeros(x_shape, dtype=torch.float32, device=self.dev)
+        t_in = torch.zeros(B, dtype=torch.float32, device=self.dev)
+        self.keep += [x_in, t_in]
+        split_on = bool(getattr(model.config, "split_shortcut", False))
+        temb0 = self.new_f32(B, model.ch)
+        self.misc(_lib.QD_OP_TIMESTEP_EMB, t_in.data_ptr(), temb0.ptr, B, model.ch, 1, label="timestep_embedding")
+        e = self.qlinear(model.temb.dense[0], temb0, "temb.dense.0")
+        temb = self.qlinear(model.temb.dense[1], e, "temb.dense.1", act=1)
+        xh = self.new_f32(B * H * W, Cin)
+        self.misc(_lib.QD_OP_NCHW_TO_NHWC, x_in.data_ptr(), xh.ptr, B, Cin, H * W, label="x.nhwc")
+        a = self.quantize(xh, model.conv_in.act_quantizer, "conv_in.q")
+        hw = (H, W)
+        h = self.conv_im2col(model.conv_in, a, hw, "conv_in", 1, (1, 1), hw, (9 * Cin + 31) // 32 * 32)
+        hs = [(h, hw)]
+        nres = model.num_resolutions
+        for lv in range(nres):
+            st = model.down[lv]
+            for ib in range(model.num_res_blocks):
+                h = self.ddim_resnet(st.block[ib], hs[-1][0], temb, hw, 0)
+                if len(st.attn) > 0:
+                    h = self.ddim_attn(st.attn[ib], h, hw)
+                hs.append((h, hw))
+            if lv != nres - 1:
+                conv = st.downsample.conv
+                a = self.quantize(hs[-1][0], conv.act_quantizer, self.key(conv) + ".q")
+                ohw = (hw[0] // 2, hw[1] // 2)
+                # F.pad (0,1,0,1) then 3x3 stride 2, padding 0 (ddim/models/diffusion.py:67-71)
+                h = self.conv_im2col(conv, a, hw, self.key(conv), 2, (0, 0), ohw, 9 * a.cols)
+                hw = ohw
+                hs.append((h, hw))
+        h = hs[-1][0]
+        h = self.ddim_resnet(model.mid.block_1, h, temb, hw, 0)
+        h = self.ddim_attn(model.mid.attn_1, h, hw)
+        h = self.ddim_resnet(model.mid.block_2, h, temb, hw, 0)
+        self.traces["mid"] = (h, hw)
+        for lv in reversed(range(nres)):
+            st = model.up[lv]
+            for ib in range(model.num_res_blocks + 1):
+                split = h.cols if (lv < 4 and split_on) else 0
+                skip_t, _ = hs.pop()
+                cat = self.concat(h, skip_t, f"up.{lv}.block.{ib}")
+                h = self.ddim_resnet(st.block[ib], cat, temb, hw, split)
+                if len(st.attn) > 0:
+                    h = self.ddim_attn(st.attn[ib], h, hw)
+            if lv != 0:
+                conv = st.upsample.conv
+                a = self.quantize(h, conv.act_quantizer, self.key(conv) + ".q", upsample=(B, hw[0], hw[1]))
+                hw = (2 * hw[0], 2 * hw[1])
+                h = self.conv3x3_s1(conv, a, hw, self.key(conv))
+        (a,), _ = self.groupnorm(h, model.norm_out, hw[0] * hw[1], [model.conv_out.act_quantizer], True, "norm_out")
+        o = self.conv3x3_s1(model.conv_out, a, hw, "conv_out")
+        out = torch.zeros((B, o.cols, hw[0], hw[1]), dtype=torch.float32, device=self.dev)
+        self.keep.append(out)
+        self.misc(_lib.QD_OP_NHWC_TO_NCHW, o.ptr, out.data_ptr(), B, o.cols, hw[0] * hw[1], label="eps.nchw")
+        return x_in, t_in, None, out
+
+
+class _RowView:
+    """A QuantModule restricted to a subset of its output rows (regrouping the fused qkv conv)."""
+
+    def __init__(self, qm, rows):
+        self.qm, self.rows = qm, rows
+        self.weight = _Sel(qm.weight, rows)
+        self.bias = _Sel(qm.bias, rows) if qm.bias is not None else None
+        wq = qm.weight_quantizer
+        self.weight_quantizer = _WQView(wq, rows)
+        self.act_quantizer = qm.act_quantizer
+
+
+class _Sel:
+    def __init__(self, t, rows):
+        self.t, self.rows = t, rows
+
+    def detach(self):
+        return self.t.detach()[self.rows.to(self.t.device)]
+
+    @property
+    def shape(self):
+        return (len(self.rows),) + tuple(self.t.shape[1:])
+
+
+class _WQView:
+    def __init__(self, wq, rows):
+        self.n_bits = wq.n_bits
+        r = rows.to(wq.delta.device)
+        self.delta = wq.delta.detach().reshape(wq.delta.shape[0], -1)[r]
+        self.zero_point = wq.zero_point.detach().reshape(wq.zero_point.shape[0], -1)[r]
+        alpha = getattr(wq, "alpha", None)
+        self.alpha = alpha.detach()[rows.to(alpha.device)] if alpha is not None else None
+
+
+def compile_unet(qnn, x_shape, ctx_shape, device, use_cuda_graph=True):
+    """Lower `qnn` (QuantModel) for a fixed input shape; returns a Program."""
+    lib()  # fail loudly if the CUDA library is missing
+    if not torch.cuda.is_available():
+        raise RuntimeError("qdiff_b200: no CUDA device; the engine has no CPU fallback")
+    states = {(m.use_weight_quant, m.use_act_quant) for m in qnn.model.modules() if _name(m) == "QuantModule"}
+    if states != {(True, True)}:
+        raise NotImplementedError(
+            f"engine realises set_quant_state(True, True) (W4A8-style) only; got states {states}. "
+            "Weight-only sampling (cfg 1) is the next hot-path row.")
+    b = Builder(qnn, device, x_shape[0])
+    model = qnn.model
+    with torch.no_grad():
+        if _name(model) == "UNetModel":
+            x_in, t_in, ctx_in, out = b.lower_ldm(model, x_shape, ctx_shape)
+        elif _name(model) == "Model":
+            x_in, t_in, ctx_in, out = b.lower_ddim(model, x_shape)
+        else:
+            raise NotImplementedError(f"unknown UNet type {_name(model)}")
+    check(lib().qd_engine_finalize(b.engine), "qd_engine_finalize")
+    prog = Program(b.engine, b.keep, x_in, t_in, ctx_in, out, b.nops, b.traces, use_cuda_graph)
+    prog.op_names = b.op_names
+    return prog

@@ -1,0 +1,98 @@
+"""Host-side mirror of qdiff/quant_model.py -- the drop-in API boundary (reference :12-97).
+
+QuantModel(model, weight_quant_params, act_quant_params, sm_abit=8) wraps a UNet module tree
+in place exactly like the reference (layers -> QuantModule, blocks -> Quant*Block) so state-dict
+keys match `ckpt.pth`; `forward(x, timesteps, context)` lowers the tree once per input shape to an
+engine program (qdiff_b200/graph.py) and replays it on the current CUDA stream.
+"""
+import torch
+import torch.nn as nn
+
+from .quant_block import (BaseQuantBlock, QuantAttnBlock, QuantBasicTransformerBlock, QuantQKMatMul, QuantSMVMatMul,
+                          get_specials)
+from .quant_layer import QuantModule, StraightThrough
+
+
+class QuantModel(nn.Module):
+    def __init__(self, model: nn.Module, weight_quant_params: dict = {}, act_quant_params: dict = {}, **kwargs):
+        super().__init__()
+        self.model = model
+        self.sm_abit = kwargs.get('sm_abit', 8)
+        self.in_channels = model.in_channels
+        if hasattr(model, 'image_size'):
+            self.image_size = model.image_size
+        self.weight_quant_params, self.act_quant_params = dict(weight_quant_params), dict(act_quant_params)
+        self.specials = get_specials(act_quant_params['leaf_param'])
+        self.quant_module_refactor(self.model, weight_quant_params, act_quant_params)
+        self.quant_block_refactor(self.model, weight_quant_params, act_quant_params)
+        self._programs = {}
+        self.use_cuda_graph = kwargs.get('cuda_graph', True)
+
+    # ---- tree rewriting (same traversal order as the reference so nested names coincide)
+    def quant_module_refactor(self, module, weight_quant_params={}, act_quant_params={}):
+        for name, child in module.named_children():
+            if isinstance(child, (nn.Conv2d, nn.Conv1d, nn.Linear)):
+                setattr(module, name, QuantModule(child, weight_quant_params, act_quant_params))
+            elif isinstance(child, (StraightThrough, QuantModule)):
+                continue
+            else:
+                self.quant_module_refactor(child, weight_quant_params, act_quant_params)
+
+    def quant_block_refactor(self, module, weight_quant_params={}, act_quant_params={}):
+        for name, child in module.named_children():
+            wrapper = self.specials.get(type(child).__name__)
+            if wrapper is None:
+                self.quant_block_refactor(child, weight_quant_params, act_quant_params)
+            elif wrapper in (QuantBasicTransformerBlock, QuantAttnBlock):
+                setattr(module, name, wrapper(child, act_quant_params, sm_abit=self.sm_abit))
+            elif wrapper is QuantSMVMatMul:
+                setattr(module, name, wrapper(act_quant_params, sm_abit=self.sm_abit))
+            elif wrapper is QuantQKMatMul:
+                setattr(module, name, wrapper(act_quant_params))
+            else:
+                setattr(module, name, wrapper(child, act_quant_params))
+
+    # ---- state toggles
+    def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
+        for m in self.model.modules():
+            if isinstance(m, (QuantModule, BaseQuantBlock)):
+                m.set_quant_state(weight_quant, act_quant)
+        self._programs = {}
+
+    def set_running_stat(self, running_stat: bool, sm_only=False):
+        for m in self.model.modules():
+            if isinstance(m, QuantBasicTransformerBlock):
+                names = ["act_quantizer_w"] if sm_only else ["act_quantizer_q", "act_quantizer_k", "act_quantizer_v",
+                                                             "act_quantizer_w"]
+                for attn in (m.attn1, m.attn2):
+                    for n in names:
+                        getattr(attn, n).running_stat = running_stat
+            if isinstance(m, QuantModule) and not sm_only:
+                m.set_running_stat(running_stat)
+
+    def set_grad_ckpt(self, grad_ckpt: bool):
+        for _, m in self.model.named_modules():
+            if type(m).__name__ in ("QuantBasicTransformerBlock", "BasicTransformerBlock"):
+                m.checkpoint = grad_ckpt
+
+    # ---- the hot path
+    def invalidate(self):
+        """Drop compiled engine programs (call after changing quantizer parameters or weights)."""
+        self._programs = {}
+
+    def program(self, x, context=None):
+        from . import graph
+        key = (tuple(x.shape), None if context is None else tuple(context.shape), x.device.index)
+        prog = self._programs.get(key)
+        if prog is None:
+            prog = graph.compile_unet(self, tuple(x.shape), None if context is None else tuple(context.shape),
+                                      x.device, use_cuda_graph=self.use_cuda_graph)
+            self._programs[key] = prog
+        return prog
+
+    def forward(self, x, timesteps=None, context=None):
+        if timesteps is None and isinstance(x, (tuple, list)):  # ddim Model.forward accepts (x, t) as one argument
+            x, timesteps = x
+        if not x.is_cuda:
+            raise RuntimeError("qdiff_b200.QuantModel.forward needs CUDA tensors: the engine has no CPU fallback")
+        return self.program(x, context).run(x, timesteps, context)

@@ -59,6 +59,12 @@ class ResBlock(_NoForward):
         self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_channels, 2 * oc if use_scale_shift_norm else oc))
         self.out_layers = nn.Sequential(_gn(oc, 1e-5), nn.SiLU(), nn.Dropout(0.0), nn.Conv2d(oc, oc, 3, padding=1))
         self.skip_connection = nn.Identity() if oc == channels else nn.Conv2d(channels, oc, 1)
+        if up:
+            self.h_upd, self.x_upd = Upsample(channels, False), Upsample(channels, False)
+        elif down:
+            self.h_upd, self.x_upd = Downsample(channels, False), Downsample(channels, False)
+        else:
+            self.h_upd = self.x_upd = nn.Identity()
 
 
 class QKMatMul(_NoForward):

@@ -133,7 +133,7 @@ def test_qgemm_epilogue_variants(cuda):
     out_t = torch.zeros(Bt, N, T, dtype=torch.uint8, device=cuda)
     out2 = torch.zeros(M, N, device=cuda)
     d2 = ops.gemm_desc(a_dev, w_dev, L["scale"].to(cuda), M=M, N=N, C=C, a_signed=False, bias=L["bias"].to(cuda),
-                       corr=corr, rows_per_batch=T, out=out2, ldo=N, out_q=out_t, ldq=N, oq=oq,
+                       corr=corr, rows_per_batch=T, out=out2, ldo=N, out_q=out_t, ldq=T, oq=oq,
                        out_q_transposed=True)
     ops.qgemm(d2)
     torch.cuda.synchronize()
