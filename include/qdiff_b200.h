@@ -199,14 +199,16 @@ int qd_qattention(const qd_attention_desc* d, qd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Small fp32 helpers on the path.
- *  qd_timestep_embedding: mode 0 = ldm timestep_embedding ([cos,sin], freq exp(-ln(1e4)*i/half),
- *      ldm/modules/diffusionmodules/util.py:151-171); mode 1 = ddim get_timestep_embedding
- *      ([sin,cos], divisor half-1, ddim/models/diffusion.py:6-24).
+ *  qd_timestep_embedding: out[b] = trig(t[b] * freqs[k]); freqs[dim/2] is the host-computed frequency
+ *      table (same fp32 expression as the reference, so the angles are bit-identical).
+ *      mode 0 = ldm timestep_embedding order [cos,sin] (ldm/modules/diffusionmodules/util.py:151-171);
+ *      mode 1 = ddim get_timestep_embedding order [sin,cos] (ddim/models/diffusion.py:6-24).
  *  qd_copy2d: strided fp32 copy (torch.cat along channels, openaimodel.py:776).
  *  qd_nchw_to_nhwc / qd_nhwc_to_nchw: UNet boundary layout change (latents are NCHW fp32).
  *  qd_avgpool2x / qd_upsample2x_f32: Downsample(use_conv=False) / Upsample for resblock_updown.
  * ------------------------------------------------------------------------------------------ */
-int qd_timestep_embedding(const float* t, int32_t B, int32_t dim, int32_t mode, float* out, qd_stream_t s);
+int qd_timestep_embedding(const float* t, const float* freqs, int32_t B, int32_t dim, int32_t mode, float* out,
+                          qd_stream_t s);
 int qd_copy2d(const float* src, long long ld_src, float* dst, long long ld_dst, int32_t M, int32_t C, qd_stream_t s);
 int qd_nchw_to_nhwc(const float* src, float* dst, int32_t B, int32_t C, int32_t HW, qd_stream_t s);
 int qd_nhwc_to_nchw(const float* src, float* dst, int32_t B, int32_t C, int32_t HW, qd_stream_t s);
@@ -270,6 +272,7 @@ typedef struct qd_misc_desc {
   float* dst;
   long long ld_src, ld_dst;
   int32_t a, b, c, d;   /* meaning per op: see qd_engine_add_op */
+  const float* aux;     /* QD_OP_TIMESTEP_EMB: frequency table */
 } qd_misc_desc;
 
 int qd_engine_create(int device, qd_engine** out);

@@ -252,18 +252,15 @@ __global__ void im2col_kernel(const qd_im2col_desc p) {
 }
 
 // ------------------------------------------------------------------------------------ misc fp32
-__global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, int dim, int mode,
-                                          float* __restrict__ out) {
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, const float* __restrict__ freqs, int B, int dim,
+                                          int mode, float* __restrict__ out) {
   const int half = dim / 2;
   const int total = B * half;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int b = i / half, k = i - b * half;
-    // mode 0 (ldm util.py:162-166): freqs = exp(-log(10000) * k / half); emb = [cos, sin]
-    // mode 1 (ddim diffusion.py:16-21): freqs = exp(k * -(log(10000)/(half-1))); emb = [sin, cos]
-    float freq;
-    if (mode == 0) freq = expf(-9.210340371976184f * (float)k / (float)half);
-    else           freq = expf((float)k * -(9.210340371976184f / (float)(half - 1)));
-    const float a = t[b] * freq;
+    // mode 0 (ldm util.py:162-166): emb = [cos, sin]; mode 1 (ddim diffusion.py:16-21): emb = [sin, cos].
+    // freqs[] comes from the host (identical fp32 expression as the reference) so a = t*freq is bit-identical.
+    const float a = t[b] * freqs[k];
     const float sv = sinf(a), cv = cosf(a);
     float* o = out + (long long)b * dim;
     if (mode == 0) { o[k] = cv; o[half + k] = sv; }

@@ -287,7 +287,8 @@ int launch_attention(const qd_attention_desc& d, cudaStream_t s) {
 int launch_misc(int kind, const qd_misc_desc& m, cudaStream_t s) {
   switch (kind) {
     case QD_OP_TIMESTEP_EMB:
-      qd::timestep_embedding_kernel<<<grid_for((long long)m.a * (m.b / 2), 128), 128, 0, s>>>(m.src, m.a, m.b, m.c, m.dst);
+      if (!m.aux) return fail(QD_ERR_BAD_ARG, "timestep_embedding: missing frequency table");
+      qd::timestep_embedding_kernel<<<grid_for((long long)m.a * (m.b / 2), 128), 128, 0, s>>>(m.src, m.aux, m.a, m.b, m.c, m.dst);
       return check_launch("timestep_embedding_kernel");
     case QD_OP_COPY2D:
       if (m.b % 4 || m.ld_src % 4 || m.ld_dst % 4) return fail(QD_ERR_UNSUPPORTED, "copy2d: alignment");
@@ -378,28 +379,29 @@ int qd_qattention(const qd_attention_desc* d, qd_stream_t s) {
   if (!d) return fail(QD_ERR_BAD_ARG, "null desc");
   return launch_attention(*d, (cudaStream_t)s);
 }
-int qd_timestep_embedding(const float* t, int32_t B, int32_t dim, int32_t mode, float* out, qd_stream_t s) {
-  qd_misc_desc m{t, out, 0, 0, B, dim, mode, 0};
+int qd_timestep_embedding(const float* t, const float* freqs, int32_t B, int32_t dim, int32_t mode, float* out,
+                          qd_stream_t s) {
+  qd_misc_desc m{t, out, 0, 0, B, dim, mode, 0, freqs};
   return launch_misc(QD_OP_TIMESTEP_EMB, m, (cudaStream_t)s);
 }
 int qd_copy2d(const float* src, long long ld_src, float* dst, long long ld_dst, int32_t M, int32_t C, qd_stream_t s) {
-  qd_misc_desc m{src, dst, ld_src, ld_dst, M, C, 0, 0};
+  qd_misc_desc m{src, dst, ld_src, ld_dst, M, C, 0, 0, nullptr};
   return launch_misc(QD_OP_COPY2D, m, (cudaStream_t)s);
 }
 int qd_nchw_to_nhwc(const float* src, float* dst, int32_t B, int32_t C, int32_t HW, qd_stream_t s) {
-  qd_misc_desc m{src, dst, 0, 0, B, C, HW, 0};
+  qd_misc_desc m{src, dst, 0, 0, B, C, HW, 0, nullptr};
   return launch_misc(QD_OP_NCHW_TO_NHWC, m, (cudaStream_t)s);
 }
 int qd_nhwc_to_nchw(const float* src, float* dst, int32_t B, int32_t C, int32_t HW, qd_stream_t s) {
-  qd_misc_desc m{src, dst, 0, 0, B, C, HW, 0};
+  qd_misc_desc m{src, dst, 0, 0, B, C, HW, 0, nullptr};
   return launch_misc(QD_OP_NHWC_TO_NCHW, m, (cudaStream_t)s);
 }
 int qd_avgpool2x(const float* src, float* dst, int32_t B, int32_t H, int32_t W, int32_t C, qd_stream_t s) {
-  qd_misc_desc m{src, dst, 0, 0, B, H, W, C};
+  qd_misc_desc m{src, dst, 0, 0, B, H, W, C, nullptr};
   return launch_misc(QD_OP_AVGPOOL2X, m, (cudaStream_t)s);
 }
 int qd_upsample2x_f32(const float* src, float* dst, int32_t B, int32_t H, int32_t W, int32_t C, qd_stream_t s) {
-  qd_misc_desc m{src, dst, 0, 0, B, H, W, C};
+  qd_misc_desc m{src, dst, 0, 0, B, H, W, C, nullptr};
   return launch_misc(QD_OP_UPSAMPLE2X, m, (cudaStream_t)s);
 }
 int qd_sampler_step(const qd_sampler_desc* d, qd_stream_t s) {

@@ -50,9 +50,12 @@ struct GemmArgs {
   long long ldr;
 };
 
+constexpr int GEMM_EPI_TILE_BYTES = 32 * 128;  // per-epilogue-warp staging tile (32 rows x 32 int32)
+
 struct GemmSmemLayout {
   int stage_bytes;
   int bar_offset;
+  int stage_off;  // epilogue staging tiles (4 warps)
   int total;
 };
 
@@ -60,8 +63,24 @@ __host__ __device__ inline GemmSmemLayout gemm_smem_layout(int BN, int stages) {
   GemmSmemLayout l;
   l.stage_bytes = GEMM_A_STAGE_BYTES + BN * GEMM_BK;
   l.bar_offset = l.stage_bytes * stages;
-  l.total = l.bar_offset + 256 + 1024;  // barriers + alignment slack
+  l.stage_off = l.bar_offset + 256;
+  l.total = l.stage_off + 4 * GEMM_EPI_TILE_BYTES + 1024;  // + alignment slack
   return l;
+}
+
+// border class (3x3 conv zero-point correction) and image index of output row m
+__device__ __forceinline__ void gemm_row_meta(const GemmArgs& p, int m, int& cls, int& img) {
+  cls = 0;
+  img = 0;
+  if (p.rows_per_batch > 0) img = m / p.rows_per_batch;
+  if (p.taps == 9) {
+    const int hw = p.H * p.W;
+    const int r = m % hw;
+    const int h = r / p.W, w = r - h * p.W;
+    const int rc = (h == 0) ? 0 : (h == p.H - 1 ? 2 : 1);
+    const int cc = (w == 0) ? 0 : (w == p.W - 1 ? 2 : 1);
+    cls = rc * 3 + cc;
+  }
 }
 
 template <int NC>
@@ -260,39 +279,133 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
+    // TMEM gives each thread one accumulator ROW; storing that way makes every warp store touch 32
+    // different rows (16 B each).  Non-transposed outputs therefore go through a per-warp 32x32 int32
+    // staging tile in shared memory (128 B rows, 16 B chunks XOR-swizzled by row&7: conflict-free both
+    // ways) and are finalised in the transposed mapping: 8 lanes x 16 B = one full 128 B line per row,
+    // 4 rows per instruction, per-column parameters loaded once per thread per chunk.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint8_t* stg = smem + lay.stage_off + q * GEMM_EPI_TILE_BYTES;
+    const int rsub = lane >> 3;   // row within a group of 4
+    const int cq = lane & 7;      // column quad within the 32-column chunk
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tm = tile / p.tiles_n;
       const int tn = tile - tm * p.tiles_n;
-      const int m = tm * GEMM_BM + q * 32 + lane;
       const int n_base = tn * p.BN;
-      int cls = 0, img = 0;
-      if (p.rows_per_batch > 0) img = m / p.rows_per_batch;
-      if (p.taps == 9) {
-        const int hw = p.H * p.W;
-        const int r = m % hw;
-        const int h = r / p.W, w = r - h * p.W;
-        const int rc = (h == 0) ? 0 : (h == p.H - 1 ? 2 : 1);
-        const int cc = (w == 0) ? 0 : (w == p.W - 1 ? 2 : 1);
-        cls = rc * 3 + cc;
-      }
+      const int m_warp = tm * GEMM_BM + q * 32;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
-      int c = 0;
-      for (; c + 32 <= p.BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + (uint32_t)c, v);
-        tmem_ld_wait();
-        if (m < p.M && n_base + c < p.N) gemm_epilogue_chunk<32>(p, v, m, n_base + c, cls, img);
-      }
-      if (c < p.BN) {
-        uint32_t v[16];
-        tmem_ld_32x16(t_row + (uint32_t)c, v);
-        tmem_ld_wait();
-        if (m < p.M && n_base + c < p.N) gemm_epilogue_chunk<16>(p, v, m, n_base + c, cls, img);
+      if (p.out_q_transposed) {
+        // thread-per-row mapping: consecutive lanes = consecutive tokens -> byte-coalesced V^T stores
+        const int m = m_warp + lane;
+        int cls, img;
+        gemm_row_meta(p, m, cls, img);
+        int c = 0;
+        for (; c + 32 <= p.BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + (uint32_t)c, v);
+          tmem_ld_wait();
+          if (m < p.M && n_base + c < p.N) gemm_epilogue_chunk<32>(p, v, m, n_base + c, cls, img);
+        }
+        if (c < p.BN) {
+          uint32_t v[16];
+          tmem_ld_32x16(t_row + (uint32_t)c, v);
+          tmem_ld_wait();
+          if (m < p.M && n_base + c < p.N) gemm_epilogue_chunk<16>(p, v, m, n_base + c, cls, img);
+        }
+      } else {
+        int cls8[8], img8[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) gemm_row_meta(p, m_warp + it * 4 + rsub, cls8[it], img8[it]);
+        for (int c = 0; c < p.BN; c += 32) {
+          const int ncols = (p.BN - c) >= 32 ? 32 : 16;
+          if (ncols == 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + (uint32_t)c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint32_t v[16];
+            tmem_ld_32x16(t_row + (uint32_t)c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          __syncwarp();
+          const int n = n_base + c + cq * 4;
+          if (cq * 4 < ncols && n < p.N) {
+            const bool full = (n + 3 < p.N);
+            float sc[4], bi[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const bool ok = full || (n + j < p.N);
+              sc[j] = ok ? __ldg(p.scale + n + j) : 0.f;
+              bi[j] = (ok && p.bias) ? __ldg(p.bias + n + j) : 0.f;
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int row = it * 4 + rsub;
+              const int m = m_warp + row;
+              if (m >= p.M) continue;
+              const uint4 a4 = *reinterpret_cast<const uint4*>(stg + row * 128 + ((cq ^ (row & 7)) << 4));
+              int a[4] = {(int)a4.x, (int)a4.y, (int)a4.z, (int)a4.w};
+              float y[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (p.corr && (full || n + j < p.N)) a[j] -= __ldg(p.corr + (long long)cls8[it] * p.N + n + j);
+                y[j] = (float)a[j] * sc[j] + bi[j];
+                if (p.rowvec && (full || n + j < p.N)) y[j] += __ldg(p.rowvec + (long long)img8[it] * p.ld_rowvec + n + j);
+              }
+              if (p.residual) {
+                const float* r = p.residual + (long long)m * p.ldr + n;
+                if (full && ((p.ldr & 3) == 0)) {
+                  const float4 rv = *reinterpret_cast<const float4*>(r);
+                  y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    if (n + j < p.N) y[j] += r[j];
+                }
+              }
+              if (p.out) {
+                float* o = p.out + (long long)m * p.ldo + n;
+                if (full && ((p.ldo & 3) == 0)) {
+                  *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    if (n + j < p.N) o[j] = y[j];
+                }
+              }
+              if (p.out_q) {
+                uint32_t qc[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float t = rintf(__fdiv_rn(y[j], p.q_delta)) + (float)p.q_zp;
+                  t = fminf(fmaxf(t, (float)p.q_lo), (float)p.q_hi);
+                  qc[j] = (uint32_t)(int)t & 0xFFu;
+                }
+                int8_t* o = p.out_q + (long long)m * p.ldq + n;
+                if (full && ((p.ldq & 3) == 0)) {
+                  *reinterpret_cast<uint32_t*>(o) = qc[0] | (qc[1] << 8) | (qc[2] << 16) | (qc[3] << 24);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    if (n + j < p.N) o[j] = (int8_t)qc[j];
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
       }
       tc_fence_before();
       __syncwarp();

@@ -94,7 +94,7 @@ class AttentionDesc(C.Structure):
 
 class MiscDesc(C.Structure):
     _fields_ = [("src", c_vp), ("dst", c_vp), ("ld_src", c_ll), ("ld_dst", c_ll),
-                ("a", c_i32), ("b", c_i32), ("c", c_i32), ("d", c_i32)]
+                ("a", c_i32), ("b", c_i32), ("c", c_i32), ("d", c_i32), ("aux", c_vp)]
 
 
 class SamplerDesc(C.Structure):
@@ -135,7 +135,7 @@ def lib():
                  "qd_qattention", "qd_sampler_step"):
         getattr(L, name).argtypes = [c_vp, c_vp]
         getattr(L, name).restype = C.c_int
-    L.qd_timestep_embedding.argtypes = [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]
+    L.qd_timestep_embedding.argtypes = [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]
     L.qd_copy2d.argtypes = [c_vp, c_ll, c_vp, c_ll, c_i32, c_i32, c_vp]
     L.qd_nchw_to_nhwc.argtypes = [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]
     L.qd_nhwc_to_nchw.argtypes = [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]

@@ -73,10 +73,10 @@ def border_corr(ws4, zx):
     """
     tap_sum = ws4.to(torch.float64).sum(dim=1)  # [N, 3, 3]
     rows_valid = {0: [1, 2], 1: [0, 1, 2], 2: [0, 1]}
-    out = torch.zeros(9, ws4.shape[0], dtype=torch.float64)
+    out = torch.zeros(9, ws4.shape[0], dtype=torch.float64, device=ws4.device)
     for rc in range(3):
         for cc in range(3):
-            s = torch.zeros(ws4.shape[0], dtype=torch.float64)
+            s = torch.zeros(ws4.shape[0], dtype=torch.float64, device=ws4.device)
             for ky in rows_valid[rc]:
                 for kx in rows_valid[cc]:
                     s += tap_sum[:, ky, kx]

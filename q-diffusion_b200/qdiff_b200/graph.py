@@ -104,7 +104,8 @@ class Builder:
         self.engine = e
         self.keep = []       # tensors referenced by recorded ops
         self.nops = 0
-        self.traces = {}     # block name -> (Act, (B, H, W)) for parity debugging
+        self.traces = {}     # block name -> (Act, (H, W)) for parity debugging
+        self.layer_traces = {}  # module key -> fp32 Act of that QuantModule's output
         self.op_names = []
         self.aq = qnn.act_quant_params
         self.wbits = qnn.weight_quant_params['n_bits']
@@ -133,7 +134,8 @@ class Builder:
         self.op_names.append(label)
 
     def key(self, m):
-        return self.names[id(m)]
+        n = self.names[id(m)]
+        return n[6:] if n.startswith("model.") else n
 
     def qp(self, q):
         """QParams of an activation quantizer object (delta, zero_point, clamp range)."""
@@ -198,9 +200,12 @@ class Builder:
         self.add(_lib.QD_OP_LAYERNORM, d, label)
         return acts
 
-    def misc(self, kind, src, dst, a, b, c=0, d_=0, ld_src=0, ld_dst=0, label="misc"):
+    def misc(self, kind, src, dst, a, b, c=0, d_=0, ld_src=0, ld_dst=0, label="misc", aux=None):
         m = MiscDesc()
         m.src, m.dst = src, dst
+        if aux is not None:
+            self.keep.append(aux)
+            m.aux = aux.data_ptr()
         m.ld_src, m.ld_dst, m.a, m.b, m.c, m.d = ld_src, ld_dst, a, b, c, d_
         self.add(kind, m, label)
 
@@ -302,6 +307,8 @@ class Builder:
         if o is not None:
             d.out = o.ptr + 4 * out_cols_offset
         self.add(_lib.QD_OP_GEMM, d, label)
+        if o is not None:
+            self.layer_traces[label] = o
         return oq_act if out_q is not None else o
 
     def qlinear(self, qm, x_f32, label, act=0, **kw):
@@ -397,11 +404,11 @@ class Builder:
                 if skip.split == 0:
                     raise RuntimeError(f"{k}.skip_connection: model.split is set but the checkpoint has no split quantizers")
                 a = self.quantize(x_res, skip.act_quantizer, k + ".skip.q", split=split, q1=skip.act_quantizer_0)
-                s = self.gemm(skip, a, k + ".skip.0", cols=(0, split), suffix="", zx=a.zp[0], dx=a.delta[0])
-                self.gemm(skip, a, k + ".skip.1", cols=(split, a.cols), suffix="_0", zx=a.zp[1], dx=a.delta[1],
+                s = self.gemm(skip, a, k + ".skip_connection.half0", cols=(0, split), suffix="", zx=a.zp[0], dx=a.delta[0])
+                self.gemm(skip, a, k + ".skip_connection", cols=(split, a.cols), suffix="_0", zx=a.zp[1], dx=a.delta[1],
                           accumulate_into=s, use_bias=False)
             else:
-                s = self.qlinear(skip, x_res, k + ".skip")
+                s = self.qlinear(skip, x_res, k + ".skip_connection")
         else:
             s = x_res
         out = self.conv3x3_s1(conv2, a2, (oh, ow), k + ".out_layers.3", residual=s)
@@ -483,7 +490,8 @@ class Builder:
         self.keep += [x_in, t_in] + ([ctx_in] if ctx_in is not None else [])
         mc = model.model_channels
         temb = self.new_f32(B, mc)
-        self.misc(_lib.QD_OP_TIMESTEP_EMB, t_in.data_ptr(), temb.ptr, B, mc, 0, label="timestep_embedding")
+        self.misc(_lib.QD_OP_TIMESTEP_EMB, t_in.data_ptr(), temb.ptr, B, mc, 0, label="timestep_embedding",
+                  aux=ops.timestep_freqs(mc, 0).to(self.dev))
         e = self.qlinear(model.time_embed[0], temb, "time_embed.0")
         emb = self.qlinear(model.time_embed[2], e, "time_embed.2", act=1)
         ctx = None
@@ -562,11 +570,11 @@ class Builder:
                 if nin.split == 0:
                     raise RuntimeError(f"{k}.nin_shortcut: split_shortcut is set but the checkpoint has no split quantizers")
                 a = self.quantize(x, nin.act_quantizer, k + ".nin.q", split=split, q1=nin.act_quantizer_0)
-                s = self.gemm(nin, a, k + ".nin.0", cols=(0, split), suffix="", zx=a.zp[0], dx=a.delta[0])
-                self.gemm(nin, a, k + ".nin.1", cols=(split, a.cols), suffix="_0", zx=a.zp[1], dx=a.delta[1],
+                s = self.gemm(nin, a, k + ".nin_shortcut.half0", cols=(0, split), suffix="", zx=a.zp[0], dx=a.delta[0])
+                self.gemm(nin, a, k + ".nin_shortcut", cols=(split, a.cols), suffix="_0", zx=a.zp[1], dx=a.delta[1],
                           accumulate_into=s, use_bias=False)
             else:
-                s = self.qlinear(nin, x, k + ".nin")
+                s = self.qlinear(nin, x, k + ".nin_shortcut")
         return self.conv3x3_s1(blk.conv2, a2, hw, k + ".conv2", residual=s)
 
     def ddim_attn(self, blk, x, hw):
@@ -590,7 +598,8 @@ class Builder:
         self.keep += [x_in, t_in]
         split_on = bool(getattr(model.config, "split_shortcut", False))
         temb0 = self.new_f32(B, model.ch)
-        self.misc(_lib.QD_OP_TIMESTEP_EMB, t_in.data_ptr(), temb0.ptr, B, model.ch, 1, label="timestep_embedding")
+        self.misc(_lib.QD_OP_TIMESTEP_EMB, t_in.data_ptr(), temb0.ptr, B, model.ch, 1, label="timestep_embedding",
+                  aux=ops.timestep_freqs(model.ch, 1).to(self.dev))
         e = self.qlinear(model.temb.dense[0], temb0, "temb.dense.0")
         temb = self.qlinear(model.temb.dense[1], e, "temb.dense.1", act=1)
         xh = self.new_f32(B * H * W, Cin)
@@ -698,4 +707,5 @@ def compile_unet(qnn, x_shape, ctx_shape, device, use_cuda_graph=True):
     check(lib().qd_engine_finalize(b.engine), "qd_engine_finalize")
     prog = Program(b.engine, b.keep, x_in, t_in, ctx_in, out, b.nops, b.traces, use_cuda_graph)
     prog.op_names = b.op_names
+    prog.layer_traces = b.layer_traces
     return prog

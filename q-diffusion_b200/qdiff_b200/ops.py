@@ -137,8 +137,21 @@ def sampler_step(desc):
     check(lib().qd_sampler_step(C.byref(desc), stream_ptr()), "qd_sampler_step")
 
 
+def timestep_freqs(dim, mode):
+    """Frequency table, evaluated on the host with the reference's own fp32 expression.
+    mode 0: ldm/modules/diffusionmodules/util.py:162-164; mode 1: ddim/models/diffusion.py:16-18."""
+    import math
+    half = dim // 2
+    if mode == 0:
+        return torch.exp(-math.log(10000) * torch.arange(start=0, end=half, dtype=torch.float32) / half)
+    emb = math.log(10000) / (half - 1)
+    return torch.exp(torch.arange(half, dtype=torch.float32) * -emb)
+
+
 def timestep_embedding(t, dim, mode):
     _require_cuda(t)
     out = torch.empty(t.shape[0], dim, device=t.device, dtype=torch.float32)
-    check(lib().qd_timestep_embedding(ptr(t), t.shape[0], dim, mode, ptr(out), stream_ptr()), "qd_timestep_embedding")
+    freqs = timestep_freqs(dim, mode).to(t.device)
+    check(lib().qd_timestep_embedding(ptr(t), ptr(freqs), t.shape[0], dim, mode, ptr(out), stream_ptr()),
+          "qd_timestep_embedding")
     return out

@@ -337,7 +337,7 @@ def test_timestep_embedding(cuda):
     for mode, fn, dim in ((0, O.timestep_embedding_ldm, 320), (1, O.timestep_embedding_ddim, 128)):
         got = ops.timestep_embedding(t.to(cuda), dim, mode).cpu()
         ref = fn(t, dim)
-        assert (got - ref).abs().max().item() < 2e-4, (mode, (got - ref).abs().max().item())
+        assert (got - ref).abs().max().item() < 2e-6, (mode, (got - ref).abs().max().item())
 
 
 def test_sampler_step(cuda):

@@ -18,17 +18,36 @@ def load_case(name):
     return g
 
 
-def oracle_forward(g, trace=None):
+def oracle_forward(g, trace=None, dtype=torch.float32):
+    """dtype=float64 evaluates the SAME algorithm with (almost) no rounding noise: the distance between that
+    and the fp32 result is the reference's intrinsic noise band (fake-quant networks amplify ulp-level
+    perturbations up to quantisation-noise level within a few layers; see DESIGN.md, Parity)."""
     q = g["qcfg"]
     qc = U.QuantCfg(q["weight_bit"], q["act_bit"], q["a_sym"], q["sm_abit"], q["quant_act"], adaround=True)
-    if g["family"] == "ddim":
-        p = g["params"]
-        cfg = dict(ch=p["ch"], ch_mult=p["ch_mult"], num_res_blocks=p["num_res_blocks"],
-                   attn_resolutions=p["attn_resolutions"], resolution=p["resolution"], resamp_with_conv=True,
-                   split_shortcut=p["split_shortcut"])
-        return U.ddim_unet_forward(g["ckpt"], cfg, qc, g["x"], g["t"], trace=trace)
-    arch = U.ldm_arch_from_params(split=g["params"].get("split", False), **g["params"]["unet"])
-    return U.ldm_unet_forward(g["ckpt"], arch, qc, g["x"], g["t"], g["context"], trace=trace)
+    te = (O.timestep_embedding_ldm, O.timestep_embedding_ddim)
+    U.set_dtype(dtype)
+    if dtype != torch.float32:   # keep the fp32 sinusoid table, widen afterwards
+        O.timestep_embedding_ldm = lambda t, dim, **k: te[0](t, dim).to(dtype)
+        O.timestep_embedding_ddim = lambda t, dim: te[1](t, dim).to(dtype)
+    try:
+        x = g["x"].to(dtype)
+        ctx = g["context"].to(dtype) if g["context"] is not None else None
+        if g["family"] == "ddim":
+            p = g["params"]
+            cfg = dict(ch=p["ch"], ch_mult=p["ch_mult"], num_res_blocks=p["num_res_blocks"],
+                       attn_resolutions=p["attn_resolutions"], resolution=p["resolution"], resamp_with_conv=True,
+                       split_shortcut=p["split_shortcut"])
+            return U.ddim_unet_forward(g["ckpt"], cfg, qc, x, g["t"], trace=trace)
+        arch = U.ldm_arch_from_params(split=g["params"].get("split", False), **g["params"]["unet"])
+        return U.ldm_unet_forward(g["ckpt"], arch, qc, x, g["t"], ctx, trace=trace)
+    finally:
+        U.set_dtype(torch.float32)
+        O.timestep_embedding_ldm, O.timestep_embedding_ddim = te
+
+
+def noise_band_mse(g, ref):
+    """MSE between the fp64 evaluation of the reference algorithm and its fp32 result `ref`."""
+    return ((oracle_forward(g, dtype=torch.float64).double() - ref.double()) ** 2).mean().item()
 
 
 def test_quantizer_known_answers():
@@ -60,6 +79,6 @@ def test_oracle_matches_reference(name):
     # same fp32 torch ops in the same order -> expect (near) bit equality; allow reduction-order noise only
     assert err <= 1e-5 * max(1.0, ref.abs().max().item()), (name, err, mse)
     for key, t in g["traces"].items():
-        if key in trace:
+        if key in trace and key != "layers":
             e = (trace[key] - t).abs().max().item()
             assert e <= 1e-5 * max(1.0, t.abs().max().item()), (name, key, e)
