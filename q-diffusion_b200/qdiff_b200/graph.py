@@ -107,6 +107,8 @@ class Builder:
         self.traces = {}     # block name -> (Act, (H, W)) for parity debugging
         self.layer_traces = {}  # module key -> fp32 Act of that QuantModule's output
         self.op_names = []
+        self.op_kinds = []
+        self.op_flops = []   # algorithmic integer ops (2*MACs) of each recorded op
         self.aq = qnn.act_quant_params
         self.wbits = qnn.weight_quant_params['n_bits']
         self.gn_ws = None
@@ -128,10 +130,12 @@ class Builder:
         self.keep.append(t)
         return t
 
-    def add(self, kind, desc, label):
+    def add(self, kind, desc, label, flops=0):
         check(lib().qd_engine_add_op(self.engine, kind, C.byref(desc)), f"qd_engine_add_op[{label}]")
         self.nops += 1
         self.op_names.append(label)
+        self.op_kinds.append(kind)
+        self.op_flops.append(flops)
 
     def key(self, m):
         n = self.names[id(m)]
@@ -306,7 +310,7 @@ class Builder:
             d.residual = res.ptr
         if o is not None:
             d.out = o.ptr + 4 * out_cols_offset
-        self.add(_lib.QD_OP_GEMM, d, label)
+        self.add(_lib.QD_OP_GEMM, d, label, flops=2 * M * N * Cred * taps)
         if o is not None:
             self.layer_traces[label] = o
         return oq_act if out_q is not None else o
@@ -355,7 +359,7 @@ class Builder:
         a.delta_w = qpw.delta
         a.out_scale = float(qpw.delta) * float(vt.delta[0])
         a.out, a.ld_out = out.ptr, out.ld
-        self.add(_lib.QD_OP_ATTENTION, a, label)
+        self.add(_lib.QD_OP_ATTENTION, a, label, flops=4 * self.B * heads * Tq * Tk * d)
         return out
 
     # ================================================================== LDM / SD family
@@ -706,6 +710,7 @@ def compile_unet(qnn, x_shape, ctx_shape, device, use_cuda_graph=True):
             raise NotImplementedError(f"unknown UNet type {_name(model)}")
     check(lib().qd_engine_finalize(b.engine), "qd_engine_finalize")
     prog = Program(b.engine, b.keep, x_in, t_in, ctx_in, out, b.nops, b.traces, use_cuda_graph)
-    prog.op_names = b.op_names
+    prog.op_names, prog.op_kinds, prog.op_flops = b.op_names, b.op_kinds, b.op_flops
+    prog.kernel_launches = sum(3 if k == _lib.QD_OP_GROUPNORM else 1 for k in b.op_kinds)
     prog.layer_traces = b.layer_traces
     return prog

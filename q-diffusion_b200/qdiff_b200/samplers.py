@@ -1,0 +1,199 @@
+"""Host loops of the denoising samplers around the engine UNet (the L4 layer of SURVEY section 1).
+
+One UNet program replay + ONE fused update kernel (qd_sampler_step: classifier-free-guidance combine,
+PLMS multistep weights, x0 prediction, x_{t-1}) per step; nothing leaves the device inside the loop
+(the reference copies x_t / x0 to the CPU every step, ddim/functions/denoising.py:24,30).
+
+Restates, with the same argument names:
+  generalized_steps                     ddim/functions/denoising.py:10-32
+  DDIMSampler.sample / p_sample_ddim    ldm/models/diffusion/ddim.py:57-220
+  PLMSSampler.sample / p_sample_plms    ldm/models/diffusion/plms.py:58-240
+  schedules                             ldm/modules/diffusionmodules/util.py:21-74, ddpm.py:118-146
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import SamplerDesc, ptr
+
+
+# ------------------------------------------------------------------------------- schedules
+def make_beta_schedule(schedule="linear", n_timestep=1000, linear_start=1e-4, linear_end=2e-2):
+    if schedule == "linear":     # LDM / SD: linear in sqrt(beta) (util.py:22-25)
+        return (torch.linspace(linear_start ** 0.5, linear_end ** 0.5, n_timestep, dtype=torch.float64) ** 2).numpy()
+    if schedule == "ddim_linear":  # the ddim runner: np.linspace(beta_start, beta_end, T) in float64
+        return np.linspace(linear_start, linear_end, n_timestep, dtype=np.float64)
+    raise ValueError(f"schedule '{schedule}' unknown")
+
+
+class Schedule:
+    """The buffers LatentDiffusion.register_schedule creates (ddpm.py:118-146), fp32 like the reference."""
+
+    def __init__(self, beta_schedule="linear", timesteps=1000, linear_start=1e-4, linear_end=2e-2):
+        betas = make_beta_schedule(beta_schedule, timesteps, linear_start, linear_end)
+        ac = np.cumprod(1.0 - betas, axis=0)
+        self.num_timesteps = int(timesteps)
+        self.betas = torch.tensor(betas, dtype=torch.float32)
+        self.alphas_cumprod = torch.tensor(ac, dtype=torch.float32)
+        self.alphas_cumprod_prev = torch.tensor(np.append(1.0, ac[:-1]), dtype=torch.float32)
+
+
+def make_ddim_timesteps(ddim_discr_method, num_ddim_timesteps, num_ddpm_timesteps):
+    """util.py:46-60 (note: 'uniform' with c = T // S yields more than S steps when S does not divide T)."""
+    if ddim_discr_method == "uniform":
+        c = num_ddpm_timesteps // num_ddim_timesteps
+        steps = np.asarray(list(range(0, num_ddpm_timesteps, c)))
+    elif ddim_discr_method == "quad":
+        steps = ((np.linspace(0, np.sqrt(num_ddpm_timesteps * .8), num_ddim_timesteps)) ** 2).astype(int)
+    else:
+        raise NotImplementedError(ddim_discr_method)
+    return steps + 1
+
+
+def make_ddim_sampling_parameters(alphacums, ddim_timesteps, eta):
+    """util.py:63-74."""
+    alphas = alphacums[ddim_timesteps]
+    alphas_prev = np.asarray([alphacums[0]] + alphacums[ddim_timesteps[:-1]].tolist())
+    sigmas = eta * np.sqrt((1 - alphas_prev) / (1 - alphas) * (1 - alphas / alphas_prev))
+    return sigmas, alphas, alphas_prev
+
+
+# ------------------------------------------------------------------------------- fused update
+def _step(x, eps, x_prev, *, a_t, a_prev, sigma, sqrt_one_minus_at=None, cfg_scale=0.0, coef=(1.0, 0, 0, 0),
+          olds=(None, None, None), noise=None, pred_x0=None, eps_out=None):
+    d = SamplerDesc()
+    d.x, d.eps, d.x_prev = ptr(x), ptr(eps), ptr(x_prev)
+    d.old1, d.old2, d.old3 = ptr(olds[0]), ptr(olds[1]), ptr(olds[2])
+    d.noise, d.pred_x0, d.eps_out = ptr(noise), ptr(pred_x0), ptr(eps_out)
+    d.n = x.numel()
+    d.cfg_scale = float(cfg_scale)
+    d.c_e0, d.c_e1, d.c_e2, d.c_e3 = [float(v) for v in coef]
+    d.sqrt_at = math.sqrt(float(a_t))
+    d.sqrt_one_minus_at = float(sqrt_one_minus_at) if sqrt_one_minus_at is not None else math.sqrt(1.0 - float(a_t))
+    d.sqrt_a_prev = math.sqrt(float(a_prev))
+    d.dir_coef = math.sqrt(max(1.0 - float(a_prev) - float(sigma) ** 2, 0.0))
+    d.sigma = float(sigma)
+    ops.sampler_step(d)
+
+
+class _LatentSampler:
+    """Shared part of DDIMSampler / PLMSSampler.  `unet` is a QuantModel (or any callable
+    (x, t, context) -> eps on CUDA); `schedule` a Schedule."""
+
+    def __init__(self, unet, schedule=None, schedule_name="linear", **kwargs):
+        self.unet = unet
+        self.schedule = schedule or Schedule(schedule_name)
+        self.ddpm_num_timesteps = self.schedule.num_timesteps
+
+    def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0., verbose=False):
+        self.ddim_timesteps = make_ddim_timesteps(ddim_discretize, ddim_num_steps, self.ddpm_num_timesteps)
+        ac = self.schedule.alphas_cumprod.cpu()
+        self.ddim_sigmas, self.ddim_alphas, self.ddim_alphas_prev = make_ddim_sampling_parameters(
+            ac, self.ddim_timesteps, ddim_eta)
+        self.ddim_sqrt_one_minus_alphas = np.sqrt(1. - self.ddim_alphas)
+
+    def _model_eps(self, x, t, cond, uc, scale):
+        """Returns (eps tensor, cfg_scale for the fused kernel): with guidance the UNet sees the doubled
+        batch [uncond; cond] (plms.py:185-189) and the combine happens inside qd_sampler_step."""
+        if uc is None or scale == 1.:
+            return self.unet(x, t, cond), 0.0
+        x_in = torch.cat([x] * 2)
+        t_in = torch.cat([t] * 2)
+        c_in = torch.cat([uc, cond])
+        return self.unet(x_in, t_in, c_in), float(scale)
+
+
+class DDIMSampler(_LatentSampler):
+    @torch.no_grad()
+    def sample(self, S, batch_size, shape, conditioning=None, eta=0., x_T=None, unconditional_guidance_scale=1.,
+               unconditional_conditioning=None, noise_fn=None, verbose=False, **kwargs):
+        self.make_schedule(S, ddim_eta=eta)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        size = (batch_size,) + tuple(shape)
+        img = torch.randn(size, device=dev) if x_T is None else x_T.to(dev, torch.float32).clone()
+        nxt = torch.empty_like(img)
+        time_range = np.flip(self.ddim_timesteps)
+        total = self.ddim_timesteps.shape[0]
+        for i, step in enumerate(time_range):
+            index = total - i - 1
+            ts = torch.full((batch_size,), int(step), device=dev, dtype=torch.long)
+            eps, s = self._model_eps(img, ts, conditioning, unconditional_conditioning, unconditional_guidance_scale)
+            sigma = float(self.ddim_sigmas[index])
+            noise = None
+            if sigma != 0.0:
+                noise = noise_fn(i, size, dev) if noise_fn is not None else torch.randn(size, device=dev)
+            _step(img, eps, nxt, a_t=self.ddim_alphas[index], a_prev=self.ddim_alphas_prev[index], sigma=sigma,
+                  sqrt_one_minus_at=self.ddim_sqrt_one_minus_alphas[index], cfg_scale=s, noise=noise)
+            img, nxt = nxt, img
+        return img, {}
+
+
+class PLMSSampler(_LatentSampler):
+    _AB = {1: (1.5, -0.5, 0, 0), 2: (23 / 12, -16 / 12, 5 / 12, 0), 3: (55 / 24, -59 / 24, 37 / 24, -9 / 24)}
+
+    @torch.no_grad()
+    def sample(self, S, batch_size, shape, conditioning=None, eta=0., x_T=None, unconditional_guidance_scale=1.,
+               unconditional_conditioning=None, verbose=False, **kwargs):
+        if eta != 0:
+            raise ValueError('ddim_eta must be 0 for PLMS')
+        self.make_schedule(S, ddim_eta=0.)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        size = (batch_size,) + tuple(shape)
+        img = torch.randn(size, device=dev) if x_T is None else x_T.to(dev, torch.float32).clone()
+        nxt, tmp = torch.empty_like(img), torch.empty_like(img)
+        time_range = np.flip(self.ddim_timesteps)
+        total = self.ddim_timesteps.shape[0]
+        old_eps = []
+        uc, sc = unconditional_conditioning, unconditional_guidance_scale
+        for i, step in enumerate(time_range):
+            index = total - i - 1
+            ts = torch.full((batch_size,), int(step), device=dev, dtype=torch.long)
+            kw = dict(a_t=self.ddim_alphas[index], a_prev=self.ddim_alphas_prev[index], sigma=0.0,
+                      sqrt_one_minus_at=self.ddim_sqrt_one_minus_alphas[index])
+            eps, s = self._model_eps(img, ts, conditioning, uc, sc)
+            e_t = torch.empty_like(img)
+            if len(old_eps) == 0:
+                # pseudo improved Euler: provisional x_prev, second UNet call at t_next (plms.py:222-227)
+                _step(img, eps, tmp, cfg_scale=s, eps_out=e_t, **kw)
+                ts_next = torch.full((batch_size,), int(time_range[min(i + 1, len(time_range) - 1)]), device=dev,
+                                     dtype=torch.long)
+                eps2, s2 = self._model_eps(tmp, ts_next, conditioning, uc, sc)
+                e_next = torch.empty_like(img)
+                _step(tmp, eps2, nxt, cfg_scale=s2, eps_out=e_next, **kw)        # only to materialise guided e_next
+                _step(img, e_t, nxt, coef=(0.5, 0.5, 0, 0), olds=(e_next, None, None), **kw)
+            else:
+                o = old_eps[::-1] + [None] * 3
+                _step(img, eps, nxt, cfg_scale=s, coef=self._AB[min(len(old_eps), 3)], olds=(o[0], o[1], o[2]),
+                      eps_out=e_t, **kw)
+            old_eps.append(e_t)
+            if len(old_eps) >= 4:
+                old_eps.pop(0)
+            img, nxt = nxt, img
+        return img, {}
+
+
+@torch.no_grad()
+def generalized_steps(x, seq, model, b, eta=0.0, noise_fn=None):
+    """DDIM loop of the CIFAR script (ddim/functions/denoising.py:10-32).  x: [n,C,H,W] on CUDA, seq: list of
+    timesteps, b: betas (1-D tensor).  Returns the final x only (device resident; no per-step host copies)."""
+    n = x.size(0)
+    dev = x.device
+    beta = torch.cat([torch.zeros(1), b.detach().cpu().float()], dim=0)
+    acp = (1 - beta).cumprod(dim=0)  # compute_alpha: index t+1
+    seq = list(seq)
+    seq_next = [-1] + seq[:-1]
+    cur, nxt = x.to(torch.float32).clone(), torch.empty_like(x, dtype=torch.float32)
+    for k, (i, j) in enumerate(zip(reversed(seq), reversed(seq_next))):
+        t = (torch.ones(n) * i).to(dev)
+        at, at_next = float(acp[int(i) + 1]), float(acp[int(j) + 1])
+        et = model(cur, t)
+        c1 = eta * math.sqrt((1 - at / at_next) * (1 - at_next) / (1 - at))
+        noise = None
+        if c1 != 0.0:
+            noise = noise_fn(k, tuple(x.shape), dev) if noise_fn is not None else torch.randn_like(cur)
+        _step(cur, et, nxt, a_t=at, a_prev=at_next, sigma=c1, noise=noise)
+        cur, nxt = nxt, cur
+    return cur
