@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels individually (for ncu launch lists)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -193,7 +194,7 @@ def main():
     from qdiff_b200 import _lib, samplers, synth
     L = _lib.lib()
 
-    qnn, _ = synth.build_qnn(WORKLOAD)
+    qnn, _ = synth.build_qnn(WORKLOAD, cuda_graph=not args.no_graph)
     B = IMAGES_PER_GPU
     # every rank draws the FULL batch from the same seed and keeps its shard (N-rank == 1-rank results)
     g = torch.Generator().manual_seed(42)

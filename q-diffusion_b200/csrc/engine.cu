@@ -88,7 +88,7 @@ int encode_u8_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* 
 struct GemmPlan {
   CUtensorMap tmA, tmB;
   qd::GemmArgs args;
-  int grid, smem;
+  int grid, smem, mode;
 };
 
 int pick_bn(int N, int tiles_m, int sms, int hint) {
@@ -108,6 +108,8 @@ int pick_bn(int N, int tiles_m, int sms, int hint) {
   }
   return best;
 }
+
+int gemm_mode(const qd::GemmArgs& a);
 
 int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
   if (!d || !d->a || !d->w || !d->scale) return fail(QD_ERR_BAD_ARG, "gemm: null operand");
@@ -183,18 +185,49 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
   a.residual = d->residual; a.ldr = d->ldr;
   const int tiles = a.tiles_m * a.tiles_n;
   pl->grid = tiles < sms ? tiles : sms;
+  pl->mode = gemm_mode(a);
   return QD_OK;
 }
 
-int launch_gemm(const GemmPlan& pl, cudaStream_t s) {
+template <int MODE>
+int launch_gemm_mode(const GemmPlan& pl, cudaStream_t s) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(qd::gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(qd::gemm_i8_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) return fail(QD_ERR_CUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-  qd::gemm_i8_kernel<<<pl.grid, qd::GEMM_THREADS, pl.smem, s>>>(pl.tmA, pl.tmB, pl.args);
+  qd::gemm_i8_kernel<MODE><<<pl.grid, qd::GEMM_THREADS, pl.smem, s>>>(pl.tmA, pl.tmB, pl.args);
   return check_launch("gemm_i8_kernel");
+}
+
+// Specialised epilogues for the hot combinations; everything else runs the generic (-1) kernel.
+int gemm_mode(const qd::GemmArgs& a) {
+  const bool f = a.out != nullptr, q = a.out_q != nullptr;
+  if (f == q || a.out_q_transposed || (a.N & 3)) return -1;
+  if (a.rowvec && a.residual) return -1;
+  if (q && (a.rowvec || a.residual)) return -1;
+  if (f && (a.ldo & 3)) return -1;
+  if (q && (a.ldq & 3)) return -1;
+  if (a.residual && (a.ldr & 3)) return -1;
+  if (a.rowvec && (a.ld_rowvec & 3)) return -1;
+  return (a.corr ? qd::EPI_CORR : 0) | (a.rowvec ? qd::EPI_ROWVEC : 0) | (a.residual ? qd::EPI_RESIDUAL : 0) |
+         (f ? qd::EPI_OUT_F32 : qd::EPI_OUT_Q);
+}
+
+int launch_gemm(const GemmPlan& pl, cudaStream_t s) {
+  using namespace qd;
+  switch (pl.mode) {
+    case EPI_OUT_F32: return launch_gemm_mode<EPI_OUT_F32>(pl, s);
+    case EPI_OUT_F32 | EPI_CORR: return launch_gemm_mode<EPI_OUT_F32 | EPI_CORR>(pl, s);
+    case EPI_OUT_F32 | EPI_ROWVEC: return launch_gemm_mode<EPI_OUT_F32 | EPI_ROWVEC>(pl, s);
+    case EPI_OUT_F32 | EPI_ROWVEC | EPI_CORR: return launch_gemm_mode<EPI_OUT_F32 | EPI_ROWVEC | EPI_CORR>(pl, s);
+    case EPI_OUT_F32 | EPI_RESIDUAL: return launch_gemm_mode<EPI_OUT_F32 | EPI_RESIDUAL>(pl, s);
+    case EPI_OUT_F32 | EPI_RESIDUAL | EPI_CORR: return launch_gemm_mode<EPI_OUT_F32 | EPI_RESIDUAL | EPI_CORR>(pl, s);
+    case EPI_OUT_Q: return launch_gemm_mode<EPI_OUT_Q>(pl, s);
+    case EPI_OUT_Q | EPI_CORR: return launch_gemm_mode<EPI_OUT_Q | EPI_CORR>(pl, s);
+    default: return launch_gemm_mode<-1>(pl, s);
+  }
 }
 
 // ------------------------------------------------------------------ elementwise launchers

@@ -10,7 +10,12 @@
 //   warp 0   : TMA producer  (A tile 128 x 128 B, B tile BN x 128 B, 128B swizzle, mbarrier ring)
 //   warp 1   : MMA issuer    (tcgen05.mma.kind::i8, M=128, N=BN, K=32 per instruction, int32 acc in TMEM)
 //   warp 2   : TMEM allocator (512 columns: two accumulator stages of up to 256 columns)
-//   warps 4-7: epilogue      (tcgen05.ld -> zero-point correction -> scale/bias/adds -> fp32 or requantised store)
+//   warps 4-7: epilogue      (tcgen05.ld -> smem transpose -> zero-point correction / scale / bias /
+//                             adds -> coalesced fp32 or requantised stores)
+//
+// The kernel is templated on the epilogue MODE so the hot variants carry no runtime flag tests
+// (the first version with runtime flags was instruction-issue / I-cache bound in the epilogue:
+// profiles/r01_gemm_epilogue_v1.txt).  MODE = -1 keeps every runtime option (ragged N, both outputs).
 #pragma once
 #include "ptx.cuh"
 
@@ -21,6 +26,14 @@ constexpr int GEMM_BK = 128;  // bytes == int8 elements per k-block (one 128B sw
 constexpr int GEMM_THREADS = 256;
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK;
 constexpr int GEMM_MAX_STAGES = 8;
+constexpr int GEMM_EPI_TILE_BYTES = 32 * 128;  // per-epilogue-warp staging tile (32 rows x 32 int32)
+
+// epilogue MODE bits (MODE < 0: generic)
+constexpr int EPI_CORR = 1;       // subtract zero-point correction
+constexpr int EPI_ROWVEC = 2;     // + per-image per-channel vector (timestep embedding)
+constexpr int EPI_RESIDUAL = 4;   // + residual[m, n]
+constexpr int EPI_OUT_F32 = 8;    // fp32 output
+constexpr int EPI_OUT_Q = 16;     // requantised code output (row-major)
 
 struct GemmArgs {
   int M, N;            // logical output rows / columns (columns >= N are masked)
@@ -49,8 +62,6 @@ struct GemmArgs {
   const float* residual;   // [M, ldr] or nullptr (may alias out)
   long long ldr;
 };
-
-constexpr int GEMM_EPI_TILE_BYTES = 32 * 128;  // per-epilogue-warp staging tile (32 rows x 32 int32)
 
 struct GemmSmemLayout {
   int stage_bytes;
@@ -83,10 +94,18 @@ __device__ __forceinline__ void gemm_row_meta(const GemmArgs& p, int m, int& cls
   }
 }
 
+__device__ __forceinline__ uint32_t gemm_quant_code(float y, const GemmArgs& p) {
+  // consumer's activation quantizer (qdiff/quant_layer.py:82-88): rne(y/delta)+zp, clamp
+  float t = rintf(__fdiv_rn(y, p.q_delta)) + (float)p.q_zp;
+  t = fminf(fmaxf(t, (float)p.q_lo), (float)p.q_hi);
+  return (uint32_t)(int)t & 0xFFu;
+}
+
+// Thread-per-row epilogue (used for the transposed V^T code output: consecutive lanes = consecutive
+// tokens, so each per-column byte store of the warp fills one 32 B sector).
 template <int NC>
-__device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& p, const uint32_t (&acc)[NC], int m, int n0,
-                                                    int cls, int img) {
-  // One thread: row m, columns n0 .. n0+NC-1.
+__device__ __forceinline__ void gemm_epilogue_rowwise(const GemmArgs& p, const uint32_t (&acc)[NC], int m, int n0,
+                                                      int cls, int img) {
   float y[NC];
 #pragma unroll
   for (int j = 0; j < NC; ++j) {
@@ -97,74 +116,105 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& p, const uin
       float v = (float)a * __ldg(p.scale + n);
       if (p.bias) v += __ldg(p.bias + n);
       if (p.rowvec) v += __ldg(p.rowvec + (long long)img * p.ld_rowvec + n);
+      if (p.residual) v += p.residual[(long long)m * p.ldr + n];
       y[j] = v;
     } else {
       y[j] = 0.f;
     }
   }
-  if (p.residual) {
-    const float* r = p.residual + (long long)m * p.ldr + n0;
-    if ((n0 + NC <= p.N) && ((p.ldr & 3) == 0)) {
-#pragma unroll
-      for (int j = 0; j < NC; j += 4) {
-        float4 rv = *reinterpret_cast<const float4*>(r + j);
-        y[j] += rv.x; y[j + 1] += rv.y; y[j + 2] += rv.z; y[j + 3] += rv.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < NC; ++j)
-        if (n0 + j < p.N) y[j] += r[j];
-    }
-  }
   if (p.out) {
     float* o = p.out + (long long)m * p.ldo + n0;
-    if ((n0 + NC <= p.N) && ((p.ldo & 3) == 0)) {
 #pragma unroll
-      for (int j = 0; j < NC; j += 4)
-        *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < NC; ++j)
-        if (n0 + j < p.N) o[j] = y[j];
-    }
+    for (int j = 0; j < NC; ++j)
+      if (n0 + j < p.N) o[j] = y[j];
   }
   if (p.out_q) {
-    // consumer's activation quantizer (qdiff/quant_layer.py:82-88): rne(y/delta)+zp, clamp
-    uint8_t q[NC];
+    const int t_in = m - img * p.rows_per_batch;
+    int8_t* o = p.out_q + ((long long)img * p.N + n0) * p.ldq + t_in;
 #pragma unroll
-    for (int j = 0; j < NC; ++j) {
-      float t = rintf(__fdiv_rn(y[j], p.q_delta)) + (float)p.q_zp;
-      t = fminf(fmaxf(t, (float)p.q_lo), (float)p.q_hi);
-      q[j] = (uint8_t)(int)t;
-    }
-    if (!p.out_q_transposed) {
-      int8_t* o = p.out_q + (long long)m * p.ldq + n0;
-      if ((n0 + NC <= p.N) && ((p.ldq & 15) == 0)) {
-#pragma unroll
-        for (int j = 0; j < NC; j += 16) {
-          uint4 v;
-          v.x = q[j] | (q[j + 1] << 8) | (q[j + 2] << 16) | ((uint32_t)q[j + 3] << 24);
-          v.y = q[j + 4] | (q[j + 5] << 8) | (q[j + 6] << 16) | ((uint32_t)q[j + 7] << 24);
-          v.z = q[j + 8] | (q[j + 9] << 8) | (q[j + 10] << 16) | ((uint32_t)q[j + 11] << 24);
-          v.w = q[j + 12] | (q[j + 13] << 8) | (q[j + 14] << 16) | ((uint32_t)q[j + 15] << 24);
-          *reinterpret_cast<uint4*>(o + j) = v;
-        }
+    for (int j = 0; j < NC; ++j)
+      if (n0 + j < p.N) o[(long long)j * p.ldq] = (int8_t)gemm_quant_code(y[j], p);
+  }
+}
+
+// Finalise 4 consecutive columns of one row.  MODE >= 0: flags are compile-time, N % 4 == 0 and all
+// leading dimensions are vector-aligned (checked on the host).  MODE < 0: everything at run time.
+template <int MODE>
+__device__ __forceinline__ void gemm_finalise4(const GemmArgs& p, const uint4 a4, const float (&sc)[4],
+                                               const float (&bi)[4], const int4 corr4, int m, int n, int cls, int img) {
+  constexpr bool G = MODE < 0;
+  const bool has_corr = G ? (p.corr != nullptr) : bool(MODE & EPI_CORR);
+  const bool has_rowvec = G ? (p.rowvec != nullptr) : bool(MODE & EPI_ROWVEC);
+  const bool has_res = G ? (p.residual != nullptr) : bool(MODE & EPI_RESIDUAL);
+  const bool out_f = G ? (p.out != nullptr) : bool(MODE & EPI_OUT_F32);
+  const bool out_q = G ? (p.out_q != nullptr) : bool(MODE & EPI_OUT_Q);
+  const bool full = G ? (n + 3 < p.N) : true;
+  int a[4] = {(int)a4.x, (int)a4.y, (int)a4.z, (int)a4.w};
+  if (has_corr) {
+    if (p.taps == 9) {
+      if (full) {
+        const int4 c = *reinterpret_cast<const int4*>(p.corr + (long long)cls * p.N + n);
+        a[0] -= c.x; a[1] -= c.y; a[2] -= c.z; a[3] -= c.w;
       } else {
 #pragma unroll
-        for (int j = 0; j < NC; ++j)
-          if (n0 + j < p.N) o[j] = (int8_t)q[j];
+        for (int j = 0; j < 4; ++j)
+          if (n + j < p.N) a[j] -= __ldg(p.corr + (long long)cls * p.N + n + j);
       }
     } else {
-      // [img][n][ldq]: consecutive lanes = consecutive t -> byte-coalesced across the warp
-      int t_in = m - img * p.rows_per_batch;
-      int8_t* o = p.out_q + ((long long)img * p.N + n0) * p.ldq + t_in;
+      a[0] -= corr4.x; a[1] -= corr4.y; a[2] -= corr4.z; a[3] -= corr4.w;
+    }
+  }
+  float y[4];
 #pragma unroll
-      for (int j = 0; j < NC; ++j)
-        if (n0 + j < p.N) o[(long long)j * p.ldq] = (int8_t)q[j];
+  for (int j = 0; j < 4; ++j) y[j] = (float)a[j] * sc[j] + bi[j];
+  if (has_rowvec) {
+    const float* rv = p.rowvec + (long long)img * p.ld_rowvec + n;
+    if (full && (G ? ((p.ld_rowvec & 3) == 0) : true)) {
+      const float4 r = *reinterpret_cast<const float4*>(rv);
+      y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n + j < p.N) y[j] += rv[j];
+    }
+  }
+  if (has_res) {
+    const float* r = p.residual + (long long)m * p.ldr + n;
+    if (full && (G ? ((p.ldr & 3) == 0) : true)) {
+      const float4 rv = *reinterpret_cast<const float4*>(r);
+      y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n + j < p.N) y[j] += r[j];
+    }
+  }
+  if (out_f) {
+    float* o = p.out + (long long)m * p.ldo + n;
+    if (full && (G ? ((p.ldo & 3) == 0) : true)) {
+      *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n + j < p.N) o[j] = y[j];
+    }
+  }
+  if (out_q) {
+    const uint32_t q0 = gemm_quant_code(y[0], p), q1 = gemm_quant_code(y[1], p);
+    const uint32_t q2 = gemm_quant_code(y[2], p), q3 = gemm_quant_code(y[3], p);
+    int8_t* o = p.out_q + (long long)m * p.ldq + n;
+    if (full && (G ? ((p.ldq & 3) == 0) : true)) {
+      *reinterpret_cast<uint32_t*>(o) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+    } else {
+      const uint32_t qq[4] = {q0, q1, q2, q3};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n + j < p.N) o[j] = (int8_t)qq[j];
     }
   }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -280,7 +330,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     // TMEM gives each thread one accumulator ROW; storing that way makes every warp store touch 32
-    // different rows (16 B each).  Non-transposed outputs therefore go through a per-warp 32x32 int32
+    // different rows (16 B each).  Row-major outputs therefore go through a per-warp 32x32 int32
     // staging tile in shared memory (128 B rows, 16 B chunks XOR-swizzled by row&7: conflict-free both
     // ways) and are finalised in the transposed mapping: 8 lanes x 16 B = one full 128 B line per row,
     // 4 rows per instruction, per-column parameters loaded once per thread per chunk.
@@ -295,11 +345,16 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int tn = tile - tm * p.tiles_n;
       const int n_base = tn * p.BN;
       const int m_warp = tm * GEMM_BM + q * 32;
+      const bool transposed = (MODE < 0) && p.out_q_transposed;
+      int cls8[8], img8[8];
+      if (!transposed) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) gemm_row_meta(p, m_warp + it * 4 + rsub, cls8[it], img8[it]);
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
-      if (p.out_q_transposed) {
-        // thread-per-row mapping: consecutive lanes = consecutive tokens -> byte-coalesced V^T stores
+      if (transposed) {
         const int m = m_warp + lane;
         int cls, img;
         gemm_row_meta(p, m, cls, img);
@@ -308,18 +363,15 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint32_t v[32];
           tmem_ld_32x32(t_row + (uint32_t)c, v);
           tmem_ld_wait();
-          if (m < p.M && n_base + c < p.N) gemm_epilogue_chunk<32>(p, v, m, n_base + c, cls, img);
+          if (m < p.M && n_base + c < p.N) gemm_epilogue_rowwise<32>(p, v, m, n_base + c, cls, img);
         }
         if (c < p.BN) {
           uint32_t v[16];
           tmem_ld_32x16(t_row + (uint32_t)c, v);
           tmem_ld_wait();
-          if (m < p.M && n_base + c < p.N) gemm_epilogue_chunk<16>(p, v, m, n_base + c, cls, img);
+          if (m < p.M && n_base + c < p.N) gemm_epilogue_rowwise<16>(p, v, m, n_base + c, cls, img);
         }
       } else {
-        int cls8[8], img8[8];
-#pragma unroll
-        for (int it = 0; it < 8; ++it) gemm_row_meta(p, m_warp + it * 4 + rsub, cls8[it], img8[it]);
         for (int c = 0; c < p.BN; c += 32) {
           const int ncols = (p.BN - c) >= 32 ? 32 : 16;
           if (ncols == 32) {
@@ -342,65 +394,36 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           const int n = n_base + c + cq * 4;
           if (cq * 4 < ncols && n < p.N) {
-            const bool full = (n + 3 < p.N);
             float sc[4], bi[4];
+            int4 corr4 = make_int4(0, 0, 0, 0);
+            if (MODE >= 0 || n + 3 < p.N) {
+              const float4 s4 = *reinterpret_cast<const float4*>(p.scale + n);
+              sc[0] = s4.x; sc[1] = s4.y; sc[2] = s4.z; sc[3] = s4.w;
+              if (p.bias) {
+                const float4 b4 = *reinterpret_cast<const float4*>(p.bias + n);
+                bi[0] = b4.x; bi[1] = b4.y; bi[2] = b4.z; bi[3] = b4.w;
+              } else {
+                bi[0] = bi[1] = bi[2] = bi[3] = 0.f;
+              }
+              if (p.corr && p.taps == 1) corr4 = *reinterpret_cast<const int4*>(p.corr + n);
+            } else {
+              int cc[4] = {0, 0, 0, 0};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const bool ok = full || (n + j < p.N);
-              sc[j] = ok ? __ldg(p.scale + n + j) : 0.f;
-              bi[j] = (ok && p.bias) ? __ldg(p.bias + n + j) : 0.f;
+              for (int j = 0; j < 4; ++j) {
+                const bool ok = n + j < p.N;
+                sc[j] = ok ? __ldg(p.scale + n + j) : 0.f;
+                bi[j] = (ok && p.bias) ? __ldg(p.bias + n + j) : 0.f;
+                cc[j] = (ok && p.corr && p.taps == 1) ? __ldg(p.corr + n + j) : 0;
+              }
+              corr4 = make_int4(cc[0], cc[1], cc[2], cc[3]);
             }
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int row = it * 4 + rsub;
               const int m = m_warp + row;
-              if (m >= p.M) continue;
-              const uint4 a4 = *reinterpret_cast<const uint4*>(stg + row * 128 + ((cq ^ (row & 7)) << 4));
-              int a[4] = {(int)a4.x, (int)a4.y, (int)a4.z, (int)a4.w};
-              float y[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (p.corr && (full || n + j < p.N)) a[j] -= __ldg(p.corr + (long long)cls8[it] * p.N + n + j);
-                y[j] = (float)a[j] * sc[j] + bi[j];
-                if (p.rowvec && (full || n + j < p.N)) y[j] += __ldg(p.rowvec + (long long)img8[it] * p.ld_rowvec + n + j);
-              }
-              if (p.residual) {
-                const float* r = p.residual + (long long)m * p.ldr + n;
-                if (full && ((p.ldr & 3) == 0)) {
-                  const float4 rv = *reinterpret_cast<const float4*>(r);
-                  y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    if (n + j < p.N) y[j] += r[j];
-                }
-              }
-              if (p.out) {
-                float* o = p.out + (long long)m * p.ldo + n;
-                if (full && ((p.ldo & 3) == 0)) {
-                  *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    if (n + j < p.N) o[j] = y[j];
-                }
-              }
-              if (p.out_q) {
-                uint32_t qc[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float t = rintf(__fdiv_rn(y[j], p.q_delta)) + (float)p.q_zp;
-                  t = fminf(fmaxf(t, (float)p.q_lo), (float)p.q_hi);
-                  qc[j] = (uint32_t)(int)t & 0xFFu;
-                }
-                int8_t* o = p.out_q + (long long)m * p.ldq + n;
-                if (full && ((p.ldq & 3) == 0)) {
-                  *reinterpret_cast<uint32_t*>(o) = qc[0] | (qc[1] << 8) | (qc[2] << 16) | (qc[3] << 24);
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    if (n + j < p.N) o[j] = (int8_t)qc[j];
-                }
+              if (m < p.M) {
+                const uint4 a4 = *reinterpret_cast<const uint4*>(stg + row * 128 + ((cq ^ (row & 7)) << 4));
+                gemm_finalise4<MODE>(p, a4, sc, bi, corr4, m, n, cls8[it], img8[it]);
               }
             }
           }
