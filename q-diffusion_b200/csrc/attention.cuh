@@ -5,10 +5,19 @@
 //                                                       calibrated step (qdiff/quant_block.py:217)
 //   Pq = min(rne(P / delta_w), p_qmax)                  8- or 16-bit codes (zero point 0)
 //   O[i,:] = out_scale * (sum_j Pq[i,j] v[j,:] - zv * sum_j Pq[i,j])
-// 16-bit codes are contracted exactly as two byte planes (hi, lo) against the 8-bit V codes.
-// Round-1 implementation uses the legacy mma.sync tensor path with register-resident P
-// (FlashAttention-2 style); the key permutation below lets the S accumulator fragment feed the
-// PV A-operand without shuffles: inside each 32-key chunk, MMA k-slot (4t+e) <-> key 8*(e>>1)+2t+(e&1).
+// 16-bit codes are contracted exactly as two byte planes (hi, lo) against the 8-bit V codes, both
+// accumulated in int32 over the whole key range (exact: 255*255*Tk < 2^31 for Tk < 33k).
+//
+// v2 (this file): the kernel is bound by the per-score scalar work (two exp2 + conversions per score:
+// MUFU 16/clk/SM and issue slots), not by the tensor pipe, so the design minimises instructions per score:
+//   * exp2 domain with the row maximum taken on the INTEGER scores and the normalisation folded into
+//     the exponent:  code = rni(exp2(S*c + (rowconst - max*c + log2(1/(l*delta_w)))))  (1 FFMA + 1 MUFU)
+//   * row sums of P codes come out of the PV MMA through an all-ones extra V^T row (no per-score add)
+//   * int32 O accumulators live across the whole pass (no per-tile conversion)
+//   * K / V^T tiles stream through a cp.async double buffer, one __syncthreads per tile
+//   * 8 warps x 16 query rows per CTA; the key permutation lets the S accumulator fragment feed the PV
+//     A-operand without shuffles: MMA k-slot (4t+e) <-> key 8*(e>>1)+2t+(e&1) inside each 32-key chunk.
+// Tensor path: legacy mma.sync IMMA (register-resident P); see DESIGN.md for why tcgen05 does not pay here yet.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -37,27 +46,57 @@ __device__ __forceinline__ void mma_i8_16832(int (&c)[4], const uint32_t (&a)[4]
   }
 }
 
-constexpr int ATT_WARPS = 4;
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr int ATT_WARPS = 8;
 constexpr int ATT_BM = 16 * ATT_WARPS;  // query rows per CTA
 constexpr int ATT_BN = 64;              // keys per tile
 
-template <int DQ, bool SIGNED>
+template <bool SIGNED>
 __device__ __forceinline__ int bytesum(uint32_t w) {
   if constexpr (SIGNED) return __dp4a((int)w, 0x01010101, 0);
   else return (int)__dp4a(w, 0x01010101u, 0u);
 }
 
+struct AttSmemLayout {
+  int kp, vp, k_bytes, v_bytes, zrk_off, total;
+};
+__host__ __device__ inline AttSmemLayout att_smem_layout(int DQ, int DV, int Tk, bool need_zrk) {
+  AttSmemLayout l;
+  l.kp = DQ + 16;
+  l.vp = ATT_BN + 16;
+  l.k_bytes = ATT_BN * l.kp;
+  l.v_bytes = (DV + 8) * l.vp;
+  l.zrk_off = 2 * l.k_bytes + 2 * l.v_bytes;
+  l.total = l.zrk_off + (need_zrk ? ((Tk + ATT_BN - 1) / ATT_BN) * ATT_BN * 4 : 0);
+  return l;
+}
+
 // DQ: reduction length of QK^T padded to a multiple of 32; DV: head dim (multiple of 8).
-template <int DQ, int DV, bool QK_SIGNED, bool V_SIGNED, bool SM16>
-__global__ void __launch_bounds__(ATT_WARPS * 32)
+template <int DQ, int DV, bool QK_SIGNED, bool V_SIGNED, bool SM16, int MINB>
+__global__ void __launch_bounds__(ATT_WARPS * 32, MINB)
 qattention_kernel(const qd_attention_desc p) {
-  constexpr int KP = DQ + 16;       // K tile row pitch (bytes)
+  constexpr int KP = DQ + 16;       // K tile row pitch (bytes): conflict-free B-fragment loads
   constexpr int VP = ATT_BN + 16;   // V^T tile row pitch (bytes)
   constexpr int NKC = DQ / 32;      // k-chunks for QK^T
-  constexpr int NDT = DV / 8;       // n8 tiles of the output
-  __shared__ __align__(16) uint8_t sK[ATT_BN * KP];
-  __shared__ __align__(16) uint8_t sV[DV * VP];
-  __shared__ int sRsk[ATT_BN];
+  constexpr int NDT = DV / 8 + 1;   // n8 tiles of the output + the all-ones row-sum tile
+  constexpr int KB = ATT_BN * KP, VB = (DV + 8) * VP;
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  uint8_t* sKb[2] = {att_smem, att_smem + KB};
+  uint8_t* sVb[2] = {att_smem + 2 * KB, att_smem + 2 * KB + VB};
+  int* sZrk = reinterpret_cast<int*>(att_smem + 2 * KB + 2 * VB);   // zq * rowsum(k_j), all keys
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -71,10 +110,47 @@ qattention_kernel(const qd_attention_desc p) {
                          h * p.head_stride_k;
   const uint8_t* vbase = reinterpret_cast<const uint8_t*>(p.vt) + (long long)b * p.v_batch_stride +
                          (long long)(p.v_off + h * p.head_stride_v) * p.ld_vt;
+  const int ntiles = (p.Tk + ATT_BN - 1) / ATT_BN;
 
-  // ---- Q fragments (rows g, g+8 of this warp's 16-row slab), zero-padded beyond d
+  // ---- prologue: zero both K buffers (the d..DQ padding must stay 0) and V^T buffers, ones row for row sums
+  for (int i = threadIdx.x; i < (2 * KB + 2 * VB) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(att_smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * ATT_BN; i += blockDim.x) sVb[i / ATT_BN][DV * VP + (i % ATT_BN)] = 1;
+  if (p.zq != 0) {
+    for (int j = threadIdx.x; j < ntiles * ATT_BN; j += blockDim.x) {
+      int s = 0;
+      if (j < p.Tk) {
+        const uint8_t* kr = kbase + (long long)j * p.ld_k;
+        for (int w = 0; w < p.d / 4; ++w) s += bytesum<QK_SIGNED>(*reinterpret_cast<const uint32_t*>(kr + 4 * w));
+      }
+      sZrk[j] = p.zq * s;
+    }
+  }
+
+  auto prefetch = [&](int vt) {
+    const int tile = vt % ntiles, pass = vt / ntiles, buf = vt & 1;
+    const int j0 = tile * ATT_BN;
+    const int rows = min(ATT_BN, p.Tk - j0);
+    const int wpr = p.d / 8;  // 8-byte pieces per K row
+    for (int idx = threadIdx.x; idx < rows * wpr; idx += blockDim.x) {
+      const int r = idx / wpr, w = idx - r * wpr;
+      cp_async8(sKb[buf] + r * KP + 8 * w, kbase + (long long)(j0 + r) * p.ld_k + 8 * w);
+    }
+    if (pass == 1) {
+      for (int idx = threadIdx.x; idx < DV * (ATT_BN / 16); idx += blockDim.x) {
+        const int r = idx / (ATT_BN / 16), w = idx - r * (ATT_BN / 16);
+        if (j0 + 16 * w < p.Tk) cp_async16(sVb[buf] + r * VP + 16 * w, vbase + (long long)r * p.ld_vt + j0 + 16 * w);
+      }
+    }
+    cp_async_commit();
+  };
+  prefetch(0);
+
+  // ---- Q fragments (rows g, g+8 of this warp's 16-row slab), zero-padded beyond d.
+  // Of the zero-point cross terms only -zq*rowsum(k_j) depends on the key; -zk*rowsum(q_i) + d*zq*zk is a
+  // per-row constant and cancels in the softmax, so it is never formed.
   uint32_t qf[NKC][4];
-  int rsq0 = 0, rsq1 = 0;  // row sums of q codes (for the zk correction)
   {
     const int r0 = min(row0 + g, p.Tq - 1), r1 = min(row0 + g + 8, p.Tq - 1);
     const uint8_t* q0 = qbase + (long long)r0 * p.ld_q;
@@ -86,182 +162,151 @@ qattention_kernel(const qd_attention_desc p) {
       qf[kc][1] = c0 < p.d ? *reinterpret_cast<const uint32_t*>(q1 + c0) : 0u;
       qf[kc][2] = c1 < p.d ? *reinterpret_cast<const uint32_t*>(q0 + c1) : 0u;
       qf[kc][3] = c1 < p.d ? *reinterpret_cast<const uint32_t*>(q1 + c1) : 0u;
-      rsq0 += bytesum<DQ, QK_SIGNED>(qf[kc][0]) + bytesum<DQ, QK_SIGNED>(qf[kc][2]);
-      rsq1 += bytesum<DQ, QK_SIGNED>(qf[kc][1]) + bytesum<DQ, QK_SIGNED>(qf[kc][3]);
     }
-    rsq0 += __shfl_xor_sync(0xffffffffu, rsq0, 1);
-    rsq0 += __shfl_xor_sync(0xffffffffu, rsq0, 2);
-    rsq1 += __shfl_xor_sync(0xffffffffu, rsq1, 1);
-    rsq1 += __shfl_xor_sync(0xffffffffu, rsq1, 2);
   }
-  const int cc0 = p.d * p.zq * p.zk - p.zk * rsq0;  // constant part of the zero-point correction, row g
-  const int cc1 = p.d * p.zq * p.zk - p.zk * rsq1;  // row g+8
+  // s2 = S_int * c  with c = sim_scale * log2(e)
+  const float c = p.sim_scale * 1.4426950408889634f;
+  const bool has_zq = p.zq != 0;
+  const bool ragged = (p.Tk % ATT_BN) != 0;
 
-  const int ntiles = (p.Tk + ATT_BN - 1) / ATT_BN;
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  float inv_l0 = 0.f, inv_l1 = 0.f;
-  const float inv_dw = 1.0f / p.delta_w;
+  int mi0 = INT_MIN, mi1 = INT_MIN;   // running integer row maxima (of S_raw - zrk; cc is a row constant)
+  float l0 = 0.f, l1 = 0.f;           // running sums of exp2((S - max) * c)
+  float off0 = 0.f, off1 = 0.f;       // pass-2 exponent offsets
+  int olo[NDT][4], ohi[SM16 ? NDT : 1][4];
+#pragma unroll
+  for (int i = 0; i < NDT; ++i) { olo[i][0] = olo[i][1] = olo[i][2] = olo[i][3] = 0; }
+#pragma unroll
+  for (int i = 0; i < (SM16 ? NDT : 1); ++i) { ohi[i][0] = ohi[i][1] = ohi[i][2] = ohi[i][3] = 0; }
   const float pmax = (float)p.p_qmax;
 
-  float of[NDT][4];
-#pragma unroll
-  for (int i = 0; i < NDT; ++i) { of[i][0] = of[i][1] = of[i][2] = of[i][3] = 0.f; }
-  int rsp0 = 0, rsp1 = 0;  // row sums of P codes (for the zv correction)
-
-  for (int pass = 0; pass < 2; ++pass) {
-    for (int tile = 0; tile < ntiles; ++tile) {
-      const int j0 = tile * ATT_BN;
-      __syncthreads();  // previous tile fully consumed
-      // ---- K tile -> smem (zero-padded in d and beyond Tk)
-      for (int idx = threadIdx.x; idx < ATT_BN * (DQ / 4); idx += blockDim.x) {
-        const int r = idx / (DQ / 4), w = idx - r * (DQ / 4);
-        uint32_t v = 0u;
-        if (j0 + r < p.Tk && 4 * w < p.d) v = *reinterpret_cast<const uint32_t*>(kbase + (long long)(j0 + r) * p.ld_k + 4 * w);
-        *reinterpret_cast<uint32_t*>(sK + r * KP + 4 * w) = v;
-      }
-      if (pass == 1) {
-        // ---- V^T tile -> smem
-        for (int idx = threadIdx.x; idx < DV * (ATT_BN / 16); idx += blockDim.x) {
-          const int r = idx / (ATT_BN / 16), w = idx - r * (ATT_BN / 16);
-          uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if (j0 + 16 * w < p.Tk) v = *reinterpret_cast<const uint4*>(vbase + (long long)r * p.ld_vt + j0 + 16 * w);
-          *reinterpret_cast<uint4*>(sV + r * VP + 16 * w) = v;
-        }
-      }
-      __syncthreads();
-      if (p.zq != 0) {
-        if (threadIdx.x < ATT_BN) {
-          int s = 0;
-          for (int w = 0; w < DQ / 4; ++w) s += bytesum<DQ, QK_SIGNED>(*reinterpret_cast<const uint32_t*>(sK + threadIdx.x * KP + 4 * w));
-          sRsk[threadIdx.x] = s;
-        }
-        __syncthreads();
-      }
-
-      // ---- S = Q K^T for this warp: 16 x 64
-      int sacc[8][4];
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0;
-#pragma unroll
-        for (int kc = 0; kc < NKC; ++kc) {
-          uint32_t bf[2];
-          const uint8_t* kr = sK + (8 * nt + g) * KP + kc * 32 + 4 * t;
-          bf[0] = *reinterpret_cast<const uint32_t*>(kr);
-          bf[1] = *reinterpret_cast<const uint32_t*>(kr + 16);
-          mma_i8_16832<QK_SIGNED, QK_SIGNED>(sacc[nt], qf[kc], bf);
-        }
-      }
-      // ---- scores in fp32
-      float sf[8][4];
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = 8 * nt + 2 * t + (e & 1);
-          int v = sacc[nt][e] + ((e < 2) ? cc0 : cc1);
-          if (p.zq != 0) v -= p.zq * sRsk[j];
-          sf[nt][e] = (j0 + j < p.Tk) ? (float)v * p.sim_scale : -INFINITY;
-        }
-      }
-      if (pass == 0) {
-        float tm0 = -INFINITY, tm1 = -INFINITY;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          tm0 = fmaxf(tm0, fmaxf(sf[nt][0], sf[nt][1]));
-          tm1 = fmaxf(tm1, fmaxf(sf[nt][2], sf[nt][3]));
-        }
-        tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 1));
-        tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 2));
-        tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 1));
-        tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 2));
-        const float mn0 = fmaxf(m0, tm0), mn1 = fmaxf(m1, tm1);
-        l0 *= expf(m0 - mn0);
-        l1 *= expf(m1 - mn1);
-        m0 = mn0; m1 = mn1;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          l0 += expf(sf[nt][0] - m0) + expf(sf[nt][1] - m0);
-          l1 += expf(sf[nt][2] - m1) + expf(sf[nt][3] - m1);
-        }
-      } else {
-        // ---- P codes, packed straight into PV A-fragments (byte planes)
-        uint32_t plo[2][4], phi[2][4];
-#pragma unroll
-        for (int kc = 0; kc < 2; ++kc) {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {      // a0/a1 (keys 0..15 of chunk) then a2/a3 (16..31)
-            const int ntA = 4 * kc + 2 * half, ntB = ntA + 1;
-            uint32_t c[8];
-            const float pv[8] = {sf[ntA][0], sf[ntA][1], sf[ntB][0], sf[ntB][1],
-                                 sf[ntA][2], sf[ntA][3], sf[ntB][2], sf[ntB][3]};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float pr = expf(pv[e] - (e < 4 ? m0 : m1)) * (e < 4 ? inv_l0 : inv_l1);
-              c[e] = (uint32_t)(int)fminf(rintf(pr * inv_dw), pmax);
-            }
-            rsp0 += (int)(c[0] + c[1] + c[2] + c[3]);
-            rsp1 += (int)(c[4] + c[5] + c[6] + c[7]);
-            plo[kc][2 * half] = (c[0] & 0xFF) | ((c[1] & 0xFF) << 8) | ((c[2] & 0xFF) << 16) | ((c[3] & 0xFF) << 24);
-            plo[kc][2 * half + 1] = (c[4] & 0xFF) | ((c[5] & 0xFF) << 8) | ((c[6] & 0xFF) << 16) | ((c[7] & 0xFF) << 24);
-            if constexpr (SM16) {
-              phi[kc][2 * half] = ((c[0] >> 8) & 0xFF) | (((c[1] >> 8) & 0xFF) << 8) | (((c[2] >> 8) & 0xFF) << 16) | (((c[3] >> 8) & 0xFF) << 24);
-              phi[kc][2 * half + 1] = ((c[4] >> 8) & 0xFF) | (((c[5] >> 8) & 0xFF) << 8) | (((c[6] >> 8) & 0xFF) << 16) | (((c[7] >> 8) & 0xFF) << 24);
-            }
-          }
-        }
-        // ---- O += P V
-#pragma unroll
-        for (int nd = 0; nd < NDT; ++nd) {
-          int alo[4] = {0, 0, 0, 0}, ahi[4] = {0, 0, 0, 0};
-#pragma unroll
-          for (int kc = 0; kc < 2; ++kc) {
-            const uint8_t* vr = sV + (8 * nd + g) * VP + 32 * kc + 2 * t;
-            uint32_t bf[2];
-            bf[0] = (uint32_t)*reinterpret_cast<const uint16_t*>(vr) | ((uint32_t)*reinterpret_cast<const uint16_t*>(vr + 8) << 16);
-            bf[1] = (uint32_t)*reinterpret_cast<const uint16_t*>(vr + 16) | ((uint32_t)*reinterpret_cast<const uint16_t*>(vr + 24) << 16);
-            mma_i8_16832<false, V_SIGNED>(alo, plo[kc], bf);
-            if constexpr (SM16) mma_i8_16832<false, V_SIGNED>(ahi, phi[kc], bf);
-          }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float v = (float)alo[e];
-            if constexpr (SM16) v += 256.0f * (float)ahi[e];
-            of[nd][e] += v;
-          }
-        }
-      }
-    }
-    if (pass == 0) {
+  for (int vt = 0; vt < 2 * ntiles; ++vt) {
+    const int tile = vt % ntiles, pass = vt / ntiles, buf = vt & 1;
+    const int j0 = tile * ATT_BN;
+    cp_async_wait_all();
+    __syncthreads();                       // tile vt landed for everyone; everyone is done with tile vt-1
+    if (vt + 1 < 2 * ntiles) prefetch(vt + 1);
+    if (vt == ntiles) {                    // pass boundary: freeze the softmax statistics
       l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
       l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
       l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
       l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-      inv_l0 = 1.0f / l0;
-      inv_l1 = 1.0f / l1;
+      // code = rni(exp2(S*c - max*c + log2(1/(l*delta_w))))
+      off0 = -(float)mi0 * c + log2f(1.0f / (l0 * p.delta_w));
+      off1 = -(float)mi1 * c + log2f(1.0f / (l1 * p.delta_w));
+    }
+    const uint8_t* sK = sKb[buf];
+    const uint8_t* sV = sVb[buf];
+
+    // ---- S = Q K^T for this warp: 16 x 64 (int32)
+    int sacc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0;
+#pragma unroll
+      for (int kc = 0; kc < NKC; ++kc) {
+        uint32_t bf[2];
+        const uint8_t* kr = sK + (8 * nt + g) * KP + kc * 32 + 4 * t;
+        bf[0] = *reinterpret_cast<const uint32_t*>(kr);
+        bf[1] = *reinterpret_cast<const uint32_t*>(kr + 16);
+        mma_i8_16832<QK_SIGNED, QK_SIGNED>(sacc[nt], qf[kc], bf);
+      }
+    }
+    if (has_zq) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int2 z = *reinterpret_cast<const int2*>(sZrk + j0 + 8 * nt + 2 * t);
+        sacc[nt][0] -= z.x; sacc[nt][1] -= z.y; sacc[nt][2] -= z.x; sacc[nt][3] -= z.y;
+      }
+    }
+    if (ragged && tile == ntiles - 1) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int j = j0 + 8 * nt + 2 * t;
+        if (j >= p.Tk) { sacc[nt][0] = INT_MIN / 2; sacc[nt][2] = INT_MIN / 2; }
+        if (j + 1 >= p.Tk) { sacc[nt][1] = INT_MIN / 2; sacc[nt][3] = INT_MIN / 2; }
+      }
+    }
+    if (pass == 0) {
+      int tm0 = sacc[0][0], tm1 = sacc[0][2];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        tm0 = max(tm0, max(sacc[nt][0], sacc[nt][1]));
+        tm1 = max(tm1, max(sacc[nt][2], sacc[nt][3]));
+      }
+      tm0 = max(tm0, __shfl_xor_sync(0xffffffffu, tm0, 1));
+      tm0 = max(tm0, __shfl_xor_sync(0xffffffffu, tm0, 2));
+      tm1 = max(tm1, __shfl_xor_sync(0xffffffffu, tm1, 1));
+      tm1 = max(tm1, __shfl_xor_sync(0xffffffffu, tm1, 2));
+      if (tm0 > mi0) { l0 *= (mi0 == INT_MIN) ? 0.f : ex2_approx((float)(mi0 - tm0) * c); mi0 = tm0; }
+      if (tm1 > mi1) { l1 *= (mi1 == INT_MIN) ? 0.f : ex2_approx((float)(mi1 - tm1) * c); mi1 = tm1; }
+      const float b0 = -(float)mi0 * c, b1 = -(float)mi1 * c;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        l0 += ex2_approx(fmaf((float)sacc[nt][0], c, b0)) + ex2_approx(fmaf((float)sacc[nt][1], c, b0));
+        l1 += ex2_approx(fmaf((float)sacc[nt][2], c, b1)) + ex2_approx(fmaf((float)sacc[nt][3], c, b1));
+      }
+    } else {
+      // ---- P codes, packed straight into PV A-fragments (byte planes), then O += P V
+#pragma unroll
+      for (int kc = 0; kc < 2; ++kc) {
+        uint32_t plo[4], phi[4];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {      // a0/a1 (keys 0..15 of the chunk) then a2/a3 (16..31)
+          const int ntA = 4 * kc + 2 * half, ntB = ntA + 1;
+          uint32_t cd[8];
+          const int sv[8] = {sacc[ntA][0], sacc[ntA][1], sacc[ntB][0], sacc[ntB][1],
+                             sacc[ntA][2], sacc[ntA][3], sacc[ntB][2], sacc[ntB][3]};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float pr = ex2_approx(fmaf((float)sv[e], c, e < 4 ? off0 : off1));
+            cd[e] = (uint32_t)__float2int_rn(fminf(pr, pmax));
+          }
+          plo[2 * half] = __byte_perm(__byte_perm(cd[0], cd[1], 0x0040), __byte_perm(cd[2], cd[3], 0x0040), 0x5410);
+          plo[2 * half + 1] = __byte_perm(__byte_perm(cd[4], cd[5], 0x0040), __byte_perm(cd[6], cd[7], 0x0040), 0x5410);
+          if constexpr (SM16) {
+            phi[2 * half] = __byte_perm(__byte_perm(cd[0], cd[1], 0x0051), __byte_perm(cd[2], cd[3], 0x0051), 0x5410);
+            phi[2 * half + 1] = __byte_perm(__byte_perm(cd[4], cd[5], 0x0051), __byte_perm(cd[6], cd[7], 0x0051), 0x5410);
+          }
+        }
+#pragma unroll
+        for (int nd = 0; nd < NDT; ++nd) {
+          const uint8_t* vr = sV + (8 * nd + g) * VP + 32 * kc + 2 * t;
+          uint32_t bf[2];
+          bf[0] = (uint32_t)*reinterpret_cast<const uint16_t*>(vr) | ((uint32_t)*reinterpret_cast<const uint16_t*>(vr + 8) << 16);
+          bf[1] = (uint32_t)*reinterpret_cast<const uint16_t*>(vr + 16) | ((uint32_t)*reinterpret_cast<const uint16_t*>(vr + 24) << 16);
+          if (nd == NDT - 1) {   // all-ones row (unsigned) -> row sums of the codes
+            mma_i8_16832<false, false>(olo[nd], plo, bf);
+            if constexpr (SM16) mma_i8_16832<false, false>(ohi[nd], phi, bf);
+          } else {
+            mma_i8_16832<false, V_SIGNED>(olo[nd], plo, bf);
+            if constexpr (SM16) mma_i8_16832<false, V_SIGNED>(ohi[nd], phi, bf);
+          }
+        }
+      }
     }
   }
-  rsp0 += __shfl_xor_sync(0xffffffffu, rsp0, 1);
-  rsp0 += __shfl_xor_sync(0xffffffffu, rsp0, 2);
-  rsp1 += __shfl_xor_sync(0xffffffffu, rsp1, 1);
-  rsp1 += __shfl_xor_sync(0xffffffffu, rsp1, 2);
 
-  // ---- write O
+  // ---- write O: (256*hi + lo - zv * rowsum) * out_scale.  Row sums sit in column 0 of the extra tile (t == 0).
+  float rs0 = (float)olo[NDT - 1][0], rs1 = (float)olo[NDT - 1][2];
+  if constexpr (SM16) { rs0 += 256.0f * (float)ohi[NDT - 1][0]; rs1 += 256.0f * (float)ohi[NDT - 1][2]; }
+  rs0 = __shfl_sync(0xffffffffu, rs0, lane & ~3);
+  rs1 = __shfl_sync(0xffffffffu, rs1, lane & ~3);
   const int r0 = row0 + g, r1 = row0 + g + 8;
-  const float z0 = (float)p.zv * (float)rsp0, z1 = (float)p.zv * (float)rsp1;
+  const float z0 = (float)p.zv * rs0, z1 = (float)p.zv * rs1;
 #pragma unroll
-  for (int nd = 0; nd < NDT; ++nd) {
+  for (int nd = 0; nd < NDT - 1; ++nd) {
     const int col = h * p.d + 8 * nd + 2 * t;
-    if (8 * nd + 2 * t < p.d) {
-      if (r0 < p.Tq) {
-        float2 o = make_float2((of[nd][0] - z0) * p.out_scale, (of[nd][1] - z0) * p.out_scale);
-        *reinterpret_cast<float2*>(p.out + ((long long)b * p.Tq + r0) * p.ld_out + col) = o;
-      }
-      if (r1 < p.Tq) {
-        float2 o = make_float2((of[nd][2] - z1) * p.out_scale, (of[nd][3] - z1) * p.out_scale);
-        *reinterpret_cast<float2*>(p.out + ((long long)b * p.Tq + r1) * p.ld_out + col) = o;
-      }
+    float v0 = (float)olo[nd][0], v1 = (float)olo[nd][1], v2 = (float)olo[nd][2], v3 = (float)olo[nd][3];
+    if constexpr (SM16) {
+      v0 += 256.0f * (float)ohi[nd][0]; v1 += 256.0f * (float)ohi[nd][1];
+      v2 += 256.0f * (float)ohi[nd][2]; v3 += 256.0f * (float)ohi[nd][3];
     }
+    if (r0 < p.Tq)
+      *reinterpret_cast<float2*>(p.out + ((long long)b * p.Tq + r0) * p.ld_out + col) =
+          make_float2((v0 - z0) * p.out_scale, (v1 - z0) * p.out_scale);
+    if (r1 < p.Tq)
+      *reinterpret_cast<float2*>(p.out + ((long long)b * p.Tq + r1) * p.ld_out + col) =
+          make_float2((v2 - z1) * p.out_scale, (v3 - z1) * p.out_scale);
   }
 }
 

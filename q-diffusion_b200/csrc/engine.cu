@@ -280,18 +280,29 @@ int launch_im2col(const qd_im2col_desc& d, cudaStream_t s) {
   return check_launch("im2col_kernel");
 }
 
+template <int DQ, int DV, bool QS, bool VS, bool S16>
+int launch_attention_inst(const qd_attention_desc& d, cudaStream_t s) {
+  constexpr int MINB = (DV <= 48) ? 2 : 1;
+  auto kern = qd::qattention_kernel<DQ, DV, QS, VS, S16, MINB>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+  if (attr_err != cudaSuccess) return fail(QD_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  const qd::AttSmemLayout lay = qd::att_smem_layout(DQ, DV, d.Tk, d.zq != 0);
+  if (lay.total > 200 * 1024) return fail(QD_ERR_UNSUPPORTED, "attention: Tk=%d needs %d B of shared memory", d.Tk, lay.total);
+  dim3 grid((d.Tq + qd::ATT_BM - 1) / qd::ATT_BM, d.B * d.heads);
+  kern<<<grid, qd::ATT_WARPS * 32, lay.total, s>>>(d);
+  return check_launch("qattention_kernel");
+}
+
 template <int DQ, int DV>
 int launch_attention_t(const qd_attention_desc& d, cudaStream_t s) {
-  dim3 grid((d.Tq + qd::ATT_BM - 1) / qd::ATT_BM, d.B * d.heads);
   const bool qs = d.q_signed != 0, vs = d.v_signed != 0, s16 = d.sm_bits > 8;
-#define QD_ATT(QS, VS, S16) qd::qattention_kernel<DQ, DV, QS, VS, S16><<<grid, qd::ATT_WARPS * 32, 0, s>>>(d)
-  if (qs && vs && s16) QD_ATT(true, true, true);
-  else if (qs && vs && !s16) QD_ATT(true, true, false);
-  else if (!qs && !vs && s16) QD_ATT(false, false, true);
-  else if (!qs && !vs && !s16) QD_ATT(false, false, false);
-  else return fail(QD_ERR_UNSUPPORTED, "attention: mixed signedness q=%d v=%d", d.q_signed, d.v_signed);
-#undef QD_ATT
-  return check_launch("qattention_kernel");
+  if (qs && vs && s16) return launch_attention_inst<DQ, DV, true, true, true>(d, s);
+  if (qs && vs && !s16) return launch_attention_inst<DQ, DV, true, true, false>(d, s);
+  if (!qs && !vs && s16) return launch_attention_inst<DQ, DV, false, false, true>(d, s);
+  if (!qs && !vs && !s16) return launch_attention_inst<DQ, DV, false, false, false>(d, s);
+  return fail(QD_ERR_UNSUPPORTED, "attention: mixed signedness q=%d v=%d", d.q_signed, d.v_signed);
 }
 
 int launch_attention(const qd_attention_desc& d, cudaStream_t s) {
@@ -300,7 +311,8 @@ int launch_attention(const qd_attention_desc& d, cudaStream_t s) {
   if (d.zw != 0) return fail(QD_ERR_UNSUPPORTED, "attention: softmax zero point must be 0 (got %d)", d.zw);
   if (d.sm_bits != 8 && d.sm_bits != 16) return fail(QD_ERR_UNSUPPORTED, "attention: sm_bits %d", d.sm_bits);
   if (d.ld_vt % 16 || d.ld_vt < d.Tk) return fail(QD_ERR_BAD_ARG, "attention: ld_vt");
-  if ((d.q_off | d.k_off | d.head_stride_q | d.head_stride_k | (int)d.ld_q | (int)d.ld_k) & 3) return fail(QD_ERR_UNSUPPORTED, "attention: 4-byte alignment");
+  if ((d.q_off | d.head_stride_q | (int)d.ld_q) & 3) return fail(QD_ERR_UNSUPPORTED, "attention: q needs 4-byte alignment");
+  if ((d.k_off | d.head_stride_k | (int)d.ld_k | d.d) & 7) return fail(QD_ERR_UNSUPPORTED, "attention: k rows need 8-byte alignment");
   if (d.ld_out % 2) return fail(QD_ERR_UNSUPPORTED, "attention: ld_out");
   switch (d.d) {
     case 16: return launch_attention_t<32, 16>(d, s);
