@@ -48,7 +48,8 @@ typedef struct qd_qparams {
  * corr: zx * sum_k w[n,k]; for taps==9 one row per border class (3x3 classes, row-major:
  *       top/mid/bottom x left/mid/right) because the reference zero-pads after de-quantisation.
  * Output: fp32 `out` and/or re-quantised codes `out_q` with the consumer's quantizer `oq`
- *       (out_q_transposed: [M/rows_per_batch][N][ldq] with ldq >= rows_per_batch, used for attention V^T).
+ *       (out_q_transposed: [M/rows_per_batch][N][ldq], ldq >= rows_per_batch, 16-token groups permuted as
+ *       qd_qattention expects its V^T operand).
  * ------------------------------------------------------------------------------------------ */
 typedef struct qd_gemm_desc {
   const void* a;
@@ -171,7 +172,9 @@ int qd_im2col_i8(const qd_im2col_desc* d, qd_stream_t stream);
  *   LDM    QuantQKMatMul/QuantSMVMatMul      qdiff/quant_block.py:123-157 (+ openaimodel.py:384-406)
  *   SD     cross_attn_forward                qdiff/quant_block.py:190-221
  * q,k: codes [B, Tq|Tk, *] with head h at columns q_off + h*head_stride (d codes each);
- * vt: V codes TRANSPOSED [B, n_rows_v, Tk_pad] with head h at rows v_off + h*head_stride.
+ * vt: V codes TRANSPOSED [B, n_rows_v, Tk_pad] with head h at rows v_off + h*head_stride; inside every
+ *     group of 16 keys, key 8a+2b+c is stored at byte 4b+2a+c (what qd_qgemm_i8 out_q_transposed writes).
+ * ws: int32 workspace, B*heads*roundup(Tk,64) entries (zero-point row sums of K; unused when zq == 0).
  * S = sum_d (q-zq)(k-zk) * sim_scale (sim_scale = dq*dk*softmax scale), P = softmax_j(S) in fp32,
  * Pq = clamp(rne(P/dw)+zw, 0.., 2^sm_bits-1) (sm_bits 8 or 16), out = dw*dv * sum_j (Pq-zw)(v-zv).
  * out: fp32 [B, Tq, ld_out] at columns h*d.
@@ -193,6 +196,7 @@ typedef struct qd_attention_desc {
   float out_scale;           /* delta_w * delta_v */
   float* out;
   long long ld_out;
+  void* ws;
 } qd_attention_desc;
 
 int qd_qattention(const qd_attention_desc* d, qd_stream_t stream);

@@ -60,6 +60,32 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Position of key t inside a V^T row: within each group of 16 keys, key 8a+2b+c sits at byte 4b+2a+c.
+__host__ __device__ __forceinline__ int att_vt_perm(int t) {
+  return (t & ~15) | (((t >> 1) & 3) << 2) | (((t >> 3) & 1) << 1) | (t & 1);
+}
+
+// zq * rowsum_d(k[b, j, head h]) for every key: the only zero-point cross term that survives the softmax.
+template <bool SIGNED>
+__global__ void att_krowsum_kernel(const qd_attention_desc p, int tk_pad) {
+  const long long total = (long long)p.B * p.heads * tk_pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % tk_pad);
+    const long long bh = i / tk_pad;
+    const int h = (int)(bh % p.heads);
+    const long long b = bh / p.heads;
+    int s = 0;
+    if (j < p.Tk) {
+      const uint8_t* kr = reinterpret_cast<const uint8_t*>(p.k) + (b * p.Tk + j) * p.ld_k + p.k_off + h * p.head_stride_k;
+      for (int w = 0; w < p.d / 4; ++w) {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(kr + 4 * w);
+        s += SIGNED ? __dp4a((int)v, 0x01010101, 0) : (int)__dp4a(v, 0x01010101u, 0u);
+      }
+    }
+    reinterpret_cast<int*>(p.ws)[i] = p.zq * s;
+  }
+}
+
 constexpr int ATT_WARPS = 8;
 constexpr int ATT_BM = 16 * ATT_WARPS;  // query rows per CTA
 constexpr int ATT_BN = 64;              // keys per tile
@@ -70,39 +96,54 @@ __device__ __forceinline__ int bytesum(uint32_t w) {
   else return (int)__dp4a(w, 0x01010101u, 0u);
 }
 
+__host__ __device__ constexpr int att_kp(int DQ) { return ((DQ / 32) & 1) ? DQ : DQ + 32; }
+
 struct AttSmemLayout {
   int kp, vp, k_bytes, v_bytes, zrk_off, total;
 };
 __host__ __device__ inline AttSmemLayout att_smem_layout(int DQ, int DV, int Tk, bool need_zrk) {
   AttSmemLayout l;
-  l.kp = DQ + 16;
+  l.kp = att_kp(DQ);
   l.vp = ATT_BN + 16;
   l.k_bytes = ATT_BN * l.kp;
   l.v_bytes = (DV + 8) * l.vp;
   l.zrk_off = 2 * l.k_bytes + 2 * l.v_bytes;
-  l.total = l.zrk_off + (need_zrk ? ((Tk + ATT_BN - 1) / ATT_BN) * ATT_BN * 4 : 0);
+  l.total = l.zrk_off + 2 * ATT_BN * 4;   // double-buffered zq*rowsum(k) slices
   return l;
 }
 
-// DQ: reduction length of QK^T padded to a multiple of 32; DV: head dim (multiple of 8).
+// int32 -> float without the XU pipe (valid for |s| < 2^22): 1.5*2^23 + s is exact in fp32.
+template <bool MAGIC>
+__device__ __forceinline__ float att_i2f(int s) {
+  if constexpr (MAGIC) return __int_as_float(s + 0x4B400000) - 12582912.0f;
+  else return (float)s;
+}
+
+// DQ: reduction length of QK^T padded to a multiple of 32; DV: head dim d (multiple of 8).
+// v2.1 (profiles/r01_attention_v2.txt): shared-memory tiles are addressed from the array symbol (the
+// pointer-array version compiled to generic LD + 64-bit IMAD address math, 30% of all instructions), the
+// int<->float conversions avoid the XU pipe (it was the binding unit: I2F + F2I + 2 MUFU per score at
+// 16 lanes/clk/SM), and the d index inside a 32-byte k-chunk is permuted (slot 4t+e <-> d 8t+e, slot
+// 16+4t+e <-> d 8t+4+e, identically for Q and K) so each B fragment is one 8-byte shared load.
 template <int DQ, int DV, bool QK_SIGNED, bool V_SIGNED, bool SM16, int MINB>
 __global__ void __launch_bounds__(ATT_WARPS * 32, MINB)
 qattention_kernel(const qd_attention_desc p) {
-  constexpr int KP = DQ + 16;       // K tile row pitch (bytes): conflict-free B-fragment loads
+  constexpr int KP = att_kp(DQ);    // K tile row pitch (bytes): odd multiple of 32 -> conflict-free 8-byte B-fragment loads
   constexpr int VP = ATT_BN + 16;   // V^T tile row pitch (bytes)
   constexpr int NKC = DQ / 32;      // k-chunks for QK^T
   constexpr int NDT = DV / 8 + 1;   // n8 tiles of the output + the all-ones row-sum tile
   constexpr int KB = ATT_BN * KP, VB = (DV + 8) * VP;
+  constexpr int ZB = ATT_BN * 4;    // per-tile zq*rowsum(k) slice
+  constexpr bool MAGIC = DV <= 64;  // |S| <= 255*255*d < 2^22
+  constexpr int WPR = DV / 8;       // 8-byte pieces per K row
   extern __shared__ __align__(16) uint8_t att_smem[];
-  uint8_t* sKb[2] = {att_smem, att_smem + KB};
-  uint8_t* sVb[2] = {att_smem + 2 * KB, att_smem + 2 * KB + VB};
-  int* sZrk = reinterpret_cast<int*>(att_smem + 2 * KB + 2 * VB);   // zq * rowsum(k_j), all keys
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int bh = blockIdx.y;
   const int b = bh / p.heads, h = bh - b * p.heads;
   const int row0 = blockIdx.x * ATT_BM + warp * 16;
+  const int* zrk_g = reinterpret_cast<const int*>(p.ws) + (long long)bh * (long long)(((p.Tk + ATT_BN - 1) / ATT_BN) * ATT_BN);
 
   const uint8_t* qbase = reinterpret_cast<const uint8_t*>(p.q) + (long long)b * p.Tq * p.ld_q + p.q_off +
                          h * p.head_stride_q;
@@ -116,38 +157,30 @@ qattention_kernel(const qd_attention_desc p) {
   for (int i = threadIdx.x; i < (2 * KB + 2 * VB) / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(att_smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * ATT_BN; i += blockDim.x) sVb[i / ATT_BN][DV * VP + (i % ATT_BN)] = 1;
-  if (p.zq != 0) {
-    for (int j = threadIdx.x; j < ntiles * ATT_BN; j += blockDim.x) {
-      int s = 0;
-      if (j < p.Tk) {
-        const uint8_t* kr = kbase + (long long)j * p.ld_k;
-        for (int w = 0; w < p.d / 4; ++w) s += bytesum<QK_SIGNED>(*reinterpret_cast<const uint32_t*>(kr + 4 * w));
-      }
-      sZrk[j] = p.zq * s;
-    }
-  }
-
-  auto prefetch = [&](int vt) {
-    const int tile = vt % ntiles, pass = vt / ntiles, buf = vt & 1;
+  for (int i = threadIdx.x; i < 2 * ATT_BN; i += blockDim.x)
+    att_smem[2 * KB + (i / ATT_BN) * VB + DV * VP + (i % ATT_BN)] = 1;
+  auto prefetch = [&](int tile, int pass, int buf) {
     const int j0 = tile * ATT_BN;
     const int rows = min(ATT_BN, p.Tk - j0);
-    const int wpr = p.d / 8;  // 8-byte pieces per K row
-    for (int idx = threadIdx.x; idx < rows * wpr; idx += blockDim.x) {
-      const int r = idx / wpr, w = idx - r * wpr;
-      cp_async8(sKb[buf] + r * KP + 8 * w, kbase + (long long)(j0 + r) * p.ld_k + 8 * w);
+    uint8_t* dK = att_smem + buf * KB;
+    for (int idx = threadIdx.x; idx < rows * WPR; idx += ATT_WARPS * 32) {
+      const int r = idx / WPR, w = idx - r * WPR;
+      cp_async8(dK + r * KP + 8 * w, kbase + (long long)(j0 + r) * p.ld_k + 8 * w);
     }
+    if (p.zq != 0 && threadIdx.x < ATT_BN / 4)
+      cp_async16(att_smem + 2 * KB + 2 * VB + buf * ZB + 16 * threadIdx.x, zrk_g + j0 + 4 * threadIdx.x);
     if (pass == 1) {
-      for (int idx = threadIdx.x; idx < DV * (ATT_BN / 16); idx += blockDim.x) {
+      uint8_t* dV = att_smem + 2 * KB + buf * VB;
+      for (int idx = threadIdx.x; idx < DV * (ATT_BN / 16); idx += ATT_WARPS * 32) {
         const int r = idx / (ATT_BN / 16), w = idx - r * (ATT_BN / 16);
-        if (j0 + 16 * w < p.Tk) cp_async16(sVb[buf] + r * VP + 16 * w, vbase + (long long)r * p.ld_vt + j0 + 16 * w);
+        if (j0 + 16 * w < p.Tk) cp_async16(dV + r * VP + 16 * w, vbase + (long long)r * p.ld_vt + j0 + 16 * w);
       }
     }
     cp_async_commit();
   };
-  prefetch(0);
+  prefetch(0, 0, 0);
 
-  // ---- Q fragments (rows g, g+8 of this warp's 16-row slab), zero-padded beyond d.
+  // ---- Q fragments (rows g, g+8 of this warp's 16-row slab), zero-padded beyond d, d-permuted (see above).
   // Of the zero-point cross terms only -zq*rowsum(k_j) depends on the key; -zk*rowsum(q_i) + d*zq*zk is a
   // per-row constant and cancels in the softmax, so it is never formed.
   uint32_t qf[NKC][4];
@@ -157,11 +190,11 @@ qattention_kernel(const qd_attention_desc p) {
     const uint8_t* q1 = qbase + (long long)r1 * p.ld_q;
 #pragma unroll
     for (int kc = 0; kc < NKC; ++kc) {
-      const int c0 = kc * 32 + 4 * t, c1 = c0 + 16;
-      qf[kc][0] = c0 < p.d ? *reinterpret_cast<const uint32_t*>(q0 + c0) : 0u;
-      qf[kc][1] = c0 < p.d ? *reinterpret_cast<const uint32_t*>(q1 + c0) : 0u;
-      qf[kc][2] = c1 < p.d ? *reinterpret_cast<const uint32_t*>(q0 + c1) : 0u;
-      qf[kc][3] = c1 < p.d ? *reinterpret_cast<const uint32_t*>(q1 + c1) : 0u;
+      const int c0 = kc * 32 + 8 * t, c1 = c0 + 4;
+      qf[kc][0] = c0 < DV ? *reinterpret_cast<const uint32_t*>(q0 + c0) : 0u;
+      qf[kc][1] = c0 < DV ? *reinterpret_cast<const uint32_t*>(q1 + c0) : 0u;
+      qf[kc][2] = c1 < DV ? *reinterpret_cast<const uint32_t*>(q0 + c1) : 0u;
+      qf[kc][3] = c1 < DV ? *reinterpret_cast<const uint32_t*>(q1 + c1) : 0u;
     }
   }
   // s2 = S_int * c  with c = sim_scale * log2(e)
@@ -169,7 +202,7 @@ qattention_kernel(const qd_attention_desc p) {
   const bool has_zq = p.zq != 0;
   const bool ragged = (p.Tk % ATT_BN) != 0;
 
-  int mi0 = INT_MIN, mi1 = INT_MIN;   // running integer row maxima (of S_raw - zrk; cc is a row constant)
+  int mi0 = INT_MIN, mi1 = INT_MIN;   // running integer row maxima (of S_raw - zrk)
   float l0 = 0.f, l1 = 0.f;           // running sums of exp2((S - max) * c)
   float off0 = 0.f, off1 = 0.f;       // pass-2 exponent offsets
   int olo[NDT][4], ohi[SM16 ? NDT : 1][4];
@@ -179,107 +212,113 @@ qattention_kernel(const qd_attention_desc p) {
   for (int i = 0; i < (SM16 ? NDT : 1); ++i) { ohi[i][0] = ohi[i][1] = ohi[i][2] = ohi[i][3] = 0; }
   const float pmax = (float)p.p_qmax;
 
-  for (int vt = 0; vt < 2 * ntiles; ++vt) {
-    const int tile = vt % ntiles, pass = vt / ntiles, buf = vt & 1;
-    const int j0 = tile * ATT_BN;
-    cp_async_wait_all();
-    __syncthreads();                       // tile vt landed for everyone; everyone is done with tile vt-1
-    if (vt + 1 < 2 * ntiles) prefetch(vt + 1);
-    if (vt == ntiles) {                    // pass boundary: freeze the softmax statistics
+  int buf = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1) {                       // freeze the softmax statistics
       l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
       l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
       l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
       l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-      // code = rni(exp2(S*c - max*c + log2(1/(l*delta_w))))
+      // code = rne(exp2(S*c - max*c + log2(1/(l*delta_w))))
       off0 = -(float)mi0 * c + log2f(1.0f / (l0 * p.delta_w));
       off1 = -(float)mi1 * c + log2f(1.0f / (l1 * p.delta_w));
     }
-    const uint8_t* sK = sKb[buf];
-    const uint8_t* sV = sVb[buf];
+    for (int tile = 0; tile < ntiles; ++tile, buf ^= 1) {
+      const int j0 = tile * ATT_BN;
+      cp_async_wait_all();
+      __syncthreads();                     // this tile landed for everyone; everyone is done with the previous one
+      if (tile + 1 < ntiles) prefetch(tile + 1, pass, buf ^ 1);
+      else if (pass == 0) prefetch(0, 1, buf ^ 1);
+      const uint8_t* sK = att_smem + buf * KB;
+      const uint8_t* sV = att_smem + 2 * KB + buf * VB;
+      const int* sZrk = reinterpret_cast<const int*>(att_smem + 2 * KB + 2 * VB + buf * ZB);
 
-    // ---- S = Q K^T for this warp: 16 x 64 (int32)
-    int sacc[8][4];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0;
-#pragma unroll
-      for (int kc = 0; kc < NKC; ++kc) {
-        uint32_t bf[2];
-        const uint8_t* kr = sK + (8 * nt + g) * KP + kc * 32 + 4 * t;
-        bf[0] = *reinterpret_cast<const uint32_t*>(kr);
-        bf[1] = *reinterpret_cast<const uint32_t*>(kr + 16);
-        mma_i8_16832<QK_SIGNED, QK_SIGNED>(sacc[nt], qf[kc], bf);
-      }
-    }
-    if (has_zq) {
+      // ---- S = Q K^T for this warp: 16 x 64 (int32)
+      int sacc[8][4];
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-        const int2 z = *reinterpret_cast<const int2*>(sZrk + j0 + 8 * nt + 2 * t);
-        sacc[nt][0] -= z.x; sacc[nt][1] -= z.y; sacc[nt][2] -= z.x; sacc[nt][3] -= z.y;
-      }
-    }
-    if (ragged && tile == ntiles - 1) {
+        sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0;
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int j = j0 + 8 * nt + 2 * t;
-        if (j >= p.Tk) { sacc[nt][0] = INT_MIN / 2; sacc[nt][2] = INT_MIN / 2; }
-        if (j + 1 >= p.Tk) { sacc[nt][1] = INT_MIN / 2; sacc[nt][3] = INT_MIN / 2; }
-      }
-    }
-    if (pass == 0) {
-      int tm0 = sacc[0][0], tm1 = sacc[0][2];
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        tm0 = max(tm0, max(sacc[nt][0], sacc[nt][1]));
-        tm1 = max(tm1, max(sacc[nt][2], sacc[nt][3]));
-      }
-      tm0 = max(tm0, __shfl_xor_sync(0xffffffffu, tm0, 1));
-      tm0 = max(tm0, __shfl_xor_sync(0xffffffffu, tm0, 2));
-      tm1 = max(tm1, __shfl_xor_sync(0xffffffffu, tm1, 1));
-      tm1 = max(tm1, __shfl_xor_sync(0xffffffffu, tm1, 2));
-      if (tm0 > mi0) { l0 *= (mi0 == INT_MIN) ? 0.f : ex2_approx((float)(mi0 - tm0) * c); mi0 = tm0; }
-      if (tm1 > mi1) { l1 *= (mi1 == INT_MIN) ? 0.f : ex2_approx((float)(mi1 - tm1) * c); mi1 = tm1; }
-      const float b0 = -(float)mi0 * c, b1 = -(float)mi1 * c;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        l0 += ex2_approx(fmaf((float)sacc[nt][0], c, b0)) + ex2_approx(fmaf((float)sacc[nt][1], c, b0));
-        l1 += ex2_approx(fmaf((float)sacc[nt][2], c, b1)) + ex2_approx(fmaf((float)sacc[nt][3], c, b1));
-      }
-    } else {
-      // ---- P codes, packed straight into PV A-fragments (byte planes), then O += P V
-#pragma unroll
-      for (int kc = 0; kc < 2; ++kc) {
-        uint32_t plo[4], phi[4];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {      // a0/a1 (keys 0..15 of the chunk) then a2/a3 (16..31)
-          const int ntA = 4 * kc + 2 * half, ntB = ntA + 1;
-          uint32_t cd[8];
-          const int sv[8] = {sacc[ntA][0], sacc[ntA][1], sacc[ntB][0], sacc[ntB][1],
-                             sacc[ntA][2], sacc[ntA][3], sacc[ntB][2], sacc[ntB][3]};
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float pr = ex2_approx(fmaf((float)sv[e], c, e < 4 ? off0 : off1));
-            cd[e] = (uint32_t)__float2int_rn(fminf(pr, pmax));
-          }
-          plo[2 * half] = __byte_perm(__byte_perm(cd[0], cd[1], 0x0040), __byte_perm(cd[2], cd[3], 0x0040), 0x5410);
-          plo[2 * half + 1] = __byte_perm(__byte_perm(cd[4], cd[5], 0x0040), __byte_perm(cd[6], cd[7], 0x0040), 0x5410);
-          if constexpr (SM16) {
-            phi[2 * half] = __byte_perm(__byte_perm(cd[0], cd[1], 0x0051), __byte_perm(cd[2], cd[3], 0x0051), 0x5410);
-            phi[2 * half + 1] = __byte_perm(__byte_perm(cd[4], cd[5], 0x0051), __byte_perm(cd[6], cd[7], 0x0051), 0x5410);
-          }
+        for (int kc = 0; kc < NKC; ++kc) {
+          const uint2 kk = *reinterpret_cast<const uint2*>(sK + (8 * nt + g) * KP + kc * 32 + 8 * t);
+          const uint32_t bf[2] = {kk.x, kk.y};
+          mma_i8_16832<QK_SIGNED, QK_SIGNED>(sacc[nt], qf[kc], bf);
         }
+      }
+      if (has_zq) {
 #pragma unroll
-        for (int nd = 0; nd < NDT; ++nd) {
-          const uint8_t* vr = sV + (8 * nd + g) * VP + 32 * kc + 2 * t;
-          uint32_t bf[2];
-          bf[0] = (uint32_t)*reinterpret_cast<const uint16_t*>(vr) | ((uint32_t)*reinterpret_cast<const uint16_t*>(vr + 8) << 16);
-          bf[1] = (uint32_t)*reinterpret_cast<const uint16_t*>(vr + 16) | ((uint32_t)*reinterpret_cast<const uint16_t*>(vr + 24) << 16);
-          if (nd == NDT - 1) {   // all-ones row (unsigned) -> row sums of the codes
-            mma_i8_16832<false, false>(olo[nd], plo, bf);
-            if constexpr (SM16) mma_i8_16832<false, false>(ohi[nd], phi, bf);
-          } else {
-            mma_i8_16832<false, V_SIGNED>(olo[nd], plo, bf);
-            if constexpr (SM16) mma_i8_16832<false, V_SIGNED>(ohi[nd], phi, bf);
+        for (int nt = 0; nt < 8; ++nt) {
+          const int2 z = *reinterpret_cast<const int2*>(sZrk + 8 * nt + 2 * t);
+          sacc[nt][0] -= z.x; sacc[nt][1] -= z.y; sacc[nt][2] -= z.x; sacc[nt][3] -= z.y;
+        }
+      }
+      if (ragged && tile == ntiles - 1) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const int j = j0 + 8 * nt + 2 * t;
+          if (j >= p.Tk) { sacc[nt][0] = -(1 << 21); sacc[nt][2] = -(1 << 21); }
+          if (j + 1 >= p.Tk) { sacc[nt][1] = -(1 << 21); sacc[nt][3] = -(1 << 21); }
+        }
+      }
+      if (pass == 0) {
+        int tm0 = sacc[0][0], tm1 = sacc[0][2];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          tm0 = max(tm0, max(sacc[nt][0], sacc[nt][1]));
+          tm1 = max(tm1, max(sacc[nt][2], sacc[nt][3]));
+        }
+        tm0 = max(tm0, __shfl_xor_sync(0xffffffffu, tm0, 1));
+        tm0 = max(tm0, __shfl_xor_sync(0xffffffffu, tm0, 2));
+        tm1 = max(tm1, __shfl_xor_sync(0xffffffffu, tm1, 1));
+        tm1 = max(tm1, __shfl_xor_sync(0xffffffffu, tm1, 2));
+        if (tm0 > mi0) { l0 *= (mi0 == INT_MIN) ? 0.f : ex2_approx((float)(mi0 - tm0) * c); mi0 = tm0; }
+        if (tm1 > mi1) { l1 *= (mi1 == INT_MIN) ? 0.f : ex2_approx((float)(mi1 - tm1) * c); mi1 = tm1; }
+        const float b0 = -(float)mi0 * c, b1 = -(float)mi1 * c;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          a0 += ex2_approx(fmaf(att_i2f<MAGIC>(sacc[nt][0]), c, b0)) + ex2_approx(fmaf(att_i2f<MAGIC>(sacc[nt][1]), c, b0));
+          a1 += ex2_approx(fmaf(att_i2f<MAGIC>(sacc[nt][2]), c, b1)) + ex2_approx(fmaf(att_i2f<MAGIC>(sacc[nt][3]), c, b1));
+        }
+        l0 += a0;
+        l1 += a1;
+      } else {
+        // ---- P codes, packed straight into PV A-fragments (byte planes), then O += P V.
+        // rne(pr) for 0 <= pr < 2^22 sits in the low mantissa bits of pr + 1.5*2^23: no F2I (XU pipe) needed.
+#pragma unroll
+        for (int kc = 0; kc < 2; ++kc) {
+          uint32_t plo[4], phi[4];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {      // a0/a1 (keys 0..15 of the chunk) then a2/a3 (16..31)
+            const int ntA = 4 * kc + 2 * half, ntB = ntA + 1;
+            uint32_t cd[8];
+            const int sv[8] = {sacc[ntA][0], sacc[ntA][1], sacc[ntB][0], sacc[ntB][1],
+                               sacc[ntA][2], sacc[ntA][3], sacc[ntB][2], sacc[ntB][3]};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float pr = ex2_approx(fmaf(att_i2f<MAGIC>(sv[e]), c, e < 4 ? off0 : off1));
+              cd[e] = __float_as_uint(fminf(pr, pmax) + 12582912.0f);
+            }
+            plo[2 * half] = __byte_perm(__byte_perm(cd[0], cd[1], 0x0040), __byte_perm(cd[2], cd[3], 0x0040), 0x5410);
+            plo[2 * half + 1] = __byte_perm(__byte_perm(cd[4], cd[5], 0x0040), __byte_perm(cd[6], cd[7], 0x0040), 0x5410);
+            if constexpr (SM16) {
+              phi[2 * half] = __byte_perm(__byte_perm(cd[0], cd[1], 0x0051), __byte_perm(cd[2], cd[3], 0x0051), 0x5410);
+              phi[2 * half + 1] = __byte_perm(__byte_perm(cd[4], cd[5], 0x0051), __byte_perm(cd[6], cd[7], 0x0051), 0x5410);
+            }
+          }
+#pragma unroll
+          for (int nd = 0; nd < NDT; ++nd) {
+            // V^T rows are stored with the 16-key groups permuted (key 8a+2b+c at byte 4b+2a+c, see
+            // att_vt_perm) so the k-slots of this thread are 4 contiguous bytes
+            const uint8_t* vr = sV + (8 * nd + g) * VP + 32 * kc + 4 * t;
+            const uint32_t bf[2] = {*reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 16)};
+            if (nd == NDT - 1) {   // all-ones row (unsigned) -> row sums of the codes
+              mma_i8_16832<false, false>(olo[nd], plo, bf);
+              if constexpr (SM16) mma_i8_16832<false, false>(ohi[nd], phi, bf);
+            } else {
+              mma_i8_16832<false, V_SIGNED>(olo[nd], plo, bf);
+              if constexpr (SM16) mma_i8_16832<false, V_SIGNED>(ohi[nd], phi, bf);
+            }
           }
         }
       }
@@ -295,7 +334,7 @@ qattention_kernel(const qd_attention_desc p) {
   const float z0 = (float)p.zv * rs0, z1 = (float)p.zv * rs1;
 #pragma unroll
   for (int nd = 0; nd < NDT - 1; ++nd) {
-    const int col = h * p.d + 8 * nd + 2 * t;
+    const int col = h * DV + 8 * nd + 2 * t;
     float v0 = (float)olo[nd][0], v1 = (float)olo[nd][1], v2 = (float)olo[nd][2], v3 = (float)olo[nd][3];
     if constexpr (SM16) {
       v0 += 256.0f * (float)ohi[nd][0]; v1 += 256.0f * (float)ohi[nd][1];

@@ -290,6 +290,13 @@ int launch_attention_inst(const qd_attention_desc& d, cudaStream_t s) {
   if (attr_err != cudaSuccess) return fail(QD_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   const qd::AttSmemLayout lay = qd::att_smem_layout(DQ, DV, d.Tk, d.zq != 0);
   if (lay.total > 200 * 1024) return fail(QD_ERR_UNSUPPORTED, "attention: Tk=%d needs %d B of shared memory", d.Tk, lay.total);
+  if (d.zq != 0) {
+    if (!d.ws) return fail(QD_ERR_BAD_ARG, "attention: workspace required when zq != 0");
+    const int tk_pad = (d.Tk + qd::ATT_BN - 1) / qd::ATT_BN * qd::ATT_BN;
+    qd::att_krowsum_kernel<QS><<<grid_for((long long)d.B * d.heads * tk_pad, 256), 256, 0, s>>>(d, tk_pad);
+    int rc = check_launch("att_krowsum_kernel");
+    if (rc) return rc;
+  }
   dim3 grid((d.Tq + qd::ATT_BM - 1) / qd::ATT_BM, d.B * d.heads);
   kern<<<grid, qd::ATT_WARPS * 32, lay.total, s>>>(d);
   return check_launch("qattention_kernel");

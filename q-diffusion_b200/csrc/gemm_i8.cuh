@@ -129,8 +129,10 @@ __device__ __forceinline__ void gemm_epilogue_rowwise(const GemmArgs& p, const u
       if (n0 + j < p.N) o[j] = y[j];
   }
   if (p.out_q) {
+    // V^T layout for qattention: 16-key groups permuted (attention.cuh: att_vt_perm)
     const int t_in = m - img * p.rows_per_batch;
-    int8_t* o = p.out_q + ((long long)img * p.N + n0) * p.ldq + t_in;
+    const int t_pos = (t_in & ~15) | (((t_in >> 1) & 3) << 2) | (((t_in >> 3) & 1) << 1) | (t_in & 1);
+    int8_t* o = p.out_q + ((long long)img * p.N + n0) * p.ldq + t_pos;
 #pragma unroll
     for (int j = 0; j < NC; ++j)
       if (n0 + j < p.N) o[(long long)j * p.ldq] = (int8_t)gemm_quant_code(y[j], p);

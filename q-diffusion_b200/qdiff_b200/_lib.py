@@ -88,7 +88,7 @@ class AttentionDesc(C.Structure):
         ("zq", c_i32), ("zk", c_i32), ("zv", c_i32), ("zw", c_i32),
         ("p_qmin", c_i32), ("p_qmax", c_i32), ("sm_bits", c_i32),
         ("sim_scale", c_f), ("delta_w", c_f), ("out_scale", c_f),
-        ("out", c_vp), ("ld_out", c_ll),
+        ("out", c_vp), ("ld_out", c_ll), ("ws", c_vp),
     ]
 
 

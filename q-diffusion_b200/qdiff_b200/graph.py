@@ -359,6 +359,10 @@ class Builder:
         a.delta_w = qpw.delta
         a.out_scale = float(qpw.delta) * float(vt.delta[0])
         a.out, a.ld_out = out.ptr, out.ld
+        if a.zq != 0:
+            ws = torch.empty(self.B * heads * ((Tk + 63) // 64 * 64), dtype=torch.int32, device=self.dev)
+            self.keep.append(ws)
+            a.ws = ws.data_ptr()
         self.add(_lib.QD_OP_ATTENTION, a, label, flops=4 * self.B * heads * Tq * Tk * d)
         return out
 

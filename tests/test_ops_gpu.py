@@ -138,7 +138,9 @@ def test_qgemm_epilogue_variants(cuda):
     ops.qgemm(d2)
     torch.cuda.synchronize()
     codes2 = O.uaq_codes(out2.cpu(), 0.05, 131, 8, False).reshape(Bt, T, N).permute(0, 2, 1)
-    assert torch.equal(out_t.cpu().long(), codes2.long())
+    tt = torch.arange(T)
+    pos = (tt & ~15) | (((tt >> 1) & 3) << 2) | (((tt >> 3) & 1) << 1) | (tt & 1)   # V^T key permutation
+    assert torch.equal(out_t.cpu().long()[:, :, pos], codes2.long())
 
 
 @pytest.mark.parametrize("act,split,sym", [(0, 0, False), (1, 0, True), (2, 0, False), (0, 64, False)])
@@ -288,8 +290,11 @@ def _run_attention(cuda, B, heads, d, Tq, Tk, sym, sm_bits, seed):
     vc = O.uaq_codes(v, *qp_v).to(dt)
     Tk_pad = (Tk + 15) // 16 * 16
     vt = torch.zeros(B, heads * d, Tk_pad, dtype=dt)
-    vt[:, :, :Tk] = vc.permute(0, 2, 1)
+    tt = torch.arange(Tk)
+    pos = (tt & ~15) | (((tt >> 1) & 3) << 2) | (((tt >> 3) & 1) << 1) | (tt & 1)   # att_vt_perm
+    vt[:, :, pos] = vc.permute(0, 2, 1)
     vt = vt.to(cuda)
+    ws = torch.zeros(B * heads * ((Tk + 63) // 64 * 64), dtype=torch.int32, device=cuda)
     out = torch.full((B, Tq, heads * d), float("nan"), device=cuda)
     a = AttentionDesc()
     a.q, a.k, a.vt = ptr(qc), ptr(kc), ptr(vt)
@@ -305,6 +310,7 @@ def _run_attention(cuda, B, heads, d, Tq, Tk, sym, sm_bits, seed):
     a.delta_w = dw
     a.out_scale = dw * qp_v[0]
     a.out, a.ld_out = ptr(out), heads * d
+    a.ws = ptr(ws)
     ops.attention(a)
     torch.cuda.synchronize()
     return out.cpu(), ref
