@@ -177,7 +177,7 @@ int qd_im2col_i8(const qd_im2col_desc* d, qd_stream_t stream);
  * ws: int32 workspace, B*heads*roundup(Tk,64) entries (zero-point row sums of K; unused when zq == 0).
  * S = sum_d (q-zq)(k-zk) * sim_scale (sim_scale = dq*dk*softmax scale), P = softmax_j(S) in fp32,
  * Pq = clamp(rne(P/dw)+zw, 0.., 2^sm_bits-1) (sm_bits 8 or 16), out = dw*dv * sum_j (Pq-zw)(v-zv).
- * out: fp32 [B, Tq, ld_out] at columns h*d.
+ * out: fp32 [B, Tq, ld_out] at columns h*d, and/or out_q: the same values re-quantised with `oq`.
  * ------------------------------------------------------------------------------------------ */
 typedef struct qd_attention_desc {
   const void* q;
@@ -194,9 +194,12 @@ typedef struct qd_attention_desc {
   float sim_scale;
   float delta_w;             /* softmax quantizer step */
   float out_scale;           /* delta_w * delta_v */
-  float* out;
+  float* out;            /* fp32 output or NULL */
   long long ld_out;
   void* ws;
+  void* out_q;           /* optional: codes of the consumer's activation quantizer `oq` (to_out / proj_out input) */
+  long long ld_out_q;
+  qd_qparams oq;
 } qd_attention_desc;
 
 int qd_qattention(const qd_attention_desc* d, qd_stream_t stream);

@@ -86,6 +86,12 @@ __global__ void att_krowsum_kernel(const qd_attention_desc p, int tk_pad) {
   }
 }
 
+__device__ __forceinline__ uint32_t att_quant(float y, const qd_qparams& q) {
+  float t = rintf(__fdiv_rn(y, q.delta)) + (float)q.zero_point;
+  t = fminf(fmaxf(t, (float)q.qmin), (float)q.qmax);
+  return (uint32_t)(int)t & 0xFFu;
+}
+
 constexpr int ATT_WARPS = 8;
 constexpr int ATT_BM = 16 * ATT_WARPS;  // query rows per CTA
 constexpr int ATT_BN = 64;              // keys per tile
@@ -340,12 +346,21 @@ qattention_kernel(const qd_attention_desc p) {
       v0 += 256.0f * (float)ohi[nd][0]; v1 += 256.0f * (float)ohi[nd][1];
       v2 += 256.0f * (float)ohi[nd][2]; v3 += 256.0f * (float)ohi[nd][3];
     }
-    if (r0 < p.Tq)
-      *reinterpret_cast<float2*>(p.out + ((long long)b * p.Tq + r0) * p.ld_out + col) =
-          make_float2((v0 - z0) * p.out_scale, (v1 - z0) * p.out_scale);
-    if (r1 < p.Tq)
-      *reinterpret_cast<float2*>(p.out + ((long long)b * p.Tq + r1) * p.ld_out + col) =
-          make_float2((v2 - z1) * p.out_scale, (v3 - z1) * p.out_scale);
+    const float y0 = (v0 - z0) * p.out_scale, y1 = (v1 - z0) * p.out_scale;
+    const float y2 = (v2 - z1) * p.out_scale, y3 = (v3 - z1) * p.out_scale;
+    if (p.out) {
+      if (r0 < p.Tq) *reinterpret_cast<float2*>(p.out + ((long long)b * p.Tq + r0) * p.ld_out + col) = make_float2(y0, y1);
+      if (r1 < p.Tq) *reinterpret_cast<float2*>(p.out + ((long long)b * p.Tq + r1) * p.ld_out + col) = make_float2(y2, y3);
+    }
+    if (p.out_q) {   // consumer's activation quantizer (to_out.0 / proj_out input), qdiff/quant_layer.py:82-88
+      uint8_t* oq = reinterpret_cast<uint8_t*>(p.out_q);
+      if (r0 < p.Tq)
+        *reinterpret_cast<uint16_t*>(oq + ((long long)b * p.Tq + r0) * p.ld_out_q + col) =
+            (uint16_t)(att_quant(y0, p.oq) | (att_quant(y1, p.oq) << 8));
+      if (r1 < p.Tq)
+        *reinterpret_cast<uint16_t*>(oq + ((long long)b * p.Tq + r1) * p.ld_out_q + col) =
+            (uint16_t)(att_quant(y2, p.oq) | (att_quant(y3, p.oq) << 8));
+    }
   }
 }
 

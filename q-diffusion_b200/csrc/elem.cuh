@@ -88,6 +88,7 @@ __global__ void gn_partial_kernel(const float* __restrict__ x, long long ld_x, i
   for (int q = threadIdx.x; q < cq; q += blockDim.x) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = make_float4(0.f, 0.f, 0.f, 0.f);
     const float* base = x + ((long long)b * HW + p0) * ld_x + (q << 2);
+#pragma unroll 8
     for (int p = p0; p < p1; ++p) {
       const float4 v = *reinterpret_cast<const float4*>(base);
       base += ld_x;
@@ -138,36 +139,60 @@ __global__ void gn_finalize_kernel(const float* __restrict__ ws, int HW, int C, 
   }
 }
 // Pass 3: normalise + affine (+scale-shift) (+SiLU) + quantise for each consumer.
-__global__ void gn_apply_kernel(const qd_groupnorm_desc p, const float* __restrict__ stats) {
+// grid (row chunks, B); a thread owns fixed channel quads, folds mean/rstd/gamma/beta(/scale-shift) into
+// y = a*x + b once, then streams GN_ROWS pixels: no integer division and no table lookups in the loop.
+constexpr int GN_ROWS = 32;
+constexpr int GN_MAXQ = 4;   // channel quads per thread: C <= 4 * 256 * GN_MAXQ
+__global__ void __launch_bounds__(256) gn_apply_kernel(const qd_groupnorm_desc p, const float* __restrict__ stats) {
+  const int b = blockIdx.y;
   const int cq = p.C >> 2;
   const int cpg = p.C / p.groups;
-  const long long total = (long long)p.B * p.HW * cq;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / cq;
-    const int c = (int)(i - r * cq) << 2;
-    const int b = (int)(r / p.HW);
-    const float4 v = *reinterpret_cast<const float4*>(p.x + r * p.ld_x + c);
-    float y[4] = {v.x, v.y, v.z, v.w};
+  const int r0 = blockIdx.x * GN_ROWS;
+  const int r1 = min(p.HW, r0 + GN_ROWS);
+  float ca[GN_MAXQ][4], cb[GN_MAXQ][4];
+  int nq = 0;
+  for (int q = threadIdx.x; q < cq && nq < GN_MAXQ; q += blockDim.x, ++nq) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int ch = c + j;
+      const int ch = (q << 2) + j;
       const int g = ch / cpg;
-      const float mean = __ldg(stats + ((long long)b * p.groups + g) * 2);
-      const float rstd = __ldg(stats + ((long long)b * p.groups + g) * 2 + 1);
-      float t = (y[j] - mean) * rstd * __ldg(p.gamma + ch) + __ldg(p.beta + ch);
-      if (p.ss_scale)
-        t = t * (1.0f + __ldg(p.ss_scale + (long long)b * p.ld_ss + ch)) + __ldg(p.ss_shift + (long long)b * p.ld_ss + ch);
-      if (p.silu) t = silu_f(t);
-      y[j] = t;
+      const float mean = stats[((long long)b * p.groups + g) * 2];
+      const float rstd = stats[((long long)b * p.groups + g) * 2 + 1];
+      float a = rstd * p.gamma[ch];
+      float bb = p.beta[ch] - mean * a;
+      if (p.ss_scale) {
+        const float s1 = 1.0f + p.ss_scale[(long long)b * p.ld_ss + ch];
+        a *= s1;
+        bb = bb * s1 + p.ss_shift[(long long)b * p.ld_ss + ch];
+      }
+      ca[nq][j] = a;
+      cb[nq][j] = bb;
     }
-    if (p.out_f) *reinterpret_cast<float4*>(p.out_f + r * p.ld_f + c) = make_float4(y[0], y[1], y[2], y[3]);
+  }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      if (k < p.n_out) {
-        const uint32_t o = pack4(quant_code(y[0], p.q[k]), quant_code(y[1], p.q[k]), quant_code(y[2], p.q[k]),
-                                 quant_code(y[3], p.q[k]));
-        *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.out_q[k]) + r * p.ld_q[k] + c) = o;
+  for (int k = 0; k < GN_MAXQ; ++k) {
+    if (k < nq) {
+      const int c = (threadIdx.x + k * blockDim.x) << 2;
+      const float* xp = p.x + ((long long)b * p.HW + r0) * p.ld_x + c;
+#pragma unroll 4
+      for (int r = r0; r < r1; ++r, xp += p.ld_x) {
+        const float4 v = *reinterpret_cast<const float4*>(xp);
+        float y[4] = {fmaf(v.x, ca[k][0], cb[k][0]), fmaf(v.y, ca[k][1], cb[k][1]), fmaf(v.z, ca[k][2], cb[k][2]),
+                      fmaf(v.w, ca[k][3], cb[k][3])};
+        if (p.silu) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) y[j] = silu_f(y[j]);
+        }
+        const long long row = (long long)b * p.HW + r;
+        if (p.out_f) *reinterpret_cast<float4*>(p.out_f + row * p.ld_f + c) = make_float4(y[0], y[1], y[2], y[3]);
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+          if (o < p.n_out) {
+            const uint32_t code = pack4(quant_code(y[0], p.q[o]), quant_code(y[1], p.q[o]), quant_code(y[2], p.q[o]),
+                                        quant_code(y[3], p.q[o]));
+            *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.out_q[o]) + row * p.ld_q[o] + c) = code;
+          }
+        }
       }
     }
   }

@@ -259,7 +259,10 @@ int launch_groupnorm(const qd_groupnorm_desc& d, cudaStream_t s) {
   qd::gn_finalize_kernel<<<dim3(d.groups, d.B), 128, 0, s>>>(d.ws, d.HW, d.C, d.groups, nslab, d.eps, stats);
   rc = check_launch("gn_finalize_kernel");
   if (rc) return rc;
-  qd::gn_apply_kernel<<<grid_for((long long)d.B * d.HW * (d.C / 4), 256), 256, 0, s>>>(d, stats);
+  if (d.C > 4 * 256 * qd::GN_MAXQ) return fail(QD_ERR_UNSUPPORTED, "groupnorm: C=%d too large", d.C);
+  int at = ((d.C / 4) + 31) / 32 * 32;
+  if (at > 256) at = 256;
+  qd::gn_apply_kernel<<<dim3((d.HW + qd::GN_ROWS - 1) / qd::GN_ROWS, d.B), at, 0, s>>>(d, stats);
   return check_launch("gn_apply_kernel");
 }
 
@@ -313,14 +316,15 @@ int launch_attention_t(const qd_attention_desc& d, cudaStream_t s) {
 }
 
 int launch_attention(const qd_attention_desc& d, cudaStream_t s) {
-  if (!d.q || !d.k || !d.vt || !d.out) return fail(QD_ERR_BAD_ARG, "attention: null arg");
+  if (!d.q || !d.k || !d.vt || (!d.out && !d.out_q)) return fail(QD_ERR_BAD_ARG, "attention: null arg");
+  if (d.out_q && (d.ld_out_q & 1)) return fail(QD_ERR_UNSUPPORTED, "attention: ld_out_q");
   if (d.q_signed != d.k_signed) return fail(QD_ERR_UNSUPPORTED, "attention: q/k signedness differ");
   if (d.zw != 0) return fail(QD_ERR_UNSUPPORTED, "attention: softmax zero point must be 0 (got %d)", d.zw);
   if (d.sm_bits != 8 && d.sm_bits != 16) return fail(QD_ERR_UNSUPPORTED, "attention: sm_bits %d", d.sm_bits);
   if (d.ld_vt % 16 || d.ld_vt < d.Tk) return fail(QD_ERR_BAD_ARG, "attention: ld_vt");
   if ((d.q_off | d.head_stride_q | (int)d.ld_q) & 3) return fail(QD_ERR_UNSUPPORTED, "attention: q needs 4-byte alignment");
   if ((d.k_off | d.head_stride_k | (int)d.ld_k | d.d) & 7) return fail(QD_ERR_UNSUPPORTED, "attention: k rows need 8-byte alignment");
-  if (d.ld_out % 2) return fail(QD_ERR_UNSUPPORTED, "attention: ld_out");
+  if (d.out && (d.ld_out % 2)) return fail(QD_ERR_UNSUPPORTED, "attention: ld_out");
   switch (d.d) {
     case 16: return launch_attention_t<32, 16>(d, s);
     case 24: return launch_attention_t<32, 24>(d, s);

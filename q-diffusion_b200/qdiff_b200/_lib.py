@@ -89,6 +89,7 @@ class AttentionDesc(C.Structure):
         ("p_qmin", c_i32), ("p_qmax", c_i32), ("sm_bits", c_i32),
         ("sim_scale", c_f), ("delta_w", c_f), ("out_scale", c_f),
         ("out", c_vp), ("ld_out", c_ll), ("ws", c_vp),
+        ("out_q", c_vp), ("ld_out_q", c_ll), ("oq", QParams),
     ]
 
 

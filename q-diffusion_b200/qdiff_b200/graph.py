@@ -338,9 +338,14 @@ class Builder:
         return self.gemm(qm, patches, label, k_pad=k_to, **kw)
 
     # ------------------------------------------------------------------ attention recorder
-    def attention(self, qc, kc, vt, *, heads, d, Tq, Tk, q_layout, k_layout, v_layout, sim_scale_extra, qw, label):
+    def attention(self, qc, kc, vt, *, heads, d, Tq, Tk, q_layout, k_layout, v_layout, sim_scale_extra, qw, label,
+                  consumer=None):
         """qc/kc: code Acts [B*T, *]; vt: transposed codes.  *_layout = (col offset, head stride)."""
-        out = self.new_f32(self.B * Tq, heads * d)
+        """consumer: the QuantModule fed by this attention (to_out.0 / proj_out); its activation quantizer is then
+        applied inside the attention epilogue and the codes are returned instead of fp32."""
+        out = None
+        if consumer is None:
+            out = self.new_f32(self.B * Tq, heads * d)
         qpw, _ = self.qp(qw)
         a = AttentionDesc()
         a.q, a.k, a.vt = qc.ptr, kc.ptr, vt.ptr
@@ -358,7 +363,13 @@ class Builder:
         a.sim_scale = float(qc.delta[0]) * float(kc.delta[0]) * sim_scale_extra
         a.delta_w = qpw.delta
         a.out_scale = float(qpw.delta) * float(vt.delta[0])
-        a.out, a.ld_out = out.ptr, out.ld
+        if out is not None:
+            a.out, a.ld_out = out.ptr, out.ld
+        else:
+            oqp, osigned = self.qp(consumer.act_quantizer)
+            out = self.new_codes(self.B * Tq, heads * d, osigned)
+            out.zp, out.delta = (oqp.zero_point, None), (oqp.delta, None)
+            a.out_q, a.ld_out_q, a.oq = out.ptr, out.ld, oqp
         if a.zq != 0:
             ws = torch.empty(self.B * heads * ((Tk + 63) // 64 * 64), dtype=torch.int32, device=self.dev)
             self.keep.append(ws)
@@ -433,8 +444,8 @@ class Builder:
         vt = self.gemm(attn.to_v, kv_codes[1], label + ".to_v", out_q=(attn.act_quantizer_v, True), rows_per_batch=Tk)
         o = self.attention(qc, kc, vt, heads=heads, d=d, Tq=Tq, Tk=Tk, q_layout=(0, d), k_layout=(0, d),
                            v_layout=(0, d), sim_scale_extra=float(attn.scale), qw=attn.act_quantizer_w,
-                           label=label + ".attn")
-        return self.qlinear(attn.to_out[0], o, label + ".to_out.0", residual=h_res)
+                           label=label + ".attn", consumer=attn.to_out[0])
+        return self.gemm(attn.to_out[0], o, label + ".to_out.0", residual=h_res)
 
     def spatial_transformer(self, st, x, ctx, hw):
         """SpatialTransformer.forward (ldm/modules/attention.py:276-287) + QuantBasicTransformerBlock._forward
@@ -487,8 +498,9 @@ class Builder:
                                    rows_per_batch=T))
         qc, kc, vt = parts
         o = self.attention(qc, kc, vt, heads=heads, d=ch, Tq=T, Tk=T, q_layout=(0, ch), k_layout=(0, ch),
-                           v_layout=(0, ch), sim_scale_extra=1.0, qw=smv.act_quantizer_w, label=k + ".attention")
-        return self.qlinear(blk.proj_out, o, k + ".proj_out", residual=x)
+                           v_layout=(0, ch), sim_scale_extra=1.0, qw=smv.act_quantizer_w, label=k + ".attention",
+                           consumer=blk.proj_out)
+        return self.gemm(blk.proj_out, o, k + ".proj_out", residual=x)
 
     def lower_ldm(self, model, x_shape, ctx_shape):
         B, Cin, H, W = x_shape
@@ -596,8 +608,9 @@ class Builder:
         kc = self.gemm(blk.k, ak, k + ".k", out_q=(blk.act_quantizer_k, False))
         vt = self.gemm(blk.v, av, k + ".v", out_q=(blk.act_quantizer_v, True), rows_per_batch=T)
         o = self.attention(qc, kc, vt, heads=1, d=C_, Tq=T, Tk=T, q_layout=(0, C_), k_layout=(0, C_), v_layout=(0, C_),
-                           sim_scale_extra=float(int(C_) ** (-0.5)), qw=blk.act_quantizer_w, label=k + ".attn")
-        return self.qlinear(blk.proj_out, o, k + ".proj_out", residual=x)
+                           sim_scale_extra=float(int(C_) ** (-0.5)), qw=blk.act_quantizer_w, label=k + ".attn",
+                           consumer=blk.proj_out)
+        return self.gemm(blk.proj_out, o, k + ".proj_out", residual=x)
 
     def lower_ddim(self, model, x_shape):
         B, Cin, H, W = x_shape
