@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/qdiff_b200.h"
+#include "quant_math.cuh"
 
 namespace qd {
 
@@ -86,11 +87,7 @@ __global__ void att_krowsum_kernel(const qd_attention_desc p, int tk_pad) {
   }
 }
 
-__device__ __forceinline__ uint32_t att_quant(float y, const qd_qparams& q) {
-  float t = rintf(__fdiv_rn(y, q.delta)) + (float)q.zero_point;
-  t = fminf(fmaxf(t, (float)q.qmin), (float)q.qmax);
-  return (uint32_t)(int)t & 0xFFu;
-}
+__device__ __forceinline__ uint32_t att_quant(float y, const qd_qparams& q) { return quant_code(y, make_quantk(q)); }
 
 constexpr int ATT_WARPS = 8;
 constexpr int ATT_BM = 16 * ATT_WARPS;  // query rows per CTA

@@ -7,19 +7,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/qdiff_b200.h"
+#include "quant_math.cuh"
 
 namespace qd {
 
-__device__ __forceinline__ uint32_t quant_code(float y, const qd_qparams& q) {
-  // UniformAffineQuantizer.forward, qdiff/quant_layer.py:82-87: rne(x/delta) + zp, clamp.
-  float t = rintf(__fdiv_rn(y, q.delta)) + (float)q.zero_point;
-  t = fminf(fmaxf(t, (float)q.qmin), (float)q.qmax);
-  return (uint32_t)(int)t & 0xFFu;
-}
 __device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   return a | (b << 8) | (c << 16) | (d << 24);
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return silu_fast(x); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // ------------------------------------------------------------------------------------ quantize
@@ -28,6 +23,7 @@ __global__ void quantize_kernel(const qd_quantize_desc p) {
   const int cq = p.C >> 2;
   const long long rows_out = p.upsample2x ? (long long)p.B * (2 * p.H) * (2 * p.W) : (long long)p.M;
   const long long total = rows_out * cq;
+  const QuantK k0 = make_quantk(p.q0), k1 = make_quantk(p.q1);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long ro = i / cq;
@@ -51,9 +47,9 @@ __global__ void quantize_kernel(const qd_quantize_desc p) {
     }
     uint32_t out;
     if (p.split > 0 && c >= p.split) {
-      out = pack4(quant_code(v.x, p.q1), quant_code(v.y, p.q1), quant_code(v.z, p.q1), quant_code(v.w, p.q1));
+      out = pack4(quant_code(v.x, k1), quant_code(v.y, k1), quant_code(v.z, k1), quant_code(v.w, k1));
     } else {
-      out = pack4(quant_code(v.x, p.q0), quant_code(v.y, p.q0), quant_code(v.z, p.q0), quant_code(v.w, p.q0));
+      out = pack4(quant_code(v.x, k0), quant_code(v.y, k0), quant_code(v.z, k0), quant_code(v.w, k0));
     }
     *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.dst) + ro * p.ld_dst + c) = out;
   }
@@ -69,8 +65,8 @@ __global__ void quantize_scalar_kernel(const qd_quantize_desc p) {
     float v = p.src[r * p.ld_src + c];
     if (p.act == 1) v = silu_f(v);
     else if (p.act == 2) v *= gelu_erf_f(p.src[r * p.ld_src + p.C + c]);
-    const qd_qparams& q = (p.split > 0 && c >= p.split) ? p.q1 : p.q0;
-    reinterpret_cast<uint8_t*>(p.dst)[r * p.ld_dst + c] = (uint8_t)quant_code(v, q);
+    const QuantK k = make_quantk((p.split > 0 && c >= p.split) ? p.q1 : p.q0);
+    reinterpret_cast<uint8_t*>(p.dst)[r * p.ld_dst + c] = (uint8_t)quant_code(v, k);
   }
 }
 
@@ -150,6 +146,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const qd_groupnorm_desc p
   const int r0 = blockIdx.x * GN_ROWS;
   const int r1 = min(p.HW, r0 + GN_ROWS);
   float ca[GN_MAXQ][4], cb[GN_MAXQ][4];
+  const QuantK qk[3] = {make_quantk(p.q[0]), make_quantk(p.q[1]), make_quantk(p.q[2])};
   int nq = 0;
   for (int q = threadIdx.x; q < cq && nq < GN_MAXQ; q += blockDim.x, ++nq) {
 #pragma unroll
@@ -188,8 +185,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const qd_groupnorm_desc p
 #pragma unroll
         for (int o = 0; o < 3; ++o) {
           if (o < p.n_out) {
-            const uint32_t code = pack4(quant_code(y[0], p.q[o]), quant_code(y[1], p.q[o]), quant_code(y[2], p.q[o]),
-                                        quant_code(y[3], p.q[o]));
+            const uint32_t code = pack4(quant_code(y[0], qk[o]), quant_code(y[1], qk[o]), quant_code(y[2], qk[o]),
+                                        quant_code(y[3], qk[o]));
             *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.out_q[o]) + row * p.ld_q[o] + c) = code;
           }
         }
@@ -205,6 +202,7 @@ __global__ void layernorm_quant_kernel(const qd_layernorm_desc p) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int cq = p.C >> 2;
+  const QuantK qk[3] = {make_quantk(p.q[0]), make_quantk(p.q[1]), make_quantk(p.q[2])};
   for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < p.M;
        row += (long long)gridDim.x * warps_per_block) {
     const float* xr = p.x + row * p.ld_x;
@@ -236,8 +234,8 @@ __global__ void layernorm_quant_kernel(const qd_layernorm_desc p) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         if (k < p.n_out) {
-          const uint32_t o = pack4(quant_code(y0, p.q[k]), quant_code(y1, p.q[k]), quant_code(y2, p.q[k]),
-                                   quant_code(y3, p.q[k]));
+          const uint32_t o = pack4(quant_code(y0, qk[k]), quant_code(y1, qk[k]), quant_code(y2, qk[k]),
+                                   quant_code(y3, qk[k]));
           *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.out_q[k]) + row * p.ld_q[k] + c) = o;
         }
       }

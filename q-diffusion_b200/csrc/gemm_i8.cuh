@@ -18,6 +18,7 @@
 // profiles/r01_gemm_epilogue_v1.txt).  MODE = -1 keeps every runtime option (ragged N, both outputs).
 #pragma once
 #include "ptx.cuh"
+#include "quant_math.cuh"
 
 namespace qd {
 
@@ -95,10 +96,8 @@ __device__ __forceinline__ void gemm_row_meta(const GemmArgs& p, int m, int& cls
 }
 
 __device__ __forceinline__ uint32_t gemm_quant_code(float y, const GemmArgs& p) {
-  // consumer's activation quantizer (qdiff/quant_layer.py:82-88): rne(y/delta)+zp, clamp
-  float t = rintf(__fdiv_rn(y, p.q_delta)) + (float)p.q_zp;
-  t = fminf(fmaxf(t, (float)p.q_lo), (float)p.q_hi);
-  return (uint32_t)(int)t & 0xFFu;
+  // consumer's activation quantizer (qdiff/quant_layer.py:82-88), XU-free form of quant_math.cuh
+  return quant_code(y, make_quantk(p.q_delta, p.q_zp, p.q_lo, p.q_hi));
 }
 
 // Thread-per-row epilogue (used for the transposed V^T code output: consecutive lanes = consecutive

@@ -1,0 +1,54 @@
+// Activation-quantizer arithmetic shared by every kernel that emits codes
+// (UniformAffineQuantizer.forward, qdiff/quant_layer.py:82-87:  code = clamp(rne(y / delta) + zp, lo, hi)).
+//
+// The straightforward form rintf(__fdiv_rn(y, d)) + zp -> clamp -> (int) costs 4 XU-pipe operations per
+// element (FCHK, MUFU.RCP, FRND, F2I; the XU pipe runs at 16 lanes/clk/SM), which made the "memory-bound"
+// norm/quantise kernels XU-bound at ~15-25% of HBM bandwidth (profiles/r01_elementwise_xu.txt).  This
+// version uses no XU operation per element:
+//   * y/d as q0 = y*r, q = fma(fma(-q0, d, y), r, q0) with r = RN(1/d): one Newton step on the FMA pipe,
+//     correctly rounded except for vanishingly rare halfway cases;
+//   * rne() and float->int through the 1.5*2^23 magic constant (valid for |q| < 2^22, enforced by a clamp);
+//   * zero point and clamp in integer arithmetic.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/qdiff_b200.h"
+
+namespace qd {
+
+struct QuantK {
+  float delta, rdelta;
+  int bias;     // 0x4B400000 - zero_point
+  int lo, hi;
+};
+
+__device__ __forceinline__ QuantK make_quantk(float delta, int zero_point, int lo, int hi) {
+  QuantK k;
+  k.delta = delta;
+  k.rdelta = __frcp_rn(delta);
+  k.bias = 0x4B400000 - zero_point;
+  k.lo = lo;
+  k.hi = hi;
+  return k;
+}
+__device__ __forceinline__ QuantK make_quantk(const qd_qparams& q) {
+  return make_quantk(q.delta, q.zero_point, q.qmin, q.qmax);
+}
+
+__device__ __forceinline__ uint32_t quant_code(float y, const QuantK& k) {
+  const float q0 = y * k.rdelta;
+  float q = fmaf(fmaf(-q0, k.delta, y), k.rdelta, q0);
+  q = fminf(fmaxf(q, -4.0e6f), 4.0e6f);
+  int i = __float_as_int(q + 12582912.0f) - k.bias;   // rne(q) + zero_point
+  i = min(max(i, k.lo), k.hi);
+  return (uint32_t)i & 0xFFu;
+}
+
+// x * sigmoid(x) with 2 XU operations (ex2, rcp); ~2 ulp, inside the reference's own fp32 noise band.
+__device__ __forceinline__ float silu_fast(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+  return __fdividef(x, 1.0f + e);
+}
+
+}  // namespace qd
