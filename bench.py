@@ -197,13 +197,12 @@ def main():
     qnn, _ = synth.build_qnn(WORKLOAD, cuda_graph=not args.no_graph)
     B = IMAGES_PER_GPU
     # every rank draws the FULL batch from the same seed and keeps its shard (N-rank == 1-rank results)
-    g = torch.Generator().manual_seed(42)
-    x_all = torch.randn(world * B, 4, 64, 64, generator=g)
-    c_all = torch.randn(world * B, 77, 768, generator=g)
-    uc_all = torch.randn(1, 77, 768, generator=g).expand(world * B, 77, 768).contiguous()
-    sl = slice(rank * B, (rank + 1) * B)
-    x_host = x_all[sl].contiguous().pin_memory()
-    c_host = torch.cat([uc_all[sl], c_all[sl]]).contiguous().pin_memory()   # [uncond; cond] as plms.py:187
+    from qdiff_b200 import dist as qdist
+    x_sh, c_sh = qdist.shard_like_single_process((world * B, 4, 64, 64), 42, rank, world,
+                                                 extra_shapes=[(world * B, 77, 768)])
+    uc = torch.randn(1, 77, 768, generator=torch.Generator().manual_seed(43)).expand(B, 77, 768)
+    x_host = x_sh.pin_memory()
+    c_host = torch.cat([uc, c_sh]).contiguous().pin_memory()   # [uncond; cond] as plms.py:187
     sched = samplers.Schedule("linear", 1000, 0.00085, 0.0120)               # configs/stable-diffusion/v1-inference.yaml
     sampler = samplers.PLMSSampler(qnn, sched)
     sampler.make_schedule(50)
@@ -275,8 +274,7 @@ def main():
     times = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        gathered = [torch.empty_like(nxt) for _ in range(world)]
-        dist.all_gather(gathered, nxt)     # the path's only collective: final latent gather
+        qdist.gather_latents(nxt, world)   # the path's only collective: final latent gather
     ms, ms_e2e = float(times[0]), float(times[1])
     if rank != 0:
         if dist is not None:

@@ -47,6 +47,8 @@ typedef struct qd_qparams {
  * w: weight codes minus zero point (s8), [n_rows][taps*C], tap-major then channel (OHWI).
  * corr: zx * sum_k w[n,k]; for taps==9 one row per border class (3x3 classes, row-major:
  *       top/mid/bottom x left/mid/right) because the reference zero-pads after de-quantisation.
+ * geglu: GEGLU projection fused with its consumer's quantizer: N counts x AND gate columns, interleaved in
+ *       groups of 4 (w row 8b+i = x-feature 4b+i, row 8b+4+i = gate-feature 4b+i); out_q is [M, N/2].
  * Output: fp32 `out` and/or re-quantised codes `out_q` with the consumer's quantizer `oq`
  *       (out_q_transposed: [M/rows_per_batch][N][ldq], ldq >= rows_per_batch, 16-token groups permuted as
  *       qd_qattention expects its V^T operand).
@@ -74,7 +76,8 @@ typedef struct qd_gemm_desc {
   long long ldq;
   qd_qparams oq;
   int32_t bn_hint;       /* 0 = auto N-tile */
-  int32_t reserved;
+  int32_t geglu;         /* 1: rows of w (and scale/bias/corr) are interleaved [4 x-features, 4 gate-features]...;
+                            out_q receives Q(x * gelu_erf(gate)) with N/2 columns (ldm/modules/attention.py:42-44) */
 } qd_gemm_desc;
 
 int qd_qgemm_i8(const qd_gemm_desc* d, qd_stream_t stream);

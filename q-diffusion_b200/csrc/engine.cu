@@ -91,12 +91,12 @@ struct GemmPlan {
   int grid, smem, mode;
 };
 
-int pick_bn(int N, int tiles_m, int sms, int hint) {
+int pick_bn(int N, int tiles_m, int sms, int hint, int step = 16) {
   if (hint > 0) return hint;
-  int best = 16;
+  int best = step;
   long long best_cost = -1;
-  const int n16 = (N + 15) / 16 * 16;
-  for (int bn = 16; bn <= 256; bn += 16) {
+  const int n16 = (N + step - 1) / step * step;
+  for (int bn = step; bn <= 256; bn += step) {
     if (bn > n16) break;
     const long long tiles = (long long)tiles_m * ((N + bn - 1) / bn);
     const long long waves = (tiles + sms - 1) / sms;
@@ -124,7 +124,12 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
   memset(&a, 0, sizeof(a));
   a.M = d->M; a.N = d->N; a.C = d->C; a.taps = d->taps;
   a.tiles_m = (d->M + qd::GEMM_BM - 1) / qd::GEMM_BM;
-  a.BN = pick_bn(d->N, a.tiles_m, sms, d->bn_hint);
+  a.geglu = d->geglu;
+  if (d->geglu) {
+    if ((d->N & 7) || !d->out_q || d->out || d->rowvec || d->residual || d->out_q_transposed || (d->ldq & 3) || d->taps != 1)
+      return fail(QD_ERR_BAD_ARG, "gemm: geglu needs N %% 8 == 0, out_q only, plain GEMM");
+  }
+  a.BN = pick_bn(d->N, a.tiles_m, sms, d->bn_hint, d->geglu ? 32 : 16);
   if (a.BN % 16 || a.BN < 16 || a.BN > 256) return fail(QD_ERR_BAD_ARG, "gemm: bad BN %d", a.BN);
   a.tiles_n = (d->N + a.BN - 1) / a.BN;
   a.a_signed = d->a_signed; a.b_signed = 1;
@@ -204,9 +209,10 @@ int launch_gemm_mode(const GemmPlan& pl, cudaStream_t s) {
 // Specialised epilogues for the hot combinations; everything else runs the generic (-1) kernel.
 int gemm_mode(const qd::GemmArgs& a) {
   const bool f = a.out != nullptr, q = a.out_q != nullptr;
+  if (a.geglu) return qd::EPI_GEGLU | qd::EPI_OUT_Q | (a.corr ? qd::EPI_CORR : 0);
   if (f == q || a.out_q_transposed || (a.N & 3)) return -1;
   if (a.rowvec && a.residual) return -1;
-  if (q && (a.rowvec || a.residual)) return -1;
+  if (q && a.rowvec) return -1;
   if (f && (a.ldo & 3)) return -1;
   if (q && (a.ldq & 3)) return -1;
   if (a.residual && (a.ldr & 3)) return -1;
@@ -226,6 +232,10 @@ int launch_gemm(const GemmPlan& pl, cudaStream_t s) {
     case EPI_OUT_F32 | EPI_RESIDUAL | EPI_CORR: return launch_gemm_mode<EPI_OUT_F32 | EPI_RESIDUAL | EPI_CORR>(pl, s);
     case EPI_OUT_Q: return launch_gemm_mode<EPI_OUT_Q>(pl, s);
     case EPI_OUT_Q | EPI_CORR: return launch_gemm_mode<EPI_OUT_Q | EPI_CORR>(pl, s);
+    case EPI_OUT_Q | EPI_RESIDUAL: return launch_gemm_mode<EPI_OUT_Q | EPI_RESIDUAL>(pl, s);
+    case EPI_OUT_Q | EPI_RESIDUAL | EPI_CORR: return launch_gemm_mode<EPI_OUT_Q | EPI_RESIDUAL | EPI_CORR>(pl, s);
+    case EPI_GEGLU | EPI_OUT_Q: return launch_gemm_mode<EPI_GEGLU | EPI_OUT_Q>(pl, s);
+    case EPI_GEGLU | EPI_OUT_Q | EPI_CORR: return launch_gemm_mode<EPI_GEGLU | EPI_OUT_Q | EPI_CORR>(pl, s);
     default: return launch_gemm_mode<-1>(pl, s);
   }
 }

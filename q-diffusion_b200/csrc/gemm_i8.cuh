@@ -35,6 +35,7 @@ constexpr int EPI_ROWVEC = 2;     // + per-image per-channel vector (timestep em
 constexpr int EPI_RESIDUAL = 4;   // + residual[m, n]
 constexpr int EPI_OUT_F32 = 8;    // fp32 output
 constexpr int EPI_OUT_Q = 16;     // requantised code output (row-major)
+constexpr int EPI_GEGLU = 32;     // columns interleaved [4 x, 4 gate]: out_q = Q(x * gelu(gate)), N/2 columns
 
 struct GemmArgs {
   int M, N;            // logical output rows / columns (columns >= N are masked)
@@ -62,6 +63,7 @@ struct GemmArgs {
   long long ld_rowvec;
   const float* residual;   // [M, ldr] or nullptr (may alias out)
   long long ldr;
+  int geglu;
 };
 
 struct GemmSmemLayout {
@@ -382,7 +384,54 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
-      if (transposed) {
+      if constexpr (MODE >= 0 && (MODE & EPI_GEGLU) != 0) {
+        // GEGLU projection (ldm/modules/attention.py:42-44) fused with the consumer's quantizer: a 32-column chunk
+        // holds 4 x (4 x-features | 4 gate-features); lane -> (row group of 8, pair); 4 iterations cover 32 rows.
+        const int r8 = lane >> 2, pq = lane & 3;
+        const QuantK qk = make_quantk(p.q_delta, p.q_zp, p.q_lo, p.q_hi);
+        for (int c = 0; c < p.BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + (uint32_t)c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+          const int nx = n_base + c + 8 * pq;          // 4 x columns, then 4 gate columns
+          if (nx < p.N) {
+            const float4 sx = __ldg(reinterpret_cast<const float4*>(p.scale + nx));
+            const float4 sg = __ldg(reinterpret_cast<const float4*>(p.scale + nx + 4));
+            float4 bx = make_float4(0.f, 0.f, 0.f, 0.f), bg = bx;
+            if (p.bias) {
+              bx = __ldg(reinterpret_cast<const float4*>(p.bias + nx));
+              bg = __ldg(reinterpret_cast<const float4*>(p.bias + nx + 4));
+            }
+            int4 cx = make_int4(0, 0, 0, 0), cg = cx;
+            if constexpr ((MODE & EPI_CORR) != 0) {
+              cx = __ldg(reinterpret_cast<const int4*>(p.corr + nx));
+              cg = __ldg(reinterpret_cast<const int4*>(p.corr + nx + 4));
+            }
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int row = it * 8 + r8;
+              const int m = m_warp + row;
+              if (m < p.M) {
+                const uint4 ax = *reinterpret_cast<const uint4*>(stg + row * 128 + (((2 * pq) ^ (row & 7)) << 4));
+                const uint4 ag = *reinterpret_cast<const uint4*>(stg + row * 128 + (((2 * pq + 1) ^ (row & 7)) << 4));
+                const float x0 = (float)((int)ax.x - cx.x) * sx.x + bx.x, g0 = (float)((int)ag.x - cg.x) * sg.x + bg.x;
+                const float x1 = (float)((int)ax.y - cx.y) * sx.y + bx.y, g1 = (float)((int)ag.y - cg.y) * sg.y + bg.y;
+                const float x2 = (float)((int)ax.z - cx.z) * sx.z + bx.z, g2 = (float)((int)ag.z - cg.z) * sg.z + bg.z;
+                const float x3 = (float)((int)ax.w - cx.w) * sx.w + bx.w, g3 = (float)((int)ag.w - cg.w) * sg.w + bg.w;
+                const uint32_t code = quant_code(x0 * gelu_erf(g0), qk) | (quant_code(x1 * gelu_erf(g1), qk) << 8) |
+                                      (quant_code(x2 * gelu_erf(g2), qk) << 16) | (quant_code(x3 * gelu_erf(g3), qk) << 24);
+                *reinterpret_cast<uint32_t*>(p.out_q + (long long)m * p.ldq + (nx >> 1)) = code;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      } else if (transposed) {
         const int m = m_warp + lane;
         int cls, img;
         gemm_row_meta(p, m, cls, img);

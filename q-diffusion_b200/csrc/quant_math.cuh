@@ -51,4 +51,7 @@ __device__ __forceinline__ float silu_fast(float x) {
   return __fdividef(x, 1.0f + e);
 }
 
+// exact-erf GELU (F.gelu default, ldm/modules/attention.py:44)
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
 }  // namespace qd

@@ -245,13 +245,21 @@ class Builder:
 
     def gemm(self, qm, a, label, *, conv_bhw=None, out=None, out_cols_offset=0, rowvec=None, residual=None,
              out_q=None, out_scale=1.0, k_pad=None, cols=None, suffix="", zx=None, dx=None, accumulate_into=None,
-             rows_per_batch=0, use_bias=True):
+             rows_per_batch=0, use_bias=True, geglu_q=None):
         """Record one INT8 GEMM for QuantModule `qm` on activation codes `a`.
 
         cols/suffix select a split-shortcut half.  out_q = (quantizer, transposed) requantises in the
         epilogue.  out_scale multiplies scale and bias (LDM legacy attention q*s, k*s)."""
         ws, delta_w = self._fold(qm, cols, suffix)
         N = ws.shape[0]
+        perm = None
+        if geglu_q is not None:
+            # GEGLU fused into the epilogue: interleave rows [4 x-features, 4 gate-features] (qd_gemm_desc.geglu)
+            r = torch.arange(N, device=ws.device)
+            f = 4 * (r // 8) + (r % 8) % 4
+            perm = torch.where((r % 8) < 4, f, N // 2 + f)
+            ws, delta_w = ws[perm], delta_w[perm]
+            out_q = (geglu_q, False)
         taps = 9 if (ws.dim() == 4 and ws.shape[-1] == 3 and conv_bhw is not None) else 1
         if zx is None:
             zx, dx = a.zp[0], a.delta[0]
@@ -273,7 +281,10 @@ class Builder:
             self.keep.append(corr)
         bias = None
         if use_bias and qm.bias is not None:
-            bias = (qm.bias.detach().to(self.dev, torch.float64) * out_scale).to(torch.float32).contiguous()
+            bias = (qm.bias.detach().to(self.dev, torch.float64) * out_scale).to(torch.float32)
+            if perm is not None:
+                bias = bias[perm]
+            bias = bias.contiguous()
             self.keep.append(bias)
         M = a.rows
         o = None
@@ -291,7 +302,7 @@ class Builder:
                 oq_act = Act(t, M // T * N, t_pad, signed=signed)
                 oq_act.t_pad = t_pad
             else:
-                oq_act = self.new_codes(M, N, signed)
+                oq_act = self.new_codes(M, N // 2 if geglu_q is not None else N, signed)
             oq_act.zp, oq_act.delta = (oq_params.zero_point, None), (oq_params.delta, None)
         res = accumulate_into if accumulate_into is not None else residual
         d = ops.gemm_desc(a.t, w_dev, scale, M=M, N=N, C=Cred, taps=taps, lda=a.ld, conv_bhw=conv_bhw,
@@ -302,7 +313,7 @@ class Builder:
                           out=o.t if o is not None else None, ldo=o.ld if o is not None else 0,
                           out_q=oq_act.t if oq_act is not None else None,
                           ldq=(oq_act.t_pad if transposed else oq_act.ld) if oq_act is not None else 0,
-                          oq=oq_params, out_q_transposed=transposed)
+                          oq=oq_params, out_q_transposed=transposed, geglu=geglu_q is not None)
         d.a = a.ptr + (cols[0] if cols is not None else 0)
         if rowvec is not None:
             d.rowvec = rowvec.ptr
@@ -470,9 +481,13 @@ class Builder:
             h = self.sd_cross_attention(a2, cq2, (kk, kv), h, T, Tk, bk + ".attn2")
             proj, ff_out = blk.ff.net[0].proj, blk.ff.net[2]
             (cf,) = self.layernorm(h, blk.norm3, [proj.act_quantizer], bk + ".norm3")
-            f = self.gemm(proj, cf, bk + ".ff.net.0.proj")
-            h = self.qlinear(ff_out, f, bk + ".ff.net.2", act=2, residual=h)
-        return self.qlinear(st.proj_out, h, k + ".proj_out", residual=x)
+            a_ff = self.gemm(proj, cf, bk + ".ff.net.0.proj", geglu_q=ff_out.act_quantizer)
+            if i == len(st.transformer_blocks) - 1:
+                # the block output only feeds proj_out: emit proj_out's input codes directly (no fp32 round trip)
+                hq = self.gemm(ff_out, a_ff, bk + ".ff.net.2", residual=h, out_q=(st.proj_out.act_quantizer, False))
+                return self.gemm(st.proj_out, hq, k + ".proj_out", residual=x)
+            h = self.gemm(ff_out, a_ff, bk + ".ff.net.2", residual=h)
+        raise RuntimeError("SpatialTransformer without transformer blocks")
 
     def ldm_attention_block(self, blk, x, hw):
         """AttentionBlock._forward + QKVAttentionLegacy (openaimodel.py:321-327,384-406) with QuantQKMatMul /

@@ -371,3 +371,29 @@ def test_sampler_step(cuda):
     ops.sampler_step(d)
     torch.cuda.synchronize()
     assert (out.cpu() - ref).abs().max().item() < 1e-5
+
+
+def test_qgemm_geglu_fused(cuda):
+    """ff.net.0.proj + GEGLU + ff.net.2's input quantizer in one GEMM epilogue (interleaved x/gate rows)."""
+    ops, fold = _ops()
+    gen = torch.Generator().manual_seed(77)
+    M, C, inner = 520, 96, 128
+    N = 2 * inner
+    L = _make_layer(N, C, 1, 4, gen, True)
+    a = torch.randint(0, 256, (M, C), generator=gen)
+    y = O.int_linear(a, L["zx"], L["ws"], L["scale"], L["bias"]).float()      # [M, 2*inner] = [x | gate]
+    q = ops.act_qparams(0.004, 119, 8, False)
+    ref = O.uaq_codes(O.geglu(y), q.delta, q.zero_point, 8, False)
+    r = torch.arange(N)
+    f = 4 * (r // 8) + (r % 8) % 4
+    perm = torch.where((r % 8) < 4, f, inner + f)
+    a_dev = a.to(torch.uint8).to(cuda)
+    w_dev = L["ws"][perm].to(torch.int8).contiguous().to(cuda)
+    corr = (L["zx"] * L["ws"].double().sum(dim=1)).to(torch.int32)[perm].contiguous().to(cuda)
+    out_q = torch.zeros(M, inner, dtype=torch.uint8, device=cuda)
+    d = ops.gemm_desc(a_dev, w_dev, L["scale"][perm].contiguous().to(cuda), M=M, N=N, C=C, a_signed=False,
+                      bias=L["bias"][perm].contiguous().to(cuda), corr=corr, out_q=out_q, ldq=inner, oq=q, geglu=True)
+    ops.qgemm(d)
+    torch.cuda.synchronize()
+    diff = (out_q.cpu().long() - ref.long()).abs()
+    assert diff.max() <= 1 and (diff > 0).float().mean() < 1e-3, (int(diff.max()), float((diff > 0).float().mean()))
