@@ -135,7 +135,7 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
   a.a_signed = d->a_signed; a.b_signed = 1;
 
   const int stage_bytes = qd::GEMM_A_STAGE_BYTES + a.BN * qd::GEMM_BK;
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = (232448 - 256 - qd::GEMM_EPI_WARPS * qd::GEMM_EPI_TILE_BYTES - 1024 - 1024) / stage_bytes;
   if (stages > qd::GEMM_MAX_STAGES) stages = qd::GEMM_MAX_STAGES;
   if (stages < 2) stages = 2;
   a.stages = stages;

@@ -10,7 +10,7 @@
 //   warp 0   : TMA producer  (A tile 128 x 128 B, B tile BN x 128 B, 128B swizzle, mbarrier ring)
 //   warp 1   : MMA issuer    (tcgen05.mma.kind::i8, M=128, N=BN, K=32 per instruction, int32 acc in TMEM)
 //   warp 2   : TMEM allocator (512 columns: two accumulator stages of up to 256 columns)
-//   warps 4-7: epilogue      (tcgen05.ld -> smem transpose -> zero-point correction / scale / bias /
+//   warps 4-11: epilogue     (tcgen05.ld -> smem transpose -> zero-point correction / scale / bias /
 //                             adds -> coalesced fp32 or requantised stores)
 //
 // The kernel is templated on the epilogue MODE so the hot variants carry no runtime flag tests
@@ -24,7 +24,8 @@ namespace qd {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 128;  // bytes == int8 elements per k-block (one 128B swizzle row)
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;   // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
+constexpr int GEMM_EPI_WARPS = 8;    // two warps per TMEM lane quarter, alternating 32-column chunks
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK;
 constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_EPI_TILE_BYTES = 32 * 128;  // per-epilogue-warp staging tile (32 rows x 32 int32)
@@ -78,7 +79,7 @@ __host__ __device__ inline GemmSmemLayout gemm_smem_layout(int BN, int stages) {
   l.stage_bytes = GEMM_A_STAGE_BYTES + BN * GEMM_BK;
   l.bar_offset = l.stage_bytes * stages;
   l.stage_off = l.bar_offset + 256;
-  l.total = l.stage_off + 4 * GEMM_EPI_TILE_BYTES + 1024;  // + alignment slack
+  l.total = l.stage_off + GEMM_EPI_WARPS * GEMM_EPI_TILE_BYTES + 1024;  // + alignment slack
   return l;
 }
 
@@ -277,7 +278,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], GEMM_EPI_WARPS);
     }
     fence_mbar_init();
     fence_proxy_async();
@@ -365,7 +366,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ways) and are finalised in the transposed mapping: 8 lanes x 16 B = one full 128 B line per row,
     // 4 rows per instruction, per-column parameters loaded once per thread per chunk.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    uint8_t* stg = smem + lay.stage_off + q * GEMM_EPI_TILE_BYTES;
+    const int half = (warp - 4) >> 2;   // which of the two warps sharing this lane quarter
+    uint8_t* stg = smem + lay.stage_off + (warp - 4) * GEMM_EPI_TILE_BYTES;
     const int rsub = lane >> 3;   // row within a group of 4
     const int cq = lane & 7;      // column quad within the 32-column chunk
     int acc = 0;
@@ -389,7 +391,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // holds 4 x (4 x-features | 4 gate-features); lane -> (row group of 8, pair); 4 iterations cover 32 rows.
         const int r8 = lane >> 2, pq = lane & 3;
         const QuantK qk = make_quantk(p.q_delta, p.q_zp, p.q_lo, p.q_hi);
-        for (int c = 0; c < p.BN; c += 32) {
+        for (int c = half * 32; c < p.BN; c += 64) {
           uint32_t v[32];
           tmem_ld_32x32(t_row + (uint32_t)c, v);
           tmem_ld_wait();
@@ -435,21 +437,21 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int m = m_warp + lane;
         int cls, img;
         gemm_row_meta(p, m, cls, img);
-        int c = 0;
-        for (; c + 32 <= p.BN; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(t_row + (uint32_t)c, v);
-          tmem_ld_wait();
-          if (m < p.M && n_base + c < p.N) gemm_epilogue_rowwise<32>(p, v, m, n_base + c, cls, img);
-        }
-        if (c < p.BN) {
-          uint32_t v[16];
-          tmem_ld_32x16(t_row + (uint32_t)c, v);
-          tmem_ld_wait();
-          if (m < p.M && n_base + c < p.N) gemm_epilogue_rowwise<16>(p, v, m, n_base + c, cls, img);
+        for (int c = half * 32; c < p.BN; c += 64) {
+          if (p.BN - c >= 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + (uint32_t)c, v);
+            tmem_ld_wait();
+            if (m < p.M && n_base + c < p.N) gemm_epilogue_rowwise<32>(p, v, m, n_base + c, cls, img);
+          } else {
+            uint32_t v[16];
+            tmem_ld_32x16(t_row + (uint32_t)c, v);
+            tmem_ld_wait();
+            if (m < p.M && n_base + c < p.N) gemm_epilogue_rowwise<16>(p, v, m, n_base + c, cls, img);
+          }
         }
       } else {
-        for (int c = 0; c < p.BN; c += 32) {
+        for (int c = half * 32; c < p.BN; c += 64) {
           const int ncols = (p.BN - c) >= 32 ? 32 : 16;
           if (ncols == 32) {
             uint32_t v[32];
