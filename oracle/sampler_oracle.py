@@ -1,0 +1,83 @@
+"""ORACLE (test infrastructure only): CPU restatement of the reference's sampler loops around an arbitrary
+eps-model callable.  PLMS: ldm/models/diffusion/plms.py:118-240; DDIM: ldm/models/diffusion/ddim.py:117-220;
+generalized_steps: ddim/functions/denoising.py:10-32.  Schedules: util.py:21-74, ddpm.py:118-146."""
+import numpy as np
+import torch
+
+
+def ldm_schedule(n_timestep=1000, linear_start=1e-4, linear_end=2e-2):
+    betas = (torch.linspace(linear_start ** 0.5, linear_end ** 0.5, n_timestep, dtype=torch.float64) ** 2).numpy()
+    ac = np.cumprod(1.0 - betas, axis=0)
+    return torch.tensor(ac, dtype=torch.float32)
+
+
+def ddim_params(alphas_cumprod, S, eta=0.0):
+    T = alphas_cumprod.shape[0]
+    c = T // S
+    steps = np.asarray(list(range(0, T, c))) + 1
+    ac = alphas_cumprod.cpu()
+    alphas = ac[steps]
+    alphas_prev = np.asarray([ac[0]] + ac[steps[:-1]].tolist())
+    sigmas = eta * np.sqrt((1 - alphas_prev) / (1 - alphas) * (1 - alphas / alphas_prev))
+    return steps, alphas, alphas_prev, sigmas, np.sqrt(1. - alphas)
+
+
+def plms_sample(model, x_T, cond, uc, scale, alphas_cumprod, S):
+    """model(x, t, context) -> eps.  Mirrors plms_sampling + p_sample_plms (eta = 0)."""
+    steps, alphas, alphas_prev, sigmas, sqrt_1ma = ddim_params(alphas_cumprod, S)
+    b = x_T.shape[0]
+    img = x_T.clone()
+    time_range = np.flip(steps)
+    total = steps.shape[0]
+    old_eps = []
+
+    def eps_of(x, t):
+        if uc is None or scale == 1.0:
+            return model(x, t, cond)
+        e_u, e_c = model(torch.cat([x] * 2), torch.cat([t] * 2), torch.cat([uc, cond])).chunk(2)
+        return e_u + scale * (e_c - e_u)
+
+    def x_prev_of(x, e, index):
+        a_t, a_prev = float(alphas[index]), float(alphas_prev[index])
+        pred_x0 = (x - float(sqrt_1ma[index]) * e) / np.sqrt(a_t)
+        return float(np.sqrt(a_prev)) * pred_x0 + float(np.sqrt(1. - a_prev)) * e
+
+    for i, step in enumerate(time_range):
+        index = total - i - 1
+        ts = torch.full((b,), int(step), dtype=torch.long)
+        ts_next = torch.full((b,), int(time_range[min(i + 1, len(time_range) - 1)]), dtype=torch.long)
+        e_t = eps_of(img, ts)
+        if len(old_eps) == 0:
+            x_prev = x_prev_of(img, e_t, index)
+            e_t_next = eps_of(x_prev, ts_next)
+            e_p = (e_t + e_t_next) / 2
+        elif len(old_eps) == 1:
+            e_p = (3 * e_t - old_eps[-1]) / 2
+        elif len(old_eps) == 2:
+            e_p = (23 * e_t - 16 * old_eps[-1] + 5 * old_eps[-2]) / 12
+        else:
+            e_p = (55 * e_t - 59 * old_eps[-1] + 37 * old_eps[-2] - 9 * old_eps[-3]) / 24
+        img = x_prev_of(img, e_p, index)
+        old_eps.append(e_t)
+        if len(old_eps) >= 4:
+            old_eps.pop(0)
+    return img
+
+
+def generalized_steps(model, x, seq, betas, eta=0.0, noises=None):
+    """ddim/functions/denoising.py:10-32; returns the final x."""
+    n = x.size(0)
+    beta = torch.cat([torch.zeros(1), betas.float()], dim=0)
+    acp = (1 - beta).cumprod(dim=0)
+    seq_next = [-1] + list(seq[:-1])
+    xt = x
+    for k, (i, j) in enumerate(zip(reversed(seq), reversed(seq_next))):
+        t = torch.ones(n) * i
+        at, at_next = acp[int(i) + 1], acp[int(j) + 1]
+        et = model(xt, t)
+        x0_t = (xt - et * (1 - at).sqrt()) / at.sqrt()
+        c1 = eta * ((1 - at / at_next) * (1 - at_next) / (1 - at)).sqrt()
+        c2 = ((1 - at_next) - c1 ** 2).sqrt()
+        noise = noises[k] if noises is not None else torch.zeros_like(x)
+        xt = at_next.sqrt() * x0_t + c1 * noise + c2 * et
+    return xt

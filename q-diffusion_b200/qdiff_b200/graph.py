@@ -237,20 +237,38 @@ class Builder:
             alpha = alpha.detach().to(self.dev, torch.float32).reshape(w.shape)
         codes = fold.weight_codes(w, delta, zp, wq.n_bits, alpha)
         ws = codes - zp.reshape(-1, *([1] * (w.dim() - 1)))
-        if float(ws.abs().max()) > 127:
-            raise NotImplementedError(
-                f"{self.key(qm)}: {wq.n_bits}-bit weight codes minus zero point exceed s8; the W8 operand split "
-                "(SURVEY H3) is the next hot-path row, W4 is realised")
         return ws, delta
 
     def gemm(self, qm, a, label, *, conv_bhw=None, out=None, out_cols_offset=0, rowvec=None, residual=None,
              out_q=None, out_scale=1.0, k_pad=None, cols=None, suffix="", zx=None, dx=None, accumulate_into=None,
-             rows_per_batch=0, use_bias=True, geglu_q=None):
+             rows_per_batch=0, use_bias=True, geglu_q=None, _ws=None, _wscale=1.0):
         """Record one INT8 GEMM for QuantModule `qm` on activation codes `a`.
+
+        W8: wq - zw spans [-255, 255] and does not fit the s8 operand.  Such layers run as TWO exact s8
+        GEMMs, ws = 2*a + b with a = floor(ws/2) in [-128,127], b in {0,1}:  y = 2s(acc_a - corr_a) + s(acc_b - corr_b) + bias,
+        the second one accumulating into the first one's fp32 output and carrying the requantising epilogue.
 
         cols/suffix select a split-shortcut half.  out_q = (quantizer, transposed) requantises in the
         epilogue.  out_scale multiplies scale and bias (LDM legacy attention q*s, k*s)."""
-        ws, delta_w = self._fold(qm, cols, suffix)
+        if _ws is None:
+            ws, delta_w = self._fold(qm, cols, suffix)
+            if float(ws.abs().max()) > 127:
+                if geglu_q is not None:     # fused GEGLU has no accumulate form: unfused fallback
+                    f32 = self.gemm(qm, a, label, conv_bhw=conv_bhw, k_pad=k_pad, cols=cols, suffix=suffix, zx=zx, dx=dx,
+                                    rows_per_batch=rows_per_batch)
+                    return self.quantize(f32, geglu_q, label + ".geglu.q", act=2, out_cols=f32.cols // 2)
+                wa = torch.floor(ws / 2)
+                wb = ws - 2 * wa
+                kw = dict(conv_bhw=conv_bhw, k_pad=k_pad, cols=cols, suffix=suffix, zx=zx, dx=dx, rows_per_batch=rows_per_batch)
+                first_target = accumulate_into if accumulate_into is not None else out
+                part = self.gemm(qm, a, label + ".w8hi", out=first_target, out_cols_offset=out_cols_offset, rowvec=rowvec,
+                                 residual=residual if accumulate_into is None else None,
+                                 accumulate_into=accumulate_into, out_scale=out_scale, use_bias=use_bias,
+                                 _ws=(wa, delta_w), _wscale=2.0, **kw)
+                return self.gemm(qm, a, label, out_q=out_q, accumulate_into=part, out_scale=out_scale, use_bias=False,
+                                 _ws=(wb, delta_w), _wscale=1.0, **kw)
+        else:
+            ws, delta_w = _ws
         N = ws.shape[0]
         perm = None
         if geglu_q is not None:
@@ -270,7 +288,7 @@ class Builder:
             Cred = k_pad
         w_dev = wk.to(torch.int8).contiguous()
         self.keep.append(w_dev)
-        scale = (delta_w.double() * float(dx) * out_scale).to(torch.float32).contiguous()
+        scale = (delta_w.double() * float(dx) * out_scale * _wscale).to(torch.float32).contiguous()
         self.keep.append(scale)
         corr = None
         if zx != 0:

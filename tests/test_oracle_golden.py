@@ -9,7 +9,7 @@ from oracle import ops_oracle as O
 from oracle import unet_oracle as U
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["ddim_w4a8_split", "ldm_legacy_w4a8", "ldm_updown_w4a8", "sd_tiny_w4a8_sm16"]
+CASES = ["ddim_w4a8_split", "ldm_legacy_w4a8", "ldm_updown_w4a8", "sd_tiny_w4a8_sm16", "ldm_updown_w8a8"]
 
 
 def load_case(name):

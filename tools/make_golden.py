@@ -178,6 +178,12 @@ CASES = [
                     num_res_blocks=1, channel_mult=[1, 2], num_heads=2, use_scale_shift_norm=True,
                     resblock_updown=True), res=16),
      dict(weight_bit=4, act_bit=8, a_sym=False, sm_abit=8, quant_act=True), None),
+    # cfg 5 proper: the same church-style UNet with 8-bit weights (wq - zw spans [-255,255]: exercises the W8 operand split)
+    ("ldm_updown_w8a8", "ldm",
+     dict(unet=dict(image_size=16, in_channels=4, out_channels=4, model_channels=32, attention_resolutions=[1, 2],
+                    num_res_blocks=1, channel_mult=[1, 2], num_heads=2, use_scale_shift_norm=True,
+                    resblock_updown=True), res=16),
+     dict(weight_bit=8, act_bit=8, a_sym=False, sm_abit=8, quant_act=True), None),
     # cfg 4: SD-style spatial transformer with cross attention, asymmetric W4A8, sm_abit 16, split shortcut
     ("sd_tiny_w4a8_sm16", "ldm",
      dict(unet=dict(image_size=16, in_channels=4, out_channels=4, model_channels=32, attention_resolutions=[2, 1],
@@ -217,6 +223,12 @@ def make_quantizer_kats():
 if __name__ == "__main__":
     _import_reference()
     os.makedirs(OUT, exist_ok=True)
-    make_quantizer_kats()
-    for i, (name, family, params, qcfg, ctx) in enumerate(CASES):
-        make_case(name, family, params, qcfg, batch=2, ctx_dim=ctx, seed=100 + i)
+    only = set(sys.argv[1:])
+    if not only:
+        make_quantizer_kats()
+    seeds = {"ddim_w4a8_split": 100, "ldm_legacy_w4a8": 101, "ldm_updown_w4a8": 102, "sd_tiny_w4a8_sm16": 103,
+             "ldm_updown_w8a8": 104}
+    for (name, family, params, qcfg, ctx) in CASES:
+        if only and name not in only:
+            continue
+        make_case(name, family, params, qcfg, batch=2, ctx_dim=ctx, seed=seeds[name])
