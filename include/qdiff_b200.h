@@ -177,7 +177,7 @@ int qd_im2col_i8(const qd_im2col_desc* d, qd_stream_t stream);
  * q,k: codes [B, Tq|Tk, *] with head h at columns q_off + h*head_stride (d codes each);
  * vt: V codes TRANSPOSED [B, n_rows_v, Tk_pad] with head h at rows v_off + h*head_stride; inside every
  *     group of 16 keys, key 8a+2b+c is stored at byte 4b+2a+c (what qd_qgemm_i8 out_q_transposed writes).
- * ws: int32 workspace, B*heads*roundup(Tk,64) entries (zero-point row sums of K; unused when zq == 0).
+ * ws: int32 workspace, B*heads*roundup(Tk,128) entries (zero-point row sums of K; unused when zq == 0).
  * S = sum_d (q-zq)(k-zk) * sim_scale (sim_scale = dq*dk*softmax scale), P = softmax_j(S) in fp32,
  * Pq = clamp(rne(P/dw)+zw, 0.., 2^sm_bits-1) (sm_bits 8 or 16), out = dw*dv * sum_j (Pq-zw)(v-zv).
  * out: fp32 [B, Tq, ld_out] at columns h*d, and/or out_q: the same values re-quantised with `oq`.

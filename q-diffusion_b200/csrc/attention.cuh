@@ -61,6 +61,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// entries per (batch, head) of the zq*rowsum(k) workspace (padded for 128-key tiles)
+__host__ __device__ __forceinline__ int att_ws_stride(int Tk) { return (Tk + 127) / 128 * 128; }
+
 // Position of key t inside a V^T row: within each group of 16 keys, key 8a+2b+c sits at byte 4b+2a+c.
 __host__ __device__ __forceinline__ int att_vt_perm(int t) {
   return (t & ~15) | (((t >> 1) & 3) << 2) | (((t >> 3) & 1) << 1) | (t & 1);
@@ -146,7 +149,7 @@ qattention_kernel(const qd_attention_desc p) {
   const int bh = blockIdx.y;
   const int b = bh / p.heads, h = bh - b * p.heads;
   const int row0 = blockIdx.x * ATT_BM + warp * 16;
-  const int* zrk_g = reinterpret_cast<const int*>(p.ws) + (long long)bh * (long long)(((p.Tk + ATT_BN - 1) / ATT_BN) * ATT_BN);
+  const int* zrk_g = reinterpret_cast<const int*>(p.ws) + (long long)bh * (long long)att_ws_stride(p.Tk);
 
   const uint8_t* qbase = reinterpret_cast<const uint8_t*>(p.q) + (long long)b * p.Tq * p.ld_q + p.q_off +
                          h * p.head_stride_q;

@@ -1,0 +1,406 @@
+// Quantised attention on the 5th-generation tensor cores (tcgen05 + TMEM), head dim d <= 112.
+//
+// Same arithmetic as attention.cuh (integer QK^T, fp32 softmax in the exp2 domain, P re-quantised after
+// normalisation with the calibrated step, integer PV with hi/lo byte planes) but S and O live in TMEM, the
+// MMAs are issued by one thread, and each softmax thread owns one query ROW (half of the 128 key columns of
+// a tile): no fragment bookkeeping, no quad shuffles, no IMMA / fragment-LDS issue slots -> ~16 scalar
+// instructions per score instead of ~24 (profiles/r01_attention_v2.txt).
+//
+// CTA = 128 query rows of one (batch, head); 10 warps:
+//   warp 0      loader : K tile (128 keys x d bytes) by cp.async into the 128B-swizzled K-major layout,
+//                        zq*rowsum(k) slice, V^T tile (NV rows x 128 keys) by TMA
+//   warp 1      MMA    : S = Q K^T  (M=128, N=128, K=32 x ceil(d/32)) into a double-buffered TMEM slot;
+//                        O_lo/O_hi += P_lo/P_hi V^T (M=128, N=NV, K=32 x 4), int32 in TMEM for the whole pass
+//   warps 2-9   softmax: thread = (row, column half); pass 1: integer row max + sum of exp2; pass 2: codes ->
+//                        byte planes written to shared memory as the next MMA's A operand (128B swizzle,
+//                        V^T key permutation applied while packing)
+// Row sums of the P codes come from an all-ones V^T row (row d of the tile).
+#pragma once
+#include "attention.cuh"
+#include "ptx.cuh"
+
+namespace qd {
+
+constexpr int ATC_THREADS = 320;
+constexpr int ATC_BM = 128, ATC_BN = 128;
+
+struct AtcSmem {
+  int q_off, k_off, v_off, p_off, zrk_off, stat_off, bar_off, total, v_stage;
+};
+__host__ __device__ inline AtcSmem atc_smem_layout(int NV) {
+  AtcSmem l;
+  l.q_off = 0;
+  l.k_off = 16384;
+  l.v_stage = NV * 128;
+  l.v_off = l.k_off + 2 * 16384;
+  l.p_off = l.v_off + 2 * l.v_stage;       // multiple of 1024 because NV % 8 == 0
+  l.zrk_off = l.p_off + 4 * 16384;          // [buffer][plane]
+  l.stat_off = l.zrk_off + 2 * 512;
+  l.bar_off = l.stat_off + 128 * 8;
+  l.total = l.bar_off + 256 + 1024;
+  return l;
+}
+
+template <bool SM16, bool MAGIC>
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+qattention_tc_kernel(const __grid_constant__ CUtensorMap tmV, const qd_attention_desc p, const int NV) {
+  extern __shared__ uint8_t atc_raw[];
+  const uint32_t raw_addr = smem_u32(atc_raw);
+  uint8_t* smem = atc_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  const AtcSmem L = atc_smem_layout(NV);
+  uint8_t* sQ = smem + L.q_off;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* kv_full = bars;        // [2]
+  uint64_t* kv_empty = bars + 2;   // [2]
+  uint64_t* s_full = bars + 4;     // [2]
+  uint64_t* s_empty = bars + 6;    // [2]
+  uint64_t* p_full = bars + 8;     // [2]
+  uint64_t* p_empty = bars + 10;   // [2]
+  uint64_t* o_done = bars + 12;    // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int b = bh / p.heads, h = bh - b * p.heads;
+  const int row_base = blockIdx.x * ATC_BM;
+  const int d = p.d;
+  const int nks = (d + 31) >> 5;                 // K=32 slices of QK^T
+  const int ntiles = (p.Tk + ATC_BN - 1) / ATC_BN;
+  const bool has_zq = p.zq != 0;
+
+  const uint8_t* qbase = reinterpret_cast<const uint8_t*>(p.q) + (long long)b * p.Tq * p.ld_q + p.q_off + h * p.head_stride_q;
+  const uint8_t* kbase = reinterpret_cast<const uint8_t*>(p.k) + (long long)b * p.Tk * p.ld_k + p.k_off + h * p.head_stride_k;
+  const int* zrk_g = reinterpret_cast<const int*>(p.ws) + (long long)bh * (long long)att_ws_stride(p.Tk);
+
+  // ---- one-time setup: zero Q/K regions (padding beyond d must be 0), constant rows of the V^T stages, Q tile
+  for (int i = threadIdx.x; i < (16384 * 3) / 16; i += ATC_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < (2 * L.v_stage) / 16; i += ATC_THREADS)
+    reinterpret_cast<uint4*>(smem + L.v_off)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  {
+    // all-ones row d of both V^T stages (a constant row is invariant under the 128B swizzle)
+    for (int i = threadIdx.x; i < 2 * 8; i += ATC_THREADS)
+      reinterpret_cast<uint4*>(smem + L.v_off + (i >> 3) * L.v_stage + d * 128)[i & 7] =
+          make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+    // Q tile: 8-byte pieces into the swizzled K-major layout (16 B chunk index ^= row & 7)
+    const int wpr = d >> 3;
+    for (int idx = threadIdx.x; idx < ATC_BM * wpr; idx += ATC_THREADS) {
+      const int r = idx / wpr, w = idx - r * wpr;
+      const int gr = min(row_base + r, p.Tq - 1);
+      const uint2 v = *reinterpret_cast<const uint2*>(qbase + (long long)gr * p.ld_q + 8 * w);
+      *reinterpret_cast<uint2*>(sQ + r * 128 + ((((w >> 1) ^ (r & 7)) << 4) | ((w & 1) << 3))) = v;
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 9);    // MMA commit + 8 softmax warps (they read the zq*rowsum(k) slice of the stage)
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 8);
+      mbar_init(&p_full[i], 8);
+      mbar_init(&p_empty[i], 1);
+    }
+    mbar_init(o_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    if (lane == 0) tma_prefetch_desc(&tmV);
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async();   // generic-proxy writes of Q / constant rows -> visible to the tensor-core (async) proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tm_s = tmem_base;             // S slots: columns [0,128) and [128,256)
+  const uint32_t tm_olo = tmem_base + 256;     // O_lo: NV columns
+  const uint32_t tm_ohi = tmem_base + 256 + 128;
+
+  if (warp == 0) {
+    // ===================== loader =====================
+    int st = 0;
+    uint32_t ph = 0;
+    const int wpr = d >> 3;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int t = 0; t < ntiles; ++t) {
+        const int j0 = t * ATC_BN;
+        mbar_wait(&kv_empty[st], ph ^ 1);
+        uint8_t* dK = smem + L.k_off + st * 16384;
+        const int rows = min(ATC_BN, p.Tk - j0);
+        for (int idx = lane; idx < rows * wpr; idx += 32) {
+          const int r = idx / wpr, w = idx - r * wpr;
+          cp_async8(dK + r * 128 + ((((w >> 1) ^ (r & 7)) << 4) | ((w & 1) << 3)), kbase + (long long)(j0 + r) * p.ld_k + 8 * w);
+        }
+        if (has_zq) cp_async16(smem + L.zrk_off + st * 512 + 16 * lane, zrk_g + j0 + 4 * lane);
+        cp_async_commit();
+        cp_async_wait_all();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (pass == 1) {
+            mbar_arrive_expect_tx(&kv_full[st], (uint32_t)(d * 128));
+            tma_load_2d(smem + L.v_off + st * L.v_stage, &tmV, &kv_full[st], j0, bh * d);
+          } else {
+            mbar_arrive(&kv_full[st]);
+          }
+        }
+        if (++st == 2) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_i8(128, 128, p.q_signed, p.k_signed);
+      const uint32_t idesc_o = make_idesc_i8(128, NV, 0, p.v_signed);
+      const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ));
+      int st = 0, sb = 0, pb = 0;
+      uint32_t ph_kv = 0, ph_s = 0, ph_p = 0;
+      // ---- pass 1: S only
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_wait(&kv_full[st], ph_kv);
+        mbar_wait(&s_empty[sb], ph_s ^ 1);
+        tc_fence_after();
+        const uint64_t dk = make_smem_desc_sw128(smem_u32(smem + L.k_off + st * 16384));
+        for (int j = 0; j < nks; ++j) umma_i8(tm_s + sb * 128, dq + 2 * j, dk + 2 * j, idesc_s, j ? 1u : 0u);
+        umma_commit(&s_full[sb]);
+        umma_commit(&kv_empty[st]);
+        if (++st == 2) { st = 0; ph_kv ^= 1; }
+        if (++sb == 2) { sb = 0; ph_s ^= 1; }
+      }
+      // ---- pass 2: S(t+1) is issued before PV(t) so the softmax of t+1 overlaps the PV MMAs of t
+      auto issue_s = [&](int st_, int sb_) {
+        const uint64_t dk = make_smem_desc_sw128(smem_u32(smem + L.k_off + st_ * 16384));
+        for (int j = 0; j < nks; ++j) umma_i8(tm_s + sb_ * 128, dq + 2 * j, dk + 2 * j, idesc_s, j ? 1u : 0u);
+      };
+      int st_s = st, sb_s = sb;
+      uint32_t ph_kv_s = ph_kv, ph_s_s = ph_s;
+      mbar_wait(&kv_full[st_s], ph_kv_s);
+      mbar_wait(&s_empty[sb_s], ph_s_s ^ 1);
+      tc_fence_after();
+      issue_s(st_s, sb_s);
+      umma_commit(&s_full[sb_s]);
+      for (int t = 0; t < ntiles; ++t) {
+        const int st_cur = st_s;
+        if (++st_s == 2) { st_s = 0; ph_kv_s ^= 1; }
+        if (++sb_s == 2) { sb_s = 0; ph_s_s ^= 1; }
+        if (t + 1 < ntiles) {
+          mbar_wait(&kv_full[st_s], ph_kv_s);
+          mbar_wait(&s_empty[sb_s], ph_s_s ^ 1);
+          tc_fence_after();
+          issue_s(st_s, sb_s);
+          umma_commit(&s_full[sb_s]);
+        }
+        mbar_wait(&p_full[pb], ph_p);
+        tc_fence_after();
+        const uint64_t dv = make_smem_desc_sw128(smem_u32(smem + L.v_off + st_cur * L.v_stage));
+        const uint64_t dplo = make_smem_desc_sw128(smem_u32(smem + L.p_off + (pb * 2) * 16384));
+        for (int j = 0; j < 4; ++j) umma_i8(tm_olo, dplo + 2 * j, dv + 2 * j, idesc_o, (t | j) ? 1u : 0u);
+        if (SM16) {
+          const uint64_t dphi = make_smem_desc_sw128(smem_u32(smem + L.p_off + (pb * 2 + 1) * 16384));
+          for (int j = 0; j < 4; ++j) umma_i8(tm_ohi, dphi + 2 * j, dv + 2 * j, idesc_o, (t | j) ? 1u : 0u);
+        }
+        umma_commit(&p_empty[pb]);
+        umma_commit(&kv_empty[st_cur]);
+        if (++pb == 2) { pb = 0; ph_p ^= 1; }
+      }
+      umma_commit(o_done);
+    }
+  } else {
+    // ===================== softmax warps =====================
+    const int q4 = warp & 3;                 // TMEM lane quarter of this warp
+    const int half = (warp - 2) >> 2;        // which 64 key columns of a tile
+    const int row = q4 * 32 + lane;          // query row inside the CTA tile == TMEM lane
+    const uint32_t t_lane = (uint32_t)(q4 * 32) << 16;
+    const float c = p.sim_scale * 1.4426950408889634f;
+    const float pmax = (float)p.p_qmax;
+    float2* stat = reinterpret_cast<float2*>(smem + L.stat_off);
+    int sb = 0, st = 0;
+    uint32_t ph_s = 0, ph_kv = 0;
+    int mi = INT_MIN;
+    float l = 0.f;
+    // ---- pass 1
+    for (int t = 0; t < ntiles; ++t) {
+      const int j0 = t * ATC_BN + half * 64;
+      mbar_wait(&s_full[sb], ph_s);
+      tc_fence_after();
+      const int* zr = reinterpret_cast<const int*>(smem + L.zrk_off + st * 512) + half * 64;
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) {
+        uint32_t v[32];
+        tmem_ld_32x32(tm_s + t_lane + sb * 128 + half * 64 + cb * 32, v);
+        tmem_ld_wait();
+        int s[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          int4 z = make_int4(0, 0, 0, 0);
+          if (has_zq) z = *reinterpret_cast<const int4*>(zr + cb * 32 + j);
+          s[j] = (int)v[j] - z.x; s[j + 1] = (int)v[j + 1] - z.y; s[j + 2] = (int)v[j + 2] - z.z; s[j + 3] = (int)v[j + 3] - z.w;
+        }
+        if (j0 + cb * 32 + 32 > p.Tk) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j0 + cb * 32 + j >= p.Tk) s[j] = INT_MIN / 2;
+        }
+        int tm = s[0];
+#pragma unroll
+        for (int j = 1; j < 32; ++j) tm = max(tm, s[j]);
+        if (MAGIC) {   // keep masked entries inside the exact range of the magic-constant conversion
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s[j] = max(s[j], -(1 << 22) + 1);
+        }
+        if (tm != INT_MIN / 2) {   // a fully masked chunk contributes nothing (and must not seed the running max)
+          if (tm > mi) { l *= (mi == INT_MIN) ? 0.f : ex2_approx((float)(mi - tm) * c); mi = tm; }
+          const float b0 = -(float)mi * c;
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            a0 += ex2_approx(fmaf(att_i2f<MAGIC>(s[j]), c, b0));
+            a1 += ex2_approx(fmaf(att_i2f<MAGIC>(s[j + 1]), c, b0));
+          }
+          l += a0 + a1;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&s_empty[sb]);
+        mbar_arrive(&kv_empty[st]);
+      }
+      if (++sb == 2) { sb = 0; ph_s ^= 1; }
+      if (++st == 2) { st = 0; ph_kv ^= 1; }
+    }
+    // ---- combine the two column halves of every row (named barrier over the 8 softmax warps)
+    if (half == 1) stat[row] = make_float2(__int_as_float(mi), l);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float off;
+    {
+      if (half == 0) {
+        const float2 o = stat[row];
+        const int mo = __float_as_int(o.x);
+        const int mm = max(mi, mo);
+        const float lt = l * ((mi == INT_MIN) ? 0.f : ex2_approx((float)(mi - mm) * c)) +
+                         o.y * ((mo == INT_MIN) ? 0.f : ex2_approx((float)(mo - mm) * c));
+        off = -(float)mm * c + log2f(1.0f / (lt * p.delta_w));
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (half == 0) stat[row] = make_float2(off, 0.f);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      off = stat[row].x;
+    }
+    // ---- pass 2
+    int pb = 0;
+    uint32_t ph_p = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      const int j0 = t * ATC_BN + half * 64;
+      mbar_wait(&s_full[sb], ph_s);
+      mbar_wait(&p_empty[pb], ph_p ^ 1);
+      tc_fence_after();
+      const int* zr = reinterpret_cast<const int*>(smem + L.zrk_off + st * 512) + half * 64;
+      uint8_t* pl = smem + L.p_off + (pb * 2) * 16384 + row * 128;
+      uint8_t* phh = pl + 16384;
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) {
+        uint32_t v[32];
+        tmem_ld_32x32(tm_s + t_lane + sb * 128 + half * 64 + cb * 32, v);
+        tmem_ld_wait();
+        uint32_t cd[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          int4 z = make_int4(0, 0, 0, 0);
+          if (has_zq) z = *reinterpret_cast<const int4*>(zr + cb * 32 + j);
+          const int s0 = (int)v[j] - z.x, s1 = (int)v[j + 1] - z.y, s2 = (int)v[j + 2] - z.z, s3 = (int)v[j + 3] - z.w;
+          cd[j] = __float_as_uint(fminf(ex2_approx(fmaf(att_i2f<MAGIC>(s0), c, off)), pmax) + 12582912.0f);
+          cd[j + 1] = __float_as_uint(fminf(ex2_approx(fmaf(att_i2f<MAGIC>(s1), c, off)), pmax) + 12582912.0f);
+          cd[j + 2] = __float_as_uint(fminf(ex2_approx(fmaf(att_i2f<MAGIC>(s2), c, off)), pmax) + 12582912.0f);
+          cd[j + 3] = __float_as_uint(fminf(ex2_approx(fmaf(att_i2f<MAGIC>(s3), c, off)), pmax) + 12582912.0f);
+        }
+        if (j0 + cb * 32 + 32 > p.Tk) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j0 + cb * 32 + j >= p.Tk) cd[j] = 0x4B400000u;   // code 0
+        }
+        // two groups of 16 keys; inside a group key 8a+2b+c goes to byte 4b+2a+c (att_vt_perm)
+#pragma unroll
+        for (int gq = 0; gq < 2; ++gq) {
+          const uint32_t* e = cd + 16 * gq;
+          uint32_t lo[4], hi[4];
+#pragma unroll
+          for (int bq = 0; bq < 4; ++bq) {
+            lo[bq] = __byte_perm(__byte_perm(e[2 * bq], e[2 * bq + 1], 0x0040), __byte_perm(e[8 + 2 * bq], e[9 + 2 * bq], 0x0040), 0x5410);
+            if (SM16) hi[bq] = __byte_perm(__byte_perm(e[2 * bq], e[2 * bq + 1], 0x0051), __byte_perm(e[8 + 2 * bq], e[9 + 2 * bq], 0x0051), 0x5410);
+          }
+          const int chunk = half * 4 + cb * 2 + gq;                 // 16-byte chunk of the 128-key row
+          const int sw = (chunk ^ (row & 7)) << 4;
+          *reinterpret_cast<uint4*>(pl + sw) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          if (SM16) *reinterpret_cast<uint4*>(phh + sw) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        }
+      }
+      fence_proxy_async();       // P bytes (generic proxy) -> visible to the MMA (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&s_empty[sb]);
+        mbar_arrive(&kv_empty[st]);
+        mbar_arrive(&p_full[pb]);
+      }
+      if (++sb == 2) { sb = 0; ph_s ^= 1; }
+      if (++st == 2) { st = 0; ph_kv ^= 1; }
+      if (++pb == 2) { pb = 0; ph_p ^= 1; }
+    }
+    // ---- epilogue: O = (256*hi + lo - zv*rowsum) * out_scale
+    mbar_wait(o_done, 0);
+    tc_fence_after();
+    if (half == 0) {
+      const int grow = row_base + row;
+      float rs = 0.f;
+      {
+        uint32_t v[16];
+        tmem_ld_32x16(tm_olo + t_lane + (uint32_t)((d >> 4) << 4), v);
+        tmem_ld_wait();
+        rs = (float)(int)v[d & 15];
+        if (SM16) {
+          uint32_t w[16];
+          tmem_ld_32x16(tm_ohi + t_lane + (uint32_t)((d >> 4) << 4), w);
+          tmem_ld_wait();
+          rs += 256.0f * (float)(int)w[d & 15];
+        }
+      }
+      const float zc = (float)p.zv * rs;
+      const QuantK qk = make_quantk(p.oq);
+      for (int c0 = 0; c0 < d; c0 += 16) {
+        uint32_t v[16], w[16];
+        tmem_ld_32x16(tm_olo + t_lane + (uint32_t)c0, v);
+        if (SM16) tmem_ld_32x16(tm_ohi + t_lane + (uint32_t)c0, w);
+        tmem_ld_wait();
+        if (grow < p.Tq) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            if (c0 + j < d) {    // d % 8 == 0: handle 4 columns at a time
+              float y[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float val = (float)(int)v[j + e];
+                if (SM16) val += 256.0f * (float)(int)w[j + e];
+                y[e] = (val - zc) * p.out_scale;
+              }
+              const long long o = ((long long)b * p.Tq + grow);
+              const int col = h * d + c0 + j;
+              if (p.out) *reinterpret_cast<float4*>(p.out + o * p.ld_out + col) = make_float4(y[0], y[1], y[2], y[3]);
+              if (p.out_q)
+                *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.out_q) + o * p.ld_out_q + col) =
+                    quant_code(y[0], qk) | (quant_code(y[1], qk) << 8) | (quant_code(y[2], qk) << 16) | (quant_code(y[3], qk) << 24);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace qd

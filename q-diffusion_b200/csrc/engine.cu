@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -13,6 +14,7 @@
 
 #include "../../include/qdiff_b200.h"
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "elem.cuh"
 #include "gemm_i8.cuh"
 
@@ -305,7 +307,7 @@ int launch_attention_inst(const qd_attention_desc& d, cudaStream_t s) {
   if (lay.total > 200 * 1024) return fail(QD_ERR_UNSUPPORTED, "attention: Tk=%d needs %d B of shared memory", d.Tk, lay.total);
   if (d.zq != 0) {
     if (!d.ws) return fail(QD_ERR_BAD_ARG, "attention: workspace required when zq != 0");
-    const int tk_pad = (d.Tk + qd::ATT_BN - 1) / qd::ATT_BN * qd::ATT_BN;
+    const int tk_pad = qd::att_ws_stride(d.Tk);
     qd::att_krowsum_kernel<QS><<<grid_for((long long)d.B * d.heads * tk_pad, 256), 256, 0, s>>>(d, tk_pad);
     int rc = check_launch("att_krowsum_kernel");
     if (rc) return rc;
@@ -325,6 +327,58 @@ int launch_attention_t(const qd_attention_desc& d, cudaStream_t s) {
   return fail(QD_ERR_UNSUPPORTED, "attention: mixed signedness q=%d v=%d", d.q_signed, d.v_signed);
 }
 
+// tcgen05 path (attention_tc.cuh): d <= 112, dense V^T [B][heads*d][ld_vt]
+template <bool S16, bool MAGIC>
+int launch_attention_tc_inst(const qd_attention_desc& d, const CUtensorMap& tmV, int NV, cudaStream_t s) {
+  auto kern = qd::qattention_tc_kernel<S16, MAGIC>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  if (attr_err != cudaSuccess) return fail(QD_ERR_CUDA, "attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  const qd::AtcSmem lay = qd::atc_smem_layout(NV);
+  dim3 grid((d.Tq + qd::ATC_BM - 1) / qd::ATC_BM, d.B * d.heads);
+  kern<<<grid, qd::ATC_THREADS, lay.total, s>>>(tmV, d, NV);
+  return check_launch("qattention_tc_kernel");
+}
+
+bool attention_tc_eligible(const qd_attention_desc& d) {
+  static int mode = -1;   // QDIFF_ATTENTION=mma forces the mma.sync kernel (A/B comparisons)
+  if (mode < 0) {
+    const char* e = getenv("QDIFF_ATTENTION");
+    mode = (e && !strcmp(e, "mma")) ? 0 : 1;
+  }
+  if (!mode) return false;
+  if (d.d > 112 || (d.d & 7)) return false;
+  if (d.v_off != 0 || d.head_stride_v != d.d || d.v_batch_stride != (long long)d.heads * d.d * d.ld_vt) return false;
+  if (d.out && ((d.ld_out & 3) || (((uintptr_t)d.out) & 15))) return false;
+  if (d.out_q && (d.ld_out_q & 3)) return false;
+  if ((d.d * 255LL * 255LL) >= (1LL << 31)) return false;
+  return true;
+}
+
+int launch_attention_tc(const qd_attention_desc& d, cudaStream_t s) {
+  const int NV = (d.d + 1 + 15) / 16 * 16;
+  CUtensorMap tmV;
+  cuuint64_t dims[2] = {(cuuint64_t)d.ld_vt, (cuuint64_t)d.B * d.heads * d.d};
+  cuuint64_t strides[1] = {(cuuint64_t)d.ld_vt};
+  cuuint32_t box[2] = {128, (cuuint32_t)d.d};
+  int rc = encode_u8_map(&tmV, d.vt, 2, dims, strides, box);
+  if (rc) return rc;
+  if (d.zq != 0) {
+    if (!d.ws) return fail(QD_ERR_BAD_ARG, "attention: workspace required when zq != 0");
+    const int tk_pad = qd::att_ws_stride(d.Tk);
+    if (d.q_signed) qd::att_krowsum_kernel<true><<<grid_for((long long)d.B * d.heads * tk_pad, 256), 256, 0, s>>>(d, tk_pad);
+    else qd::att_krowsum_kernel<false><<<grid_for((long long)d.B * d.heads * tk_pad, 256), 256, 0, s>>>(d, tk_pad);
+    rc = check_launch("att_krowsum_kernel");
+    if (rc) return rc;
+  }
+  const bool s16 = d.sm_bits > 8, magic = d.d <= 64;
+  if (s16 && magic) return launch_attention_tc_inst<true, true>(d, tmV, NV, s);
+  if (s16 && !magic) return launch_attention_tc_inst<true, false>(d, tmV, NV, s);
+  if (!s16 && magic) return launch_attention_tc_inst<false, true>(d, tmV, NV, s);
+  return launch_attention_tc_inst<false, false>(d, tmV, NV, s);
+}
+
 int launch_attention(const qd_attention_desc& d, cudaStream_t s) {
   if (!d.q || !d.k || !d.vt || (!d.out && !d.out_q)) return fail(QD_ERR_BAD_ARG, "attention: null arg");
   if (d.out_q && (d.ld_out_q & 1)) return fail(QD_ERR_UNSUPPORTED, "attention: ld_out_q");
@@ -335,6 +389,7 @@ int launch_attention(const qd_attention_desc& d, cudaStream_t s) {
   if ((d.q_off | d.head_stride_q | (int)d.ld_q) & 3) return fail(QD_ERR_UNSUPPORTED, "attention: q needs 4-byte alignment");
   if ((d.k_off | d.head_stride_k | (int)d.ld_k | d.d) & 7) return fail(QD_ERR_UNSUPPORTED, "attention: k rows need 8-byte alignment");
   if (d.out && (d.ld_out % 2)) return fail(QD_ERR_UNSUPPORTED, "attention: ld_out");
+  if (attention_tc_eligible(d)) return launch_attention_tc(d, s);
   switch (d.d) {
     case 16: return launch_attention_t<32, 16>(d, s);
     case 24: return launch_attention_t<32, 24>(d, s);

@@ -400,7 +400,7 @@ class Builder:
             out.zp, out.delta = (oqp.zero_point, None), (oqp.delta, None)
             a.out_q, a.ld_out_q, a.oq = out.ptr, out.ld, oqp
         if a.zq != 0:
-            ws = torch.empty(self.B * heads * ((Tk + 63) // 64 * 64), dtype=torch.int32, device=self.dev)
+            ws = torch.empty(self.B * heads * ((Tk + 127) // 128 * 128), dtype=torch.int32, device=self.dev)
             self.keep.append(ws)
             a.ws = ws.data_ptr()
         self.add(_lib.QD_OP_ATTENTION, a, label, flops=4 * self.B * heads * Tq * Tk * d)

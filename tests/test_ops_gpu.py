@@ -294,7 +294,7 @@ def _run_attention(cuda, B, heads, d, Tq, Tk, sym, sm_bits, seed):
     pos = (tt & ~15) | (((tt >> 1) & 3) << 2) | (((tt >> 3) & 1) << 1) | (tt & 1)   # att_vt_perm
     vt[:, :, pos] = vc.permute(0, 2, 1)
     vt = vt.to(cuda)
-    ws = torch.zeros(B * heads * ((Tk + 63) // 64 * 64), dtype=torch.int32, device=cuda)
+    ws = torch.zeros(B * heads * ((Tk + 127) // 128 * 128), dtype=torch.int32, device=cuda)
     out = torch.full((B, Tq, heads * d), float("nan"), device=cuda)
     a = AttentionDesc()
     a.q, a.k, a.vt = ptr(qc), ptr(kc), ptr(vt)
