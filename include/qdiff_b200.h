@@ -76,6 +76,8 @@ typedef struct qd_gemm_desc {
   long long ldq;
   qd_qparams oq;
   int32_t bn_hint;       /* 0 = auto N-tile */
+  int32_t out_q_head_dim;   /* > 0: row-major out_q is written per head with padding: column n -> */
+  int32_t out_q_head_pitch; /*      (n / head_dim) * head_pitch + n % head_dim   (attention Q / K operands) */
   int32_t geglu;         /* 1: rows of w (and scale/bias/corr) are interleaved [4 x-features, 4 gate-features]...;
                             out_q receives Q(x * gelu_erf(gate)) with N/2 columns (ldm/modules/attention.py:42-44) */
 } qd_gemm_desc;

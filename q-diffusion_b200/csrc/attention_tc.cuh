@@ -7,8 +7,9 @@
 // instructions per score instead of ~24 (profiles/r01_attention_v2.txt).
 //
 // CTA = 128 query rows of one (batch, head); 10 warps:
-//   warp 0      loader : K tile (128 keys x d bytes) by cp.async into the 128B-swizzled K-major layout,
-//                        zq*rowsum(k) slice, V^T tile (NV rows x 128 keys) by TMA
+//   warp 0      loader : Q / K tiles by TMA from the per-head padded code layout (pitch P = 32/64/128 bytes ==
+//                        the swizzle span, written by the to_q / to_k GEMM epilogues), V^T tile (d rows x 128
+//                        keys) by TMA, zq*rowsum(k) slice by cp.async; 4-stage ring
 //   warp 1      MMA    : S = Q K^T  (M=128, N=128, K=32 x ceil(d/32)) into a double-buffered TMEM slot;
 //                        O_lo/O_hi += P_lo/P_hi V^T (M=128, N=NV, K=32 x 4), int32 in TMEM for the whole pass
 //   warps 2-9   softmax: thread = (row, column half); pass 1: integer row max + sum of exp2; pass 2: codes ->
@@ -24,40 +25,56 @@ namespace qd {
 constexpr int ATC_THREADS = 320;
 constexpr int ATC_BM = 128, ATC_BN = 128;
 
+constexpr int ATC_STAGES = 4;
+
 struct AtcSmem {
-  int q_off, k_off, v_off, p_off, zrk_off, stat_off, bar_off, total, v_stage;
+  int q_off, k_off, v_off, p_off, zrk_off, stat_off, bar_off, total, v_stage, k_stage;
 };
-__host__ __device__ inline AtcSmem atc_smem_layout(int NV) {
+__host__ __device__ inline AtcSmem atc_smem_layout(int NV, int P) {
   AtcSmem l;
   l.q_off = 0;
   l.k_off = 16384;
+  l.k_stage = 128 * P;                       // 128 keys x P bytes (P = swizzle span)
   l.v_stage = NV * 128;
-  l.v_off = l.k_off + 2 * 16384;
-  l.p_off = l.v_off + 2 * l.v_stage;       // multiple of 1024 because NV % 8 == 0
+  l.v_off = l.k_off + ATC_STAGES * l.k_stage;
+  l.p_off = (l.v_off + ATC_STAGES * l.v_stage + 1023) / 1024 * 1024;
   l.zrk_off = l.p_off + 4 * 16384;          // [buffer][plane]
-  l.stat_off = l.zrk_off + 2 * 512;
+  l.stat_off = l.zrk_off + ATC_STAGES * 512;
   l.bar_off = l.stat_off + 128 * 8;
   l.total = l.bar_off + 256 + 1024;
   return l;
 }
 
+// K-major smem matrix descriptor for rows of P bytes with the P-byte swizzle (P = 32, 64, 128)
+__device__ __forceinline__ uint64_t make_smem_desc_sw(uint32_t smem_addr, int P) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * P) >> 4) << 32;                       // stride between 8-row groups
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(P == 128 ? 2 : (P == 64 ? 4 : 6)) << 61;  // SWIZZLE_128B / 64B / 32B
+  return d;
+}
+
 template <bool SM16, bool MAGIC>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
-qattention_tc_kernel(const __grid_constant__ CUtensorMap tmV, const qd_attention_desc p, const int NV) {
+qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const qd_attention_desc p, const int NV, const int P) {
   extern __shared__ uint8_t atc_raw[];
   const uint32_t raw_addr = smem_u32(atc_raw);
   uint8_t* smem = atc_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  const AtcSmem L = atc_smem_layout(NV);
+  const AtcSmem L = atc_smem_layout(NV, P);
   uint8_t* sQ = smem + L.q_off;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
-  uint64_t* kv_full = bars;        // [2]
-  uint64_t* kv_empty = bars + 2;   // [2]
-  uint64_t* s_full = bars + 4;     // [2]
-  uint64_t* s_empty = bars + 6;    // [2]
-  uint64_t* p_full = bars + 8;     // [2]
-  uint64_t* p_empty = bars + 10;   // [2]
-  uint64_t* o_done = bars + 12;    // [1]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* kv_full = bars;        // [ATC_STAGES]
+  uint64_t* kv_empty = bars + 4;   // [ATC_STAGES]
+  uint64_t* s_full = bars + 8;     // [2]
+  uint64_t* s_empty = bars + 10;   // [2]
+  uint64_t* p_full = bars + 12;    // [2]
+  uint64_t* p_empty = bars + 14;   // [2]
+  uint64_t* o_done = bars + 16;    // [1]
+  uint64_t* q_full = bars + 17;    // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
@@ -68,33 +85,22 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmV, const qd_attention
   const int ntiles = (p.Tk + ATC_BN - 1) / ATC_BN;
   const bool has_zq = p.zq != 0;
 
-  const uint8_t* qbase = reinterpret_cast<const uint8_t*>(p.q) + (long long)b * p.Tq * p.ld_q + p.q_off + h * p.head_stride_q;
-  const uint8_t* kbase = reinterpret_cast<const uint8_t*>(p.k) + (long long)b * p.Tk * p.ld_k + p.k_off + h * p.head_stride_k;
   const int* zrk_g = reinterpret_cast<const int*>(p.ws) + (long long)bh * (long long)att_ws_stride(p.Tk);
 
-  // ---- one-time setup: zero Q/K regions (padding beyond d must be 0), constant rows of the V^T stages, Q tile
-  for (int i = threadIdx.x; i < (16384 * 3) / 16; i += ATC_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
-  for (int i = threadIdx.x; i < (2 * L.v_stage) / 16; i += ATC_THREADS)
+  // ---- one-time setup: V^T stages zeroed (rows beyond d feed the MMA), all-ones row d for the row sums
+  for (int i = threadIdx.x; i < (ATC_STAGES * L.v_stage) / 16; i += ATC_THREADS)
     reinterpret_cast<uint4*>(smem + L.v_off)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
-  {
-    // all-ones row d of both V^T stages (a constant row is invariant under the 128B swizzle)
-    for (int i = threadIdx.x; i < 2 * 8; i += ATC_THREADS)
-      reinterpret_cast<uint4*>(smem + L.v_off + (i >> 3) * L.v_stage + d * 128)[i & 7] =
-          make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
-    // Q tile: 8-byte pieces into the swizzled K-major layout (16 B chunk index ^= row & 7)
-    const int wpr = d >> 3;
-    for (int idx = threadIdx.x; idx < ATC_BM * wpr; idx += ATC_THREADS) {
-      const int r = idx / wpr, w = idx - r * wpr;
-      const int gr = min(row_base + r, p.Tq - 1);
-      const uint2 v = *reinterpret_cast<const uint2*>(qbase + (long long)gr * p.ld_q + 8 * w);
-      *reinterpret_cast<uint2*>(sQ + r * 128 + ((((w >> 1) ^ (r & 7)) << 4) | ((w & 1) << 3))) = v;
-    }
-  }
+  for (int i = threadIdx.x; i < ATC_STAGES * 8; i += ATC_THREADS)   // a constant row is invariant under the swizzle
+    reinterpret_cast<uint4*>(smem + L.v_off + (i >> 3) * L.v_stage + d * 128)[i & 7] =
+        make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < ATC_STAGES; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 9);    // MMA commit + 8 softmax warps (they read the zq*rowsum(k) slice of the stage)
+    }
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 8);
       mbar_init(&p_full[i], 8);
@@ -104,7 +110,7 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmV, const qd_attention
     fence_mbar_init();
   }
   if (warp == 0) {
-    if (lane == 0) tma_prefetch_desc(&tmV);
+    if (lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
     tmem_alloc(tmem_ptr, 512);
     tmem_relinquish();
   }
@@ -121,31 +127,26 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmV, const qd_attention
     // ===================== loader =====================
     int st = 0;
     uint32_t ph = 0;
-    const int wpr = d >> 3;
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, (uint32_t)(128 * P));
+      tma_load_2d(sQ, &tmQ, q_full, h * P, b * p.Tq + row_base);
+    }
     for (int pass = 0; pass < 2; ++pass) {
       for (int t = 0; t < ntiles; ++t) {
         const int j0 = t * ATC_BN;
         mbar_wait(&kv_empty[st], ph ^ 1);
-        uint8_t* dK = smem + L.k_off + st * 16384;
-        const int rows = min(ATC_BN, p.Tk - j0);
-        for (int idx = lane; idx < rows * wpr; idx += 32) {
-          const int r = idx / wpr, w = idx - r * wpr;
-          cp_async8(dK + r * 128 + ((((w >> 1) ^ (r & 7)) << 4) | ((w & 1) << 3)), kbase + (long long)(j0 + r) * p.ld_k + 8 * w);
+        if (has_zq) {
+          cp_async16(smem + L.zrk_off + st * 512 + 16 * lane, zrk_g + j0 + 4 * lane);
+          cp_async_commit();
+          cp_async_wait_all();
         }
-        if (has_zq) cp_async16(smem + L.zrk_off + st * 512 + 16 * lane, zrk_g + j0 + 4 * lane);
-        cp_async_commit();
-        cp_async_wait_all();
-        fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (pass == 1) {
-            mbar_arrive_expect_tx(&kv_full[st], (uint32_t)(d * 128));
-            tma_load_2d(smem + L.v_off + st * L.v_stage, &tmV, &kv_full[st], j0, bh * d);
-          } else {
-            mbar_arrive(&kv_full[st]);
-          }
+          mbar_arrive_expect_tx(&kv_full[st], (uint32_t)(128 * P + (pass == 1 ? d * 128 : 0)));
+          tma_load_2d(smem + L.k_off + st * L.k_stage, &tmK, &kv_full[st], h * P, b * p.Tk + j0);
+          if (pass == 1) tma_load_2d(smem + L.v_off + st * L.v_stage, &tmV, &kv_full[st], j0, bh * d);
         }
-        if (++st == 2) { st = 0; ph ^= 1; }
+        if (++st == ATC_STAGES) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -153,7 +154,8 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmV, const qd_attention
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_i8(128, 128, p.q_signed, p.k_signed);
       const uint32_t idesc_o = make_idesc_i8(128, NV, 0, p.v_signed);
-      const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ));
+      const uint64_t dq = make_smem_desc_sw(smem_u32(sQ), P);
+      mbar_wait(q_full, 0);
       int st = 0, sb = 0, pb = 0;
       uint32_t ph_kv = 0, ph_s = 0, ph_p = 0;
       // ---- pass 1: S only
@@ -161,16 +163,16 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmV, const qd_attention
         mbar_wait(&kv_full[st], ph_kv);
         mbar_wait(&s_empty[sb], ph_s ^ 1);
         tc_fence_after();
-        const uint64_t dk = make_smem_desc_sw128(smem_u32(smem + L.k_off + st * 16384));
+        const uint64_t dk = make_smem_desc_sw(smem_u32(smem + L.k_off + st * L.k_stage), P);
         for (int j = 0; j < nks; ++j) umma_i8(tm_s + sb * 128, dq + 2 * j, dk + 2 * j, idesc_s, j ? 1u : 0u);
         umma_commit(&s_full[sb]);
         umma_commit(&kv_empty[st]);
-        if (++st == 2) { st = 0; ph_kv ^= 1; }
+        if (++st == ATC_STAGES) { st = 0; ph_kv ^= 1; }
         if (++sb == 2) { sb = 0; ph_s ^= 1; }
       }
       // ---- pass 2: S(t+1) is issued before PV(t) so the softmax of t+1 overlaps the PV MMAs of t
       auto issue_s = [&](int st_, int sb_) {
-        const uint64_t dk = make_smem_desc_sw128(smem_u32(smem + L.k_off + st_ * 16384));
+        const uint64_t dk = make_smem_desc_sw(smem_u32(smem + L.k_off + st_ * L.k_stage), P);
         for (int j = 0; j < nks; ++j) umma_i8(tm_s + sb_ * 128, dq + 2 * j, dk + 2 * j, idesc_s, j ? 1u : 0u);
       };
       int st_s = st, sb_s = sb;
@@ -182,7 +184,7 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmV, const qd_attention
       umma_commit(&s_full[sb_s]);
       for (int t = 0; t < ntiles; ++t) {
         const int st_cur = st_s;
-        if (++st_s == 2) { st_s = 0; ph_kv_s ^= 1; }
+        if (++st_s == ATC_STAGES) { st_s = 0; ph_kv_s ^= 1; }
         if (++sb_s == 2) { sb_s = 0; ph_s_s ^= 1; }
         if (t + 1 < ntiles) {
           mbar_wait(&kv_full[st_s], ph_kv_s);
@@ -268,7 +270,7 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmV, const qd_attention
         mbar_arrive(&kv_empty[st]);
       }
       if (++sb == 2) { sb = 0; ph_s ^= 1; }
-      if (++st == 2) { st = 0; ph_kv ^= 1; }
+      if (++st == ATC_STAGES) { st = 0; ph_kv ^= 1; }
     }
     // ---- combine the two column halves of every row (named barrier over the 8 softmax warps)
     if (half == 1) stat[row] = make_float2(__int_as_float(mi), l);
@@ -345,7 +347,7 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmV, const qd_attention
         mbar_arrive(&p_full[pb]);
       }
       if (++sb == 2) { sb = 0; ph_s ^= 1; }
-      if (++st == 2) { st = 0; ph_kv ^= 1; }
+      if (++st == ATC_STAGES) { st = 0; ph_kv ^= 1; }
       if (++pb == 2) { pb = 0; ph_p ^= 1; }
     }
     // ---- epilogue: O = (256*hi + lo - zv*rowsum) * out_scale

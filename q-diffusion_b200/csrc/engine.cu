@@ -75,12 +75,13 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 int encode_u8_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                  const cuuint32_t* box) {
+                  const cuuint32_t* box, int swizzle_bytes = 128) {
   auto enc = get_encode();
   if (!enc) return fail(QD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(QD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return QD_OK;
@@ -186,6 +187,9 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
   a.out_q_transposed = d->out_q_transposed;
   a.rows_per_batch = d->rows_per_batch;
   if ((d->rowvec || d->out_q_transposed) && d->rows_per_batch <= 0) return fail(QD_ERR_BAD_ARG, "gemm: rows_per_batch required");
+  a.oq_d = d->out_q_head_dim; a.oq_pitch = d->out_q_head_pitch;
+  if (a.oq_d > 0 && ((a.oq_d & 3) || (a.oq_pitch & 3) || a.oq_pitch < a.oq_d || d->out_q_transposed || !d->out_q))
+    return fail(QD_ERR_BAD_ARG, "gemm: bad out_q head layout");
   a.q_delta = d->oq.delta; a.q_zp = d->oq.zero_point; a.q_lo = d->oq.qmin; a.q_hi = d->oq.qmax;
   a.scale = d->scale; a.bias = d->bias; a.corr = d->corr;
   a.rowvec = d->rowvec; a.ld_rowvec = d->ld_rowvec;
@@ -327,17 +331,19 @@ int launch_attention_t(const qd_attention_desc& d, cudaStream_t s) {
   return fail(QD_ERR_UNSUPPORTED, "attention: mixed signedness q=%d v=%d", d.q_signed, d.v_signed);
 }
 
-// tcgen05 path (attention_tc.cuh): d <= 112, dense V^T [B][heads*d][ld_vt]
+// tcgen05 path (attention_tc.cuh): d <= 112, Q/K codes in the per-head padded layout (pitch 32/64/128), dense V^T
 template <bool S16, bool MAGIC>
-int launch_attention_tc_inst(const qd_attention_desc& d, const CUtensorMap& tmV, int NV, cudaStream_t s) {
+int launch_attention_tc_inst(const qd_attention_desc& d, const CUtensorMap& tmQ, const CUtensorMap& tmK,
+                             const CUtensorMap& tmV, int NV, int P, cudaStream_t s) {
   auto kern = qd::qattention_tc_kernel<S16, MAGIC>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
   if (attr_err != cudaSuccess) return fail(QD_ERR_CUDA, "attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-  const qd::AtcSmem lay = qd::atc_smem_layout(NV);
+  const qd::AtcSmem lay = qd::atc_smem_layout(NV, P);
+  if (lay.total > 227 * 1024) return fail(QD_ERR_UNSUPPORTED, "attention_tc: %d B of shared memory", lay.total);
   dim3 grid((d.Tq + qd::ATC_BM - 1) / qd::ATC_BM, d.B * d.heads);
-  kern<<<grid, qd::ATC_THREADS, lay.total, s>>>(tmV, d, NV);
+  kern<<<grid, qd::ATC_THREADS, lay.total, s>>>(tmQ, tmK, tmV, d, NV, P);
   return check_launch("qattention_tc_kernel");
 }
 
@@ -348,17 +354,30 @@ bool attention_tc_eligible(const qd_attention_desc& d) {
     mode = (e && !strcmp(e, "mma")) ? 0 : 1;
   }
   if (!mode) return false;
+  const int P = d.head_stride_q;
   if (d.d > 112 || (d.d & 7)) return false;
+  if ((P != 32 && P != 64 && P != 128) || P < d.d || d.head_stride_k != P) return false;
+  if (d.q_off != 0 || d.k_off != 0 || d.ld_q != (long long)d.heads * P || d.ld_k != (long long)d.heads * P) return false;
   if (d.v_off != 0 || d.head_stride_v != d.d || d.v_batch_stride != (long long)d.heads * d.d * d.ld_vt) return false;
   if (d.out && ((d.ld_out & 3) || (((uintptr_t)d.out) & 15))) return false;
   if (d.out_q && (d.ld_out_q & 3)) return false;
-  if ((d.d * 255LL * 255LL) >= (1LL << 31)) return false;
   return true;
 }
 
 int launch_attention_tc(const qd_attention_desc& d, cudaStream_t s) {
   const int NV = (d.d + 1 + 15) / 16 * 16;
-  CUtensorMap tmV;
+  const int P = d.head_stride_q;
+  CUtensorMap tmQ, tmK, tmV;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d.ld_q, (cuuint64_t)d.B * d.Tq};
+    cuuint64_t strides[1] = {(cuuint64_t)d.ld_q};
+    cuuint32_t box[2] = {(cuuint32_t)P, 128};
+    int rc = encode_u8_map(&tmQ, d.q, 2, dims, strides, box, P);
+    if (rc) return rc;
+    dims[1] = (cuuint64_t)d.B * d.Tk;
+    rc = encode_u8_map(&tmK, d.k, 2, dims, strides, box, P);
+    if (rc) return rc;
+  }
   cuuint64_t dims[2] = {(cuuint64_t)d.ld_vt, (cuuint64_t)d.B * d.heads * d.d};
   cuuint64_t strides[1] = {(cuuint64_t)d.ld_vt};
   cuuint32_t box[2] = {128, (cuuint32_t)d.d};
@@ -373,10 +392,10 @@ int launch_attention_tc(const qd_attention_desc& d, cudaStream_t s) {
     if (rc) return rc;
   }
   const bool s16 = d.sm_bits > 8, magic = d.d <= 64;
-  if (s16 && magic) return launch_attention_tc_inst<true, true>(d, tmV, NV, s);
-  if (s16 && !magic) return launch_attention_tc_inst<true, false>(d, tmV, NV, s);
-  if (!s16 && magic) return launch_attention_tc_inst<false, true>(d, tmV, NV, s);
-  return launch_attention_tc_inst<false, false>(d, tmV, NV, s);
+  if (s16 && magic) return launch_attention_tc_inst<true, true>(d, tmQ, tmK, tmV, NV, P, s);
+  if (s16 && !magic) return launch_attention_tc_inst<true, false>(d, tmQ, tmK, tmV, NV, P, s);
+  if (!s16 && magic) return launch_attention_tc_inst<false, true>(d, tmQ, tmK, tmV, NV, P, s);
+  return launch_attention_tc_inst<false, false>(d, tmQ, tmK, tmV, NV, P, s);
 }
 
 int launch_attention(const qd_attention_desc& d, cudaStream_t s) {

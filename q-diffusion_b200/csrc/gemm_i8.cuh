@@ -65,6 +65,7 @@ struct GemmArgs {
   const float* residual;   // [M, ldr] or nullptr (may alias out)
   long long ldr;
   int geglu;
+  int oq_d, oq_pitch;      // > 0: per-head padded code layout for row-major out_q
 };
 
 struct GemmSmemLayout {
@@ -233,7 +234,9 @@ __device__ __forceinline__ void gemm_finalise4(const GemmArgs& p, const uint4 a4
   if (out_q) {
     const uint32_t q0 = gemm_quant_code(y[0], p), q1 = gemm_quant_code(y[1], p);
     const uint32_t q2 = gemm_quant_code(y[2], p), q3 = gemm_quant_code(y[3], p);
-    int8_t* o = p.out_q + (long long)m * p.ldq + n;
+    int nq = n;
+    if (p.oq_d > 0) { const int hq = n / p.oq_d; nq = hq * p.oq_pitch + (n - hq * p.oq_d); }
+    int8_t* o = p.out_q + (long long)m * p.ldq + nq;
     if (full && (G ? ((p.ldq & 3) == 0) : true)) {
       *reinterpret_cast<uint32_t*>(o) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
     } else {

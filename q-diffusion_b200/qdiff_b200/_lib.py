@@ -35,7 +35,7 @@ class GemmDesc(C.Structure):
         ("out", c_vp), ("ldo", c_ll),
         ("out_q", c_vp), ("ldq", c_ll),
         ("oq", QParams),
-        ("bn_hint", c_i32), ("geglu", c_i32),
+        ("bn_hint", c_i32), ("out_q_head_dim", c_i32), ("out_q_head_pitch", c_i32), ("geglu", c_i32),
     ]
 
 

@@ -241,7 +241,7 @@ class Builder:
 
     def gemm(self, qm, a, label, *, conv_bhw=None, out=None, out_cols_offset=0, rowvec=None, residual=None,
              out_q=None, out_scale=1.0, k_pad=None, cols=None, suffix="", zx=None, dx=None, accumulate_into=None,
-             rows_per_batch=0, use_bias=True, geglu_q=None, _ws=None, _wscale=1.0):
+             rows_per_batch=0, use_bias=True, geglu_q=None, _ws=None, _wscale=1.0, out_q_head=None):
         """Record one INT8 GEMM for QuantModule `qm` on activation codes `a`.
 
         W8: wq - zw spans [-255, 255] and does not fit the s8 operand.  Such layers run as TWO exact s8
@@ -266,7 +266,7 @@ class Builder:
                                  accumulate_into=accumulate_into, out_scale=out_scale, use_bias=use_bias,
                                  _ws=(wa, delta_w), _wscale=2.0, **kw)
                 return self.gemm(qm, a, label, out_q=out_q, accumulate_into=part, out_scale=out_scale, use_bias=False,
-                                 _ws=(wb, delta_w), _wscale=1.0, **kw)
+                                 _ws=(wb, delta_w), _wscale=1.0, out_q_head=out_q_head, **kw)
         else:
             ws, delta_w = _ws
         N = ws.shape[0]
@@ -319,6 +319,12 @@ class Builder:
                 self.keep.append(t)
                 oq_act = Act(t, M // T * N, t_pad, signed=signed)
                 oq_act.t_pad = t_pad
+            elif out_q_head is not None:
+                # per-head padded layout (pads stay zero: the epilogue never writes them)
+                cols_p = (N // out_q_head[0]) * out_q_head[1]
+                tz = torch.zeros((M, cols_p), dtype=torch.int8 if signed else torch.uint8, device=self.dev)
+                self.keep.append(tz)
+                oq_act = Act(tz, M, cols_p, signed=signed)
             else:
                 oq_act = self.new_codes(M, N // 2 if geglu_q is not None else N, signed)
             oq_act.zp, oq_act.delta = (oq_params.zero_point, None), (oq_params.delta, None)
@@ -331,7 +337,8 @@ class Builder:
                           out=o.t if o is not None else None, ldo=o.ld if o is not None else 0,
                           out_q=oq_act.t if oq_act is not None else None,
                           ldq=(oq_act.t_pad if transposed else oq_act.ld) if oq_act is not None else 0,
-                          oq=oq_params, out_q_transposed=transposed, geglu=geglu_q is not None)
+                          oq=oq_params, out_q_transposed=transposed, geglu=geglu_q is not None,
+                          out_q_head=out_q_head if (out_q is not None and not transposed) else None)
         d.a = a.ptr + (cols[0] if cols is not None else 0)
         if rowvec is not None:
             d.rowvec = rowvec.ptr
@@ -365,6 +372,11 @@ class Builder:
         self.add(_lib.QD_OP_IM2COL, d, label + ".im2col")
         patches.zp, patches.delta = a.zp, a.delta
         return self.gemm(qm, patches, label, k_pad=k_to, **kw)
+
+    @staticmethod
+    def head_pitch(d):
+        """Per-head pitch of the Q/K code layout: the tcgen05 attention kernel wants d padded to the TMA swizzle span."""
+        return 32 if d <= 32 else 64 if d <= 64 else 128 if d <= 112 else d
 
     # ------------------------------------------------------------------ attention recorder
     def attention(self, qc, kc, vt, *, heads, d, Tq, Tk, q_layout, k_layout, v_layout, sim_scale_extra, qw, label,
@@ -468,10 +480,11 @@ class Builder:
         heads = attn.heads
         inner = attn.to_q.weight.shape[0]
         d = inner // heads
-        qc = self.gemm(attn.to_q, x_codes_q, label + ".to_q", out_q=(attn.act_quantizer_q, False))
-        kc = self.gemm(attn.to_k, kv_codes[0], label + ".to_k", out_q=(attn.act_quantizer_k, False))
+        P = self.head_pitch(d)
+        qc = self.gemm(attn.to_q, x_codes_q, label + ".to_q", out_q=(attn.act_quantizer_q, False), out_q_head=(d, P))
+        kc = self.gemm(attn.to_k, kv_codes[0], label + ".to_k", out_q=(attn.act_quantizer_k, False), out_q_head=(d, P))
         vt = self.gemm(attn.to_v, kv_codes[1], label + ".to_v", out_q=(attn.act_quantizer_v, True), rows_per_batch=Tk)
-        o = self.attention(qc, kc, vt, heads=heads, d=d, Tq=Tq, Tk=Tk, q_layout=(0, d), k_layout=(0, d),
+        o = self.attention(qc, kc, vt, heads=heads, d=d, Tq=Tq, Tk=Tk, q_layout=(0, P), k_layout=(0, P),
                            v_layout=(0, d), sim_scale_extra=float(attn.scale), qw=attn.act_quantizer_w,
                            label=label + ".attn", consumer=attn.to_out[0])
         return self.gemm(attn.to_out[0], o, label + ".to_out.0", residual=h_res)
@@ -528,9 +541,10 @@ class Builder:
             rows = idx[:, j, :].reshape(-1)
             view = _RowView(blk.qkv, rows)
             parts.append(self.gemm(view, a, f"{k}.qkv.{'qkv'[j]}", out_q=(quantizer, transposed), out_scale=sc,
-                                   rows_per_batch=T))
+                                   rows_per_batch=T, out_q_head=None if transposed else (ch, self.head_pitch(ch))))
         qc, kc, vt = parts
-        o = self.attention(qc, kc, vt, heads=heads, d=ch, Tq=T, Tk=T, q_layout=(0, ch), k_layout=(0, ch),
+        Pq = self.head_pitch(ch)
+        o = self.attention(qc, kc, vt, heads=heads, d=ch, Tq=T, Tk=T, q_layout=(0, Pq), k_layout=(0, Pq),
                            v_layout=(0, ch), sim_scale_extra=1.0, qw=smv.act_quantizer_w, label=k + ".attention",
                            consumer=blk.proj_out)
         return self.gemm(blk.proj_out, o, k + ".proj_out", residual=x)
@@ -637,10 +651,11 @@ class Builder:
         C_ = x.cols
         aq, ak, av = self.groupnorm(x, blk.norm, T, [blk.q.act_quantizer, blk.k.act_quantizer, blk.v.act_quantizer],
                                     False, k + ".norm")[0]
-        qc = self.gemm(blk.q, aq, k + ".q", out_q=(blk.act_quantizer_q, False))
-        kc = self.gemm(blk.k, ak, k + ".k", out_q=(blk.act_quantizer_k, False))
+        Pq = self.head_pitch(C_)
+        qc = self.gemm(blk.q, aq, k + ".q", out_q=(blk.act_quantizer_q, False), out_q_head=(C_, Pq))
+        kc = self.gemm(blk.k, ak, k + ".k", out_q=(blk.act_quantizer_k, False), out_q_head=(C_, Pq))
         vt = self.gemm(blk.v, av, k + ".v", out_q=(blk.act_quantizer_v, True), rows_per_batch=T)
-        o = self.attention(qc, kc, vt, heads=1, d=C_, Tq=T, Tk=T, q_layout=(0, C_), k_layout=(0, C_), v_layout=(0, C_),
+        o = self.attention(qc, kc, vt, heads=1, d=C_, Tq=T, Tk=T, q_layout=(0, Pq), k_layout=(0, Pq), v_layout=(0, C_),
                            sim_scale_extra=float(int(C_) ** (-0.5)), qw=blk.act_quantizer_w, label=k + ".attn",
                            consumer=blk.proj_out)
         return self.gemm(blk.proj_out, o, k + ".proj_out", residual=x)

@@ -32,7 +32,7 @@ def _require_cuda(*ts):
 
 def gemm_desc(a, w, scale, *, M, N, C, taps=1, lda=None, conv_bhw=None, a_signed=True, bias=None, corr=None,
               rowvec=None, ld_rowvec=0, rows_per_batch=0, residual=None, ldr=0, out=None, ldo=0, out_q=None, ldq=0,
-              oq=None, out_q_transposed=False, bn_hint=0, w_rows=None, geglu=False):
+              oq=None, out_q_transposed=False, bn_hint=0, w_rows=None, geglu=False, out_q_head=None):
     d = GemmDesc()
     d.a, d.w = ptr(a), ptr(w)
     d.lda = int(lda if lda is not None else C)
@@ -50,6 +50,8 @@ def gemm_desc(a, w, scale, *, M, N, C, taps=1, lda=None, conv_bhw=None, a_signed
     d.oq = oq if oq is not None else qparams(1.0, 0, 0, 0)
     d.bn_hint = int(bn_hint)
     d.geglu = 1 if geglu else 0
+    if out_q_head is not None:
+        d.out_q_head_dim, d.out_q_head_pitch = int(out_q_head[0]), int(out_q_head[1])
     return d
 
 

@@ -285,8 +285,15 @@ def _run_attention(cuda, B, heads, d, Tq, Tk, sym, sm_bits, seed):
     ref = ref.reshape(B, heads, Tq, d).permute(0, 2, 1, 3).reshape(B, Tq, heads * d)
 
     dt = torch.int8 if sym else torch.uint8
-    qc = O.uaq_codes(q, *qp_q).to(dt).to(cuda)
-    kc = O.uaq_codes(k, *qp_k).to(dt).to(cuda)
+    P = 32 if d <= 32 else 64 if d <= 64 else 128 if d <= 112 else d     # per-head pitch of the code layout
+
+    def padded(t, T):
+        out = torch.zeros(B, T, heads, P, dtype=dt)
+        out[..., :d] = t.reshape(B, T, heads, d).to(dt)
+        return out.reshape(B, T, heads * P).to(cuda)
+
+    qc = padded(O.uaq_codes(q, *qp_q), Tq)
+    kc = padded(O.uaq_codes(k, *qp_k), Tk)
     vc = O.uaq_codes(v, *qp_v).to(dt)
     Tk_pad = (Tk + 15) // 16 * 16
     vt = torch.zeros(B, heads * d, Tk_pad, dtype=dt)
@@ -298,11 +305,12 @@ def _run_attention(cuda, B, heads, d, Tq, Tk, sym, sm_bits, seed):
     out = torch.full((B, Tq, heads * d), float("nan"), device=cuda)
     a = AttentionDesc()
     a.q, a.k, a.vt = ptr(qc), ptr(kc), ptr(vt)
-    a.ld_q = a.ld_k = heads * d
+    a.ld_q = a.ld_k = heads * P
     a.ld_vt, a.v_batch_stride = Tk_pad, heads * d * Tk_pad
     a.B, a.heads, a.d, a.Tq, a.Tk = B, heads, d, Tq, Tk
     a.q_off = a.k_off = a.v_off = 0
-    a.head_stride_q = a.head_stride_k = a.head_stride_v = d
+    a.head_stride_q = a.head_stride_k = P
+    a.head_stride_v = d
     a.q_signed = a.k_signed = a.v_signed = 1 if sym else 0
     a.zq, a.zk, a.zv, a.zw = qp_q[1], qp_k[1], qp_v[1], 0
     a.p_qmin, a.p_qmax, a.sm_bits = 0, 2 ** sm_bits - 1, sm_bits

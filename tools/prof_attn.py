@@ -12,16 +12,20 @@ from qdiff_b200._lib import AttentionDesc, ptr  # noqa: E402
 
 dev = torch.device("cuda:0")
 B, heads, d, T = 16, 8, 40, 4096
-q = torch.randint(0, 256, (B, T, heads * d), dtype=torch.uint8, device=dev)
-k = torch.randint(0, 256, (B, T, heads * d), dtype=torch.uint8, device=dev)
+P = 64
+q = torch.zeros(B, T, heads, P, dtype=torch.uint8, device=dev)
+q[..., :d] = torch.randint(0, 256, (B, T, heads, d), dtype=torch.uint8, device=dev)
+k = torch.zeros(B, T, heads, P, dtype=torch.uint8, device=dev)
+k[..., :d] = torch.randint(0, 256, (B, T, heads, d), dtype=torch.uint8, device=dev)
 vt = torch.randint(0, 256, (B, heads * d, T), dtype=torch.uint8, device=dev)
 out = torch.empty(B, T, heads * d, device=dev)
 a = AttentionDesc()
 a.q, a.k, a.vt = ptr(q), ptr(k), ptr(vt)
-a.ld_q = a.ld_k = heads * d
+a.ld_q = a.ld_k = heads * P
 a.ld_vt, a.v_batch_stride = T, heads * d * T
 a.B, a.heads, a.d, a.Tq, a.Tk = B, heads, d, T, T
-a.head_stride_q = a.head_stride_k = a.head_stride_v = d
+a.head_stride_q = a.head_stride_k = P
+a.head_stride_v = d
 a.zq, a.zk, a.zv, a.zw = 120, 131, 127, 0
 a.p_qmin, a.p_qmax, a.sm_bits = 0, 65535, 16
 a.sim_scale = 0.04 * 0.04 * d ** -0.5 * 0.05
