@@ -3,7 +3,7 @@
 // Same arithmetic as attention.cuh (integer QK^T, fp32 softmax in the exp2 domain, P re-quantised after
 // normalisation with the calibrated step, integer PV with hi/lo byte planes) but S and O live in TMEM, the
 // MMAs are issued by one thread, and each softmax thread owns one query ROW (half of the 128 key columns of
-// a tile): no fragment bookkeeping, no quad shuffles, no IMMA / fragment-LDS issue slots -> ~16 scalar
+// a tile; now a quarter: 16 softmax warps): no fragment bookkeeping, no quad shuffles, no IMMA / fragment-LDS issue slots -> ~16 scalar
 // instructions per score instead of ~24 (profiles/r01_attention_v2.txt).
 //
 // CTA = 128 query rows of one (batch, head); 10 warps:
@@ -12,7 +12,7 @@
 //                        keys) by TMA, zq*rowsum(k) slice by cp.async; 4-stage ring
 //   warp 1      MMA    : S = Q K^T  (M=128, N=128, K=32 x ceil(d/32)) into a double-buffered TMEM slot;
 //                        O_lo/O_hi += P_lo/P_hi V^T (M=128, N=NV, K=32 x 4), int32 in TMEM for the whole pass
-//   warps 2-9   softmax: thread = (row, column half); pass 1: integer row max + sum of exp2; pass 2: codes ->
+//   warps 2-17  softmax: thread = (row, 32-column quarter); pass 1: integer row max + sum of exp2; pass 2: codes ->
 //                        byte planes written to shared memory as the next MMA's A operand (128B swizzle,
 //                        V^T key permutation applied while packing)
 // Row sums of the P codes come from an all-ones V^T row (row d of the tile).
@@ -22,7 +22,8 @@
 
 namespace qd {
 
-constexpr int ATC_THREADS = 320;
+constexpr int ATC_SOFTMAX_WARPS = 16;   // 4 warps per TMEM lane quarter, 32 key columns of a tile each
+constexpr int ATC_THREADS = 64 + 32 * ATC_SOFTMAX_WARPS;
 constexpr int ATC_BM = 128, ATC_BN = 128;
 
 constexpr int ATC_STAGES = 4;
@@ -40,7 +41,7 @@ __host__ __device__ inline AtcSmem atc_smem_layout(int NV, int P) {
   l.p_off = (l.v_off + ATC_STAGES * l.v_stage + 1023) / 1024 * 1024;
   l.zrk_off = l.p_off + 4 * 16384;          // [buffer][plane]
   l.stat_off = l.zrk_off + ATC_STAGES * 512;
-  l.bar_off = l.stat_off + 128 * 8;
+  l.bar_off = l.stat_off + 4 * 128 * 8;
   l.total = l.bar_off + 256 + 1024;
   return l;
 }
@@ -97,13 +98,13 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < ATC_STAGES; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 9);    // MMA commit + 8 softmax warps (they read the zq*rowsum(k) slice of the stage)
+      mbar_init(&kv_empty[i], 1 + ATC_SOFTMAX_WARPS);    // MMA commit + softmax warps (they read the zq*rowsum(k) slice of the stage)
     }
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 8);
-      mbar_init(&p_full[i], 8);
+      mbar_init(&s_empty[i], ATC_SOFTMAX_WARPS);
+      mbar_init(&p_full[i], ATC_SOFTMAX_WARPS);
       mbar_init(&p_empty[i], 1);
     }
     mbar_init(o_done, 1);
@@ -211,7 +212,7 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   } else {
     // ===================== softmax warps =====================
     const int q4 = warp & 3;                 // TMEM lane quarter of this warp
-    const int half = (warp - 2) >> 2;        // which 64 key columns of a tile
+    const int part = (warp - 2) >> 2;        // which 32 key columns of a tile (0..3)
     const int row = q4 * 32 + lane;          // query row inside the CTA tile == TMEM lane
     const uint32_t t_lane = (uint32_t)(q4 * 32) << 16;
     const float c = p.sim_scale * 1.4426950408889634f;
@@ -223,35 +224,32 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     float l = 0.f;
     // ---- pass 1
     for (int t = 0; t < ntiles; ++t) {
-      const int j0 = t * ATC_BN + half * 64;
+      const int j0 = t * ATC_BN + part * 32;
       mbar_wait(&s_full[sb], ph_s);
       tc_fence_after();
-      const int* zr = reinterpret_cast<const int*>(smem + L.zrk_off + st * 512) + half * 64;
-#pragma unroll
-      for (int cb = 0; cb < 2; ++cb) {
+      const int* zr = reinterpret_cast<const int*>(smem + L.zrk_off + st * 512) + part * 32;
+      {
         uint32_t v[32];
-        tmem_ld_32x32(tm_s + t_lane + sb * 128 + half * 64 + cb * 32, v);
+        tmem_ld_32x32(tm_s + t_lane + sb * 128 + part * 32, v);
         tmem_ld_wait();
         int s[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           int4 z = make_int4(0, 0, 0, 0);
-          if (has_zq) z = *reinterpret_cast<const int4*>(zr + cb * 32 + j);
+          if (has_zq) z = *reinterpret_cast<const int4*>(zr + j);
           s[j] = (int)v[j] - z.x; s[j + 1] = (int)v[j + 1] - z.y; s[j + 2] = (int)v[j + 2] - z.z; s[j + 3] = (int)v[j + 3] - z.w;
         }
-        if (j0 + cb * 32 + 32 > p.Tk) {
+        bool any_valid = true;
+        if (j0 + 32 > p.Tk) {     // ragged last tile: masked keys drop out of the max and of the sum
+          any_valid = j0 < p.Tk;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (j0 + cb * 32 + j >= p.Tk) s[j] = INT_MIN / 2;
+            if (j0 + j >= p.Tk) s[j] = MAGIC ? -(1 << 22) + 1 : INT_MIN / 2;
         }
-        int tm = s[0];
+        if (any_valid) {
+          int tm = s[0];
 #pragma unroll
-        for (int j = 1; j < 32; ++j) tm = max(tm, s[j]);
-        if (MAGIC) {   // keep masked entries inside the exact range of the magic-constant conversion
-#pragma unroll
-          for (int j = 0; j < 32; ++j) s[j] = max(s[j], -(1 << 22) + 1);
-        }
-        if (tm != INT_MIN / 2) {   // a fully masked chunk contributes nothing (and must not seed the running max)
+          for (int j = 1; j < 32; ++j) tm = max(tm, s[j]);
           if (tm > mi) { l *= (mi == INT_MIN) ? 0.f : ex2_approx((float)(mi - tm) * c); mi = tm; }
           const float b0 = -(float)mi * c;
           float a0 = 0.f, a1 = 0.f;
@@ -273,54 +271,52 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (++st == ATC_STAGES) { st = 0; ph_kv ^= 1; }
     }
     // ---- combine the two column halves of every row (named barrier over the 8 softmax warps)
-    if (half == 1) stat[row] = make_float2(__int_as_float(mi), l);
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    stat[part * 128 + row] = make_float2(__int_as_float(mi), l);
+    asm volatile("bar.sync 1, 512;" ::: "memory");
     float off;
     {
-      if (half == 0) {
-        const float2 o = stat[row];
+      int mm = INT_MIN;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mm = max(mm, __float_as_int(stat[k * 128 + row].x));
+      float lt = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 o = stat[k * 128 + row];
         const int mo = __float_as_int(o.x);
-        const int mm = max(mi, mo);
-        const float lt = l * ((mi == INT_MIN) ? 0.f : ex2_approx((float)(mi - mm) * c)) +
-                         o.y * ((mo == INT_MIN) ? 0.f : ex2_approx((float)(mo - mm) * c));
-        off = -(float)mm * c + log2f(1.0f / (lt * p.delta_w));
+        lt += o.y * ((mo == INT_MIN) ? 0.f : ex2_approx((float)(mo - mm) * c));
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (half == 0) stat[row] = make_float2(off, 0.f);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      off = stat[row].x;
+      off = -(float)mm * c + log2f(1.0f / (lt * p.delta_w));
     }
     // ---- pass 2
     int pb = 0;
     uint32_t ph_p = 0;
     for (int t = 0; t < ntiles; ++t) {
-      const int j0 = t * ATC_BN + half * 64;
+      const int j0 = t * ATC_BN + part * 32;
       mbar_wait(&s_full[sb], ph_s);
       mbar_wait(&p_empty[pb], ph_p ^ 1);
       tc_fence_after();
-      const int* zr = reinterpret_cast<const int*>(smem + L.zrk_off + st * 512) + half * 64;
+      const int* zr = reinterpret_cast<const int*>(smem + L.zrk_off + st * 512) + part * 32;
       uint8_t* pl = smem + L.p_off + (pb * 2) * 16384 + row * 128;
       uint8_t* phh = pl + 16384;
-#pragma unroll
-      for (int cb = 0; cb < 2; ++cb) {
+      {
         uint32_t v[32];
-        tmem_ld_32x32(tm_s + t_lane + sb * 128 + half * 64 + cb * 32, v);
+        tmem_ld_32x32(tm_s + t_lane + sb * 128 + part * 32, v);
         tmem_ld_wait();
         uint32_t cd[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           int4 z = make_int4(0, 0, 0, 0);
-          if (has_zq) z = *reinterpret_cast<const int4*>(zr + cb * 32 + j);
+          if (has_zq) z = *reinterpret_cast<const int4*>(zr + j);
           const int s0 = (int)v[j] - z.x, s1 = (int)v[j + 1] - z.y, s2 = (int)v[j + 2] - z.z, s3 = (int)v[j + 3] - z.w;
           cd[j] = __float_as_uint(fminf(ex2_approx(fmaf(att_i2f<MAGIC>(s0), c, off)), pmax) + 12582912.0f);
           cd[j + 1] = __float_as_uint(fminf(ex2_approx(fmaf(att_i2f<MAGIC>(s1), c, off)), pmax) + 12582912.0f);
           cd[j + 2] = __float_as_uint(fminf(ex2_approx(fmaf(att_i2f<MAGIC>(s2), c, off)), pmax) + 12582912.0f);
           cd[j + 3] = __float_as_uint(fminf(ex2_approx(fmaf(att_i2f<MAGIC>(s3), c, off)), pmax) + 12582912.0f);
         }
-        if (j0 + cb * 32 + 32 > p.Tk) {
+        if (j0 + 32 > p.Tk) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (j0 + cb * 32 + j >= p.Tk) cd[j] = 0x4B400000u;   // code 0
+            if (j0 + j >= p.Tk) cd[j] = 0x4B400000u;   // code 0
         }
         // two groups of 16 keys; inside a group key 8a+2b+c goes to byte 4b+2a+c (att_vt_perm)
 #pragma unroll
@@ -332,7 +328,7 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             lo[bq] = __byte_perm(__byte_perm(e[2 * bq], e[2 * bq + 1], 0x0040), __byte_perm(e[8 + 2 * bq], e[9 + 2 * bq], 0x0040), 0x5410);
             if (SM16) hi[bq] = __byte_perm(__byte_perm(e[2 * bq], e[2 * bq + 1], 0x0051), __byte_perm(e[8 + 2 * bq], e[9 + 2 * bq], 0x0051), 0x5410);
           }
-          const int chunk = half * 4 + cb * 2 + gq;                 // 16-byte chunk of the 128-key row
+          const int chunk = part * 2 + gq;                         // 16-byte chunk of the 128-key row
           const int sw = (chunk ^ (row & 7)) << 4;
           *reinterpret_cast<uint4*>(pl + sw) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           if (SM16) *reinterpret_cast<uint4*>(phh + sw) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -353,7 +349,7 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // ---- epilogue: O = (256*hi + lo - zv*rowsum) * out_scale
     mbar_wait(o_done, 0);
     tc_fence_after();
-    if (half == 0) {
+    if (part == 0) {
       const int grow = row_base + row;
       float rs = 0.f;
       {
