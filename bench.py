@@ -44,27 +44,44 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe), sampled through NVML
+    (same counters as the nvidia-smi query, but fast enough to get several samples inside a sub-second region)."""
 
     def __init__(self, index):
         self.rows, self.stop, self.index = [], False, index
         self.th = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            while not self.stop:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((sm, mx, [n for n, bit in names.items() if r & bit]))
+                time.sleep(0.02)
+        except Exception as e:   # NVML unavailable: fall back to nvidia-smi polling
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            while not self.stop:
+                try:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                    self.rows.append((int(out[0]), int(out[1]), [n for i, n in enumerate(names) if out[2 + i].strip().lower().startswith("active")]))
+                except Exception:
+                    pass
+                time.sleep(0.05)
 
     def __enter__(self):
         self.th.start()
+        time.sleep(0.05)
         return self
 
     def __exit__(self, *a):
@@ -72,20 +89,22 @@ class ClockSampler:
         self.th.join(timeout=6)
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
-                    samples=len(self.rows))
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted({n for r in self.rows for n in r[2]})
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max((r[1] for r in self.rows), default=None),
+                    reasons=reasons, samples=len(self.rows))
 
 
-def cpu_baseline(max_seconds=40.0):
-    """The reference's CPU path (oracle port: fake-quant fp32 torch, all host threads) on a bounded sample:
+def cpu_baseline(ckpt=None, max_seconds=40.0):
+    """The reference's CPU path (oracle port: fake-quant fp32 torch, host threads) on a bounded sample:
     ONE UNet evaluation of ONE image of the same SD workload; images/s = 1 / (2 * 51 * t_eval)."""
+    import contextlib
     from oracle import synth_cfg
     from qdiff_b200 import synth
-    model, ckpt = synth.full_ckpt(WORKLOAD)
+    if ckpt is None:
+        with contextlib.redirect_stdout(sys.stderr):
+            _, ckpt = synth.full_ckpt(WORKLOAD)
+    ckpt = {k: (v.float() if k.endswith(".alpha") else v.cpu()) for k, v in ckpt.items()}
     x, t, ctx = synth.calib_inputs(WORKLOAD, batch=1, seed=99)
     with torch.no_grad():
         t0 = time.time()
@@ -106,11 +125,15 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(min(os.cpu_count() or 1, 32))
+    import contextlib
+    from qdiff_b200 import synth
+    with contextlib.redirect_stdout(sys.stderr):
+        _, ckpt_ref = synth.full_ckpt(WORKLOAD)
     times = []
     cb = None
     for i in range(args.warmup + args.steps):
-        cb = cpu_baseline(max_seconds=0.0)
+        cb = cpu_baseline(ckpt_ref, max_seconds=0.0)
         if i >= args.warmup:
             times.append(cb["unet_eval_s"])
         if sum(times) > 150:
@@ -194,7 +217,9 @@ def main():
     from qdiff_b200 import _lib, samplers, synth
     L = _lib.lib()
 
-    qnn, _ = synth.build_qnn(WORKLOAD, cuda_graph=not args.no_graph)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):   # the reference-compatible loaders print; stdout carries ONE JSON line
+        qnn, ckpt = synth.build_qnn(WORKLOAD, cuda_graph=not args.no_graph)
     B = IMAGES_PER_GPU
     # every rank draws the FULL batch from the same seed and keeps its shard (N-rank == 1-rank results)
     from qdiff_b200 import dist as qdist
@@ -308,8 +333,8 @@ def main():
         line["roofline"] = gemm_roofline(prog, pk)
         line["roofline"]["whole_step_frac"] = step_tops / line["roofline"]["peak"]
     if world == 1 and not args.no_cpu_baseline:
-        torch.set_num_threads(os.cpu_count() or 1)
-        cb = cpu_baseline()
+        torch.set_num_threads(min(os.cpu_count() or 1, 32))
+        cb = cpu_baseline(ckpt)
         cb["value"] = cb["value"]
         line["cpu_baseline"] = cb
     print(json.dumps(line))
