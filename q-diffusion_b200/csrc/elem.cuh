@@ -185,8 +185,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const qd_groupnorm_desc p
 #pragma unroll
         for (int o = 0; o < 3; ++o) {
           if (o < p.n_out) {
-            const uint32_t code = pack4(quant_code(y[0], qk[o]), quant_code(y[1], qk[o]), quant_code(y[2], qk[o]),
-                                        quant_code(y[3], qk[o]));
+            const uint32_t code = pack4(quant_code_fast(y[0], qk[o]), quant_code_fast(y[1], qk[o]),
+                                        quant_code_fast(y[2], qk[o]), quant_code_fast(y[3], qk[o]));
             *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.out_q[o]) + row * p.ld_q[o] + c) = code;
           }
         }
@@ -196,47 +196,64 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const qd_groupnorm_desc p
 }
 
 // ------------------------------------------------------------------------------------ layernorm
-// One warp per row; row kept in registers (C <= 4096), two-pass mean / variance in fp32.
-constexpr int LN_MAX_VEC = 32;  // float4 per lane -> C <= 4096
-__global__ void layernorm_quant_kernel(const qd_layernorm_desc p) {
+// One warp per row; the row lives in registers (NVEC float4 per lane, compile-time so it is NOT demoted to local
+// memory: the first version indexed a float4[32] array with a run-time trip count and spilled it, profiles/r01_*),
+// two-pass mean / variance in fp32, then 1-3 consumer quantizers.
+template <int NVEC>
+__global__ void __launch_bounds__(256) layernorm_quant_kernel(const qd_layernorm_desc p) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int cq = p.C >> 2;
   const QuantK qk[3] = {make_quantk(p.q[0]), make_quantk(p.q[1]), make_quantk(p.q[2])};
+  float4 g[NVEC], be[NVEC];
+#pragma unroll
+  for (int k = 0; k < NVEC; ++k) {
+    const int q = lane + 32 * k;
+    g[k] = q < cq ? *reinterpret_cast<const float4*>(p.gamma + (q << 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    be[k] = q < cq ? *reinterpret_cast<const float4*>(p.beta + (q << 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float inv_c = 1.0f / (float)p.C;
   for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < p.M;
        row += (long long)gridDim.x * warps_per_block) {
     const float* xr = p.x + row * p.ld_x;
-    float4 v[LN_MAX_VEC];
+    float4 v[NVEC];
     float s = 0.f;
-    int n = 0;
-    for (int q = lane; q < cq; q += 32, ++n) {
-      v[n] = *reinterpret_cast<const float4*>(xr + (q << 2));
-      s += (v[n].x + v[n].y) + (v[n].z + v[n].w);
-    }
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    const float mean = s / (float)p.C;
-    float ss = 0.f;
-    for (int k = 0; k < n; ++k) {
-      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
-      ss += (a * a + b * b) + (c * c + d * d);
-    }
-    for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-    const float rstd = 1.0f / sqrtf(ss / (float)p.C + p.eps);
-    n = 0;
-    for (int q = lane; q < cq; q += 32, ++n) {
-      const int c = q << 2;
-      const float4 g = *reinterpret_cast<const float4*>(p.gamma + c);
-      const float4 be = *reinterpret_cast<const float4*>(p.beta + c);
-      float y0 = (v[n].x - mean) * rstd * g.x + be.x;
-      float y1 = (v[n].y - mean) * rstd * g.y + be.y;
-      float y2 = (v[n].z - mean) * rstd * g.z + be.z;
-      float y3 = (v[n].w - mean) * rstd * g.w + be.w;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        if (k < p.n_out) {
-          const uint32_t o = pack4(quant_code(y0, qk[k]), quant_code(y1, qk[k]), quant_code(y2, qk[k]),
-                                   quant_code(y3, qk[k]));
-          *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.out_q[k]) + row * p.ld_q[k] + c) = o;
+    for (int k = 0; k < NVEC; ++k) {
+      const int q = lane + 32 * k;
+      v[k] = q < cq ? *reinterpret_cast<const float4*>(xr + (q << 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    const float mean = s * inv_c;
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < NVEC; ++k) {
+      if (lane + 32 * k < cq) {
+        const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+        ss += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    const float rstd = rsqrtf(ss * inv_c + p.eps);
+#pragma unroll
+    for (int k = 0; k < NVEC; ++k) {
+      const int q = lane + 32 * k;
+      if (q < cq) {
+        const int c = q << 2;
+        const float y0 = (v[k].x - mean) * rstd * g[k].x + be[k].x;
+        const float y1 = (v[k].y - mean) * rstd * g[k].y + be[k].y;
+        const float y2 = (v[k].z - mean) * rstd * g[k].z + be[k].z;
+        const float y3 = (v[k].w - mean) * rstd * g[k].w + be[k].w;
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+          if (o < p.n_out) {
+            const uint32_t code = pack4(quant_code_fast(y0, qk[o]), quant_code_fast(y1, qk[o]), quant_code_fast(y2, qk[o]),
+                                        quant_code_fast(y3, qk[o]));
+            *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.out_q[o]) + row * p.ld_q[o] + c) = code;
+          }
         }
       }
     }
@@ -271,6 +288,33 @@ __global__ void im2col_kernel(const qd_im2col_desc p) {
         val = (uint8_t)p.pad_code;
     }
     dst[i] = val;
+  }
+}
+
+// 16-byte variant (C % 16 == 0: the stride-2 Downsample convs): one thread = 16 channels of one tap of one output pixel
+__global__ void im2col_vec_kernel(const qd_im2col_desc p) {
+  const int c16 = p.C >> 4;
+  const long long total = (long long)p.B * p.Ho * p.Wo * 9 * c16;
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(p.src);
+  uint8_t* dst = reinterpret_cast<uint8_t*>(p.dst);
+  const uint32_t pc = (uint32_t)(p.pad_code & 0xFF) * 0x01010101u;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % c16);
+    long long t = i / c16;
+    const int tap = (int)(t % 9);
+    const long long r = t / 9;
+    const int ky = tap / 3, kx = tap - ky * 3;
+    const int wo = (int)(r % p.Wo);
+    const long long t2 = r / p.Wo;
+    const int ho = (int)(t2 % p.Ho);
+    const long long b = t2 / p.Ho;
+    const int h = ho * p.stride - p.pad_top + ky;
+    const int w = wo * p.stride - p.pad_left + kx;
+    uint4 v = make_uint4(pc, pc, pc, pc);
+    if (h >= 0 && h < p.H && w >= 0 && w < p.W)
+      v = *reinterpret_cast<const uint4*>(src + ((b * p.H + h) * p.W + w) * (long long)p.C + (cc << 4));
+    *reinterpret_cast<uint4*>(dst + r * p.ld_dst + tap * p.C + (cc << 4)) = v;
   }
 }
 

@@ -282,18 +282,38 @@ int launch_groupnorm(const qd_groupnorm_desc& d, cudaStream_t s) {
   return check_launch("gn_apply_kernel");
 }
 
+template <int NVEC>
+int launch_layernorm_t(const qd_layernorm_desc& d, cudaStream_t s) {
+  const int wpb = 8;
+  qd::layernorm_quant_kernel<NVEC><<<grid_for((long long)d.M * 32, wpb * 32, 8), wpb * 32, 0, s>>>(d);
+  return check_launch("layernorm_quant_kernel");
+}
+
 int launch_layernorm(const qd_layernorm_desc& d, cudaStream_t s) {
   if (!d.x || !d.gamma || !d.beta) return fail(QD_ERR_BAD_ARG, "layernorm: null arg");
-  if (d.C % 4 || d.C > 4 * 32 * qd::LN_MAX_VEC || d.ld_x % 4) return fail(QD_ERR_UNSUPPORTED, "layernorm: C=%d", d.C);
+  if (d.C % 4 || d.ld_x % 4) return fail(QD_ERR_UNSUPPORTED, "layernorm: C=%d", d.C);
   if (d.n_out < 1 || d.n_out > 3) return fail(QD_ERR_BAD_ARG, "layernorm: n_out");
-  const int wpb = 8;
-  qd::layernorm_quant_kernel<<<grid_for((long long)d.M * 32, wpb * 32, 4), wpb * 32, 0, s>>>(d);
-  return check_launch("layernorm_quant_kernel");
+  const int nvec = (d.C / 4 + 31) / 32;
+  switch (nvec) {
+    case 1: return launch_layernorm_t<1>(d, s);
+    case 2: return launch_layernorm_t<2>(d, s);
+    case 3: return launch_layernorm_t<3>(d, s);
+    case 4: return launch_layernorm_t<4>(d, s);
+    case 5: return launch_layernorm_t<5>(d, s);
+    case 6: case 7: case 8: return launch_layernorm_t<8>(d, s);
+    case 9: case 10: return launch_layernorm_t<10>(d, s);
+    case 11: case 12: case 13: case 14: case 15: case 16: return launch_layernorm_t<16>(d, s);
+    default: return fail(QD_ERR_UNSUPPORTED, "layernorm: C=%d exceeds 2048", d.C);
+  }
 }
 
 int launch_im2col(const qd_im2col_desc& d, cudaStream_t s) {
   if (!d.src || !d.dst) return fail(QD_ERR_BAD_ARG, "im2col: null arg");
   if (d.ld_dst < 9 * d.C) return fail(QD_ERR_BAD_ARG, "im2col: ld_dst too small");
+  if ((d.C % 16) == 0 && d.ld_dst == 9 * d.C && (d.ld_dst % 16) == 0) {
+    qd::im2col_vec_kernel<<<grid_for((long long)d.B * d.Ho * d.Wo * 9 * (d.C / 16), 256), 256, 0, s>>>(d);
+    return check_launch("im2col_vec_kernel");
+  }
   const long long total = (long long)d.B * d.Ho * d.Wo * d.ld_dst;
   qd::im2col_kernel<<<grid_for(total, 256), 256, 0, s>>>(d);
   return check_launch("im2col_kernel");

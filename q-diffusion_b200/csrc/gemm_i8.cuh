@@ -428,8 +428,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float x1 = (float)((int)ax.y - cx.y) * sx.y + bx.y, g1 = (float)((int)ag.y - cg.y) * sg.y + bg.y;
                 const float x2 = (float)((int)ax.z - cx.z) * sx.z + bx.z, g2 = (float)((int)ag.z - cg.z) * sg.z + bg.z;
                 const float x3 = (float)((int)ax.w - cx.w) * sx.w + bx.w, g3 = (float)((int)ag.w - cg.w) * sg.w + bg.w;
-                const uint32_t code = quant_code(x0 * gelu_erf(g0), qk) | (quant_code(x1 * gelu_erf(g1), qk) << 8) |
-                                      (quant_code(x2 * gelu_erf(g2), qk) << 16) | (quant_code(x3 * gelu_erf(g3), qk) << 24);
+                const uint32_t code = quant_code_fast(x0 * gelu_erf(g0), qk) | (quant_code_fast(x1 * gelu_erf(g1), qk) << 8) |
+                                      (quant_code_fast(x2 * gelu_erf(g2), qk) << 16) | (quant_code_fast(x3 * gelu_erf(g3), qk) << 24);
                 *reinterpret_cast<uint32_t*>(p.out_q + (long long)m * p.ldq + (nx >> 1)) = code;
               }
             }

@@ -18,8 +18,9 @@ namespace qd {
 
 struct QuantK {
   float delta, rdelta;
-  int bias;     // 0x4B400000 - zero_point
-  int lo, hi;
+  int bias;        // 0x4B400000 - zero_point
+  float flo, fhi;  // clamp range of q = y/delta BEFORE rounding: [qmin - zp, qmax - zp] (integers, so
+                   // clamp-then-round == round-then-clamp, and |q| stays inside the magic-constant range)
 };
 
 __device__ __forceinline__ QuantK make_quantk(float delta, int zero_point, int lo, int hi) {
@@ -27,21 +28,29 @@ __device__ __forceinline__ QuantK make_quantk(float delta, int zero_point, int l
   k.delta = delta;
   k.rdelta = __frcp_rn(delta);
   k.bias = 0x4B400000 - zero_point;
-  k.lo = lo;
-  k.hi = hi;
+  k.flo = (float)(lo - zero_point);
+  k.fhi = (float)(hi - zero_point);
   return k;
 }
 __device__ __forceinline__ QuantK make_quantk(const qd_qparams& q) {
   return make_quantk(q.delta, q.zero_point, q.qmin, q.qmax);
 }
 
+// Exact form (7 instructions): used where the input fp32 value is itself exact w.r.t. the reference
+// (standalone quantizer, GEMM epilogues).
 __device__ __forceinline__ uint32_t quant_code(float y, const QuantK& k) {
   const float q0 = y * k.rdelta;
   float q = fmaf(fmaf(-q0, k.delta, y), k.rdelta, q0);
-  q = fminf(fmaxf(q, -4.0e6f), 4.0e6f);
-  int i = __float_as_int(q + 12582912.0f) - k.bias;   // rne(q) + zero_point
-  i = min(max(i, k.lo), k.hi);
-  return (uint32_t)i & 0xFFu;
+  q = fminf(fmaxf(q, k.flo), k.fhi);
+  return (uint32_t)(__float_as_int(q + 12582912.0f) - k.bias) & 0xFFu;   // rne(q) + zero_point
+}
+
+// Fast form (5 instructions, reciprocal multiply without the Newton step): y*r differs from y/delta by <= 1 ulp,
+// which can move a code only when the quotient sits within 1 ulp of a rounding boundary (~1e-5 of elements).
+// Used behind SiLU / GELU / normalisation, whose inputs already differ from the reference by ulps.
+__device__ __forceinline__ uint32_t quant_code_fast(float y, const QuantK& k) {
+  const float q = fminf(fmaxf(y * k.rdelta, k.flo), k.fhi);
+  return (uint32_t)(__float_as_int(q + 12582912.0f) - k.bias) & 0xFFu;
 }
 
 // x * sigmoid(x) with 2 XU operations (ex2, rcp); ~2 ulp, inside the reference's own fp32 noise band.

@@ -232,15 +232,16 @@ def test_layernorm_quant(cuda, C, n_out):
         assert diff.max() <= 1 and (diff > 0).float().mean() < 2e-3, (int(diff.max()), float((diff > 0).float().mean()))
 
 
-@pytest.mark.parametrize("stride,pad_tl,pad_total", [(2, (1, 1), 2), (2, (0, 0), 1), (1, (1, 1), 2)])
-def test_im2col(cuda, stride, pad_tl, pad_total):
+@pytest.mark.parametrize("stride,pad_tl,pad_total,C", [(2, (1, 1), 2, 12), (2, (0, 0), 1, 12), (1, (1, 1), 2, 12),
+                                                        (2, (1, 1), 2, 32), (2, (0, 0), 1, 16)])
+def test_im2col(cuda, stride, pad_tl, pad_total, C):
     ops, _ = _ops()
     gen = torch.Generator().manual_seed(23)
-    B, H, W, C = 2, 8, 8, 12
+    B, H, W = 2, 8, 8
     x = torch.randint(0, 256, (B, H, W, C), generator=gen).to(torch.uint8)
     Ho = (H + pad_total - 3) // stride + 1
     Wo = (W + pad_total - 3) // stride + 1
-    ld = 128
+    ld = 128 if C % 16 else 9 * C     # the 16-byte kernel needs the dense layout
     dst = torch.full((B * Ho * Wo, ld), 7, dtype=torch.uint8, device=cuda)
     d = ops.im2col_desc(x.to(cuda), dst, B=B, H=H, W=W, C_=C, Ho=Ho, Wo=Wo, stride=stride, pad_top=pad_tl[0],
                         pad_left=pad_tl[1], pad_code=77, ld_dst=ld)
