@@ -216,6 +216,9 @@ int launch_gemm_mode(const GemmPlan& pl, cudaStream_t s) {
 int gemm_mode(const qd::GemmArgs& a) {
   const bool f = a.out != nullptr, q = a.out_q != nullptr;
   if (a.geglu) return qd::EPI_GEGLU | qd::EPI_OUT_Q | (a.corr ? qd::EPI_CORR : 0);
+  if (a.out_q_transposed && q && !f && !a.rowvec && !a.residual && a.taps == 1 && a.oq_d == 0 &&
+      a.rows_per_batch % 32 == 0 && (a.ldq & 15) == 0 && (reinterpret_cast<uintptr_t>(a.out_q) & 15) == 0)
+    return qd::EPI_TRANS | qd::EPI_OUT_Q | (a.corr ? qd::EPI_CORR : 0);
   if (f == q || a.out_q_transposed || (a.N & 3)) return -1;
   if (a.rowvec && a.residual) return -1;
   if (q && a.rowvec) return -1;
@@ -240,6 +243,8 @@ int launch_gemm(const GemmPlan& pl, cudaStream_t s) {
     case EPI_OUT_Q | EPI_CORR: return launch_gemm_mode<EPI_OUT_Q | EPI_CORR>(pl, s);
     case EPI_OUT_Q | EPI_RESIDUAL: return launch_gemm_mode<EPI_OUT_Q | EPI_RESIDUAL>(pl, s);
     case EPI_OUT_Q | EPI_RESIDUAL | EPI_CORR: return launch_gemm_mode<EPI_OUT_Q | EPI_RESIDUAL | EPI_CORR>(pl, s);
+    case EPI_TRANS | EPI_OUT_Q: return launch_gemm_mode<EPI_TRANS | EPI_OUT_Q>(pl, s);
+    case EPI_TRANS | EPI_OUT_Q | EPI_CORR: return launch_gemm_mode<EPI_TRANS | EPI_OUT_Q | EPI_CORR>(pl, s);
     case EPI_GEGLU | EPI_OUT_Q: return launch_gemm_mode<EPI_GEGLU | EPI_OUT_Q>(pl, s);
     case EPI_GEGLU | EPI_OUT_Q | EPI_CORR: return launch_gemm_mode<EPI_GEGLU | EPI_OUT_Q | EPI_CORR>(pl, s);
     default: return launch_gemm_mode<-1>(pl, s);

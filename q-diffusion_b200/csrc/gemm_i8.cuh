@@ -19,6 +19,7 @@
 #pragma once
 #include "ptx.cuh"
 #include "quant_math.cuh"
+#include <type_traits>
 
 namespace qd {
 
@@ -37,6 +38,7 @@ constexpr int EPI_RESIDUAL = 4;   // + residual[m, n]
 constexpr int EPI_OUT_F32 = 8;    // fp32 output
 constexpr int EPI_OUT_Q = 16;     // requantised code output (row-major)
 constexpr int EPI_GEGLU = 32;     // columns interleaved [4 x, 4 gate]: out_q = Q(x * gelu(gate)), N/2 columns
+constexpr int EPI_TRANS = 64;     // requantised code output, transposed [img][n][token'] (V^T operand of qattention)
 
 struct GemmArgs {
   int M, N;            // logical output rows / columns (columns >= N are masked)
@@ -99,16 +101,16 @@ __device__ __forceinline__ void gemm_row_meta(const GemmArgs& p, int m, int& cls
   }
 }
 
-__device__ __forceinline__ uint32_t gemm_quant_code(float y, const GemmArgs& p) {
-  // consumer's activation quantizer (qdiff/quant_layer.py:82-88), XU-free form of quant_math.cuh
-  return quant_code(y, make_quantk(p.q_delta, p.q_zp, p.q_lo, p.q_hi));
-}
+// The consumer's activation quantizer (qdiff/quant_layer.py:82-88) is applied with quant_math.cuh's QuantK,
+// built ONCE per thread before the tile loop: building it (MUFU.RCP + Newton + slow-path test) inside the
+// per-row code, where the compiler will not hoist it out of the `m < M` conditional, tripled the instruction
+// count of the requantising epilogues (profiles/r01_gemm_smallk.txt).
 
 // Thread-per-row epilogue (used for the transposed V^T code output: consecutive lanes = consecutive
 // tokens, so each per-column byte store of the warp fills one 32 B sector).
 template <int NC>
-__device__ __forceinline__ void gemm_epilogue_rowwise(const GemmArgs& p, const uint32_t (&acc)[NC], int m, int n0,
-                                                      int cls, int img) {
+__device__ __forceinline__ void gemm_epilogue_rowwise(const GemmArgs& p, const QuantK& qk, const uint32_t (&acc)[NC],
+                                                      int m, int n0, int cls, int img) {
   float y[NC];
   if (((p.N & 3) == 0) && n0 + NC <= p.N && !p.rowvec) {
     // vector parameter loads (uniform across the warp): 3 x LDG.128 per 4 columns instead of 12 scalar loads
@@ -159,16 +161,16 @@ __device__ __forceinline__ void gemm_epilogue_rowwise(const GemmArgs& p, const u
     int8_t* o = p.out_q + ((long long)img * p.N + n0) * p.ldq + t_pos;
 #pragma unroll
     for (int j = 0; j < NC; ++j)
-      if (n0 + j < p.N) o[(long long)j * p.ldq] = (int8_t)gemm_quant_code(y[j], p);
+      if (n0 + j < p.N) o[(long long)j * p.ldq] = (int8_t)quant_code(y[j], qk);
   }
 }
 
 // Finalise 4 consecutive columns of one row.  MODE >= 0: flags are compile-time, N % 4 == 0 and all
 // leading dimensions are vector-aligned (checked on the host).  MODE < 0: everything at run time.
 template <int MODE>
-__device__ __forceinline__ void gemm_finalise4(const GemmArgs& p, const uint4 a4, const float (&sc)[4],
-                                               const float (&bi)[4], const int4 corr4, const float4 rpre, int m, int n,
-                                               int cls, int img) {
+__device__ __forceinline__ void gemm_finalise4(const GemmArgs& p, const QuantK& qk, const bool conv, const uint4 a4,
+                                               const float (&sc)[4], const float (&bi)[4], const int4 corr4,
+                                               const float4 rpre, int m, int n, int nq, int cls, int img) {
   constexpr bool G = MODE < 0;
   const bool has_corr = G ? (p.corr != nullptr) : bool(MODE & EPI_CORR);
   const bool has_rowvec = G ? (p.rowvec != nullptr) : bool(MODE & EPI_ROWVEC);
@@ -178,7 +180,7 @@ __device__ __forceinline__ void gemm_finalise4(const GemmArgs& p, const uint4 a4
   const bool full = G ? (n + 3 < p.N) : true;
   int a[4] = {(int)a4.x, (int)a4.y, (int)a4.z, (int)a4.w};
   if (has_corr) {
-    if (p.taps == 9) {
+    if (G && conv) {
       if (full) {
         const int4 c = __ldg(reinterpret_cast<const int4*>(p.corr + (long long)cls * p.N + n));
         a[0] -= c.x; a[1] -= c.y; a[2] -= c.z; a[3] -= c.w;
@@ -232,10 +234,8 @@ __device__ __forceinline__ void gemm_finalise4(const GemmArgs& p, const uint4 a4
     }
   }
   if (out_q) {
-    const uint32_t q0 = gemm_quant_code(y[0], p), q1 = gemm_quant_code(y[1], p);
-    const uint32_t q2 = gemm_quant_code(y[2], p), q3 = gemm_quant_code(y[3], p);
-    int nq = n;
-    if (p.oq_d > 0) { const int hq = n / p.oq_d; nq = hq * p.oq_pitch + (n - hq * p.oq_d); }
+    const uint32_t q0 = quant_code(y[0], qk), q1 = quant_code(y[1], qk);
+    const uint32_t q2 = quant_code(y[2], qk), q3 = quant_code(y[3], qk);
     int8_t* o = p.out_q + (long long)m * p.ldq + nq;
     if (full && (G ? ((p.ldq & 3) == 0) : true)) {
       *reinterpret_cast<uint32_t*>(o) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
@@ -373,6 +373,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* stg = smem + lay.stage_off + (warp - 4) * GEMM_EPI_TILE_BYTES;
     const int rsub = lane >> 3;   // row within a group of 4
     const int cq = lane & 7;      // column quad within the 32-column chunk
+    const QuantK qk = make_quantk(p.q_delta, p.q_zp, p.q_lo, p.q_hi);
+    const bool conv = p.taps == 9;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -381,19 +383,71 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n_base = tn * p.BN;
       const int m_warp = tm * GEMM_BM + q * 32;
       const bool transposed = (MODE < 0) && p.out_q_transposed;
+      constexpr bool kTrans = MODE >= 0 && (MODE & EPI_TRANS) != 0;
       int cls8[8], img8[8];
-      if (!transposed) {
+      if (!transposed && !kTrans) {
 #pragma unroll
         for (int it = 0; it < 8; ++it) gemm_row_meta(p, m_warp + it * 4 + rsub, cls8[it], img8[it]);
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
-      if constexpr (MODE >= 0 && (MODE & EPI_GEGLU) != 0) {
+      if constexpr (kTrans) {
+        // V^T code output [img][n][token'] (token' = att_vt_perm order inside each group of 16).  The warp's
+        // 32 tokens x 32 channels go through the staging tile; each lane then owns ONE channel and emits whole
+        // 16-token groups as 16 B stores (the thread-per-row form below needs 32 byte stores per lane and chunk).
+        // Host guarantees rows_per_batch % 32 == 0 (a warp never straddles images), ldq % 16 == 0.
+        const int img = m_warp / p.rows_per_batch;
+        const int tok0 = m_warp - img * p.rows_per_batch;
+        for (int c = half * 32; c < p.BN; c += 64) {
+          const int ncols = (p.BN - c) >= 32 ? 32 : 16;
+          if (ncols == 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + (uint32_t)c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint32_t v[16];
+            tmem_ld_32x16(t_row + (uint32_t)c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          __syncwarp();
+          const int col = ncols == 32 ? lane : (lane & 15);
+          const int n = n_base + c + col;
+          if (m_warp < p.M && n < p.N) {
+            const float sc1 = __ldg(p.scale + n);
+            const float bi1 = p.bias ? __ldg(p.bias + n) : 0.f;
+            int cr = 0;
+            if constexpr ((MODE & EPI_CORR) != 0) cr = __ldg(p.corr + n);
+            int8_t* o = p.out_q + ((long long)img * p.N + n) * p.ldq + tok0;
+            const uint8_t* src = stg + (col & 3) * 4;
+            const int cj = col >> 2;
+            const int g0 = ncols == 32 ? 0 : (lane >> 4), g1 = ncols == 32 ? 2 : g0 + 1;
+            for (int g = g0; g < g1; ++g) {
+              uint32_t w4[4];
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                const int r7 = (((k >> 1) & 1) << 3) | (((k >> 2) & 3) << 1) | (k & 1);   // token of byte k
+                const int a = *reinterpret_cast<const int*>(src + (g * 16 + r7) * 128 + ((cj ^ (r7 & 7)) << 4));
+                const uint32_t qv = quant_code((float)(a - cr) * sc1 + bi1, qk);
+                w4[k >> 2] = (k & 3) ? (w4[k >> 2] | (qv << (8 * (k & 3)))) : qv;
+              }
+              *reinterpret_cast<uint4*>(o + g * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+          }
+          __syncwarp();
+        }
+      } else if constexpr (MODE >= 0 && (MODE & EPI_GEGLU) != 0) {
         // GEGLU projection (ldm/modules/attention.py:42-44) fused with the consumer's quantizer: a 32-column chunk
         // holds 4 x (4 x-features | 4 gate-features); lane -> (row group of 8, pair); 4 iterations cover 32 rows.
         const int r8 = lane >> 2, pq = lane & 3;
-        const QuantK qk = make_quantk(p.q_delta, p.q_zp, p.q_lo, p.q_hi);
         for (int c = half * 32; c < p.BN; c += 64) {
           uint32_t v[32];
           tmem_ld_32x32(t_row + (uint32_t)c, v);
@@ -428,8 +482,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float x1 = (float)((int)ax.y - cx.y) * sx.y + bx.y, g1 = (float)((int)ag.y - cg.y) * sg.y + bg.y;
                 const float x2 = (float)((int)ax.z - cx.z) * sx.z + bx.z, g2 = (float)((int)ag.z - cg.z) * sg.z + bg.z;
                 const float x3 = (float)((int)ax.w - cx.w) * sx.w + bx.w, g3 = (float)((int)ag.w - cg.w) * sg.w + bg.w;
-                const uint32_t code = quant_code_fast(x0 * gelu_erf(g0), qk) | (quant_code_fast(x1 * gelu_erf(g1), qk) << 8) |
-                                      (quant_code_fast(x2 * gelu_erf(g2), qk) << 16) | (quant_code_fast(x3 * gelu_erf(g3), qk) << 24);
+                const uint32_t code = quant_code_fast(x0 * gelu_fast(g0), qk) | (quant_code_fast(x1 * gelu_fast(g1), qk) << 8) |
+                                      (quant_code_fast(x2 * gelu_fast(g2), qk) << 16) | (quant_code_fast(x3 * gelu_fast(g3), qk) << 24);
                 *reinterpret_cast<uint32_t*>(p.out_q + (long long)m * p.ldq + (nx >> 1)) = code;
               }
             }
@@ -445,12 +499,12 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t v[32];
             tmem_ld_32x32(t_row + (uint32_t)c, v);
             tmem_ld_wait();
-            if (m < p.M && n_base + c < p.N) gemm_epilogue_rowwise<32>(p, v, m, n_base + c, cls, img);
+            if (m < p.M && n_base + c < p.N) gemm_epilogue_rowwise<32>(p, qk, v, m, n_base + c, cls, img);
           } else {
             uint32_t v[16];
             tmem_ld_32x16(t_row + (uint32_t)c, v);
             tmem_ld_wait();
-            if (m < p.M && n_base + c < p.N) gemm_epilogue_rowwise<16>(p, v, m, n_base + c, cls, img);
+            if (m < p.M && n_base + c < p.N) gemm_epilogue_rowwise<16>(p, qk, v, m, n_base + c, cls, img);
           }
         }
       } else {
@@ -499,24 +553,44 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
               corr4 = make_int4(cc[0], cc[1], cc[2], cc[3]);
             }
-            float4 rpre[8];
+            int nq = n;   // column of the code output (per-head padded layout: attention Q/K operands)
+            if (p.oq_d > 0) { const int hq = n / p.oq_d; nq = hq * p.oq_pitch + (n - hq * p.oq_d); }
+            // Rows are finalised four at a time with everything they need from global memory (residual, conv
+            // border-class correction) fetched up front, and - on the full-tile path - without any per-row
+            // branch: the `m < M` tests split the unrolled loop into basic blocks, and with two epilogue warps
+            // per scheduler the resulting dependent-issue chains (stall_wait) bounded the small-K GEMMs.
+            auto rows = [&](auto full_tag) {
+              constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              rpre[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if constexpr (MODE >= 0 && (MODE & EPI_RESIDUAL) != 0) {
-                const int m = m_warp + it * 4 + rsub;
-                if (m < p.M) rpre[it] = *reinterpret_cast<const float4*>(p.residual + (long long)m * p.ldr + n);
-              }
-            }
+              for (int h4 = 0; h4 < 8; h4 += 4) {
+                float4 rpre[4];
+                int4 cpre[4];
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int row = it * 4 + rsub;
-              const int m = m_warp + row;
-              if (m < p.M) {
-                const uint4 a4 = *reinterpret_cast<const uint4*>(stg + row * 128 + ((cq ^ (row & 7)) << 4));
-                gemm_finalise4<MODE>(p, a4, sc, bi, corr4, rpre[it], m, n, cls8[it], img8[it]);
+                for (int i = 0; i < 4; ++i) {
+                  const int it = h4 + i;
+                  const int m = m_warp + it * 4 + rsub;
+                  rpre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                  cpre[i] = corr4;
+                  if constexpr (MODE >= 0 && (MODE & EPI_RESIDUAL) != 0) {
+                    if (FULL || m < p.M) rpre[i] = *reinterpret_cast<const float4*>(p.residual + (long long)m * p.ldr + n);
+                  }
+                  if constexpr (MODE >= 0 && (MODE & EPI_CORR) != 0) {
+                    if (conv) cpre[i] = __ldg(reinterpret_cast<const int4*>(p.corr + (long long)cls8[it] * p.N + n));
+                  }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int it = h4 + i;
+                  const int row = it * 4 + rsub;
+                  const int m = m_warp + row;
+                  if (FULL || m < p.M) {
+                    const uint4 a4 = *reinterpret_cast<const uint4*>(stg + row * 128 + ((cq ^ (row & 7)) << 4));
+                    gemm_finalise4<MODE>(p, qk, conv, a4, sc, bi, cpre[i], rpre[i], m, n, nq, cls8[it], img8[it]);
+                  }
+                }
               }
-            }
+            };
+            if (m_warp + 32 <= p.M) rows(std::true_type{}); else rows(std::false_type{});
           }
           __syncwarp();
         }
