@@ -90,8 +90,6 @@ __global__ void att_krowsum_kernel(const qd_attention_desc p, int tk_pad) {
   }
 }
 
-__device__ __forceinline__ uint32_t att_quant(float y, const qd_qparams& q) { return quant_code(y, make_quantk(q)); }
-
 constexpr int ATT_WARPS = 8;
 constexpr int ATT_BM = 16 * ATT_WARPS;  // query rows per CTA
 constexpr int ATT_BN = 64;              // keys per tile
@@ -217,6 +215,7 @@ qattention_kernel(const qd_attention_desc p) {
 #pragma unroll
   for (int i = 0; i < (SM16 ? NDT : 1); ++i) { ohi[i][0] = ohi[i][1] = ohi[i][2] = ohi[i][3] = 0; }
   const float pmax = (float)p.p_qmax;
+  const QuantK oqk = make_quantk(p.oq);
 
   int buf = 0;
   for (int pass = 0; pass < 2; ++pass) {
@@ -356,10 +355,215 @@ qattention_kernel(const qd_attention_desc p) {
       uint8_t* oq = reinterpret_cast<uint8_t*>(p.out_q);
       if (r0 < p.Tq)
         *reinterpret_cast<uint16_t*>(oq + ((long long)b * p.Tq + r0) * p.ld_out_q + col) =
-            (uint16_t)(att_quant(y0, p.oq) | (att_quant(y1, p.oq) << 8));
+            (uint16_t)(quant_code(y0, oqk) | (quant_code(y1, oqk) << 8));
       if (r1 < p.Tq)
         *reinterpret_cast<uint16_t*>(oq + ((long long)b * p.Tq + r1) * p.ld_out_q + col) =
-            (uint16_t)(att_quant(y2, p.oq) | (att_quant(y3, p.oq) << 8));
+            (uint16_t)(quant_code(y2, oqk) | (quant_code(y3, oqk) << 8));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small-Tk variant (cross-attention: Tk = 77 context tokens).  The whole key range is one tile, so
+//   * K, V^T and zq*rowsum(k) are staged in shared memory ONCE per CTA (the row sums are computed here: no
+//     separate att_krowsum launch) and each warp then streams 16-query slabs past them;
+//   * the softmax is a single pass over register-resident scores (max, sum, codes from the same accumulators).
+// The two-pass kernels above pay their per-CTA prologue (tile ring, barriers, TMEM allocation for the tcgen05
+// one) per 128 queries; with ~80 keys that prologue was 90% of the run time (profiles/r01_cross_attention.txt).
+// Arithmetic is the same as qattention_kernel (same exp2-domain formulas, same fragment/key permutations).
+constexpr int ATS_WARPS = 4;
+
+template <int DQ, int DV, int NKV>
+__host__ __device__ constexpr int ats_smem_bytes() {
+  return NKV * 32 * att_kp(DQ) + (DV + 8) * (NKV * 32 + 16) + NKV * 32 * 4;
+}
+
+template <int DQ, int DV, bool QK_SIGNED, bool V_SIGNED, bool SM16, int NKV>
+__global__ void __launch_bounds__(ATS_WARPS * 32)
+qattention_smallk_kernel(const qd_attention_desc p, int slabs_per_warp) {
+  constexpr int KP = att_kp(DQ);
+  constexpr int TKP = NKV * 32;     // padded key count
+  constexpr int NT8 = NKV * 4;      // n8 tiles of S
+  constexpr int VP = TKP + 16;
+  constexpr int NKC = DQ / 32;
+  constexpr int NDT = DV / 8 + 1;
+  constexpr int KB = TKP * KP, VB = (DV + 8) * VP;
+  constexpr bool MAGIC = DV <= 64;
+  constexpr int WPR = DV / 8;
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  uint8_t* sK = att_smem;
+  uint8_t* sV = att_smem + KB;
+  int* sZrk = reinterpret_cast<int*>(att_smem + KB + VB);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int bh = blockIdx.y;
+  const int b = bh / p.heads, h = bh - b * p.heads;
+  const uint8_t* qbase = reinterpret_cast<const uint8_t*>(p.q) + (long long)b * p.Tq * p.ld_q + p.q_off +
+                         h * p.head_stride_q;
+  const uint8_t* kbase = reinterpret_cast<const uint8_t*>(p.k) + (long long)b * p.Tk * p.ld_k + p.k_off +
+                         h * p.head_stride_k;
+  const uint8_t* vbase = reinterpret_cast<const uint8_t*>(p.vt) + (long long)b * p.v_batch_stride +
+                         (long long)(p.v_off + h * p.head_stride_v) * p.ld_vt;
+
+  // ---- stage K (d..DQ padding and rows >= Tk stay 0), V^T (+ all-ones row) and zq*rowsum(k)
+  for (int i = threadIdx.x; i < (KB + VB) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(att_smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < p.Tk * WPR; idx += blockDim.x) {
+    const int r = idx / WPR, w = idx - r * WPR;
+    *reinterpret_cast<uint2*>(sK + r * KP + 8 * w) = *reinterpret_cast<const uint2*>(kbase + (long long)r * p.ld_k + 8 * w);
+  }
+  for (int idx = threadIdx.x; idx < DV * (TKP / 16); idx += blockDim.x) {
+    const int r = idx / (TKP / 16), w = idx - r * (TKP / 16);
+    if (16 * w < p.Tk)
+      *reinterpret_cast<uint4*>(sV + r * VP + 16 * w) = *reinterpret_cast<const uint4*>(vbase + (long long)r * p.ld_vt + 16 * w);
+  }
+  for (int i = threadIdx.x; i < TKP; i += blockDim.x) sV[DV * VP + i] = 1;
+  __syncthreads();
+  for (int j = threadIdx.x; j < TKP; j += blockDim.x) {
+    int sum = 0;
+    if (p.zq != 0 && j < p.Tk) {
+#pragma unroll
+      for (int w = 0; w < DV / 4; ++w) sum += bytesum<QK_SIGNED>(*reinterpret_cast<const uint32_t*>(sK + j * KP + 4 * w));
+    }
+    sZrk[j] = p.zq * sum;
+  }
+  __syncthreads();
+
+  const float c = p.sim_scale * 1.4426950408889634f;
+  const float pmax = (float)p.p_qmax;
+  const QuantK oqk = make_quantk(p.oq);
+
+  for (int sl = 0; sl < slabs_per_warp; ++sl) {
+    const int row0 = ((blockIdx.x * slabs_per_warp + sl) * ATS_WARPS + warp) * 16;
+    if (row0 >= p.Tq) break;
+    uint32_t qf[NKC][4];
+    {
+      const int r0 = min(row0 + g, p.Tq - 1), r1 = min(row0 + g + 8, p.Tq - 1);
+      const uint8_t* q0 = qbase + (long long)r0 * p.ld_q;
+      const uint8_t* q1 = qbase + (long long)r1 * p.ld_q;
+#pragma unroll
+      for (int kc = 0; kc < NKC; ++kc) {
+        const int c0 = kc * 32 + 8 * t, c1 = c0 + 4;
+        qf[kc][0] = c0 < DV ? *reinterpret_cast<const uint32_t*>(q0 + c0) : 0u;
+        qf[kc][1] = c0 < DV ? *reinterpret_cast<const uint32_t*>(q1 + c0) : 0u;
+        qf[kc][2] = c1 < DV ? *reinterpret_cast<const uint32_t*>(q0 + c1) : 0u;
+        qf[kc][3] = c1 < DV ? *reinterpret_cast<const uint32_t*>(q1 + c1) : 0u;
+      }
+    }
+    // ---- S = Q K^T (16 x TKP), minus zq*rowsum(k), masked beyond Tk
+    int sacc[NT8][4];
+#pragma unroll
+    for (int nt = 0; nt < NT8; ++nt) {
+      sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0;
+#pragma unroll
+      for (int kc = 0; kc < NKC; ++kc) {
+        const uint2 kk = *reinterpret_cast<const uint2*>(sK + (8 * nt + g) * KP + kc * 32 + 8 * t);
+        const uint32_t bf[2] = {kk.x, kk.y};
+        mma_i8_16832<QK_SIGNED, QK_SIGNED>(sacc[nt], qf[kc], bf);
+      }
+      const int2 z = *reinterpret_cast<const int2*>(sZrk + 8 * nt + 2 * t);
+      sacc[nt][0] -= z.x; sacc[nt][1] -= z.y; sacc[nt][2] -= z.x; sacc[nt][3] -= z.y;
+      const int j = 8 * nt + 2 * t;
+      if (j >= p.Tk) { sacc[nt][0] = -(1 << 21); sacc[nt][2] = -(1 << 21); }
+      if (j + 1 >= p.Tk) { sacc[nt][1] = -(1 << 21); sacc[nt][3] = -(1 << 21); }
+    }
+    // ---- row statistics (rows g and g+8; a row lives in the 4 lanes of a quad)
+    int mi0 = sacc[0][0], mi1 = sacc[0][2];
+#pragma unroll
+    for (int nt = 0; nt < NT8; ++nt) {
+      mi0 = max(mi0, max(sacc[nt][0], sacc[nt][1]));
+      mi1 = max(mi1, max(sacc[nt][2], sacc[nt][3]));
+    }
+    mi0 = max(mi0, __shfl_xor_sync(0xffffffffu, mi0, 1));
+    mi0 = max(mi0, __shfl_xor_sync(0xffffffffu, mi0, 2));
+    mi1 = max(mi1, __shfl_xor_sync(0xffffffffu, mi1, 1));
+    mi1 = max(mi1, __shfl_xor_sync(0xffffffffu, mi1, 2));
+    const float b0 = -(float)mi0 * c, b1 = -(float)mi1 * c;
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT8; ++nt) {
+      l0 += ex2_approx(fmaf(att_i2f<MAGIC>(sacc[nt][0]), c, b0)) + ex2_approx(fmaf(att_i2f<MAGIC>(sacc[nt][1]), c, b0));
+      l1 += ex2_approx(fmaf(att_i2f<MAGIC>(sacc[nt][2]), c, b1)) + ex2_approx(fmaf(att_i2f<MAGIC>(sacc[nt][3]), c, b1));
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float off0 = b0 + log2f(1.0f / (l0 * p.delta_w));
+    const float off1 = b1 + log2f(1.0f / (l1 * p.delta_w));
+
+    // ---- P codes -> PV (same packing as qattention_kernel)
+    int olo[NDT][4], ohi[SM16 ? NDT : 1][4];
+#pragma unroll
+    for (int i = 0; i < NDT; ++i) { olo[i][0] = olo[i][1] = olo[i][2] = olo[i][3] = 0; }
+#pragma unroll
+    for (int i = 0; i < (SM16 ? NDT : 1); ++i) { ohi[i][0] = ohi[i][1] = ohi[i][2] = ohi[i][3] = 0; }
+#pragma unroll
+    for (int kc = 0; kc < NKV; ++kc) {
+      uint32_t plo[4], phi[4];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int ntA = 4 * kc + 2 * half, ntB = ntA + 1;
+        uint32_t cd[8];
+        const int sv[8] = {sacc[ntA][0], sacc[ntA][1], sacc[ntB][0], sacc[ntB][1],
+                           sacc[ntA][2], sacc[ntA][3], sacc[ntB][2], sacc[ntB][3]};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float pr = ex2_approx(fmaf(att_i2f<MAGIC>(sv[e]), c, e < 4 ? off0 : off1));
+          cd[e] = __float_as_uint(fminf(pr, pmax) + 12582912.0f);
+        }
+        plo[2 * half] = __byte_perm(__byte_perm(cd[0], cd[1], 0x0040), __byte_perm(cd[2], cd[3], 0x0040), 0x5410);
+        plo[2 * half + 1] = __byte_perm(__byte_perm(cd[4], cd[5], 0x0040), __byte_perm(cd[6], cd[7], 0x0040), 0x5410);
+        if constexpr (SM16) {
+          phi[2 * half] = __byte_perm(__byte_perm(cd[0], cd[1], 0x0051), __byte_perm(cd[2], cd[3], 0x0051), 0x5410);
+          phi[2 * half + 1] = __byte_perm(__byte_perm(cd[4], cd[5], 0x0051), __byte_perm(cd[6], cd[7], 0x0051), 0x5410);
+        }
+      }
+#pragma unroll
+      for (int nd = 0; nd < NDT; ++nd) {
+        const uint8_t* vr = sV + (8 * nd + g) * VP + 32 * kc + 4 * t;
+        const uint32_t bf[2] = {*reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 16)};
+        if (nd == NDT - 1) {
+          mma_i8_16832<false, false>(olo[nd], plo, bf);
+          if constexpr (SM16) mma_i8_16832<false, false>(ohi[nd], phi, bf);
+        } else {
+          mma_i8_16832<false, V_SIGNED>(olo[nd], plo, bf);
+          if constexpr (SM16) mma_i8_16832<false, V_SIGNED>(ohi[nd], phi, bf);
+        }
+      }
+    }
+    // ---- O = (256*hi + lo - zv*rowsum) * out_scale
+    float rs0 = (float)olo[NDT - 1][0], rs1 = (float)olo[NDT - 1][2];
+    if constexpr (SM16) { rs0 += 256.0f * (float)ohi[NDT - 1][0]; rs1 += 256.0f * (float)ohi[NDT - 1][2]; }
+    rs0 = __shfl_sync(0xffffffffu, rs0, lane & ~3);
+    rs1 = __shfl_sync(0xffffffffu, rs1, lane & ~3);
+    const int r0 = row0 + g, r1 = row0 + g + 8;
+    const float z0 = (float)p.zv * rs0, z1 = (float)p.zv * rs1;
+#pragma unroll
+    for (int nd = 0; nd < NDT - 1; ++nd) {
+      const int col = h * DV + 8 * nd + 2 * t;
+      float v0 = (float)olo[nd][0], v1 = (float)olo[nd][1], v2 = (float)olo[nd][2], v3 = (float)olo[nd][3];
+      if constexpr (SM16) {
+        v0 += 256.0f * (float)ohi[nd][0]; v1 += 256.0f * (float)ohi[nd][1];
+        v2 += 256.0f * (float)ohi[nd][2]; v3 += 256.0f * (float)ohi[nd][3];
+      }
+      const float y0 = (v0 - z0) * p.out_scale, y1 = (v1 - z0) * p.out_scale;
+      const float y2 = (v2 - z1) * p.out_scale, y3 = (v3 - z1) * p.out_scale;
+      if (p.out) {
+        if (r0 < p.Tq) *reinterpret_cast<float2*>(p.out + ((long long)b * p.Tq + r0) * p.ld_out + col) = make_float2(y0, y1);
+        if (r1 < p.Tq) *reinterpret_cast<float2*>(p.out + ((long long)b * p.Tq + r1) * p.ld_out + col) = make_float2(y2, y3);
+      }
+      if (p.out_q) {
+        uint8_t* oq = reinterpret_cast<uint8_t*>(p.out_q);
+        if (r0 < p.Tq)
+          *reinterpret_cast<uint16_t*>(oq + ((long long)b * p.Tq + r0) * p.ld_out_q + col) =
+              (uint16_t)(quant_code(y0, oqk) | (quant_code(y1, oqk) << 8));
+        if (r1 < p.Tq)
+          *reinterpret_cast<uint16_t*>(oq + ((long long)b * p.Tq + r1) * p.ld_out_q + col) =
+              (uint16_t)(quant_code(y2, oqk) | (quant_code(y3, oqk) << 8));
+      }
     }
   }
 }

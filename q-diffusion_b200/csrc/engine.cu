@@ -226,8 +226,8 @@ int gemm_mode(const qd::GemmArgs& a) {
   if (q && (a.ldq & 3)) return -1;
   if (a.residual && (a.ldr & 3)) return -1;
   if (a.rowvec && (a.ld_rowvec & 3)) return -1;
-  return (a.corr ? qd::EPI_CORR : 0) | (a.rowvec ? qd::EPI_ROWVEC : 0) | (a.residual ? qd::EPI_RESIDUAL : 0) |
-         (f ? qd::EPI_OUT_F32 : qd::EPI_OUT_Q);
+  return (a.corr ? qd::EPI_CORR : 0) | ((a.corr && a.taps == 9) ? qd::EPI_CONV : 0) | (a.rowvec ? qd::EPI_ROWVEC : 0) |
+         (a.residual ? qd::EPI_RESIDUAL : 0) | (f ? qd::EPI_OUT_F32 : qd::EPI_OUT_Q);
 }
 
 int launch_gemm(const GemmPlan& pl, cudaStream_t s) {
@@ -239,6 +239,10 @@ int launch_gemm(const GemmPlan& pl, cudaStream_t s) {
     case EPI_OUT_F32 | EPI_ROWVEC | EPI_CORR: return launch_gemm_mode<EPI_OUT_F32 | EPI_ROWVEC | EPI_CORR>(pl, s);
     case EPI_OUT_F32 | EPI_RESIDUAL: return launch_gemm_mode<EPI_OUT_F32 | EPI_RESIDUAL>(pl, s);
     case EPI_OUT_F32 | EPI_RESIDUAL | EPI_CORR: return launch_gemm_mode<EPI_OUT_F32 | EPI_RESIDUAL | EPI_CORR>(pl, s);
+    case EPI_OUT_F32 | EPI_CORR | EPI_CONV: return launch_gemm_mode<EPI_OUT_F32 | EPI_CORR | EPI_CONV>(pl, s);
+    case EPI_OUT_F32 | EPI_ROWVEC | EPI_CORR | EPI_CONV: return launch_gemm_mode<EPI_OUT_F32 | EPI_ROWVEC | EPI_CORR | EPI_CONV>(pl, s);
+    case EPI_OUT_F32 | EPI_RESIDUAL | EPI_CORR | EPI_CONV: return launch_gemm_mode<EPI_OUT_F32 | EPI_RESIDUAL | EPI_CORR | EPI_CONV>(pl, s);
+    case EPI_OUT_Q | EPI_CORR | EPI_CONV: return launch_gemm_mode<EPI_OUT_Q | EPI_CORR | EPI_CONV>(pl, s);
     case EPI_OUT_Q: return launch_gemm_mode<EPI_OUT_Q>(pl, s);
     case EPI_OUT_Q | EPI_CORR: return launch_gemm_mode<EPI_OUT_Q | EPI_CORR>(pl, s);
     case EPI_OUT_Q | EPI_RESIDUAL: return launch_gemm_mode<EPI_OUT_Q | EPI_RESIDUAL>(pl, s);
@@ -356,6 +360,28 @@ int launch_attention_t(const qd_attention_desc& d, cudaStream_t s) {
   return fail(QD_ERR_UNSUPPORTED, "attention: mixed signedness q=%d v=%d", d.q_signed, d.v_signed);
 }
 
+// small-Tk path (cross-attention): one key tile, K/V staged once per CTA, single-pass softmax
+template <int DQ, int DV, bool QS, bool VS, bool S16>
+int launch_attention_smallk_inst(const qd_attention_desc& d, cudaStream_t s) {
+  constexpr int NKV = 3;
+  auto kern = qd::qattention_smallk_kernel<DQ, DV, QS, VS, S16, NKV>;
+  const int spw = d.Tq >= 2048 ? 4 : (d.Tq >= 512 ? 2 : 1);
+  const int slabs = (d.Tq + 15) / 16;
+  dim3 grid((slabs + spw * qd::ATS_WARPS - 1) / (spw * qd::ATS_WARPS), d.B * d.heads);
+  kern<<<grid, qd::ATS_WARPS * 32, qd::ats_smem_bytes<DQ, DV, NKV>(), s>>>(d, spw);
+  return check_launch("qattention_smallk_kernel");
+}
+
+template <int DQ, int DV>
+int launch_attention_smallk(const qd_attention_desc& d, cudaStream_t s) {
+  const bool qs = d.q_signed != 0, vs = d.v_signed != 0, s16 = d.sm_bits > 8;
+  if (qs && vs && s16) return launch_attention_smallk_inst<DQ, DV, true, true, true>(d, s);
+  if (qs && vs && !s16) return launch_attention_smallk_inst<DQ, DV, true, true, false>(d, s);
+  if (!qs && !vs && s16) return launch_attention_smallk_inst<DQ, DV, false, false, true>(d, s);
+  if (!qs && !vs && !s16) return launch_attention_smallk_inst<DQ, DV, false, false, false>(d, s);
+  return fail(QD_ERR_UNSUPPORTED, "attention: mixed signedness q=%d v=%d", d.q_signed, d.v_signed);
+}
+
 // tcgen05 path (attention_tc.cuh): d <= 112, Q/K codes in the per-head padded layout (pitch 32/64/128), dense V^T
 template <bool S16, bool MAGIC>
 int launch_attention_tc_inst(const qd_attention_desc& d, const CUtensorMap& tmQ, const CUtensorMap& tmK,
@@ -433,6 +459,10 @@ int launch_attention(const qd_attention_desc& d, cudaStream_t s) {
   if ((d.q_off | d.head_stride_q | (int)d.ld_q) & 3) return fail(QD_ERR_UNSUPPORTED, "attention: q needs 4-byte alignment");
   if ((d.k_off | d.head_stride_k | (int)d.ld_k | d.d) & 7) return fail(QD_ERR_UNSUPPORTED, "attention: k rows need 8-byte alignment");
   if (d.out && (d.ld_out % 2)) return fail(QD_ERR_UNSUPPORTED, "attention: ld_out");
+  if (d.Tk <= 96 && (d.d == 40 || d.d == 80)) {
+    static const bool off = [] { const char* e = getenv("QDIFF_ATTENTION"); return e && !strcmp(e, "nosmallk"); }();
+    if (!off) return d.d == 40 ? launch_attention_smallk<64, 40>(d, s) : launch_attention_smallk<96, 80>(d, s);
+  }
   if (attention_tc_eligible(d)) return launch_attention_tc(d, s);
   switch (d.d) {
     case 16: return launch_attention_t<32, 16>(d, s);

@@ -39,6 +39,7 @@ constexpr int EPI_OUT_F32 = 8;    // fp32 output
 constexpr int EPI_OUT_Q = 16;     // requantised code output (row-major)
 constexpr int EPI_GEGLU = 32;     // columns interleaved [4 x, 4 gate]: out_q = Q(x * gelu(gate)), N/2 columns
 constexpr int EPI_TRANS = 64;     // requantised code output, transposed [img][n][token'] (V^T operand of qattention)
+constexpr int EPI_CONV = 128;     // with EPI_CORR: 3x3 conv, correction table indexed by border class (else one row)
 
 struct GemmArgs {
   int M, N;            // logical output rows / columns (columns >= N are masked)
@@ -167,10 +168,13 @@ __device__ __forceinline__ void gemm_epilogue_rowwise(const GemmArgs& p, const Q
 
 // Finalise 4 consecutive columns of one row.  MODE >= 0: flags are compile-time, N % 4 == 0 and all
 // leading dimensions are vector-aligned (checked on the host).  MODE < 0: everything at run time.
+// `of` / `oq` point at (m, n) of the fp32 / code output, `corr4` is the row's zero-point correction (plain GEMM: per
+// column; conv: the caller fetched the row's border class) except in generic conv mode, which loads it here.
 template <int MODE>
 __device__ __forceinline__ void gemm_finalise4(const GemmArgs& p, const QuantK& qk, const bool conv, const uint4 a4,
                                                const float (&sc)[4], const float (&bi)[4], const int4 corr4,
-                                               const float4 rpre, int m, int n, int nq, int cls, int img) {
+                                               const float4 rpre, float* of, int8_t* oq, const float* res, int n,
+                                               int cls, int img) {
   constexpr bool G = MODE < 0;
   const bool has_corr = G ? (p.corr != nullptr) : bool(MODE & EPI_CORR);
   const bool has_rowvec = G ? (p.rowvec != nullptr) : bool(MODE & EPI_ROWVEC);
@@ -208,42 +212,39 @@ __device__ __forceinline__ void gemm_finalise4(const GemmArgs& p, const QuantK& 
     }
   }
   if (has_res && !G) {
-    // specialised kernels pre-load the residual of all 8 row groups before the first store: `out` may
-    // alias `residual` (in-place accumulate), so the compiler cannot hoist these loads itself and they
-    // would otherwise serialise one global-memory latency per row group
+    // specialised kernels pre-load the residual of a row group before its first store: `out` may alias
+    // `residual` (in-place accumulate), so the compiler cannot hoist these loads itself and they would
+    // otherwise serialise one global-memory latency per row
     y[0] += rpre.x; y[1] += rpre.y; y[2] += rpre.z; y[3] += rpre.w;
   } else if (has_res) {
-    const float* r = p.residual + (long long)m * p.ldr + n;
     if (full && ((p.ldr & 3) == 0)) {
-      const float4 rv = *reinterpret_cast<const float4*>(r);
+      const float4 rv = *reinterpret_cast<const float4*>(res);
       y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (n + j < p.N) y[j] += r[j];
+        if (n + j < p.N) y[j] += res[j];
     }
   }
   if (out_f) {
-    float* o = p.out + (long long)m * p.ldo + n;
     if (full && (G ? ((p.ldo & 3) == 0) : true)) {
-      *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+      *reinterpret_cast<float4*>(of) = make_float4(y[0], y[1], y[2], y[3]);
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (n + j < p.N) o[j] = y[j];
+        if (n + j < p.N) of[j] = y[j];
     }
   }
   if (out_q) {
     const uint32_t q0 = quant_code(y[0], qk), q1 = quant_code(y[1], qk);
     const uint32_t q2 = quant_code(y[2], qk), q3 = quant_code(y[3], qk);
-    int8_t* o = p.out_q + (long long)m * p.ldq + nq;
     if (full && (G ? ((p.ldq & 3) == 0) : true)) {
-      *reinterpret_cast<uint32_t*>(o) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+      *reinterpret_cast<uint32_t*>(oq) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
     } else {
       const uint32_t qq[4] = {q0, q1, q2, q3};
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (n + j < p.N) o[j] = (int8_t)qq[j];
+        if (n + j < p.N) oq[j] = (int8_t)qq[j];
     }
   }
 }
@@ -374,7 +375,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int rsub = lane >> 3;   // row within a group of 4
     const int cq = lane & 7;      // column quad within the 32-column chunk
     const QuantK qk = make_quantk(p.q_delta, p.q_zp, p.q_lo, p.q_hi);
-    const bool conv = p.taps == 9;
+    const bool conv = MODE < 0 ? (p.taps == 9) : ((MODE & EPI_CONV) != 0);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -541,7 +542,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               } else {
                 bi[0] = bi[1] = bi[2] = bi[3] = 0.f;
               }
-              if (p.corr && p.taps == 1) corr4 = *reinterpret_cast<const int4*>(p.corr + n);
+              if (p.corr && !conv) corr4 = *reinterpret_cast<const int4*>(p.corr + n);
             } else {
               int cc[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -549,7 +550,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const bool ok = n + j < p.N;
                 sc[j] = ok ? __ldg(p.scale + n + j) : 0.f;
                 bi[j] = (ok && p.bias) ? __ldg(p.bias + n + j) : 0.f;
-                cc[j] = (ok && p.corr && p.taps == 1) ? __ldg(p.corr + n + j) : 0;
+                cc[j] = (ok && p.corr && !conv) ? __ldg(p.corr + n + j) : 0;
               }
               corr4 = make_int4(cc[0], cc[1], cc[2], cc[3]);
             }
@@ -559,6 +560,11 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // border-class correction) fetched up front, and - on the full-tile path - without any per-row
             // branch: the `m < M` tests split the unrolled loop into basic blocks, and with two epilogue warps
             // per scheduler the resulting dependent-issue chains (stall_wait) bounded the small-K GEMMs.
+            const long long mrow = m_warp + rsub;
+            float* of0 = p.out ? p.out + mrow * p.ldo + n : nullptr;
+            int8_t* oq0 = p.out_q ? p.out_q + mrow * p.ldq + nq : nullptr;
+            const float* res0 = p.residual ? p.residual + mrow * p.ldr + n : nullptr;
+            const long long of_step = 4 * p.ldo, oq_step = 4 * p.ldq, res_step = 4 * p.ldr;
             auto rows = [&](auto full_tag) {
               constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
@@ -568,15 +574,14 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const int it = h4 + i;
-                  const int m = m_warp + it * 4 + rsub;
+                  [[maybe_unused]] const int m = m_warp + it * 4 + rsub;
                   rpre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                   cpre[i] = corr4;
                   if constexpr (MODE >= 0 && (MODE & EPI_RESIDUAL) != 0) {
-                    if (FULL || m < p.M) rpre[i] = *reinterpret_cast<const float4*>(p.residual + (long long)m * p.ldr + n);
+                    if (FULL || m < p.M) rpre[i] = *reinterpret_cast<const float4*>(res0 + it * res_step);
                   }
-                  if constexpr (MODE >= 0 && (MODE & EPI_CORR) != 0) {
-                    if (conv) cpre[i] = __ldg(reinterpret_cast<const int4*>(p.corr + (long long)cls8[it] * p.N + n));
-                  }
+                  if constexpr (MODE >= 0 && (MODE & EPI_CORR) != 0 && (MODE & EPI_CONV) != 0)
+                    cpre[i] = __ldg(reinterpret_cast<const int4*>(p.corr + (long long)cls8[it] * p.N + n));
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -585,7 +590,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   const int m = m_warp + row;
                   if (FULL || m < p.M) {
                     const uint4 a4 = *reinterpret_cast<const uint4*>(stg + row * 128 + ((cq ^ (row & 7)) << 4));
-                    gemm_finalise4<MODE>(p, qk, conv, a4, sc, bi, cpre[i], rpre[i], m, n, nq, cls8[it], img8[it]);
+                    gemm_finalise4<MODE>(p, qk, conv, a4, sc, bi, cpre[i], rpre[i], of0 + it * of_step, oq0 + it * oq_step,
+                                         res0 + it * res_step, n, cls8[it], img8[it]);
                   }
                 }
               }

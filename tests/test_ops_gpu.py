@@ -327,7 +327,9 @@ def _run_attention(cuda, B, heads, d, Tq, Tk, sym, sm_bits, seed):
 
 @pytest.mark.parametrize("B,heads,d,Tq,Tk,sym,sm_bits", [
     (2, 8, 40, 256, 256, False, 16),   # SD self-attention head shape (sm_abit 16, asymmetric)
-    (2, 8, 40, 200, 77, False, 16),    # SD cross-attention: ragged Tq, 77 context tokens
+    (2, 8, 40, 200, 77, False, 16),    # SD cross-attention: ragged Tq, 77 context tokens (small-Tk kernel)
+    (1, 4, 80, 300, 77, False, 16),    # ... at the 32x32 level (d = 80)
+    (1, 2, 40, 2100, 77, True, 8),     # ... several slabs per warp, symmetric, 8-bit softmax codes
     (1, 4, 80, 128, 128, False, 8),
     (1, 2, 160, 64, 64, False, 16),
     (2, 1, 256, 256, 256, True, 8),    # CIFAR AttnBlock: single head, c=256, symmetric
