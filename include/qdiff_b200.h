@@ -110,7 +110,9 @@ int qd_quantize(const qd_quantize_desc* d, qd_stream_t stream);
 /* ------------------------------------------------------------------------------------------
  * qd_groupnorm_quant -- GroupNorm32 / Normalize (32 groups; ldm util.py:214-216 eps 1e-5,
  * ddim diffusion.py:32-33 eps 1e-6) [+ scale-shift] [+ SiLU] + up to 3 consumer quantizers.
- * x: fp32 NHWC [B, HW, C] (row pitch ld_x).  ws: workspace >= B*(nslab*C*2 + 64) floats.
+ * x: fp32 NHWC [B, HW, C] (row pitch ld_x).  ws: 8-byte aligned workspace of at least
+ * qd_groupnorm_workspace_floats(B, HW, C, groups) floats (small feature maps take a single-kernel path that
+ * does not touch it).
  * ------------------------------------------------------------------------------------------ */
 typedef struct qd_groupnorm_desc {
   const float* x;
@@ -131,9 +133,18 @@ typedef struct qd_groupnorm_desc {
   float* out_f;          /* optional fp32 output (NULL if unused) */
   long long ld_f;
   float* ws;
+  /* optional codes of the UN-normalised input (the block's skip_connection reads the same tensor through its own
+   * act quantizer, split in two channel ranges when --split is on: quant_layer.py:253-262).  Channels < raw_split
+   * use q_raw[0], the others q_raw[1]; raw_split % 4 == 0. */
+  void* raw_q;
+  long long ld_raw;
+  int32_t raw_split;
+  int32_t reserved2;
+  qd_qparams q_raw[2];
 } qd_groupnorm_desc;
 
 int qd_groupnorm_quant(const qd_groupnorm_desc* d, qd_stream_t stream);
+long long qd_groupnorm_workspace_floats(int B, int HW, int C, int groups);
 
 /* ------------------------------------------------------------------------------------------
  * qd_layernorm_quant -- nn.LayerNorm(C) (eps 1e-5) followed by the act quantizers of its

@@ -71,16 +71,19 @@ __global__ void quantize_scalar_kernel(const qd_quantize_desc p) {
 }
 
 // ------------------------------------------------------------------------------------ groupnorm
-// Pass 1: per (image, slab of pixels) per-channel partial sums. block = (C/4 threads rounded to warp) x rows.
-constexpr int GN_SLAB = 64;  // pixels per partial-sum slab
-__global__ void gn_partial_kernel(const float* __restrict__ x, long long ld_x, int HW, int C, int nslab,
-                                  float* __restrict__ ws) {
-  // grid: (nslab, B); threads stride over channel quads
-  const int b = blockIdx.y, slab = blockIdx.x;
-  const int p0 = slab * GN_SLAB;
-  const int p1 = min(HW, p0 + GN_SLAB);
+// Three-kernel path (large feature maps).  Pass 1: a block reduces `slab` pixels x all channels to per-GROUP
+// partial sums (fp32 per thread over the slab, then double, in a fixed order: results are run-to-run
+// identical).  The slab length is chosen by the launcher so that the grid fills the GPU at every level of the
+// UNet (the fixed 64-pixel slabs left the 8x8 / 16x16 levels with 16-64 blocks: 40 us for 5 MB).
+// ws layout: double part[B][nslab][groups][2], then float stats[B][groups][2].
+constexpr int GN_MAX_GROUPS = 64;
+__global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict__ x, long long ld_x, int HW, int C,
+                                                         int groups, int slab, int nslab, double* __restrict__ part) {
+  extern __shared__ float gn_sh[];   // [2][C] per-channel sums of this slab
+  const int b = blockIdx.y, sl = blockIdx.x;
+  const int p0 = sl * slab;
+  const int p1 = min(HW, p0 + slab);
   const int cq = C >> 2;
-  float* o = ws + ((long long)b * nslab + slab) * C * 2;
   for (int q = threadIdx.x; q < cq; q += blockDim.x) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = make_float4(0.f, 0.f, 0.f, 0.f);
     const float* base = x + ((long long)b * HW + p0) * ld_x + (q << 2);
@@ -91,62 +94,58 @@ __global__ void gn_partial_kernel(const float* __restrict__ x, long long ld_x, i
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
       ss.x += v.x * v.x; ss.y += v.y * v.y; ss.z += v.z * v.z; ss.w += v.w * v.w;
     }
-    *reinterpret_cast<float4*>(o + (q << 2)) = s;
-    *reinterpret_cast<float4*>(o + C + (q << 2)) = ss;
+    *reinterpret_cast<float4*>(gn_sh + (q << 2)) = s;
+    *reinterpret_cast<float4*>(gn_sh + C + (q << 2)) = ss;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * groups) {
+    const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+    const int cpg = C / groups;
+    const float* src = gn_sh + which * C + g * cpg;
+    double acc = 0.0;
+    for (int i = 0; i < cpg; ++i) acc += (double)src[i];
+    part[(((long long)b * nslab + sl) * groups + g) * 2 + which] = acc;
   }
 }
-// Pass 2: per (image, group): reduce slabs and channels in double -> mean, rstd.
-__global__ void gn_finalize_kernel(const float* __restrict__ ws, int HW, int C, int groups, int nslab, float eps,
-                                   float* __restrict__ stats) {
-  const int b = blockIdx.y, g = blockIdx.x;
-  const int cpg = C / groups;
-  double s = 0.0, ss = 0.0;
-  const int n = nslab * cpg;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int slab = i / cpg, c = g * cpg + (i - slab * cpg);
-    const float* o = ws + ((long long)b * nslab + slab) * C * 2;
-    s += (double)o[c];
-    ss += (double)o[C + c];
-  }
-  __shared__ double sh[2][32];
-  for (int off = 16; off > 0; off >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, off);
-    ss += __shfl_xor_sync(0xffffffffu, ss, off);
-  }
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) { sh[0][w] = s; sh[1][w] = ss; }
+// Pass 2: per image: reduce the slabs (fixed order) -> mean, rstd per group.  One block per image.
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const double* __restrict__ part, int HW, int C, int groups,
+                                                          int nslab, float eps, float* __restrict__ stats) {
+  __shared__ double sh[4][2 * GN_MAX_GROUPS];
+  const int b = blockIdx.x;
+  const int n2 = 2 * groups;
+  const int item = threadIdx.x % (2 * GN_MAX_GROUPS), lane4 = threadIdx.x / (2 * GN_MAX_GROUPS);   // 256 = 2 x 128
+  const int nl = blockDim.x / (2 * GN_MAX_GROUPS);
+  double acc = 0.0;
+  if (item < n2)
+    for (int sl = lane4; sl < nslab; sl += nl) acc += part[((long long)b * nslab + sl) * n2 + item];
+  sh[lane4][item] = acc;
   __syncthreads();
-  if (w == 0) {
-    const int nw = blockDim.x >> 5;
-    s = l < nw ? sh[0][l] : 0.0;
-    ss = l < nw ? sh[1][l] : 0.0;
-    for (int off = 16; off > 0; off >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, off);
-      ss += __shfl_xor_sync(0xffffffffu, ss, off);
-    }
-    if (l == 0) {
-      const double cnt = (double)HW * cpg;
-      const double mean = s / cnt;
-      double var = ss / cnt - mean * mean;
-      if (var < 0.0) var = 0.0;
-      stats[((long long)b * groups + g) * 2] = (float)mean;
-      stats[((long long)b * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
-    }
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    double s = 0.0, ss = 0.0;
+    for (int l = 0; l < nl; ++l) { s += sh[l][2 * g]; ss += sh[l][2 * g + 1]; }
+    const double cnt = (double)HW * (C / groups);
+    const double mean = s / cnt;
+    double var = ss / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[((long long)b * groups + g) * 2] = (float)mean;
+    stats[((long long)b * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
   }
 }
 // Pass 3: normalise + affine (+scale-shift) (+SiLU) + quantise for each consumer.
 // grid (row chunks, B); a thread owns fixed channel quads, folds mean/rstd/gamma/beta(/scale-shift) into
 // y = a*x + b once, then streams GN_ROWS pixels: no integer division and no table lookups in the loop.
-constexpr int GN_ROWS = 32;
 constexpr int GN_MAXQ = 4;   // channel quads per thread: C <= 4 * 256 * GN_MAXQ
-__global__ void __launch_bounds__(256) gn_apply_kernel(const qd_groupnorm_desc p, const float* __restrict__ stats) {
+__global__ void __launch_bounds__(256) gn_apply_kernel(const qd_groupnorm_desc p, const float* __restrict__ stats,
+                                                       int rows_per_block) {
   const int b = blockIdx.y;
   const int cq = p.C >> 2;
   const int cpg = p.C / p.groups;
-  const int r0 = blockIdx.x * GN_ROWS;
-  const int r1 = min(p.HW, r0 + GN_ROWS);
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(p.HW, r0 + rows_per_block);
   float ca[GN_MAXQ][4], cb[GN_MAXQ][4];
   const QuantK qk[3] = {make_quantk(p.q[0]), make_quantk(p.q[1]), make_quantk(p.q[2])};
+  const QuantK qraw[2] = {make_quantk(p.q_raw[0]), make_quantk(p.q_raw[1])};
   int nq = 0;
   for (int q = threadIdx.x; q < cq && nq < GN_MAXQ; q += blockDim.x, ++nq) {
 #pragma unroll
@@ -171,9 +170,14 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const qd_groupnorm_desc p
     if (k < nq) {
       const int c = (threadIdx.x + k * blockDim.x) << 2;
       const float* xp = p.x + ((long long)b * p.HW + r0) * p.ld_x + c;
-#pragma unroll 4
+#pragma unroll 4   // (8-deep unrolling with 64-row slabs measured 20% slower: fewer, fatter blocks)
       for (int r = r0; r < r1; ++r, xp += p.ld_x) {
         const float4 v = *reinterpret_cast<const float4*>(xp);
+        if (p.raw_q) {
+          const QuantK& kr = qraw[c < p.raw_split ? 0 : 1];
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.raw_q) + ((long long)b * p.HW + r) * p.ld_raw + c) =
+              pack4(quant_code(v.x, kr), quant_code(v.y, kr), quant_code(v.z, kr), quant_code(v.w, kr));
+        }
         float y[4] = {fmaf(v.x, ca[k][0], cb[k][0]), fmaf(v.y, ca[k][1], cb[k][1]), fmaf(v.z, ca[k][2], cb[k][2]),
                       fmaf(v.w, ca[k][3], cb[k][3])};
         if (p.silu) {
@@ -192,6 +196,101 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const qd_groupnorm_desc p
         }
       }
     }
+  }
+}
+
+// Single-kernel path (small feature maps: HW * C/groups <= 512 threads x 2*GN_NU values).  One block per
+// (image, group): the group's HW x cpg values are read ONCE into registers, mean and variance are computed in
+// two passes over those registers (block reductions in double, fixed order), then normalised / activated /
+// quantised straight from registers.  No workspace, one launch instead of three, x read once.
+constexpr int GN_NU = 20;   // float2 units per thread
+__device__ __forceinline__ double gn_block_sum(double v, double* sh) {
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();                 // sh may still be read from the previous reduction
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  const int nw = blockDim.x >> 5;
+  for (int i = 0; i < nw; ++i) t += sh[i];   // same order in every thread
+  return t;
+}
+__global__ void __launch_bounds__(512) gn_fused_small_kernel(const qd_groupnorm_desc p) {
+  __shared__ double red[16];
+  __shared__ float2 coef[2][64];   // per channel pair of the group: (a0, a1), (b0, b1); cpg <= 128
+  const int b = blockIdx.y, g = blockIdx.x;
+  const int cpg = p.C / p.groups;
+  const int U = cpg >> 1;                 // float2 units per row
+  const int total = p.HW * U;
+  const int T = blockDim.x;
+  const float* xg = p.x + (long long)b * p.HW * p.ld_x + g * cpg;
+  float2 v[GN_NU];
+  // unit u = threadIdx.x + k*T -> (row, cu); advanced incrementally (no division in the loop)
+  const int dr = T / U, dc = T - dr * U;
+  int row = threadIdx.x / U, cu = threadIdx.x - row * U;
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < GN_NU; ++k) {
+    v[k] = make_float2(0.f, 0.f);
+    if (threadIdx.x + k * T < total) v[k] = *reinterpret_cast<const float2*>(xg + (long long)row * p.ld_x + 2 * cu);
+    s += v[k].x + v[k].y;
+    row += dr; cu += dc;
+    if (cu >= U) { cu -= U; ++row; }
+  }
+  const double cnt = (double)p.HW * cpg;
+  const float mean = (float)(gn_block_sum((double)s, red) / cnt);
+  float s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < GN_NU; ++k) {
+    if (threadIdx.x + k * T < total) {
+      const float dx = v[k].x - mean, dy = v[k].y - mean;
+      s2 += dx * dx + dy * dy;
+    }
+  }
+  const float rstd = (float)(1.0 / sqrt(gn_block_sum((double)s2, red) / cnt + (double)p.eps));
+  if (threadIdx.x < U) {
+    float a[2], bb[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int ch = g * cpg + 2 * threadIdx.x + j;
+      a[j] = rstd * p.gamma[ch];
+      bb[j] = p.beta[ch] - mean * a[j];
+      if (p.ss_scale) {
+        const float s1 = 1.0f + p.ss_scale[(long long)b * p.ld_ss + ch];
+        a[j] *= s1;
+        bb[j] = bb[j] * s1 + p.ss_shift[(long long)b * p.ld_ss + ch];
+      }
+    }
+    coef[0][threadIdx.x] = make_float2(a[0], a[1]);
+    coef[1][threadIdx.x] = make_float2(bb[0], bb[1]);
+  }
+  __syncthreads();
+  const QuantK qk[3] = {make_quantk(p.q[0]), make_quantk(p.q[1]), make_quantk(p.q[2])};
+  const QuantK qraw[2] = {make_quantk(p.q_raw[0]), make_quantk(p.q_raw[1])};
+  row = threadIdx.x / U; cu = threadIdx.x - row * U;
+#pragma unroll
+  for (int k = 0; k < GN_NU; ++k) {
+    if (threadIdx.x + k * T < total) {
+      const float2 a = coef[0][cu], bb = coef[1][cu];
+      float y0 = fmaf(v[k].x, a.x, bb.x), y1 = fmaf(v[k].y, a.y, bb.y);
+      if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+      const long long r = (long long)b * p.HW + row;
+      const int c = g * cpg + 2 * cu;
+      if (p.out_f) *reinterpret_cast<float2*>(p.out_f + r * p.ld_f + c) = make_float2(y0, y1);
+      if (p.raw_q) {
+        const QuantK& kr = qraw[c < p.raw_split ? 0 : 1];
+        *reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(p.raw_q) + r * p.ld_raw + c) =
+            (uint16_t)(quant_code(v[k].x, kr) | (quant_code(v[k].y, kr) << 8));
+      }
+#pragma unroll
+      for (int o = 0; o < 3; ++o) {
+        if (o < p.n_out)
+          *reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(p.out_q[o]) + r * p.ld_q[o] + c) =
+              (uint16_t)(quant_code_fast(y0, qk[o]) | (quant_code_fast(y1, qk[o]) << 8));
+      }
+    }
+    row += dr; cu += dc;
+    if (cu >= U) { cu -= U; ++row; }
   }
 }
 

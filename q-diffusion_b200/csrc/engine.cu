@@ -269,25 +269,69 @@ int launch_quantize(const qd_quantize_desc& d, cudaStream_t s) {
   return check_launch("quantize_kernel");
 }
 
+// slab / rows-per-block of the three-kernel GroupNorm: enough blocks to fill the GPU at every feature-map size
+int gn_slab_rows(int B, int HW) {
+  long long r = ((long long)B * HW) / (4LL * 148);
+  int slab = 64;
+  while (slab > 8 && slab > r) slab >>= 1;
+  return slab;
+}
+
+long long gn_workspace_floats(int B, int HW, int C, int groups) {
+  const int slab = gn_slab_rows(B, HW);
+  const long long nslab = (HW + slab - 1) / slab;
+  (void)C;
+  return (long long)B * nslab * groups * 2 * 2 + (long long)B * groups * 2 + 16;   // doubles count as 2 floats
+}
+
 int launch_groupnorm(const qd_groupnorm_desc& d, cudaStream_t s) {
-  if (!d.x || !d.ws || !d.gamma || !d.beta) return fail(QD_ERR_BAD_ARG, "groupnorm: null arg");
-  if (d.C % 4 || d.C % d.groups || d.ld_x % 4) return fail(QD_ERR_UNSUPPORTED, "groupnorm: C=%d groups=%d", d.C, d.groups);
+  if (!d.x || !d.gamma || !d.beta) return fail(QD_ERR_BAD_ARG, "groupnorm: null arg");
+  if (d.groups <= 0 || d.groups > qd::GN_MAX_GROUPS || d.C % 4 || d.C % d.groups || d.ld_x % 4)
+    return fail(QD_ERR_UNSUPPORTED, "groupnorm: C=%d groups=%d", d.C, d.groups);
   if (d.n_out < 0 || d.n_out > 3) return fail(QD_ERR_BAD_ARG, "groupnorm: n_out");
-  const int nslab = (d.HW + qd::GN_SLAB - 1) / qd::GN_SLAB;
-  float* stats = d.ws + (long long)d.B * nslab * d.C * 2;
+  if (d.raw_q && ((d.raw_split & 3) || (d.ld_raw & 3) || d.raw_split < 0))
+    return fail(QD_ERR_BAD_ARG, "groupnorm: raw output needs raw_split %% 4 == 0 and ld_raw %% 4 == 0");
+  const int cpg = d.C / d.groups;
+  // ---- single-kernel path: the (image, group) slab fits the registers of one block
+  {
+    bool ok = (cpg % 2 == 0) && cpg <= 128 && (d.ld_x % 2 == 0) && (!d.out_f || d.ld_f % 2 == 0);
+    for (int o = 0; o < d.n_out; ++o) ok = ok && (d.ld_q[o] % 2 == 0);
+    const long long units = (long long)d.HW * (cpg / 2);
+    static const int force = [] {   // QDIFF_GN=fused|split: A/B switch for profiling
+      const char* e = getenv("QDIFF_GN");
+      return !e ? 0 : (!strcmp(e, "fused") ? 1 : (!strcmp(e, "split") ? 2 : 0));
+    }();
+    const long long limit = force == 1 ? 512LL * qd::GN_NU : (force == 2 ? 0 : 256LL * qd::GN_NU);
+    if (ok && units <= limit) {
+      int threads = units <= 256LL * qd::GN_NU ? 256 : 512;
+      if (units < 256) threads = (int)((units + 31) / 32 * 32);
+      if (threads < cpg / 2) threads = (cpg / 2 + 31) / 32 * 32;
+      qd::gn_fused_small_kernel<<<dim3(d.groups, d.B), threads, 0, s>>>(d);
+      return check_launch("gn_fused_small_kernel");
+    }
+  }
+  if (!d.ws) return fail(QD_ERR_BAD_ARG, "groupnorm: workspace required");
+  if ((uintptr_t)d.ws & 7) return fail(QD_ERR_BAD_ARG, "groupnorm: workspace must be 8-byte aligned");
+  const int slab = gn_slab_rows(d.B, d.HW);
+  const int nslab = (d.HW + slab - 1) / slab;
+  double* part = reinterpret_cast<double*>(d.ws);
+  float* stats = d.ws + (long long)d.B * nslab * d.groups * 4;
   int threads = d.C / 4;
   threads = (threads + 31) / 32 * 32;
   if (threads > 256) threads = 256;
-  qd::gn_partial_kernel<<<dim3(nslab, d.B), threads, 0, s>>>(d.x, d.ld_x, d.HW, d.C, nslab, d.ws);
+  if (threads < 2 * d.groups) threads = (2 * d.groups + 31) / 32 * 32;
+  qd::gn_partial_kernel<<<dim3(nslab, d.B), threads, 2 * d.C * sizeof(float), s>>>(d.x, d.ld_x, d.HW, d.C, d.groups, slab,
+                                                                                   nslab, part);
   int rc = check_launch("gn_partial_kernel");
   if (rc) return rc;
-  qd::gn_finalize_kernel<<<dim3(d.groups, d.B), 128, 0, s>>>(d.ws, d.HW, d.C, d.groups, nslab, d.eps, stats);
+  qd::gn_finalize_kernel<<<d.B, 256, 0, s>>>(part, d.HW, d.C, d.groups, nslab, d.eps, stats);
   rc = check_launch("gn_finalize_kernel");
   if (rc) return rc;
   if (d.C > 4 * 256 * qd::GN_MAXQ) return fail(QD_ERR_UNSUPPORTED, "groupnorm: C=%d too large", d.C);
   int at = ((d.C / 4) + 31) / 32 * 32;
   if (at > 256) at = 256;
-  qd::gn_apply_kernel<<<dim3((d.HW + qd::GN_ROWS - 1) / qd::GN_ROWS, d.B), at, 0, s>>>(d, stats);
+  const int rows = slab < 32 ? slab : 32;
+  qd::gn_apply_kernel<<<dim3((d.HW + rows - 1) / rows, d.B), at, 0, s>>>(d, stats, rows);
   return check_launch("gn_apply_kernel");
 }
 
@@ -558,6 +602,11 @@ int qd_quantize(const qd_quantize_desc* d, qd_stream_t s) {
   if (!d) return fail(QD_ERR_BAD_ARG, "null desc");
   return launch_quantize(*d, (cudaStream_t)s);
 }
+long long qd_groupnorm_workspace_floats(int B, int HW, int C, int groups) {
+  if (B <= 0 || HW <= 0 || C <= 0 || groups <= 0) return 0;
+  return gn_workspace_floats(B, HW, C, groups);
+}
+
 int qd_groupnorm_quant(const qd_groupnorm_desc* d, qd_stream_t s) {
   if (!d) return fail(QD_ERR_BAD_ARG, "null desc");
   return launch_groupnorm(*d, (cudaStream_t)s);

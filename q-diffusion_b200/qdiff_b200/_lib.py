@@ -57,6 +57,7 @@ class GroupNormDesc(C.Structure):
         ("n_out", c_i32), ("reserved", c_i32),
         ("out_q", c_vp * 3), ("ld_q", c_ll * 3), ("q", QParams * 3),
         ("out_f", c_vp), ("ld_f", c_ll), ("ws", c_vp),
+        ("raw_q", c_vp), ("ld_raw", c_ll), ("raw_split", c_i32), ("reserved2", c_i32), ("q_raw", QParams * 2),
     ]
 
 
@@ -109,8 +110,8 @@ class SamplerDesc(C.Structure):
 
 
 EXPORTS = [
-    "qd_qgemm_i8", "qd_quantize", "qd_groupnorm_quant", "qd_layernorm_quant", "qd_im2col_i8", "qd_qattention",
-    "qd_timestep_embedding", "qd_copy2d", "qd_nchw_to_nhwc", "qd_nhwc_to_nchw", "qd_avgpool2x", "qd_upsample2x_f32",
+    "qd_qgemm_i8", "qd_quantize", "qd_groupnorm_quant", "qd_groupnorm_workspace_floats", "qd_layernorm_quant",
+    "qd_im2col_i8", "qd_qattention", "qd_timestep_embedding", "qd_copy2d", "qd_nchw_to_nhwc", "qd_nhwc_to_nchw", "qd_avgpool2x", "qd_upsample2x_f32",
     "qd_sampler_step", "qd_engine_create", "qd_engine_add_op", "qd_engine_num_ops", "qd_engine_finalize",
     "qd_engine_run", "qd_engine_run_range", "qd_engine_destroy", "qd_last_error", "qd_num_sms", "qd_launch_count",
 ]
@@ -142,6 +143,8 @@ def lib():
     L.qd_nhwc_to_nchw.argtypes = [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]
     L.qd_avgpool2x.argtypes = [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]
     L.qd_upsample2x_f32.argtypes = [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]
+    L.qd_groupnorm_workspace_floats.argtypes = [c_i32, c_i32, c_i32, c_i32]
+    L.qd_groupnorm_workspace_floats.restype = c_ll
     L.qd_engine_create.argtypes = [C.c_int, C.POINTER(c_vp)]
     L.qd_engine_add_op.argtypes = [c_vp, C.c_int, c_vp]
     L.qd_engine_num_ops.argtypes = [c_vp]

@@ -22,14 +22,23 @@ from ._lib import AttentionDesc, MiscDesc, check, lib, ptr
 class Act:
     """A device activation: rows x cols with a row pitch (elements), fp32 or 8-bit codes."""
 
-    def __init__(self, t, rows, cols, ld=None, signed=None):
+    def __init__(self, t, rows, cols, ld=None, signed=None, col0=0):
         self.t, self.rows, self.cols = t, rows, cols
         self.ld = cols if ld is None else ld
         self.signed = signed  # None for fp32
+        self.col0 = col0      # first column inside the backing [rows, ld] tensor (views into concat buffers)
 
     @property
     def ptr(self):
-        return self.t.data_ptr()
+        return self.t.data_ptr() + self.col0 * self.t.element_size()
+
+    def view(self, col0, cols):
+        """Columns [col0, col0+cols) of this activation, sharing storage."""
+        return Act(self.t, self.rows, cols, ld=self.ld, signed=self.signed, col0=self.col0 + col0)
+
+    def logical(self):
+        """The [rows, cols] tensor this Act denotes (a strided view when it lives inside a wider buffer)."""
+        return self.t[:self.rows, self.col0:self.col0 + self.cols]
 
 
 class _Offset:
@@ -167,10 +176,12 @@ class Builder:
         dst.delta = (qp0.delta, qp1.delta if qp1 is not None else None)
         return dst
 
-    def groupnorm(self, x, norm, hw, quantizers, silu, label, ss=None, want_f32=False):
-        """GroupNorm(32) [+scale-shift] [+SiLU] -> codes for each consumer quantizer (and/or fp32)."""
+    def groupnorm(self, x, norm, hw, quantizers, silu, label, ss=None, want_f32=False, raw=None):
+        """GroupNorm(32) [+scale-shift] [+SiLU] -> codes for each consumer quantizer (and/or fp32).
+        raw = (quantizer, quantizer_0 or None, split): also emit codes of the input itself (skip_connection operand);
+        the Act is returned as a third value."""
         B = self.B
-        ws_need = ops.gn_workspace_floats(B, hw, x.cols)
+        ws_need = ops.gn_workspace_floats(B, hw, x.cols, norm.num_groups)
         if self.gn_ws is None or self.gn_ws.numel() < ws_need:
             self.gn_ws = torch.empty(max(ws_need, 1 << 20), dtype=torch.float32, device=self.dev)
             self.keep.append(self.gn_ws)
@@ -182,12 +193,23 @@ class Builder:
             outs.append((a.t, a.ld, qp_))
             acts.append(a)
         out_f = self.new_f32(x.rows, x.cols) if want_f32 else None
+        raw_arg, raw_act = None, None
+        if raw is not None:
+            q0, q1, split = raw
+            qp0, signed = self.qp(q0)
+            qp1 = self.qp(q1)[0] if q1 is not None else qp0
+            raw_act = self.new_codes(x.rows, x.cols, signed)
+            raw_act.zp = (qp0.zero_point, qp1.zero_point if q1 is not None else None)
+            raw_act.delta = (qp0.delta, qp1.delta if q1 is not None else None)
+            raw_arg = (raw_act.t, raw_act.ld, split if q1 is not None else x.cols, qp0, qp1)
         d = ops.groupnorm_desc(x.t, self.dev_t(norm.weight, torch.float32), self.dev_t(norm.bias, torch.float32),
                                self.gn_ws, B=B, HW=hw, C_=x.cols, ld_x=x.ld, eps=norm.eps, silu=silu, outs=outs,
                                groups=norm.num_groups, ss=ss, out_f=out_f.t if out_f else None,
-                               ld_f=out_f.ld if out_f else 0)
+                               ld_f=out_f.ld if out_f else 0, raw=raw_arg)
         d.x = x.ptr
         self.add(_lib.QD_OP_GROUPNORM, d, label)
+        if raw is not None:
+            return acts, out_f, raw_act
         return acts, out_f
 
     def layernorm(self, x, norm, quantizers, label):
@@ -305,6 +327,8 @@ class Builder:
             bias = bias.contiguous()
             self.keep.append(bias)
         M = a.rows
+        if out is not None and (out.rows != M or out.cols < N + out_cols_offset):
+            raise RuntimeError(f"{label}: output view [{out.rows}, {out.cols}] does not fit [{M}, {N}]")
         o = None
         if out_q is None:
             o = accumulate_into if accumulate_into is not None else (out if out is not None else self.new_f32(M, N))
@@ -419,18 +443,42 @@ class Builder:
         return out
 
     # ================================================================== LDM / SD family
-    def ldm_resblock(self, blk, x, emb, hw, split):
+    def contig(self, x, label):
+        """A dense copy of a strided view (for the few ops that take no row pitch)."""
+        if x.ld == x.cols and x.col0 == 0:
+            return x
+        out = self.new_f32(x.rows, x.cols)
+        self.misc(_lib.QD_OP_COPY2D, x.ptr, out.ptr, x.rows, x.cols, ld_src=x.ld, ld_dst=out.ld, label=label + ".dense")
+        return out
+
+    def ldm_resblock(self, blk, x, emb, hw, split, out=None):
         """QuantResBlock._forward, qdiff/quant_block.py:83-111."""
         k = self.key(blk)
         H, W = hw
+        if getattr(blk, "updown", False):
+            x = self.contig(x, k)
         norm1, conv1 = blk.in_layers[0], blk.in_layers[2]
         norm2, conv2 = blk.out_layers[0], blk.out_layers[3]
         lin = blk.emb_layers[1]
         updown = None
         if getattr(blk, "updown", False):
             updown = "up" if _name(blk.h_upd) == "Upsample" else "down"
+        skip = blk.skip_connection
+        a_skip = None
         if updown is None:
-            (a1,), _ = self.groupnorm(x, norm1, H * W, [conv1.act_quantizer], True, k + ".in_layers.0")
+            raw = None
+            if _name(skip) == "QuantModule" and skip.weight.shape[-1] == 1 and (split % 4 == 0):
+                # the skip_connection's operand is the same tensor GroupNorm reads: quantise it in that pass
+                if split:
+                    if skip.split == 0:
+                        raise RuntimeError(f"{k}.skip_connection: model.split is set but the checkpoint has no split quantizers")
+                    raw = (skip.act_quantizer, skip.act_quantizer_0, split)
+                else:
+                    raw = (skip.act_quantizer, None, 0)
+            if raw is not None:
+                (a1,), _, a_skip = self.groupnorm(x, norm1, H * W, [conv1.act_quantizer], True, k + ".in_layers.0", raw=raw)
+            else:
+                (a1,), _ = self.groupnorm(x, norm1, H * W, [conv1.act_quantizer], True, k + ".in_layers.0")
             oh, ow = H, W
             x_res = x
         else:
@@ -456,22 +504,24 @@ class Builder:
         else:
             h = self.conv3x3_s1(conv1, a1, (oh, ow), k + ".in_layers.2", rowvec=emb_out)
             (a2,), _ = self.groupnorm(h, norm2, oh * ow, [conv2.act_quantizer], True, k + ".out_layers.0")
-        skip = blk.skip_connection
         if _name(skip) == "QuantModule":
             if skip.weight.shape[-1] != 1:
                 raise NotImplementedError("3x3 skip_connection (use_conv=True) is not used by any reference config")
             if split:
                 if skip.split == 0:
                     raise RuntimeError(f"{k}.skip_connection: model.split is set but the checkpoint has no split quantizers")
-                a = self.quantize(x_res, skip.act_quantizer, k + ".skip.q", split=split, q1=skip.act_quantizer_0)
+                a = a_skip if a_skip is not None else \
+                    self.quantize(x_res, skip.act_quantizer, k + ".skip.q", split=split, q1=skip.act_quantizer_0)
                 s = self.gemm(skip, a, k + ".skip_connection.half0", cols=(0, split), suffix="", zx=a.zp[0], dx=a.delta[0])
                 self.gemm(skip, a, k + ".skip_connection", cols=(split, a.cols), suffix="_0", zx=a.zp[1], dx=a.delta[1],
                           accumulate_into=s, use_bias=False)
+            elif a_skip is not None:
+                s = self.gemm(skip, a_skip, k + ".skip_connection")
             else:
                 s = self.qlinear(skip, x_res, k + ".skip_connection")
         else:
             s = x_res
-        out = self.conv3x3_s1(conv2, a2, (oh, ow), k + ".out_layers.3", residual=s)
+        out = self.conv3x3_s1(conv2, a2, (oh, ow), k + ".out_layers.3", residual=s, out=out)
         return out, (oh, ow)
 
     def sd_cross_attention(self, attn, x_codes_q, kv_codes, h_res, Tq, Tk, label):
@@ -489,7 +539,7 @@ class Builder:
                            label=label + ".attn", consumer=attn.to_out[0])
         return self.gemm(attn.to_out[0], o, label + ".to_out.0", residual=h_res)
 
-    def spatial_transformer(self, st, x, ctx, hw):
+    def spatial_transformer(self, st, x, ctx, hw, out=None):
         """SpatialTransformer.forward (ldm/modules/attention.py:276-287) + QuantBasicTransformerBlock._forward
         (qdiff/quant_block.py:263-271)."""
         k = self.key(st)
@@ -516,11 +566,11 @@ class Builder:
             if i == len(st.transformer_blocks) - 1:
                 # the block output only feeds proj_out: emit proj_out's input codes directly (no fp32 round trip)
                 hq = self.gemm(ff_out, a_ff, bk + ".ff.net.2", residual=h, out_q=(st.proj_out.act_quantizer, False))
-                return self.gemm(st.proj_out, hq, k + ".proj_out", residual=x)
+                return self.gemm(st.proj_out, hq, k + ".proj_out", residual=x, out=out)
             h = self.gemm(ff_out, a_ff, bk + ".ff.net.2", residual=h)
         raise RuntimeError("SpatialTransformer without transformer blocks")
 
-    def ldm_attention_block(self, blk, x, hw):
+    def ldm_attention_block(self, blk, x, hw, out=None):
         """AttentionBlock._forward + QKVAttentionLegacy (openaimodel.py:321-327,384-406) with QuantQKMatMul /
         QuantSMVMatMul (qdiff/quant_block.py:123-157).  The qkv Conv1d rows are regrouped into q / k / v GEMMs;
         s = ch^-1/4 is folded into the q,k epilogue scale so the codes are those of q*s, k*s."""
@@ -547,7 +597,7 @@ class Builder:
         o = self.attention(qc, kc, vt, heads=heads, d=ch, Tq=T, Tk=T, q_layout=(0, Pq), k_layout=(0, Pq),
                            v_layout=(0, ch), sim_scale_extra=1.0, qw=smv.act_quantizer_w, label=k + ".attention",
                            consumer=blk.proj_out)
-        return self.gemm(blk.proj_out, o, k + ".proj_out", residual=x)
+        return self.gemm(blk.proj_out, o, k + ".proj_out", residual=x, out=out)
 
     def lower_ldm(self, model, x_shape, ctx_shape):
         B, Cin, H, W = x_shape
@@ -569,47 +619,106 @@ class Builder:
         h, hw = xh, (H, W)
         hs = []
 
-        def run(seq, h, hw, split):
-            for layer in seq:
+        # torch.cat([h, hs.pop()], dim=1) without copies (openaimodel.py:733): the concat buffer of decoder block j
+        # is allocated up front; the encoder block whose output is that skip writes its right-hand columns, the
+        # block before decoder block j writes the left-hand ones (their last GEMM gets the view as `out`).
+        nblk = len(model.output_blocks)
+        cat_total = []
+        for ob in model.output_blocks:
+            first = ob[0]
+            cat_total.append(int(first.in_layers[0].num_channels) if _name(first) in _RES else None)
+        cat_buf = [None] * nblk
+
+        def last_out_channels(layer, cin):
+            n = _name(layer)
+            if n == "QuantModule":
+                return int(layer.weight.shape[0])
+            if n in _RES:
+                return int(layer.out_layers[3].weight.shape[0])
+            if n == "Downsample":
+                return int(layer.op.weight.shape[0])
+            if n == "Upsample":
+                return int(layer.conv.weight.shape[0])
+            return cin
+
+        def last_out_hw(layer, hw):
+            n = _name(layer)
+            if n == "Downsample" or (n in _RES and getattr(layer, "updown", False) and _name(layer.h_upd) != "Upsample"):
+                return (hw[0] // 2, hw[1] // 2)
+            if n == "Upsample" or (n in _RES and getattr(layer, "updown", False)):
+                return (2 * hw[0], 2 * hw[1])
+            return hw
+
+        def dest_view(j, side, cs, ohw):
+            """View for decoder block j's concat: side 'skip' = right-hand columns, 'h' = left-hand ones."""
+            if j is None or j < 0 or j >= nblk or cat_total[j] is None:
+                return None
+            rows = B * ohw[0] * ohw[1]
+            if cat_buf[j] is None:
+                if side != "skip":
+                    return None
+                if cs >= cat_total[j]:
+                    return None
+                cat_buf[j] = self.new_f32(rows, cat_total[j])
+            buf = cat_buf[j]
+            if buf.rows != rows:
+                return None
+            if side == "skip":
+                return buf.view(buf.cols - cs, cs)
+            return buf.view(0, cs)
+
+        def run(seq, h, hw, split, dest=None):
+            """dest = (j, side): the last layer writes its output into decoder block j's concat buffer."""
+            seq = list(seq)
+            for li, layer in enumerate(seq):
                 n = _name(layer)
+                out = None
+                if dest is not None and li == len(seq) - 1:
+                    out = dest_view(dest[0], dest[1], last_out_channels(layer, h.cols), last_out_hw(layer, hw))
                 if n == "QuantModule":                       # conv_in
                     a = self.quantize(h, layer.act_quantizer, self.key(layer) + ".q")
                     kt = (9 * h.cols + 31) // 32 * 32
-                    h = self.conv_im2col(layer, a, hw, self.key(layer), 1, (1, 1), hw, kt)
+                    h = self.conv_im2col(layer, a, hw, self.key(layer), 1, (1, 1), hw, kt, out=out)
                 elif n in _RES:
-                    h, hw = self.ldm_resblock(layer, h, emb, hw, split)
+                    h, hw = self.ldm_resblock(layer, h, emb, hw, split, out=out)
                 elif n in _ST:
-                    h = self.spatial_transformer(layer, h, ctx, hw)
+                    h = self.spatial_transformer(layer, h, ctx, hw, out=out)
                 elif n in _ATTN:
-                    h = self.ldm_attention_block(layer, h, hw)
+                    h = self.ldm_attention_block(layer, h, hw, out=out)
                 elif n == "Downsample":
                     op = layer.op
                     if _name(op) != "QuantModule":
                         raise NotImplementedError("Downsample without conv")
                     a = self.quantize(h, op.act_quantizer, self.key(op) + ".q")
                     ohw = (hw[0] // 2, hw[1] // 2)
-                    h = self.conv_im2col(op, a, hw, self.key(op), 2, (1, 1), ohw, 9 * h.cols)
+                    h = self.conv_im2col(op, a, hw, self.key(op), 2, (1, 1), ohw, 9 * h.cols, out=out)
                     hw = ohw
                 elif n == "Upsample":
                     conv = layer.conv
                     a = self.quantize(h, conv.act_quantizer, self.key(conv) + ".q", upsample=(B, hw[0], hw[1]))
                     hw = (2 * hw[0], 2 * hw[1])
-                    h = self.conv3x3_s1(conv, a, hw, self.key(conv))
+                    h = self.conv3x3_s1(conv, a, hw, self.key(conv), out=out)
                 else:
                     raise NotImplementedError(f"unhandled layer type {n} at {self.key(layer)}")
             return h, hw
 
+        nin_blocks = len(model.input_blocks)
         for i, blk in enumerate(model.input_blocks):
-            h, hw = run(blk, h, hw, 0)
+            h, hw = run(blk, h, hw, 0, dest=(nin_blocks - 1 - i, "skip") if nin_blocks == nblk else None)
             hs.append((h, hw))
             self.traces[f"input_blocks.{i}"] = (h, hw)
-        h, hw = run(model.middle_block, h, hw, 0)
+        h, hw = run(model.middle_block, h, hw, 0, dest=(0, "h"))
         self.traces["middle_block"] = (h, hw)
         for i, blk in enumerate(model.output_blocks):
             skip_t, _ = hs.pop()
             split = h.cols if getattr(model, "split", False) else 0
-            h = self.concat(h, skip_t, f"output_blocks.{i}")
-            h, hw = run(blk, h, hw, split)
+            buf = cat_buf[i]
+            if (buf is not None and h.t is buf.t and skip_t.t is buf.t and h.col0 == 0 and skip_t.col0 == h.cols
+                    and h.cols + skip_t.cols == buf.cols):
+                h = buf                                     # both halves were produced in place
+            else:
+                h = self.concat(h, skip_t, f"output_blocks.{i}")
+            h, hw = run(blk, h, hw, split, dest=(i + 1, "h"))
             self.traces[f"output_blocks.{i}"] = (h, hw)
         norm, conv = model.out[0], model.out[2]
         (a,), _ = self.groupnorm(h, norm, hw[0] * hw[1], [conv.act_quantizer], True, "out.0")

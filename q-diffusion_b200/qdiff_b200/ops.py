@@ -75,13 +75,15 @@ def quantize(desc):
     check(lib().qd_quantize(C.byref(desc), stream_ptr()), "qd_quantize")
 
 
-def gn_workspace_floats(B, HW, C_):
-    nslab = (HW + 63) // 64
-    return B * (nslab * C_ * 2 + 64)
+def gn_workspace_floats(B, HW, C_, groups=32):
+    """Workspace of qd_groupnorm_quant in floats (the library owns the rule: slab length depends on B*HW)."""
+    return int(lib().qd_groupnorm_workspace_floats(int(B), int(HW), int(C_), int(groups)))
 
 
-def groupnorm_desc(x, gamma, beta, ws, *, B, HW, C_, ld_x, eps, silu, outs, groups=32, ss=None, out_f=None, ld_f=0):
-    """outs: list of (tensor, ld, QParams)."""
+def groupnorm_desc(x, gamma, beta, ws, *, B, HW, C_, ld_x, eps, silu, outs, groups=32, ss=None, out_f=None, ld_f=0,
+                   raw=None):
+    """outs: list of (tensor, ld, QParams).  raw: (tensor, ld, split, QParams, QParams) = codes of the un-normalised
+    input for the block's skip_connection (channels < split use the first quantizer)."""
     d = GroupNormDesc()
     d.x, d.ld_x = ptr(x), int(ld_x)
     d.B, d.HW, d.C, d.groups = int(B), int(HW), int(C_), int(groups)
@@ -96,6 +98,10 @@ def groupnorm_desc(x, gamma, beta, ws, *, B, HW, C_, ld_x, eps, silu, outs, grou
         d.q[i] = q
     d.out_f, d.ld_f = ptr(out_f), int(ld_f)
     d.ws = ptr(ws)
+    if raw is not None:
+        t, ld, split, q0, q1 = raw
+        d.raw_q, d.ld_raw, d.raw_split = t.data_ptr(), int(ld), int(split)
+        d.q_raw[0], d.q_raw[1] = q0, q1
     return d
 
 

@@ -185,7 +185,10 @@ def test_quantize_upsample(cuda):
     assert torch.equal(dst.cpu().long(), ref.long())
 
 
-@pytest.mark.parametrize("C,HW,silu,n_out", [(320, 256, True, 1), (224, 100, False, 3), (1920, 64, True, 1)])
+@pytest.mark.parametrize("C,HW,silu,n_out", [
+    (320, 256, True, 1), (1920, 64, True, 1), (2560, 256, True, 2), (640, 1024, False, 1),   # single-kernel path
+    (224, 100, False, 3), (320, 4096, True, 1), (960, 1024, True, 1),                       # partial/finalize/apply
+])
 def test_groupnorm_quant(cuda, C, HW, silu, n_out):
     ops, _ = _ops()
     gen = torch.Generator().manual_seed(5 + C)
@@ -201,10 +204,18 @@ def test_groupnorm_quant(cuda, C, HW, silu, n_out):
     outs = [(torch.zeros(B * HW, C, dtype=torch.uint8, device=cuda), C, q) for q in qs]
     out_f = torch.zeros(B * HW, C, device=cuda)
     ws = torch.zeros(ops.gn_workspace_floats(B, HW, C), device=cuda)
+    # codes of the raw input for the skip_connection (two quantizers split at a channel boundary)
+    raw_t = torch.zeros(B * HW, C, dtype=torch.uint8, device=cuda)
+    split = (C // 3) // 4 * 4
+    qr = [ops.act_qparams(0.05, 131, 8, False), ops.act_qparams(0.02, 90, 8, False)]
     d = ops.groupnorm_desc(x.to(cuda), gamma.to(cuda), beta.to(cuda), ws, B=B, HW=HW, C_=C, ld_x=C, eps=eps,
-                           silu=silu, outs=outs, out_f=out_f, ld_f=C)
+                           silu=silu, outs=outs, out_f=out_f, ld_f=C, raw=(raw_t, C, split, qr[0], qr[1]))
     ops.groupnorm_quant(d)
     torch.cuda.synchronize()
+    x2 = x.reshape(B * HW, C)
+    raw_ref = torch.cat([O.uaq_codes(x2[:, :split], qr[0].delta, qr[0].zero_point, 8, False),
+                         O.uaq_codes(x2[:, split:], qr[1].delta, qr[1].zero_point, 8, False)], dim=1)
+    assert torch.equal(raw_t.cpu().long(), raw_ref.long())
     _report("groupnorm fp32", out_f.reshape(B, HW, C), y, atol=2e-5, rtol=2e-5)
     for (t, _, q) in outs:
         ref = O.uaq_codes(y.reshape(B * HW, C), q.delta, q.zero_point, 8, False)
