@@ -91,7 +91,7 @@ int encode_u8_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* 
 struct GemmPlan {
   CUtensorMap tmA, tmB;
   qd::GemmArgs args;
-  int grid, smem, mode;
+  int grid, mode;
 };
 
 int pick_bn(int N, int tiles_m, int sms, int hint, int step = 16) {
@@ -137,12 +137,7 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
   a.tiles_n = (d->N + a.BN - 1) / a.BN;
   a.a_signed = d->a_signed; a.b_signed = 1;
 
-  const int stage_bytes = qd::GEMM_A_STAGE_BYTES + a.BN * qd::GEMM_BK;
-  int stages = (232448 - 256 - qd::GEMM_EPI_WARPS * qd::GEMM_EPI_TILE_BYTES - 1024 - 1024) / stage_bytes;
-  if (stages > qd::GEMM_MAX_STAGES) stages = qd::GEMM_MAX_STAGES;
-  if (stages < 2) stages = 2;
-  a.stages = stages;
-  pl->smem = qd::gemm_smem_layout(a.BN, stages).total;
+  // pipeline depth / shared-memory size depend on the epilogue variant (8 or 16 staging tiles): launch_gemm_mode()
 
   // ---- A map (always rank 4)
   cuuint64_t dims[4], strides[3];
@@ -208,7 +203,15 @@ int launch_gemm_mode(const GemmPlan& pl, cudaStream_t s) {
     attr_err = cudaFuncSetAttribute(qd::gemm_i8_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) return fail(QD_ERR_CUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-  qd::gemm_i8_kernel<MODE><<<pl.grid, qd::GEMM_THREADS, pl.smem, s>>>(pl.tmA, pl.tmB, pl.args);
+  constexpr int epi_warps = qd::gemm_epi_warps(MODE);
+  qd::GemmArgs a = pl.args;
+  const int stage_bytes = qd::GEMM_A_STAGE_BYTES + a.BN * qd::GEMM_BK;
+  int stages = (232448 - 256 - epi_warps * qd::GEMM_EPI_TILE_BYTES - 1024 - 1024) / stage_bytes;
+  if (stages > qd::GEMM_MAX_STAGES) stages = qd::GEMM_MAX_STAGES;
+  if (stages < 2) stages = 2;
+  a.stages = stages;
+  const int smem = qd::gemm_smem_layout(a.BN, stages, epi_warps).total;
+  qd::gemm_i8_kernel<MODE><<<pl.grid, qd::gemm_threads(MODE), smem, s>>>(pl.tmA, pl.tmB, a);
   return check_launch("gemm_i8_kernel");
 }
 

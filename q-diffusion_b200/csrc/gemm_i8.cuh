@@ -25,8 +25,13 @@ namespace qd {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 128;  // bytes == int8 elements per k-block (one 128B swizzle row)
-constexpr int GEMM_THREADS = 384;   // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
-constexpr int GEMM_EPI_WARPS = 8;    // two warps per TMEM lane quarter, alternating 32-column chunks
+// warps 0-3: TMA / MMA / TMEM alloc / idle; then EPI_WARPS epilogue warps (8 or 16): EPI_WARPS/4 warps per TMEM lane
+// quarter, taking 32-column chunks round-robin.  The instruction-bound epilogues whose register footprint
+// allows it (GEGLU, transposed V^T: <= 102 registers at 640 threads) run with 16 warps = 4 per scheduler.
+__host__ __device__ constexpr int gemm_epi_warps(int MODE) {
+  return (MODE >= 0 && (MODE & (32 | 64)) != 0) ? 16 : 8;   // EPI_GEGLU | EPI_TRANS
+}
+__host__ __device__ constexpr int gemm_threads(int MODE) { return (4 + gemm_epi_warps(MODE)) * 32; }
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK;
 constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_EPI_TILE_BYTES = 32 * 128;  // per-epilogue-warp staging tile (32 rows x 32 int32)
@@ -78,12 +83,12 @@ struct GemmSmemLayout {
   int total;
 };
 
-__host__ __device__ inline GemmSmemLayout gemm_smem_layout(int BN, int stages) {
+__host__ __device__ inline GemmSmemLayout gemm_smem_layout(int BN, int stages, int epi_warps) {
   GemmSmemLayout l;
   l.stage_bytes = GEMM_A_STAGE_BYTES + BN * GEMM_BK;
   l.bar_offset = l.stage_bytes * stages;
   l.stage_off = l.bar_offset + 256;
-  l.total = l.stage_off + GEMM_EPI_WARPS * GEMM_EPI_TILE_BYTES + 1024;  // + alignment slack
+  l.total = l.stage_off + epi_warps * GEMM_EPI_TILE_BYTES + 1024;  // + alignment slack
   return l;
 }
 
@@ -250,14 +255,16 @@ __device__ __forceinline__ void gemm_finalise4(const GemmArgs& p, const QuantK& 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(MODE), 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
   uint8_t* smem = smem_raw + pad;
 
-  const GemmSmemLayout lay = gemm_smem_layout(p.BN, p.stages);
+  constexpr int EPI_WARPS = gemm_epi_warps(MODE);
+  constexpr int CSTEP = 32 * (EPI_WARPS / 4);   // column stride between the chunks of one epilogue warp
+  const GemmSmemLayout lay = gemm_smem_layout(p.BN, p.stages, EPI_WARPS);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_offset);
   uint64_t* full_bar = bars;                          // [stages]
   uint64_t* empty_bar = bars + GEMM_MAX_STAGES;       // [stages]
@@ -282,7 +289,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], GEMM_EPI_WARPS);
+      mbar_init(&tmem_empty[s], EPI_WARPS);
     }
     fence_mbar_init();
     fence_proxy_async();
@@ -400,7 +407,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // Host guarantees rows_per_batch % 32 == 0 (a warp never straddles images), ldq % 16 == 0.
         const int img = m_warp / p.rows_per_batch;
         const int tok0 = m_warp - img * p.rows_per_batch;
-        for (int c = half * 32; c < p.BN; c += 64) {
+        for (int c = half * 32; c < p.BN; c += CSTEP) {
           const int ncols = (p.BN - c) >= 32 ? 32 : 16;
           if (ncols == 32) {
             uint32_t v[32];
@@ -449,7 +456,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // GEGLU projection (ldm/modules/attention.py:42-44) fused with the consumer's quantizer: a 32-column chunk
         // holds 4 x (4 x-features | 4 gate-features); lane -> (row group of 8, pair); 4 iterations cover 32 rows.
         const int r8 = lane >> 2, pq = lane & 3;
-        for (int c = half * 32; c < p.BN; c += 64) {
+        for (int c = half * 32; c < p.BN; c += CSTEP) {
           uint32_t v[32];
           tmem_ld_32x32(t_row + (uint32_t)c, v);
           tmem_ld_wait();
@@ -495,7 +502,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int m = m_warp + lane;
         int cls, img;
         gemm_row_meta(p, m, cls, img);
-        for (int c = half * 32; c < p.BN; c += 64) {
+        for (int c = half * 32; c < p.BN; c += CSTEP) {
           if (p.BN - c >= 32) {
             uint32_t v[32];
             tmem_ld_32x32(t_row + (uint32_t)c, v);
@@ -509,7 +516,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       } else {
-        for (int c = half * 32; c < p.BN; c += 64) {
+        for (int c = half * 32; c < p.BN; c += CSTEP) {
           const int ncols = (p.BN - c) >= 32 ? 32 : 16;
           if (ncols == 32) {
             uint32_t v[32];
