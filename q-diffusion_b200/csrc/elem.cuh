@@ -312,17 +312,29 @@ __global__ void __launch_bounds__(256) layernorm_quant_kernel(const qd_layernorm
     be[k] = q < cq ? *reinterpret_cast<const float4*>(p.beta + (q << 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float inv_c = 1.0f / (float)p.C;
-  for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < p.M;
-       row += (long long)gridDim.x * warps_per_block) {
-    const float* xr = p.x + row * p.ld_x;
-    float4 v[NVEC];
-    float s = 0.f;
+  // the next row of this warp is fetched while the current one is reduced / quantised (register double buffer)
+  auto load_row = [&](long long r, float4 (&dst)[NVEC]) {
+    const float* xr = p.x + r * p.ld_x;
 #pragma unroll
     for (int k = 0; k < NVEC; ++k) {
       const int q = lane + 32 * k;
-      v[k] = q < cq ? *reinterpret_cast<const float4*>(xr + (q << 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+      dst[k] = q < cq ? *reinterpret_cast<const float4*>(xr + (q << 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  };
+  const long long stride = (long long)gridDim.x * warps_per_block;
+  long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  constexpr bool DB = NVEC <= 5;          // wider rows: the second buffer would cost occupancy (or spill)
+  float4 v[NVEC], vn[DB ? NVEC : 1];
+  if (DB && row < p.M) load_row(row, v);
+  for (; row < p.M; row += stride) {
+    if constexpr (DB) {
+      if (row + stride < p.M) load_row(row + stride, vn);
+    } else {
+      load_row(row, v);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NVEC; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     const float mean = s * inv_c;
@@ -355,6 +367,10 @@ __global__ void __launch_bounds__(256) layernorm_quant_kernel(const qd_layernorm
           }
         }
       }
+    }
+    if constexpr (DB) {
+#pragma unroll
+      for (int k = 0; k < NVEC; ++k) v[k] = vn[k];
     }
   }
 }

@@ -29,7 +29,8 @@ constexpr int GEMM_BK = 128;  // bytes == int8 elements per k-block (one 128B sw
 // quarter, taking 32-column chunks round-robin.  The instruction-bound epilogues whose register footprint
 // allows it (GEGLU, transposed V^T: <= 102 registers at 640 threads) run with 16 warps = 4 per scheduler.
 __host__ __device__ constexpr int gemm_epi_warps(int MODE) {
-  return (MODE >= 0 && (MODE & (32 | 64)) != 0) ? 16 : 8;   // EPI_GEGLU | EPI_TRANS
+  // EPI_GEGLU | EPI_TRANS, and plain requantising epilogues (EPI_OUT_Q without residual / rowvec)
+  return (MODE >= 0 && ((MODE & (32 | 64)) != 0 || ((MODE & 16) != 0 && (MODE & (2 | 4)) == 0))) ? 16 : 8;
 }
 __host__ __device__ constexpr int gemm_threads(int MODE) { return (4 + gemm_epi_warps(MODE)) * 32; }
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK;
