@@ -70,8 +70,10 @@ __host__ __device__ __forceinline__ int att_vt_perm(int t) {
 }
 
 // zq * rowsum_d(k[b, j, head h]) for every key: the only zero-point cross term that survives the softmax.
+// bias_minus = 0: ws = zq*rowsum (subtracted by the mma.sync kernel).  Otherwise ws = bias - zq*rowsum, ADDED to the raw
+// score by the tcgen05 kernel: with bias = 0x4B400000 the sum is at once the corrected score and its magic-number float form.
 template <bool SIGNED>
-__global__ void att_krowsum_kernel(const qd_attention_desc p, int tk_pad) {
+__global__ void att_krowsum_kernel(const qd_attention_desc p, int tk_pad, int bias_minus = 0, int bias = 0) {
   const long long total = (long long)p.B * p.heads * tk_pad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(i % tk_pad);
@@ -86,7 +88,7 @@ __global__ void att_krowsum_kernel(const qd_attention_desc p, int tk_pad) {
         s += SIGNED ? __dp4a((int)v, 0x01010101, 0) : (int)__dp4a(v, 0x01010101u, 0u);
       }
     }
-    reinterpret_cast<int*>(p.ws)[i] = p.zq * s;
+    reinterpret_cast<int*>(p.ws)[i] = bias_minus ? bias - p.zq * s : p.zq * s;
   }
 }
 

@@ -220,6 +220,12 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     float2* stat = reinterpret_cast<float2*>(smem + L.stat_off);
     int sb = 0, st = 0;
     uint32_t ph_s = 0, ph_kv = 0;
+    // Scores are handled in BIASED integer form t = S_raw - zq*rowsum(k) + BIAS (one IADD against the staged
+    // "BIAS - zq*rowsum" table): with BIAS = 0x4B400000 (d <= 64, |S| < 2^22) the same register is the score for the
+    // integer row max AND the bit pattern of the float 1.5*2^23 + S, so the int->float conversion is a single FADD.
+    constexpr int BIAS = MAGIC ? 0x4B400000 : 0;
+    constexpr int MASKED = MAGIC ? BIAS - (1 << 22) + 1 : INT_MIN / 2;
+    auto tof = [](int t) -> float { return MAGIC ? __int_as_float(t) - 12582912.0f : (float)t; };
     int mi = INT_MIN;
     float l = 0.f;
     // ---- pass 1
@@ -235,28 +241,28 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         int s[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          int4 z = make_int4(0, 0, 0, 0);
+          int4 z = make_int4(BIAS, BIAS, BIAS, BIAS);
           if (has_zq) z = *reinterpret_cast<const int4*>(zr + j);
-          s[j] = (int)v[j] - z.x; s[j + 1] = (int)v[j + 1] - z.y; s[j + 2] = (int)v[j + 2] - z.z; s[j + 3] = (int)v[j + 3] - z.w;
+          s[j] = (int)v[j] + z.x; s[j + 1] = (int)v[j + 1] + z.y; s[j + 2] = (int)v[j + 2] + z.z; s[j + 3] = (int)v[j + 3] + z.w;
         }
         bool any_valid = true;
         if (j0 + 32 > p.Tk) {     // ragged last tile: masked keys drop out of the max and of the sum
           any_valid = j0 < p.Tk;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (j0 + j >= p.Tk) s[j] = MAGIC ? -(1 << 22) + 1 : INT_MIN / 2;
+            if (j0 + j >= p.Tk) s[j] = MASKED;
         }
         if (any_valid) {
           int tm = s[0];
 #pragma unroll
           for (int j = 1; j < 32; ++j) tm = max(tm, s[j]);
           if (tm > mi) { l *= (mi == INT_MIN) ? 0.f : ex2_approx((float)(mi - tm) * c); mi = tm; }
-          const float b0 = -(float)mi * c;
+          const float b0 = -(float)(mi - BIAS) * c;
           float a0 = 0.f, a1 = 0.f;
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            a0 += ex2_approx(fmaf(att_i2f<MAGIC>(s[j]), c, b0));
-            a1 += ex2_approx(fmaf(att_i2f<MAGIC>(s[j + 1]), c, b0));
+            a0 += ex2_approx(fmaf(tof(s[j]), c, b0));
+            a1 += ex2_approx(fmaf(tof(s[j + 1]), c, b0));
           }
           l += a0 + a1;
         }
@@ -285,7 +291,7 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int mo = __float_as_int(o.x);
         lt += o.y * ((mo == INT_MIN) ? 0.f : ex2_approx((float)(mo - mm) * c));
       }
-      off = -(float)mm * c + log2f(1.0f / (lt * p.delta_w));
+      off = -(float)(mm - BIAS) * c + log2f(1.0f / (lt * p.delta_w));
     }
     // ---- pass 2
     int pb = 0;
@@ -305,13 +311,13 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         uint32_t cd[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          int4 z = make_int4(0, 0, 0, 0);
+          int4 z = make_int4(BIAS, BIAS, BIAS, BIAS);
           if (has_zq) z = *reinterpret_cast<const int4*>(zr + j);
-          const int s0 = (int)v[j] - z.x, s1 = (int)v[j + 1] - z.y, s2 = (int)v[j + 2] - z.z, s3 = (int)v[j + 3] - z.w;
-          cd[j] = __float_as_uint(fminf(ex2_approx(fmaf(att_i2f<MAGIC>(s0), c, off)), pmax) + 12582912.0f);
-          cd[j + 1] = __float_as_uint(fminf(ex2_approx(fmaf(att_i2f<MAGIC>(s1), c, off)), pmax) + 12582912.0f);
-          cd[j + 2] = __float_as_uint(fminf(ex2_approx(fmaf(att_i2f<MAGIC>(s2), c, off)), pmax) + 12582912.0f);
-          cd[j + 3] = __float_as_uint(fminf(ex2_approx(fmaf(att_i2f<MAGIC>(s3), c, off)), pmax) + 12582912.0f);
+          const int s0 = (int)v[j] + z.x, s1 = (int)v[j + 1] + z.y, s2 = (int)v[j + 2] + z.z, s3 = (int)v[j + 3] + z.w;
+          cd[j] = __float_as_uint(fminf(ex2_approx(fmaf(tof(s0), c, off)), pmax) + 12582912.0f);
+          cd[j + 1] = __float_as_uint(fminf(ex2_approx(fmaf(tof(s1), c, off)), pmax) + 12582912.0f);
+          cd[j + 2] = __float_as_uint(fminf(ex2_approx(fmaf(tof(s2), c, off)), pmax) + 12582912.0f);
+          cd[j + 3] = __float_as_uint(fminf(ex2_approx(fmaf(tof(s3), c, off)), pmax) + 12582912.0f);
         }
         if (j0 + 32 > p.Tk) {
 #pragma unroll
@@ -325,8 +331,11 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           uint32_t lo[4], hi[4];
 #pragma unroll
           for (int bq = 0; bq < 4; ++bq) {
-            lo[bq] = __byte_perm(__byte_perm(e[2 * bq], e[2 * bq + 1], 0x0040), __byte_perm(e[8 + 2 * bq], e[9 + 2 * bq], 0x0040), 0x5410);
-            if (SM16) hi[bq] = __byte_perm(__byte_perm(e[2 * bq], e[2 * bq + 1], 0x0051), __byte_perm(e[8 + 2 * bq], e[9 + 2 * bq], 0x0051), 0x5410);
+            // [a.b0 a.b1 b.b0 b.b1] and [c.b0 c.b1 d.b0 d.b1], then even bytes = lo plane, odd bytes = hi plane
+            const uint32_t u = __byte_perm(e[2 * bq], e[2 * bq + 1], 0x5410);
+            const uint32_t w = __byte_perm(e[8 + 2 * bq], e[9 + 2 * bq], 0x5410);
+            lo[bq] = __byte_perm(u, w, 0x6420);
+            if (SM16) hi[bq] = __byte_perm(u, w, 0x7531);
           }
           const int chunk = part * 2 + gq;                         // 16-byte chunk of the 128-key row
           const int sw = (chunk ^ (row & 7)) << 4;

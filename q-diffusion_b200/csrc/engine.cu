@@ -484,8 +484,9 @@ int launch_attention_tc(const qd_attention_desc& d, cudaStream_t s) {
   if (d.zq != 0) {
     if (!d.ws) return fail(QD_ERR_BAD_ARG, "attention: workspace required when zq != 0");
     const int tk_pad = qd::att_ws_stride(d.Tk);
-    if (d.q_signed) qd::att_krowsum_kernel<true><<<grid_for((long long)d.B * d.heads * tk_pad, 256), 256, 0, s>>>(d, tk_pad);
-    else qd::att_krowsum_kernel<false><<<grid_for((long long)d.B * d.heads * tk_pad, 256), 256, 0, s>>>(d, tk_pad);
+    const int bias = d.d <= 64 ? 0x4B400000 : 0;   // MAGIC variant of the kernel (see attention_tc.cuh)
+    if (d.q_signed) qd::att_krowsum_kernel<true><<<grid_for((long long)d.B * d.heads * tk_pad, 256), 256, 0, s>>>(d, tk_pad, 1, bias);
+    else qd::att_krowsum_kernel<false><<<grid_for((long long)d.B * d.heads * tk_pad, 256), 256, 0, s>>>(d, tk_pad, 1, bias);
     rc = check_launch("att_krowsum_kernel");
     if (rc) return rc;
   }
