@@ -177,7 +177,16 @@ def gemm_roofline(prog, pk):
     tot_ops = sum(prog.op_flops[i] for i, _, _ in evs)
     achieved = tot_ops / (tot_ms * 1e-3) / 1e12
     peak = 2.0 * pk["bf16_sustained"]
-    return dict(bound="tensor", achieved=achieved, peak=peak, unit="TOP/s", frac=achieved / peak, traffic=None,
+    # DRAM bytes per GEMM launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over one step's launches) from the
+    # committed ncu pass over this same command: tools/launch_summary.py --traffic writes the file
+    traffic, tsrc = None, None
+    tf = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_roofline_traffic.json")
+    if os.path.exists(tf):
+        with open(tf) as f:
+            tj = json.load(f)
+        traffic, tsrc = tj.get("gemm_dram_bytes_per_launch"), tj.get("source")
+    return dict(bound="tensor", achieved=achieved, peak=peak, unit="TOP/s", frac=achieved / peak, traffic=traffic,
+                traffic_source=tsrc,
                 kernel="gemm_i8_kernel (tcgen05.mma kind::i8)", launches=len(evs), gemm_ms_per_step=tot_ms,
                 peak_source=f"2 x bf16_tflops_sustained ({pk['source']}); INT8 dense = 2x bf16 on sm_100a",
                 note="events bracket each launch individually (serialised, includes launch gaps)")
@@ -260,11 +269,13 @@ def main():
     launches0 = L.qd_launch_count()
     with ClockSampler(local) as clocks:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.profiler.start()    # no-op unless run under `ncu --profile-from-start off` (profiles/: launch list)
         e0.record()
         for i in range(args.steps):
             step(args.warmup + i, x, nxt)
         e1.record()
         barrier()
+        torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     launches = L.qd_launch_count() - launches0
     prog = qnn.program(torch.cat([x, x]), ctx)

@@ -170,28 +170,42 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const qd_groupnorm_desc p
     if (k < nq) {
       const int c = (threadIdx.x + k * blockDim.x) << 2;
       const float* xp = p.x + ((long long)b * p.HW + r0) * p.ld_x + c;
-#pragma unroll 4   // (8-deep unrolling with 64-row slabs measured 20% slower: fewer, fatter blocks)
-      for (int r = r0; r < r1; ++r, xp += p.ld_x) {
-        const float4 v = *reinterpret_cast<const float4*>(xp);
-        if (p.raw_q) {
-          const QuantK& kr = qraw[c < p.raw_split ? 0 : 1];
-          *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.raw_q) + ((long long)b * p.HW + r) * p.ld_raw + c) =
-              pack4(quant_code(v.x, kr), quant_code(v.y, kr), quant_code(v.z, kr), quant_code(v.w, kr));
-        }
-        float y[4] = {fmaf(v.x, ca[k][0], cb[k][0]), fmaf(v.y, ca[k][1], cb[k][1]), fmaf(v.z, ca[k][2], cb[k][2]),
-                      fmaf(v.w, ca[k][3], cb[k][3])};
-        if (p.silu) {
+      // Rows go in batches of GN_BATCH: all loads of a batch are issued before its first store.  The outputs may
+      // alias x as far as the compiler knows, so in a plain row loop every load waited for the previous row's
+      // stores - one DRAM round trip per row, 1.9 TB/s where gn_partial reads the same tensor at 4.1 TB/s
+      // (profiles/r01_launches_step_final.summary.txt).
+      constexpr int GN_BATCH = 8;
+      for (int rb = r0; rb < r1; rb += GN_BATCH) {
+        float4 vv[GN_BATCH];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) y[j] = silu_f(y[j]);
-        }
-        const long long row = (long long)b * p.HW + r;
-        if (p.out_f) *reinterpret_cast<float4*>(p.out_f + row * p.ld_f + c) = make_float4(y[0], y[1], y[2], y[3]);
+        for (int i = 0; i < GN_BATCH; ++i)
+          if (rb + i < r1) vv[i] = *reinterpret_cast<const float4*>(xp + (long long)i * p.ld_x);
+        xp += (long long)GN_BATCH * p.ld_x;
 #pragma unroll
-        for (int o = 0; o < 3; ++o) {
-          if (o < p.n_out) {
-            const uint32_t code = pack4(quant_code_fast(y[0], qk[o]), quant_code_fast(y[1], qk[o]),
-                                        quant_code_fast(y[2], qk[o]), quant_code_fast(y[3], qk[o]));
-            *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.out_q[o]) + row * p.ld_q[o] + c) = code;
+        for (int i = 0; i < GN_BATCH; ++i) {
+          const int r = rb + i;
+          if (r >= r1) break;
+          const float4 v = vv[i];
+          const long long row = (long long)b * p.HW + r;
+          if (p.raw_q) {
+            const QuantK& kr = qraw[c < p.raw_split ? 0 : 1];
+            *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.raw_q) + row * p.ld_raw + c) =
+                pack4(quant_code(v.x, kr), quant_code(v.y, kr), quant_code(v.z, kr), quant_code(v.w, kr));
+          }
+          float y[4] = {fmaf(v.x, ca[k][0], cb[k][0]), fmaf(v.y, ca[k][1], cb[k][1]), fmaf(v.z, ca[k][2], cb[k][2]),
+                        fmaf(v.w, ca[k][3], cb[k][3])};
+          if (p.silu) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) y[j] = silu_f(y[j]);
+          }
+          if (p.out_f) *reinterpret_cast<float4*>(p.out_f + row * p.ld_f + c) = make_float4(y[0], y[1], y[2], y[3]);
+#pragma unroll
+          for (int o = 0; o < 3; ++o) {
+            if (o < p.n_out) {
+              const uint32_t code = pack4(quant_code_fast(y[0], qk[o]), quant_code_fast(y[1], qk[o]),
+                                          quant_code_fast(y[2], qk[o]), quant_code_fast(y[3], qk[o]));
+              *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.out_q[o]) + row * p.ld_q[o] + c) = code;
+            }
           }
         }
       }
