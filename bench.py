@@ -95,6 +95,28 @@ class ClockSampler:
                     reasons=reasons, samples=len(self.rows))
 
 
+def host_threads(cap=32):
+    """CPU threads this process may really use: affinity mask and cgroup quota, not os.cpu_count() (the GPU boxes
+    report 128+ logical CPUs to a container that owns far fewer; 128 torch threads there ran the oracle 10-50x slower)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:
+                quota = int(f.read())
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                period = int(f.read())
+            if quota > 0:
+                n = min(n, max(1, quota // period))
+        except (OSError, ValueError):
+            pass
+    return max(1, min(n, cap))
+
+
 def cpu_baseline(ckpt=None, max_seconds=40.0):
     """The reference's CPU path (oracle port: fake-quant fp32 torch, host threads) on a bounded sample:
     ONE UNet evaluation of ONE image of the same SD workload; images/s = 1 / (2 * 51 * t_eval)."""
@@ -125,7 +147,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    torch.set_num_threads(min(os.cpu_count() or 1, 32))
+    torch.set_num_threads(host_threads())
     import contextlib
     from qdiff_b200 import synth
     with contextlib.redirect_stdout(sys.stderr):
@@ -144,10 +166,13 @@ def run_reference_arm(args):
     value = IMAGES_PER_GPU / (UNET_EVALS_PER_IMAGE_BATCH * ms_per_step * 1e-3)
     cb.update(value=value, sample=f"{len(times)} x 1 UNet evaluation at batch 1, scaled x16 to one batch-16 step")
     print(json.dumps({
-        "impl": "reference", "metric": "images_per_sec", "value": value, "unit": "images/s", "n_gpus": 0,
+        "impl": "reference", "metric": "images_per_sec", "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": len(times), "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "fp32 fake-quant (reference simulation)", "data": "synthetic",
-        "config": {"workload": "SD v1-4 UNet W4A8 sm_abit16 split, PLMS-50 CFG 7.5, 8 images (CPU sample: batch 1)"},
+        "config": {"workload": "SD v1-4 UNet (860M) W4A8 asymmetric, sm_abit 16, split shortcut; PLMS-50 + CFG 7.5; "
+                               "8 images/GPU -> UNet batch 16, 64x64x4 latents, 77x768 context",
+                   "step": "1 denoising step = 1 UNet evaluation at batch 16 (CPU arm: one batch-1 evaluation timed, x16)",
+                   "host_threads": torch.get_num_threads()},
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -344,7 +369,7 @@ def main():
         line["roofline"] = gemm_roofline(prog, pk)
         line["roofline"]["whole_step_frac"] = step_tops / line["roofline"]["peak"]
     if world == 1 and not args.no_cpu_baseline:
-        torch.set_num_threads(min(os.cpu_count() or 1, 32))
+        torch.set_num_threads(host_threads())
         cb = cpu_baseline(ckpt)
         cb["value"] = cb["value"]
         line["cpu_baseline"] = cb
