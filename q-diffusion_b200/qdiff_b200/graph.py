@@ -60,7 +60,9 @@ class Program:
         self.graph = None
 
     def _launch(self):
+        n0 = lib().qd_launch_count()
         check(lib().qd_engine_run(self.engine, _lib.stream_ptr()), "qd_engine_run")
+        self.kernel_launches = int(lib().qd_launch_count() - n0)   # exact: counted by the library at launch time
 
     def run(self, x, timesteps, context=None):
         self.x_in.copy_(x.to(torch.float32))
@@ -885,6 +887,6 @@ def compile_unet(qnn, x_shape, ctx_shape, device, use_cuda_graph=True):
     check(lib().qd_engine_finalize(b.engine), "qd_engine_finalize")
     prog = Program(b.engine, b.keep, x_in, t_in, ctx_in, out, b.nops, b.traces, use_cuda_graph)
     prog.op_names, prog.op_kinds, prog.op_flops = b.op_names, b.op_kinds, b.op_flops
-    prog.kernel_launches = sum(3 if k == _lib.QD_OP_GROUPNORM else 1 for k in b.op_kinds)
+    prog.kernel_launches = sum(3 if k == _lib.QD_OP_GROUPNORM else 1 for k in b.op_kinds)   # until the first run
     prog.layer_traces = b.layer_traces
     return prog
