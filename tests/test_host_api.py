@@ -23,6 +23,36 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
 
 
+def test_ctypes_mirror_matches_the_header_layout(tmp_path):
+    """sizeof / offsetof of every descriptor as the C compiler sees include/qdiff_b200.h == the ctypes mirror."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from qdiff_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    pairs = {"qd_qparams": _lib.QParams, "qd_gemm_desc": _lib.GemmDesc, "qd_quantize_desc": _lib.QuantizeDesc,
+             "qd_groupnorm_desc": _lib.GroupNormDesc, "qd_layernorm_desc": _lib.LayerNormDesc,
+             "qd_im2col_desc": _lib.Im2colDesc, "qd_attention_desc": _lib.AttentionDesc,
+             "qd_sampler_desc": _lib.SamplerDesc, "qd_misc_desc": _lib.MiscDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "qdiff_b200.h")}"',
+             'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-o", str(exe), str(src)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(out[cname]) == C.sizeof(cls), (cname, out[cname], C.sizeof(cls))
+        for fname, _ in cls._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_checkpoint_keys_roundtrip(name):
     """Wrapping our containers + resume_cali_model must consume exactly the reference's checkpoint keys."""
