@@ -49,6 +49,10 @@ typedef struct qd_qparams {
  *       top/mid/bottom x left/mid/right) because the reference zero-pads after de-quantisation.
  * geglu: GEGLU projection fused with its consumer's quantizer: N counts x AND gate columns, interleaved in
  *       groups of 4 (w row 8b+i = x-feature 4b+i, row 8b+4+i = gate-feature 4b+i); out_q is [M, N/2].
+ * w_int4_packed: the 4-bit weight codes stay packed in HBM (K3 of the survey): w is [n_rows][taps*C/2] bytes, byte j of a
+ *       row = wq[2j] | wq[2j+1] << 4 with UNSIGNED codes wq in [0,15]; w_zero[n] in [0,15] is the row's zero point.  The
+ *       kernel unpacks to wq - w_zero (s8) in shared memory between the TMA load and the MMA; everything else
+ *       (scale, corr, epilogue) is unchanged.  Halves the weight bytes in HBM and through L2.
  * Output: fp32 `out` and/or re-quantised codes `out_q` with the consumer's quantizer `oq`
  *       (out_q_transposed: [M/rows_per_batch][N][ldq], ldq >= rows_per_batch, 16-token groups permuted as
  *       qd_qattention expects its V^T operand).
@@ -80,6 +84,9 @@ typedef struct qd_gemm_desc {
   int32_t out_q_head_pitch; /*      (n / head_dim) * head_pitch + n % head_dim   (attention Q / K operands) */
   int32_t geglu;         /* 1: rows of w (and scale/bias/corr) are interleaved [4 x-features, 4 gate-features]...;
                             out_q receives Q(x * gelu_erf(gate)) with N/2 columns (ldm/modules/attention.py:42-44) */
+  int32_t w_int4_packed; /* 1: w holds packed unsigned 4-bit codes, see above */
+  int32_t reserved3;
+  const int8_t* w_zero;  /* [n_rows] zero points of the packed codes (w_int4_packed only) */
 } qd_gemm_desc;
 
 int qd_qgemm_i8(const qd_gemm_desc* d, qd_stream_t stream);

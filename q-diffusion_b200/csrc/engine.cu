@@ -81,6 +81,7 @@ int encode_u8_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* 
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE :
                    swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(QD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -168,13 +169,24 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
   }
   int rc = encode_u8_map(&pl->tmA, d->a, 4, dims, strides, box);
   if (rc) return rc;
-  // ---- B map: [w_rows][taps*C]
+  // ---- B map: [w_rows][taps*C] s8, or [w_rows][taps*C/2] packed 4-bit codes (unswizzled: warps 2-3 re-lay it out)
   {
     const int w_rows = d->w_rows > 0 ? d->w_rows : d->N;
-    cuuint64_t bd[2] = {(cuuint64_t)d->taps * d->C, (cuuint64_t)w_rows};
-    cuuint64_t bs[1] = {(cuuint64_t)d->taps * d->C};
-    cuuint32_t bb[2] = {qd::GEMM_BK, (cuuint32_t)a.BN};
-    rc = encode_u8_map(&pl->tmB, d->w, 2, bd, bs, bb);
+    if (d->w_int4_packed) {
+      if (!d->w_zero) return fail(QD_ERR_BAD_ARG, "gemm: packed INT4 weights need w_zero");
+      if (((uintptr_t)d->w) & 15) return fail(QD_ERR_BAD_ARG, "gemm: packed weights must be 16-byte aligned");
+      cuuint64_t bd[2] = {(cuuint64_t)d->taps * d->C / 2, (cuuint64_t)w_rows};
+      cuuint64_t bs[1] = {(cuuint64_t)d->taps * d->C / 2};
+      cuuint32_t bb[2] = {qd::GEMM_BK / 2, (cuuint32_t)a.BN};
+      rc = encode_u8_map(&pl->tmB, d->w, 2, bd, bs, bb, 0);
+      a.w4 = 1;
+      a.wzero = d->w_zero;
+    } else {
+      cuuint64_t bd[2] = {(cuuint64_t)d->taps * d->C, (cuuint64_t)w_rows};
+      cuuint64_t bs[1] = {(cuuint64_t)d->taps * d->C};
+      cuuint32_t bb[2] = {qd::GEMM_BK, (cuuint32_t)a.BN};
+      rc = encode_u8_map(&pl->tmB, d->w, 2, bd, bs, bb);
+    }
     if (rc) return rc;
   }
   a.out = d->out; a.ldo = d->ldo;
@@ -205,12 +217,12 @@ int launch_gemm_mode(const GemmPlan& pl, cudaStream_t s) {
   if (attr_err != cudaSuccess) return fail(QD_ERR_CUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   constexpr int epi_warps = qd::gemm_epi_warps(MODE);
   qd::GemmArgs a = pl.args;
-  const int stage_bytes = qd::GEMM_A_STAGE_BYTES + a.BN * qd::GEMM_BK;
+  const int stage_bytes = qd::gemm_stage_footprint(a.BN, a.w4);
   int stages = (232448 - 256 - epi_warps * qd::GEMM_EPI_TILE_BYTES - 1024 - 1024) / stage_bytes;
   if (stages > qd::GEMM_MAX_STAGES) stages = qd::GEMM_MAX_STAGES;
   if (stages < 2) stages = 2;
   a.stages = stages;
-  const int smem = qd::gemm_smem_layout(a.BN, stages, epi_warps).total;
+  const int smem = qd::gemm_smem_layout(a.BN, stages, epi_warps, a.w4).total;
   qd::gemm_i8_kernel<MODE><<<pl.grid, qd::gemm_threads(MODE), smem, s>>>(pl.tmA, pl.tmB, a);
   return check_launch("gemm_i8_kernel");
 }

@@ -75,19 +75,29 @@ struct GemmArgs {
   long long ldr;
   int geglu;
   int oq_d, oq_pitch;      // > 0: per-head padded code layout for row-major out_q
+  // packed INT4 weights (K3): the B tile arrives as BN x 64 packed bytes and warps 2-3 expand it to the s8
+  // 128B-swizzled operand tile in shared memory (wq - wzero[n]) before the MMA consumes the stage
+  int w4;
+  const int8_t* wzero;     // [w_rows]
 };
 
 struct GemmSmemLayout {
   int stage_bytes;
+  int pack_off;   // packed-INT4 B tiles, stages x BN x 64 bytes (w4 only)
   int bar_offset;
   int stage_off;  // epilogue staging tiles (4 warps)
   int total;
 };
 
-__host__ __device__ inline GemmSmemLayout gemm_smem_layout(int BN, int stages, int epi_warps) {
+__host__ __device__ inline int gemm_stage_footprint(int BN, int w4) {
+  return GEMM_A_STAGE_BYTES + BN * GEMM_BK + (w4 ? BN * (GEMM_BK / 2) : 0);
+}
+
+__host__ __device__ inline GemmSmemLayout gemm_smem_layout(int BN, int stages, int epi_warps, int w4 = 0) {
   GemmSmemLayout l;
   l.stage_bytes = GEMM_A_STAGE_BYTES + BN * GEMM_BK;
-  l.bar_offset = l.stage_bytes * stages;
+  l.pack_off = l.stage_bytes * stages;
+  l.bar_offset = l.pack_off + (w4 ? stages * BN * (GEMM_BK / 2) : 0);
   l.stage_off = l.bar_offset + 256;
   l.total = l.stage_off + epi_warps * GEMM_EPI_TILE_BYTES + 1024;  // + alignment slack
   return l;
@@ -265,13 +275,14 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   constexpr int EPI_WARPS = gemm_epi_warps(MODE);
   constexpr int CSTEP = 32 * (EPI_WARPS / 4);   // column stride between the chunks of one epilogue warp
-  const GemmSmemLayout lay = gemm_smem_layout(p.BN, p.stages, EPI_WARPS);
+  const GemmSmemLayout lay = gemm_smem_layout(p.BN, p.stages, EPI_WARPS, p.w4);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_offset);
   uint64_t* full_bar = bars;                          // [stages]
   uint64_t* empty_bar = bars + GEMM_MAX_STAGES;       // [stages]
   uint64_t* tmem_full = bars + 2 * GEMM_MAX_STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;               // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* ready_bar = tmem_empty + 2;               // [stages] (w4: B tile unpacked, stage ready for the MMA)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ready_bar + GEMM_MAX_STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -287,6 +298,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&ready_bar[s], 2);    // one arrival per unpack warp
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -309,7 +321,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = (uint32_t)lay.stage_bytes;
+      const uint32_t tx_bytes = (uint32_t)(GEMM_A_STAGE_BYTES + (p.w4 ? p.BN * (GEMM_BK / 2) : p.BN * GEMM_BK));
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int tm = tile / p.tiles_n;
         const int tn = tile - tm * p.tiles_n;
@@ -332,7 +344,11 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_4d(sa, &tmA, &full_bar[stage], kc * GEMM_BK, kx - 1, h0 + ky - 1, b0);
             else
               tma_load_4d(sa, &tmA, &full_bar[stage], kc * GEMM_BK, m0, 0, 0);
-            tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.C + kc * GEMM_BK, n0);
+            if (p.w4)
+              tma_load_2d(smem + lay.pack_off + (size_t)stage * p.BN * (GEMM_BK / 2), &tmB, &full_bar[stage],
+                          (tap * p.C + kc * GEMM_BK) / 2, n0);
+            else
+              tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.C + kc * GEMM_BK, n0);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -354,7 +370,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int kc = kb % kb_per_tap;
           const int rem = p.C - kc * GEMM_BK;
           const int nmma = rem >= GEMM_BK ? 4 : (rem >> 5);
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(p.w4 ? &ready_bar[stage] : &full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * lay.stage_bytes);
           const uint64_t da = make_smem_desc_sw128(sa);
@@ -370,7 +386,57 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    // ===================== INT4 unpack (warps 2-3, packed-weight GEMMs only) =====================
+    // 64 threads = 16 rows x 4 sixteen-byte pieces per pass.  A piece holds 32 codes (k = 32j .. 32j+31 of the
+    // k-block) and becomes two 16-byte chunks of the row in the 128B-swizzled s8 tile the MMA descriptor expects
+    // (chunk index XOR row&7, identical to what TMA SWIZZLE_128B writes on the unpacked path).
+    if (p.w4) {
+      const int t = threadIdx.x - 64;
+      const int r16 = t >> 2, piece = t & 3;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tn = tile % p.tiles_n;
+        const int n0 = tn * p.BN;
+        uint32_t zp4[16];     // per-row zero point replicated into 4 bytes, rows r16 + 16*i
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int n = n0 + r16 + 16 * i;
+          zp4[i] = (16 * i < p.BN && n < p.N) ? 0x01010101u * (uint32_t)(uint8_t)__ldg(p.wzero + n) : 0u;
+        }
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          const uint8_t* sp = smem + lay.pack_off + (size_t)stage * p.BN * (GEMM_BK / 2);
+          uint8_t* sb = smem + (size_t)stage * lay.stage_bytes + GEMM_A_STAGE_BYTES;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int row = r16 + 16 * i;
+            if (16 * i < p.BN) {
+              const uint4 w = *reinterpret_cast<const uint4*>(sp + row * (GEMM_BK / 2) + piece * 16);
+              const uint32_t in[4] = {w.x, w.y, w.z, w.w};
+              uint32_t o[8];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                // (code | 0x80) - zp never borrows across bytes; ^0x80 then yields the signed byte code - zp
+                const uint32_t lo = ((in[q] & 0x0F0F0F0Fu) | 0x80808080u) - zp4[i];
+                const uint32_t hi = (((in[q] >> 4) & 0x0F0F0F0Fu) | 0x80808080u) - zp4[i];
+                o[2 * q] = __byte_perm(lo, hi, 0x5140) ^ 0x80808080u;        // k = 8q+0..3: lo0 hi0 lo1 hi1
+                o[2 * q + 1] = __byte_perm(lo, hi, 0x7362) ^ 0x80808080u;    // k = 8q+4..7: lo2 hi2 lo3 hi3
+              }
+              uint8_t* dst = sb + row * GEMM_BK;
+              *reinterpret_cast<uint4*>(dst + (((2 * piece) ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<uint4*>(dst + (((2 * piece + 1) ^ (row & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+          }
+          fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ready_bar[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
     // ===================== epilogue =====================
     // TMEM gives each thread one accumulator ROW; storing that way makes every warp store touch 32
     // different rows (16 B each).  Row-major outputs therefore go through a per-warp 32x32 int32

@@ -36,6 +36,7 @@ class GemmDesc(C.Structure):
         ("out_q", c_vp), ("ldq", c_ll),
         ("oq", QParams),
         ("bn_hint", c_i32), ("out_q_head_dim", c_i32), ("out_q_head_pitch", c_i32), ("geglu", c_i32),
+        ("w_int4_packed", c_i32), ("reserved3", c_i32), ("w_zero", c_vp),
     ]
 
 

@@ -12,6 +12,7 @@ with the Quant*Block forwards of qdiff/quant_block.py (cited at each lowering fu
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -115,6 +116,10 @@ class Builder:
         self.engine = e
         self.keep = []       # tensors referenced by recorded ops
         self.nops = 0
+        # QDIFF_W4_PACKED=1: 4-bit weight layers keep their codes packed in HBM (half the weight bytes; the unpack
+        # warps add latency to the k-loop, so the default bench path uses the s8 layout: DESIGN.md section 6)
+        self.w4_packed = os.environ.get("QDIFF_W4_PACKED", "0") == "1"
+        self.packed_layers = 0
         self.traces = {}     # block name -> (Act, (H, W)) for parity debugging
         self.layer_traces = {}  # module key -> fp32 Act of that QuantModule's output
         self.op_names = []
@@ -310,7 +315,15 @@ class Builder:
         if k_pad is not None and k_pad != wk.shape[1]:
             wk = torch.nn.functional.pad(wk, (0, k_pad - wk.shape[1]))
             Cred = k_pad
-        w_dev = wk.to(torch.int8).contiguous()
+        w_dev, w_zero = None, None
+        if self.w4_packed:                      # K3: keep 4-bit codes packed in HBM, the GEMM unpacks in shared memory
+            pk = ops.pack_int4(wk.reshape(wk.shape[0], -1))
+            if pk is not None:
+                w_dev, w_zero = pk[0].to(self.dev), pk[1].to(self.dev)
+                self.keep.append(w_zero)
+                self.packed_layers += 1
+        if w_dev is None:
+            w_dev = wk.to(torch.int8).contiguous()
         self.keep.append(w_dev)
         scale = (delta_w.double() * float(dx) * out_scale * _wscale).to(torch.float32).contiguous()
         self.keep.append(scale)
@@ -364,7 +377,8 @@ class Builder:
                           out_q=oq_act.t if oq_act is not None else None,
                           ldq=(oq_act.t_pad if transposed else oq_act.ld) if oq_act is not None else 0,
                           oq=oq_params, out_q_transposed=transposed, geglu=geglu_q is not None,
-                          out_q_head=out_q_head if (out_q is not None and not transposed) else None)
+                          out_q_head=out_q_head if (out_q is not None and not transposed) else None, w_zero=w_zero,
+                          w_rows=wk.shape[0])
         d.a = a.ptr + (cols[0] if cols is not None else 0)
         if rowvec is not None:
             d.rowvec = rowvec.ptr

@@ -32,7 +32,7 @@ def _require_cuda(*ts):
 
 def gemm_desc(a, w, scale, *, M, N, C, taps=1, lda=None, conv_bhw=None, a_signed=True, bias=None, corr=None,
               rowvec=None, ld_rowvec=0, rows_per_batch=0, residual=None, ldr=0, out=None, ldo=0, out_q=None, ldq=0,
-              oq=None, out_q_transposed=False, bn_hint=0, w_rows=None, geglu=False, out_q_head=None):
+              oq=None, out_q_transposed=False, bn_hint=0, w_rows=None, geglu=False, out_q_head=None, w_zero=None):
     d = GemmDesc()
     d.a, d.w = ptr(a), ptr(w)
     d.lda = int(lda if lda is not None else C)
@@ -52,7 +52,26 @@ def gemm_desc(a, w, scale, *, M, N, C, taps=1, lda=None, conv_bhw=None, a_signed
     d.geglu = 1 if geglu else 0
     if out_q_head is not None:
         d.out_q_head_dim, d.out_q_head_pitch = int(out_q_head[0]), int(out_q_head[1])
+    if w_zero is not None:      # w = packed unsigned 4-bit codes [rows][K/2], w_zero = per-row zero points (int8)
+        d.w_int4_packed, d.w_zero = 1, ptr(w_zero)
     return d
+
+
+def pack_int4(ws):
+    """s8 zero-point-free weight codes [rows, K] (each row spanning at most 15) -> (packed u8 [rows, K/2], zero int8 [rows]),
+    with ws == unpacked - zero[:, None].  Returns None when a row does not fit 4 bits."""
+    import torch
+    ws = ws.to(torch.int16)
+    lo, hi = ws.amin(dim=1), ws.amax(dim=1)
+    if int((hi - lo).max()) > 15 or ws.shape[1] % 2:
+        return None
+    zero = (-lo).clamp(0, 15)
+    zero = torch.where(hi + zero > 15, 15 - hi, zero)        # keep wq = ws + zero inside [0, 15]
+    wq = ws + zero[:, None]
+    if int(wq.min()) < 0 or int(wq.max()) > 15 or int(zero.min()) < 0:
+        return None
+    packed = (wq[:, 0::2] | (wq[:, 1::2] << 4)).to(torch.uint8).contiguous()
+    return packed, zero.to(torch.int8).contiguous()
 
 
 def qgemm(desc):

@@ -100,6 +100,49 @@ def test_qconv3x3(cuda, B, H, W, C, N, asym):
     _report(f"qconv3x3 B{B} {H}x{W} C{C} N{N}", out, ref, atol=1e-4, rtol=2e-6)
 
 
+@pytest.mark.parametrize("taps,M_or_bhw,N,C", [
+    (1, 300, 320, 320),            # partial last k-block, ragged M
+    (1, 4096, 640, 1280),          # multi-tile persistent loop, pipeline wrap-around
+    (1, 257, 4, 64),               # N < 16
+    (9, (3, 8, 8), 160, 320),      # conv, partial k-block per tap
+    (9, (2, 32, 32), 256, 128),
+])
+def test_qgemm_packed_int4_weights(cuda, taps, M_or_bhw, N, C):
+    """K3: 4-bit weight codes packed two per byte in HBM, unpacked in shared memory by the kernel.  The result must be
+    BIT-identical to the s8-weight path (same integers reach the tensor core)."""
+    ops, fold = _ops()
+    gen = torch.Generator().manual_seed(77 + N + C + taps)
+    L = _make_layer(N, C, taps, 4, gen, True)
+    if taps == 9:
+        B, H, W = M_or_bhw
+        M = B * H * W
+        a = torch.randint(0, 256, (B, H, W, C), generator=gen).to(torch.uint8).to(cuda)
+        wk = fold.to_k_major(L["ws"])
+        corr = fold.border_corr(L["ws"], L["zx"]).to(cuda)
+        kw = dict(taps=9, conv_bhw=(B, H, W))
+    else:
+        M = M_or_bhw
+        a = torch.randint(0, 256, (M, C), generator=gen).to(torch.uint8).to(cuda)
+        wk = L["ws"]
+        corr = (L["zx"] * L["ws"].double().sum(dim=1)).to(torch.int32).to(cuda)
+        kw = {}
+    packed = ops.pack_int4(wk.reshape(N, -1))
+    assert packed is not None
+    wp, wz = packed[0].to(cuda), packed[1].to(cuda)
+    assert wp.shape == (N, taps * C // 2)
+    outs = []
+    for use_packed in (False, True):
+        out = torch.full((M, N), float("nan"), device=cuda)
+        d = ops.gemm_desc(a, wp if use_packed else wk.reshape(N, -1).to(torch.int8).to(cuda), L["scale"].to(cuda), M=M, N=N,
+                          C=C, a_signed=False, bias=L["bias"].to(cuda), corr=corr, out=out, ldo=N,
+                          w_zero=wz if use_packed else None, **kw)
+        ops.qgemm(d)
+        torch.cuda.synchronize()
+        outs.append(out.cpu())
+    assert torch.isfinite(outs[1]).all()
+    assert torch.equal(outs[0], outs[1]), float((outs[0] - outs[1]).abs().max())
+
+
 def test_qgemm_epilogue_variants(cuda):
     """rowvec (timestep-embedding add), residual (may alias out), strided out, requantised out (+transposed)."""
     ops, fold = _ops()
