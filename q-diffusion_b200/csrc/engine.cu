@@ -207,24 +207,29 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
   return QD_OK;
 }
 
-template <int MODE>
-int launch_gemm_mode(const GemmPlan& pl, cudaStream_t s) {
+template <int MODE, bool W4>
+int launch_gemm_mode_w(const GemmPlan& pl, cudaStream_t s) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(qd::gemm_i8_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(qd::gemm_i8_kernel<MODE, W4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) return fail(QD_ERR_CUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   constexpr int epi_warps = qd::gemm_epi_warps(MODE);
   qd::GemmArgs a = pl.args;
-  const int stage_bytes = qd::gemm_stage_footprint(a.BN, a.w4);
+  const int stage_bytes = qd::gemm_stage_footprint(a.BN, W4 ? 1 : 0);
   int stages = (232448 - 256 - epi_warps * qd::GEMM_EPI_TILE_BYTES - 1024 - 1024) / stage_bytes;
   if (stages > qd::GEMM_MAX_STAGES) stages = qd::GEMM_MAX_STAGES;
   if (stages < 2) stages = 2;
   a.stages = stages;
-  const int smem = qd::gemm_smem_layout(a.BN, stages, epi_warps, a.w4).total;
-  qd::gemm_i8_kernel<MODE><<<pl.grid, qd::gemm_threads(MODE), smem, s>>>(pl.tmA, pl.tmB, a);
+  const int smem = qd::gemm_smem_layout(a.BN, stages, epi_warps, W4 ? 1 : 0).total;
+  qd::gemm_i8_kernel<MODE, W4><<<pl.grid, qd::gemm_threads(MODE), smem, s>>>(pl.tmA, pl.tmB, a);
   return check_launch("gemm_i8_kernel");
+}
+
+template <int MODE>
+int launch_gemm_mode(const GemmPlan& pl, cudaStream_t s) {
+  return pl.args.w4 ? launch_gemm_mode_w<MODE, true>(pl, s) : launch_gemm_mode_w<MODE, false>(pl, s);
 }
 
 // Specialised epilogues for the hot combinations; everything else runs the generic (-1) kernel.

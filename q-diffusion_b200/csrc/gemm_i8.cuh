@@ -265,7 +265,9 @@ __device__ __forceinline__ void gemm_finalise4(const GemmArgs& p, const QuantK& 
   }
 }
 
-template <int MODE>
+// W4: packed-INT4 weight variant (compile-time, so the s8 kernels carry none of the unpack role's code: with a
+// run-time flag the register allocation of the epilogue changed and the default path lost 8 %).
+template <int MODE, bool W4 = false>
 __global__ void __launch_bounds__(gemm_threads(MODE), 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -275,7 +277,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   constexpr int EPI_WARPS = gemm_epi_warps(MODE);
   constexpr int CSTEP = 32 * (EPI_WARPS / 4);   // column stride between the chunks of one epilogue warp
-  const GemmSmemLayout lay = gemm_smem_layout(p.BN, p.stages, EPI_WARPS, p.w4);
+  const GemmSmemLayout lay = gemm_smem_layout(p.BN, p.stages, EPI_WARPS, W4 ? 1 : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_offset);
   uint64_t* full_bar = bars;                          // [stages]
   uint64_t* empty_bar = bars + GEMM_MAX_STAGES;       // [stages]
@@ -298,7 +300,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
-      mbar_init(&ready_bar[s], 2);    // one arrival per unpack warp
+      if constexpr (W4) mbar_init(&ready_bar[s], 2);    // one arrival per unpack warp
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -321,7 +323,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = (uint32_t)(GEMM_A_STAGE_BYTES + (p.w4 ? p.BN * (GEMM_BK / 2) : p.BN * GEMM_BK));
+      const uint32_t tx_bytes = (uint32_t)(GEMM_A_STAGE_BYTES + (W4 ? p.BN * (GEMM_BK / 2) : p.BN * GEMM_BK));
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int tm = tile / p.tiles_n;
         const int tn = tile - tm * p.tiles_n;
@@ -344,7 +346,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_4d(sa, &tmA, &full_bar[stage], kc * GEMM_BK, kx - 1, h0 + ky - 1, b0);
             else
               tma_load_4d(sa, &tmA, &full_bar[stage], kc * GEMM_BK, m0, 0, 0);
-            if (p.w4)
+            if constexpr (W4)
               tma_load_2d(smem + lay.pack_off + (size_t)stage * p.BN * (GEMM_BK / 2), &tmB, &full_bar[stage],
                           (tap * p.C + kc * GEMM_BK) / 2, n0);
             else
@@ -370,7 +372,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int kc = kb % kb_per_tap;
           const int rem = p.C - kc * GEMM_BK;
           const int nmma = rem >= GEMM_BK ? 4 : (rem >> 5);
-          mbar_wait(p.w4 ? &ready_bar[stage] : &full_bar[stage], phase);
+          mbar_wait(W4 ? &ready_bar[stage] : &full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * lay.stage_bytes);
           const uint64_t da = make_smem_desc_sw128(sa);
@@ -391,7 +393,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // 64 threads = 16 rows x 4 sixteen-byte pieces per pass.  A piece holds 32 codes (k = 32j .. 32j+31 of the
     // k-block) and becomes two 16-byte chunks of the row in the 128B-swizzled s8 tile the MMA descriptor expects
     // (chunk index XOR row&7, identical to what TMA SWIZZLE_128B writes on the unpacked path).
-    if (p.w4) {
+    if constexpr (W4) {
       const int t = threadIdx.x - 64;
       const int r16 = t >> 2, piece = t & 3;
       int stage = 0;
