@@ -126,3 +126,28 @@ def test_wraps_the_references_own_module_objects(name):
         sys.path.remove("/root/reference")
         for mod in [m for m in sys.modules if m.split(".")[0] in ("ldm", "ddim", "qdiff", "omegaconf")]:
             del sys.modules[mod]
+
+
+def test_pack_int4_roundtrip_and_limits():
+    """ops.pack_int4: unsigned nibbles + per-row zero point reproduce the zero-point-free codes; rows that do not fit
+    4 bits (W8 layers) are refused so the builder falls back to the s8 layout."""
+    from qdiff_b200 import ops
+    gen = torch.Generator().manual_seed(3)
+    ws = torch.randint(0, 16, (37, 96), generator=gen) - torch.randint(0, 16, (37, 1), generator=gen)
+    packed, zero = ops.pack_int4(ws)
+    assert packed.dtype == torch.uint8 and packed.shape == (37, 48) and zero.dtype == torch.int8
+    assert int(zero.min()) >= 0 and int(zero.max()) <= 15
+    un = torch.stack([packed & 15, packed >> 4], dim=2).reshape(37, 96).to(torch.int16) - zero[:, None].to(torch.int16)
+    assert torch.equal(un, ws.to(torch.int16))
+    assert ops.pack_int4(torch.randint(-128, 128, (4, 32), generator=gen)) is None     # 8-bit rows
+    assert ops.pack_int4(torch.zeros(4, 33, dtype=torch.int64)) is None                 # odd K
+
+
+def test_groupnorm_workspace_rule_is_owned_by_the_library():
+    from qdiff_b200 import ops
+    small = ops.gn_workspace_floats(16, 64, 1280)
+    big = ops.gn_workspace_floats(16, 4096, 320)
+    assert 0 < small < big
+    # partial sums: doubles [B][nslab][groups][2] with nslab >= HW/64, + stats
+    assert big >= 16 * (4096 // 64) * 32 * 2 * 2 + 16 * 32 * 2
+    assert ops.gn_workspace_floats(0, 64, 64) == 0
