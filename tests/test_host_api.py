@@ -7,7 +7,7 @@ import re
 import pytest
 import torch
 
-from tests.test_oracle_golden import CASES, load_case
+from tests.test_oracle_golden import CASES, ORACLE_ONLY, load_case
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -53,7 +53,7 @@ def test_ctypes_mirror_matches_the_header_layout(tmp_path):
             assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + ORACLE_ONLY)
 def test_checkpoint_keys_roundtrip(name):
     """Wrapping our containers + resume_cali_model must consume exactly the reference's checkpoint keys."""
     from tests.test_unet_gpu import build_qnn

@@ -10,6 +10,9 @@ from oracle import unet_oracle as U
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["ddim_w4a8_split", "ldm_legacy_w4a8", "ldm_updown_w4a8", "sd_tiny_w4a8_sm16", "ldm_updown_w8a8"]
+# BASELINE configs[0] (weight-only W8, the reference's own CPU-runnable case): the oracle is pinned against the
+# reference for it; the CUDA engine does not realise weight-only sampling yet
+ORACLE_ONLY = ["ddim_w8_weightonly"]
 
 
 def load_case(name):
@@ -68,7 +71,7 @@ def test_quantizer_known_answers():
     assert torch.equal(O.uaq_weight_fake_quant(w["w"], d, z, 4), w["y"])
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + ORACLE_ONLY)
 def test_oracle_matches_reference(name):
     g = load_case(name)
     trace = {}

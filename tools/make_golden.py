@@ -162,6 +162,11 @@ def make_case(name, family, params, qcfg, batch, ctx_dim=None, seed=0):
 
 
 CASES = [
+    # cfg 1: CIFAR-style DDIM UNet, 8-bit weights only (quant_act off): the reference's own CPU-runnable case
+    ("ddim_w8_weightonly", "ddim",
+     dict(in_channels=3, out_ch=3, ch=32, ch_mult=[1, 2], num_res_blocks=1, attn_resolutions=[8], resolution=16,
+          split_shortcut=False),
+     dict(weight_bit=8, act_bit=8, a_sym=True, sm_abit=8, quant_act=False), None),
     # cfg 2: CIFAR-style DDIM UNet, W4A8 symmetric, split shortcut
     ("ddim_w4a8_split", "ddim",
      dict(in_channels=3, out_ch=3, ch=32, ch_mult=[1, 2], num_res_blocks=1, attn_resolutions=[8], resolution=16,
@@ -227,7 +232,7 @@ if __name__ == "__main__":
     if not only:
         make_quantizer_kats()
     seeds = {"ddim_w4a8_split": 100, "ldm_legacy_w4a8": 101, "ldm_updown_w4a8": 102, "sd_tiny_w4a8_sm16": 103,
-             "ldm_updown_w8a8": 104}
+             "ldm_updown_w8a8": 104, "ddim_w8_weightonly": 105}
     for (name, family, params, qcfg, ctx) in CASES:
         if only and name not in only:
             continue
