@@ -85,3 +85,20 @@ def test_oracle_matches_reference(name):
         if key in trace and key != "layers":
             e = (trace[key] - t).abs().max().item()
             assert e <= 1e-5 * max(1.0, t.abs().max().item()), (name, key, e)
+
+
+def test_sampler_oracle_matches_reference_samplers():
+    """oracle/sampler_oracle.py vs the reference's own PLMSSampler.sample and generalized_steps run around the same toy
+    eps-model (fixture: tools/make_sampler_golden.py).  The GPU sampler tests compare the engine with this oracle."""
+    from oracle import sampler_oracle as S
+    from tools.make_sampler_golden import toy_eps
+    g = torch.load(os.path.join(GOLD, "samplers.pt"), map_location="cpu", weights_only=False)
+    p = g["plms"]
+    ac = S.ldm_schedule(1000, p["linear_start"], p["linear_end"])
+    out = S.plms_sample(lambda x, t, c: toy_eps(x, t, c), p["x_T"], p["cond"], p["uc"], p["scale"], ac, p["S"])
+    err = (out - p["out"]).abs().max().item()
+    assert err <= 2e-5 * max(1.0, p["out"].abs().max().item()), err
+    q = g["generalized"]
+    out2 = S.generalized_steps(lambda x, t: toy_eps(x, t), q["x"], q["seq"], q["betas"], eta=0.0)
+    err2 = (out2 - q["out"]).abs().max().item()
+    assert err2 <= 2e-5 * max(1.0, q["out"].abs().max().item()), err2
