@@ -10,12 +10,15 @@
 //   warp 0   : TMA producer  (A tile 128 x 128 B, B tile BN x 128 B, 128B swizzle, mbarrier ring)
 //   warp 1   : MMA issuer    (tcgen05.mma.kind::i8, M=128, N=BN, K=32 per instruction, int32 acc in TMEM)
 //   warp 2   : TMEM allocator (512 columns: two accumulator stages of up to 256 columns)
-//   warps 4-11: epilogue     (tcgen05.ld -> smem transpose -> zero-point correction / scale / bias /
-//                             adds -> coalesced fp32 or requantised stores)
+//   warps 2-3: INT4 unpack   (W4 variant only: packed 4-bit weight codes staged by TMA -> swizzled s8 operand tile)
+//   warps 4+ : epilogue, 8 or 16 warps by MODE (tcgen05.ld -> smem transpose -> zero-point correction / scale /
+//                             bias / adds / GEGLU -> coalesced fp32 or requantised stores)
 //
 // The kernel is templated on the epilogue MODE so the hot variants carry no runtime flag tests
 // (the first version with runtime flags was instruction-issue / I-cache bound in the epilogue:
-// profiles/r01_gemm_epilogue_v1.txt).  MODE = -1 keeps every runtime option (ragged N, both outputs).
+// profiles/r01_gemm_epilogue_v1.txt, r01_gemm_smallk.txt).  MODE = -1 keeps every runtime option (ragged N, both
+// outputs).  What bounds it: the K >= 2880 convs are limited by L2->SM operand delivery (profiles/
+// r01_gemm_conv_final.txt: 42 % tensor activity at the L2 slice cap), the small-K linears by their epilogue.
 #pragma once
 #include "ptx.cuh"
 #include "quant_math.cuh"
