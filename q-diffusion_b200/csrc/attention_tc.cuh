@@ -276,7 +276,7 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (++sb == 2) { sb = 0; ph_s ^= 1; }
       if (++st == ATC_STAGES) { st = 0; ph_kv ^= 1; }
     }
-    // ---- combine the two column halves of every row (named barrier over the 8 softmax warps)
+    // ---- combine the four column quarters of every row (named barrier over the 16 softmax warps)
     stat[part * 128 + row] = make_float2(__int_as_float(mi), l);
     asm volatile("bar.sync 1, 512;" ::: "memory");
     float off;
