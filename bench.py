@@ -180,9 +180,7 @@ def run_reference_arm(args):
 def gemm_roofline(prog, pk):
     """Replay the recorded program op by op; CUDA events around every INT8 GEMM launch (default stream =
     the stream the engine launches on).  achieved = sum(2*M*N*K) / sum(duration)."""
-    import ctypes as C
     from qdiff_b200 import _lib
-    L = _lib.lib()
     names = prog.op_names
     gemm_ids = [i for i, n in enumerate(names) if prog.op_kinds[i] == _lib.QD_OP_GEMM]
     prog.run_range(0, prog.nops)  # warm
@@ -371,7 +369,6 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(host_threads())
         cb = cpu_baseline(ckpt)
-        cb["value"] = cb["value"]
         line["cpu_baseline"] = cb
     print(json.dumps(line))
     if dist is not None:

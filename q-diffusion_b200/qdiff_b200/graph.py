@@ -17,7 +17,7 @@ import os
 import torch
 
 from . import _lib, fold, ops
-from ._lib import AttentionDesc, MiscDesc, check, lib, ptr
+from ._lib import AttentionDesc, MiscDesc, check, lib
 
 
 class Act:

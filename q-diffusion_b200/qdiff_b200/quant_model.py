@@ -5,7 +5,6 @@ in place exactly like the reference (layers -> QuantModule, blocks -> Quant*Bloc
 keys match `ckpt.pth`; `forward(x, timesteps, context)` lowers the tree once per input shape to an
 engine program (qdiff_b200/graph.py) and replays it on the current CUDA stream.
 """
-import torch
 import torch.nn as nn
 
 from .quant_block import (BaseQuantBlock, QuantAttnBlock, QuantBasicTransformerBlock, QuantQKMatMul, QuantSMVMatMul,

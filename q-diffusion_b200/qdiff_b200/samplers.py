@@ -10,7 +10,6 @@ Restates, with the same argument names:
   PLMSSampler.sample / p_sample_plms    ldm/models/diffusion/plms.py:58-240
   schedules                             ldm/modules/diffusionmodules/util.py:21-74, ddpm.py:118-146
 """
-import ctypes as C
 import math
 
 import numpy as np

@@ -9,7 +9,6 @@ import torch
 import torch.nn as nn
 
 from .adaptive_rounding import AdaRoundQuantizer
-from .quant_block import BaseQuantBlock
 from .quant_layer import QuantModule, UniformAffineQuantizer
 
 
