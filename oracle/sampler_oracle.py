@@ -22,6 +22,34 @@ def ddim_params(alphas_cumprod, S, eta=0.0):
     return steps, alphas, alphas_prev, sigmas, np.sqrt(1. - alphas)
 
 
+def ddim_sample(model, x_T, cond, uc, scale, alphas_cumprod, S, eta=0.0, noises=None):
+    """DDIMSampler.sample -> ddim_sampling -> p_sample_ddim (ldm/models/diffusion/ddim.py:57-220), temperature 1,
+    no mask / score corrector.  noises[i] = the torch.randn draw of step i (ddim.py:217 via util.py:264-267);
+    the reference draws it on every step, also when sigma is 0."""
+    steps, alphas, alphas_prev, sigmas, sqrt_1ma = ddim_params(alphas_cumprod, S, eta)
+    b = x_T.shape[0]
+    img = x_T.clone()
+    time_range = np.flip(steps)
+    total = steps.shape[0]
+    for i, step in enumerate(time_range):
+        index = total - i - 1
+        ts = torch.full((b,), int(step), dtype=torch.long)
+        if uc is None or scale == 1.0:
+            e_t = model(img, ts, cond)
+        else:
+            e_u, e_c = model(torch.cat([img] * 2), torch.cat([ts] * 2), torch.cat([uc, cond])).chunk(2)
+            e_t = e_u + scale * (e_c - e_u)
+        a_t = torch.full((b, 1, 1, 1), float(alphas[index]))
+        a_prev = torch.full((b, 1, 1, 1), float(alphas_prev[index]))
+        sigma_t = torch.full((b, 1, 1, 1), float(sigmas[index]))
+        s1m = torch.full((b, 1, 1, 1), float(sqrt_1ma[index]))
+        pred_x0 = (img - s1m * e_t) / a_t.sqrt()
+        dir_xt = (1. - a_prev - sigma_t ** 2).sqrt() * e_t
+        noise = sigma_t * (noises[i] if noises is not None else torch.zeros_like(img))
+        img = a_prev.sqrt() * pred_x0 + dir_xt + noise
+    return img
+
+
 def plms_sample(model, x_T, cond, uc, scale, alphas_cumprod, S):
     """model(x, t, context) -> eps.  Mirrors plms_sampling + p_sample_plms (eta = 0)."""
     steps, alphas, alphas_prev, sigmas, sqrt_1ma = ddim_params(alphas_cumprod, S)

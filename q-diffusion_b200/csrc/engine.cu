@@ -22,7 +22,8 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
-int g_num_sms = 0;
+constexpr int kMaxDevices = 64;
+std::atomic<int> g_num_sms[kMaxDevices];   // per device (zero-initialised): a process may drive several GPUs
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -39,17 +40,53 @@ int check_launch(const char* what) {
   return QD_OK;
 }
 
+int current_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  return dev;
+}
+
+// SM count of the CURRENT device (cached per device).
 int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) {
+    fail(QD_ERR_CUDA, "no CUDA device: qdiff_b200 has no CPU fallback");
+    return 0;
+  }
+  int n = g_num_sms[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
       fail(QD_ERR_CUDA, "no CUDA device: qdiff_b200 has no CPU fallback");
       return 0;
     }
-    g_num_sms = n;
+    g_num_sms[dev].store(n, std::memory_order_relaxed);
   }
-  return g_num_sms;
+  return n;
 }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: opt in once per (kernel, device).
+// `done` is the kernel instantiation's own bitmask of devices already configured.
+template <typename K>
+int ensure_smem_optin(K kern, int bytes, std::atomic<unsigned long long>& done, const char* what) {
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) return fail(QD_ERR_CUDA, "%s: no current CUDA device", what);
+  const unsigned long long bit = 1ull << dev;
+  if (done.load(std::memory_order_acquire) & bit) return QD_OK;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return fail(QD_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+  done.fetch_or(bit, std::memory_order_release);
+  return QD_OK;
+}
+
+struct DeviceGuard {   // run a block on `device`, restoring the caller's current device afterwards
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) ok = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 int grid_for(long long work_items, int threads, int per_sm = 8) {
   const int sms = num_sms();
@@ -197,6 +234,8 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
   a.oq_d = d->out_q_head_dim; a.oq_pitch = d->out_q_head_pitch;
   if (a.oq_d > 0 && ((a.oq_d & 3) || (a.oq_pitch & 3) || a.oq_pitch < a.oq_d || d->out_q_transposed || !d->out_q))
     return fail(QD_ERR_BAD_ARG, "gemm: bad out_q head layout");
+  if (d->out_q && d->oq.qmax - d->oq.qmin > 255)
+    return fail(QD_ERR_UNSUPPORTED, "gemm: the epilogue emits 8-bit codes; quantizer range [%d, %d] is wider", d->oq.qmin, d->oq.qmax);
   a.q_delta = d->oq.delta; a.q_zp = d->oq.zero_point; a.q_lo = d->oq.qmin; a.q_hi = d->oq.qmax;
   a.scale = d->scale; a.bias = d->bias; a.corr = d->corr;
   a.rowvec = d->rowvec; a.ld_rowvec = d->ld_rowvec;
@@ -209,12 +248,8 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
 
 template <int MODE, bool W4>
 int launch_gemm_mode_w(const GemmPlan& pl, cudaStream_t s) {
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(qd::gemm_i8_kernel<MODE, W4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  if (attr_err != cudaSuccess) return fail(QD_ERR_CUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  static std::atomic<unsigned long long> optin{0};
+  if (int rc = ensure_smem_optin(qd::gemm_i8_kernel<MODE, W4>, 227 * 1024, optin, "gemm")) return rc;
   constexpr int epi_warps = qd::gemm_epi_warps(MODE);
   qd::GemmArgs a = pl.args;
   const int stage_bytes = qd::gemm_stage_footprint(a.BN, W4 ? 1 : 0);
@@ -278,6 +313,8 @@ int launch_gemm(const GemmPlan& pl, cudaStream_t s) {
 // ------------------------------------------------------------------ elementwise launchers
 int launch_quantize(const qd_quantize_desc& d, cudaStream_t s) {
   if (!d.src || !d.dst || d.M <= 0 || d.C <= 0) return fail(QD_ERR_BAD_ARG, "quantize: bad args");
+  if (d.q0.qmax - d.q0.qmin > 255 || d.q1.qmax - d.q1.qmin > 255)
+    return fail(QD_ERR_UNSUPPORTED, "quantize: the engine emits 8-bit codes; quantizer range [%d, %d] is wider", d.q0.qmin, d.q0.qmax);
   const bool vec = (d.C % 4 == 0) && (d.ld_src % 4 == 0) && (d.ld_dst % 4 == 0) && (d.split % 4 == 0);
   if (d.upsample2x && !vec) return fail(QD_ERR_UNSUPPORTED, "quantize: upsample needs C %% 4 == 0");
   if (vec) {
@@ -291,7 +328,9 @@ int launch_quantize(const qd_quantize_desc& d, cudaStream_t s) {
 
 // slab / rows-per-block of the three-kernel GroupNorm: enough blocks to fill the GPU at every feature-map size
 int gn_slab_rows(int B, int HW) {
-  long long r = ((long long)B * HW) / (4LL * 148);
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  long long r = ((long long)B * HW) / (4LL * sms);
   int slab = 64;
   while (slab > 8 && slab > r) slab >>= 1;
   return slab;
@@ -396,10 +435,8 @@ template <int DQ, int DV, bool QS, bool VS, bool S16>
 int launch_attention_inst(const qd_attention_desc& d, cudaStream_t s) {
   constexpr int MINB = (DV <= 48) ? 2 : 1;
   auto kern = qd::qattention_kernel<DQ, DV, QS, VS, S16, MINB>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
-  if (attr_err != cudaSuccess) return fail(QD_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  static std::atomic<unsigned long long> optin{0};
+  if (int rc = ensure_smem_optin(kern, 200 * 1024, optin, "attention")) return rc;
   const qd::AttSmemLayout lay = qd::att_smem_layout(DQ, DV, d.Tk, d.zq != 0);
   if (lay.total > 200 * 1024) return fail(QD_ERR_UNSUPPORTED, "attention: Tk=%d needs %d B of shared memory", d.Tk, lay.total);
   if (d.zq != 0) {
@@ -451,10 +488,8 @@ template <bool S16, bool MAGIC>
 int launch_attention_tc_inst(const qd_attention_desc& d, const CUtensorMap& tmQ, const CUtensorMap& tmK,
                              const CUtensorMap& tmV, int NV, int P, cudaStream_t s) {
   auto kern = qd::qattention_tc_kernel<S16, MAGIC>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
-  if (attr_err != cudaSuccess) return fail(QD_ERR_CUDA, "attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  static std::atomic<unsigned long long> optin{0};
+  if (int rc = ensure_smem_optin(kern, 227 * 1024, optin, "attention_tc")) return rc;
   const qd::AtcSmem lay = qd::atc_smem_layout(NV, P);
   if (lay.total > 227 * 1024) return fail(QD_ERR_UNSUPPORTED, "attention_tc: %d B of shared memory", lay.total);
   dim3 grid((d.Tq + qd::ATC_BM - 1) / qd::ATC_BM, d.B * d.heads);
@@ -677,8 +712,11 @@ int qd_sampler_step(const qd_sampler_desc* d, qd_stream_t s) {
 
 int qd_engine_create(int device, qd_engine** out) {
   if (!out) return fail(QD_ERR_BAD_ARG, "null out");
-  if (cudaSetDevice(device) != cudaSuccess) return fail(QD_ERR_CUDA, "cudaSetDevice(%d) failed: no CPU fallback", device);
-  if (!num_sms()) return QD_ERR_CUDA;
+  {
+    DeviceGuard g(device);    // the caller's current device (and with it torch's current stream) is left untouched
+    if (!g.ok) return fail(QD_ERR_CUDA, "cudaSetDevice(%d) failed: no CPU fallback", device);
+    if (!num_sms()) return QD_ERR_CUDA;
+  }
   qd_engine* e = new (std::nothrow) qd_engine();
   if (!e) return fail(QD_ERR_BAD_ARG, "out of host memory");
   e->device = device;
@@ -689,6 +727,8 @@ int qd_engine_create(int device, qd_engine** out) {
 
 int qd_engine_add_op(qd_engine* e, int kind, const void* desc) {
   if (!e || !desc) return fail(QD_ERR_BAD_ARG, "null arg");
+  DeviceGuard g(e->device);   // tile choice (SM count) and descriptors are planned for the engine's device
+  if (!g.ok) return fail(QD_ERR_CUDA, "cudaSetDevice(%d) failed", e->device);
   Op op;
   op.kind = kind;
   switch (kind) {
@@ -725,6 +765,8 @@ int qd_engine_run_range(qd_engine* e, int first, int last, qd_stream_t stream) {
   if (!e) return fail(QD_ERR_BAD_ARG, "null engine");
   if (!e->finalized) return fail(QD_ERR_NOT_FINALIZED, "engine not finalized");
   if (first < 0 || last > (int)e->ops.size() || first > last) return fail(QD_ERR_BAD_ARG, "bad op range");
+  if (current_device() != e->device)
+    return fail(QD_ERR_BAD_ARG, "engine was built for device %d but the current device is %d", e->device, current_device());
   for (int i = first; i < last; ++i) {
     int rc = run_op(e->ops[i], (cudaStream_t)stream);
     if (rc) return rc;

@@ -71,12 +71,17 @@ def border_corr(ws4, zx):
     The reference pads the de-quantised activation with real zeros (F.conv2d padding=1,
     qdiff/quant_layer.py:214-216,276), so padded taps contribute nothing - not -zx*w.
     """
-    tap_sum = ws4.to(torch.float64).sum(dim=1)  # [N, 3, 3]
+    return border_corr_from_tapsum(ws4.to(torch.float64).sum(dim=1), zx)
+
+
+def border_corr_from_tapsum(tap_sum, zx):
+    """border_corr from the per-tap channel sums [N, 3, 3] (float64) - what the folded-weight cache keeps."""
     rows_valid = {0: [1, 2], 1: [0, 1, 2], 2: [0, 1]}
-    out = torch.zeros(9, ws4.shape[0], dtype=torch.float64, device=ws4.device)
+    n = tap_sum.shape[0]
+    out = torch.zeros(9, n, dtype=torch.float64, device=tap_sum.device)
     for rc in range(3):
         for cc in range(3):
-            s = torch.zeros(ws4.shape[0], dtype=torch.float64, device=ws4.device)
+            s = torch.zeros(n, dtype=torch.float64, device=tap_sum.device)
             for ky in rows_valid[rc]:
                 for kx in rows_valid[cc]:
                     s += tap_sum[:, ky, kx]

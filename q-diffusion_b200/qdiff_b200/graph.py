@@ -42,6 +42,11 @@ class Act:
         return self.t[:self.rows, self.col0:self.col0 + self.cols]
 
 
+def _qt(qp):
+    """QParams -> plain tuple (delta, zero_point, qmin, qmax) for op specs."""
+    return None if qp is None else (float(qp.delta), int(qp.zero_point), int(qp.qmin), int(qp.qmax))
+
+
 class _Offset:
     """Pointer arithmetic helper: a view `bytes` into a tensor, keeping the storage alive."""
 
@@ -53,35 +58,64 @@ class _Offset:
 
 
 class Program:
-    def __init__(self, engine, keep, x_in, t_in, ctx_in, out, nops, traces, use_cuda_graph):
+    """A compiled UNet: ops [0, n_static) depend only on the cross-attention context (replayed when it changes),
+    ops [n_static, nops) are the per-step program.  Each range is captured as one CUDA graph."""
+
+    def __init__(self, engine, keep, x_in, t_in, ctx_in, out, nops, traces, use_cuda_graph, n_static=0):
         self.engine, self.keep = engine, keep
         self.x_in, self.t_in, self.ctx_in, self.out = x_in, t_in, ctx_in, out
-        self.nops, self.traces = nops, traces
+        self.nops, self.traces, self.n_static = nops, traces, n_static
         self.use_cuda_graph = use_cuda_graph
         self.graph = None
+        self.graph_static = None
+        self._ctx_ref, self._ctx_ver = None, -1
+        self.static_kernel_launches = 0
 
-    def _launch(self):
+    def _launch(self, first, last):
         n0 = lib().qd_launch_count()
-        check(lib().qd_engine_run(self.engine, _lib.stream_ptr()), "qd_engine_run")
-        self.kernel_launches = int(lib().qd_launch_count() - n0)   # exact: counted by the library at launch time
+        check(lib().qd_engine_run_range(self.engine, first, last, _lib.stream_ptr()), "qd_engine_run_range")
+        return int(lib().qd_launch_count() - n0)   # exact: counted by the library at launch time
 
-    def run(self, x, timesteps, context=None):
+    def set_inputs(self, x, timesteps, context=None):
+        """Copy the step inputs into the program's fixed buffers; returns True when the context changed (same tensor
+        object and version as last time -> unchanged: the reference passes the same conditioning every step)."""
         self.x_in.copy_(x.to(torch.float32))
         self.t_in.copy_(timesteps.to(torch.float32))
-        if self.ctx_in is not None:
-            if context is None:
-                raise ValueError("this UNet was compiled with a cross-attention context")
-            self.ctx_in.copy_(context.to(torch.float32))
+        if self.ctx_in is None:
+            return False
+        if context is None:
+            raise ValueError("this UNet was compiled with a cross-attention context")
+        if context is self._ctx_ref and context._version == self._ctx_ver:
+            return False
+        self.ctx_in.copy_(context.to(torch.float32))
+        # holding the tensor keeps its storage alive, so identity + version cannot alias another prompt's tensor
+        self._ctx_ref, self._ctx_ver = context, context._version
+        return True
+
+    def run(self, x, timesteps, context=None):
+        ctx_changed = self.set_inputs(x, timesteps, context) and self.n_static > 0
         if not self.use_cuda_graph:
-            self._launch()
+            if ctx_changed:
+                self.static_kernel_launches = self._launch(0, self.n_static)
+            self.kernel_launches = self._launch(self.n_static, self.nops)
         else:
             if self.graph is None:
-                self._launch()  # warm-up outside capture (lazy module loading, attribute setup)
+                # warm-up outside capture (lazy module loading, per-device kernel attributes)
+                if self.n_static:
+                    self.static_kernel_launches = self._launch(0, self.n_static)
+                self.kernel_launches = self._launch(self.n_static, self.nops)
                 torch.cuda.current_stream().synchronize()
+                if self.n_static:
+                    gs = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gs):
+                        self._launch(0, self.n_static)
+                    self.graph_static = gs
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._launch()
+                    self._launch(self.n_static, self.nops)
                 self.graph = g
+            if ctx_changed:
+                self.graph_static.replay()
             self.graph.replay()
         return self.out.clone()
 
@@ -91,6 +125,7 @@ class Program:
     def __del__(self):
         try:
             self.graph = None
+            self.graph_static = None
             lib().qd_engine_destroy(self.engine)
         except Exception:
             pass
@@ -125,6 +160,14 @@ class Builder:
         self.op_names = []
         self.op_kinds = []
         self.op_flops = []   # algorithmic integer ops (2*MACs) of each recorded op
+        self.op_specs = []   # host-level description of each op (operands + semantics) for the in-situ parity tests
+        self.want_specs = bool(getattr(qnn, "record_op_specs", False))   # GEMM specs hold fp32 copies of the weights
+        if not hasattr(qnn, "_wcache"):
+            qnn._wcache = {}
+        self.wcache = qnn._wcache   # folded weight operands, shared by every program of this QuantModel
+        self._pending = []          # (kind, desc, label, flops, spec, static) in recording order; see flush()
+        self._static_depth = 0
+        self.n_static = 0
         self.aq = qnn.act_quant_params
         self.wbits = qnn.weight_quant_params['n_bits']
         self.gn_ws = None
@@ -146,22 +189,63 @@ class Builder:
         self.keep.append(t)
         return t
 
-    def add(self, kind, desc, label, flops=0):
-        check(lib().qd_engine_add_op(self.engine, kind, C.byref(desc)), f"qd_engine_add_op[{label}]")
-        self.nops += 1
-        self.op_names.append(label)
-        self.op_kinds.append(kind)
-        self.op_flops.append(flops)
+    def add(self, kind, desc, label, flops=0, spec=None):
+        """Record one engine op.  `spec` describes the op's operands and semantics in host terms (Acts, quantizer
+        tuples, folded weights): the in-situ parity tests replay the program op by op and check every op against the
+        CPU oracle on the engine's own inputs (tests/test_insitu_gpu.py).  Pure metadata, never read on the hot path."""
+        self._pending.append((kind, desc, label, flops, spec if spec is not None else {"kind": "unspecified"},
+                              self._static_depth > 0 and self.hoist_ctx))
+
+    @property
+    def hoist_ctx(self):
+        return os.environ.get("QDIFF_HOIST_CTX", "1") != "0"    # A/B switch: 0 recomputes the context K/V every step
+
+    def static_scope(self):
+        """Ops recorded inside this scope depend only on the cross-attention context and the weights (context
+        quantizers, attn2.to_k / to_v projections and their requantisation: SURVEY Appendix B "constant across all steps").
+        flush() hoists them to the front of the program; Program.run replays them only when the context changes."""
+        b = self
+
+        class _Scope:
+            def __enter__(self):
+                b._static_depth += 1
+
+            def __exit__(self, *exc):
+                b._static_depth -= 1
+        return _Scope()
+
+    def flush(self):
+        """Hand the recorded ops to the engine: context-only ops first (their relative order kept), then the per-step ops."""
+        order = [p for p in self._pending if p[5]] + [p for p in self._pending if not p[5]]
+        self.n_static = sum(1 for p in self._pending if p[5])
+        for kind, desc, label, flops, spec, _ in order:
+            check(lib().qd_engine_add_op(self.engine, kind, C.byref(desc)), f"qd_engine_add_op[{label}]")
+            self.nops += 1
+            self.op_names.append(label)
+            self.op_kinds.append(kind)
+            self.op_flops.append(flops)
+            self.op_specs.append(spec)
+        self._pending = []
 
     def key(self, m):
         n = self.names[id(m)]
         return n[6:] if n.startswith("model.") else n
 
-    def qp(self, q):
-        """QParams of an activation quantizer object (delta, zero_point, clamp range)."""
+    def qp(self, q, wide_ok=False):
+        """QParams of an activation quantizer object (delta, zero_point, clamp range).  The engine's code tensors are
+        8-bit and per-tensor: anything else (act_bit > 8, channel-wise activation quantizers) is refused here instead of
+        silently wrapping codes; the softmax quantizer (sm_abit 16) is the one wide case, handled inside the attention
+        kernels (wide_ok)."""
         if q.delta is None:
             raise RuntimeError("activation quantizer has no calibrated delta: load a checkpoint with "
                                "resume_cali_model(..., quant_act=True) first")
+        if torch.is_tensor(q.delta) and q.delta.numel() != 1:
+            raise NotImplementedError("channel-wise activation quantizers are not realised by the engine "
+                                      f"(delta has {q.delta.numel()} elements); the reference configs are per-tensor")
+        lo_, hi_ = q.clamp_range()
+        if hi_ - lo_ > 255 and not (wide_ok and hi_ - lo_ <= 65535):
+            raise NotImplementedError(f"activation quantizer with {q.n_bits} bits: the engine's activation codes are 8-bit "
+                                      "(softmax probabilities: up to 16-bit)")
         delta = float(q.delta.detach().reshape(-1)[0])
         zp = q.zero_point
         zp = int(zp.reshape(-1)[0].item()) if torch.is_tensor(zp) else int(zp)
@@ -178,12 +262,14 @@ class Builder:
         d = ops.quantize_desc(src.t, dst.t, M=src.rows, C_=cols, ld_src=src.ld, ld_dst=dst.ld, q0=qp0, q1=qp1, act=act,
                               split=split, upsample=upsample)
         d.src = src.ptr
-        self.add(_lib.QD_OP_QUANTIZE, d, label)
+        self.add(_lib.QD_OP_QUANTIZE, d, label,
+                 spec=dict(kind="quantize", src=src, dst=dst, act=act, cols=cols, split=split, q0=_qt(qp0), q1=_qt(qp1),
+                           upsample=upsample))
         dst.zp = (qp0.zero_point, qp1.zero_point if qp1 is not None else None)
         dst.delta = (qp0.delta, qp1.delta if qp1 is not None else None)
         return dst
 
-    def groupnorm(self, x, norm, hw, quantizers, silu, label, ss=None, want_f32=False, raw=None):
+    def groupnorm(self, x, norm, hw, quantizers, silu, label, ss=None, want_f32=False, raw=None, ss_src=None):
         """GroupNorm(32) [+scale-shift] [+SiLU] -> codes for each consumer quantizer (and/or fp32).
         raw = (quantizer, quantizer_0 or None, split): also emit codes of the input itself (skip_connection operand);
         the Act is returned as a third value."""
@@ -214,7 +300,12 @@ class Builder:
                                groups=norm.num_groups, ss=ss, out_f=out_f.t if out_f else None,
                                ld_f=out_f.ld if out_f else 0, raw=raw_arg)
         d.x = x.ptr
-        self.add(_lib.QD_OP_GROUPNORM, d, label)
+        self.add(_lib.QD_OP_GROUPNORM, d, label,
+                 spec=dict(kind="groupnorm", x=x, B=B, HW=hw, groups=norm.num_groups, eps=norm.eps,
+                           gamma=norm.weight.detach().float().cpu(), beta=norm.bias.detach().float().cpu(), silu=silu,
+                           outs=[(a, _qt(o[2])) for a, o in zip(acts, outs)], out_f=out_f,
+                           raw=None if raw is None else (raw_act, raw_arg[2], _qt(raw_arg[3]), _qt(raw_arg[4])),
+                           ss=ss_src))
         if raw is not None:
             return acts, out_f, raw_act
         return acts, out_f
@@ -230,23 +321,26 @@ class Builder:
         d = ops.layernorm_desc(x.t, self.dev_t(norm.weight, torch.float32), self.dev_t(norm.bias, torch.float32),
                                M=x.rows, C_=x.cols, ld_x=x.ld, eps=norm.eps, outs=outs)
         d.x = x.ptr
-        self.add(_lib.QD_OP_LAYERNORM, d, label)
+        self.add(_lib.QD_OP_LAYERNORM, d, label,
+                 spec=dict(kind="layernorm", x=x, eps=norm.eps, gamma=norm.weight.detach().float().cpu(),
+                           beta=norm.bias.detach().float().cpu(), outs=[(a, _qt(o[2])) for a, o in zip(acts, outs)]))
         return acts
 
-    def misc(self, kind, src, dst, a, b, c=0, d_=0, ld_src=0, ld_dst=0, label="misc", aux=None):
+    def misc(self, kind, src, dst, a, b, c=0, d_=0, ld_src=0, ld_dst=0, label="misc", aux=None, spec=None):
         m = MiscDesc()
         m.src, m.dst = src, dst
         if aux is not None:
             self.keep.append(aux)
             m.aux = aux.data_ptr()
         m.ld_src, m.ld_dst, m.a, m.b, m.c, m.d = ld_src, ld_dst, a, b, c, d_
-        self.add(kind, m, label)
+        self.add(kind, m, label, spec=spec)
 
     def concat(self, a, b, label):
         out = self.new_f32(a.rows, a.cols + b.cols)
-        self.misc(_lib.QD_OP_COPY2D, a.ptr, out.ptr, a.rows, a.cols, ld_src=a.ld, ld_dst=out.ld, label=label + ".cat0")
+        self.misc(_lib.QD_OP_COPY2D, a.ptr, out.ptr, a.rows, a.cols, ld_src=a.ld, ld_dst=out.ld, label=label + ".cat0",
+                  spec=dict(kind="copy2d", src=a, dst=out.view(0, a.cols)))
         self.misc(_lib.QD_OP_COPY2D, b.ptr, out.ptr + 4 * a.cols, b.rows, b.cols, ld_src=b.ld, ld_dst=out.ld,
-                  label=label + ".cat1")
+                  label=label + ".cat1", spec=dict(kind="copy2d", src=b, dst=out.view(a.cols, b.cols)))
         return out
 
     # ------------------------------------------------------------------ QuantModule -> GEMM
@@ -268,48 +362,34 @@ class Builder:
         ws = codes - zp.reshape(-1, *([1] * (w.dim() - 1)))
         return ws, delta
 
-    def gemm(self, qm, a, label, *, conv_bhw=None, out=None, out_cols_offset=0, rowvec=None, residual=None,
-             out_q=None, out_scale=1.0, k_pad=None, cols=None, suffix="", zx=None, dx=None, accumulate_into=None,
-             rows_per_batch=0, use_bias=True, geglu_q=None, _ws=None, _wscale=1.0, out_q_head=None):
-        """Record one INT8 GEMM for QuantModule `qm` on activation codes `a`.
+    def _weights(self, qm, label, *, cols, suffix, k_pad, geglu, part, conv):
+        """Folded weight operand of one recorded GEMM, shared between all programs of this QuantModel (a second input
+        shape, the doubled classifier-free-guidance batch, ... reuse the device tensors instead of re-folding and
+        holding another copy: ADVICE r1).  Keyed by the op label: one entry per (layer, split half, W8 part).
 
-        W8 (SURVEY H3): wq - zw spans [-255, 255] and does not fit the s8 operand.  Such layers run as TWO exact s8
-        GEMMs, ws = 2*a + b with a = floor(ws/2) in [-128,127], b in {0,1}:  y = 2s(acc_a - corr_a) + s(acc_b - corr_b) + bias,
-        the second one accumulating into the first one's fp32 output and carrying the requantising epilogue.
-
-        cols/suffix select a split-shortcut half.  out_q = (quantizer, transposed) requantises in the
-        epilogue.  out_scale multiplies scale and bias (LDM legacy attention q*s, k*s)."""
-        if _ws is None:
-            ws, delta_w = self._fold(qm, cols, suffix)
-            if float(ws.abs().max()) > 127:
-                if geglu_q is not None:     # fused GEGLU has no accumulate form: unfused fallback
-                    f32 = self.gemm(qm, a, label, conv_bhw=conv_bhw, k_pad=k_pad, cols=cols, suffix=suffix, zx=zx, dx=dx,
-                                    rows_per_batch=rows_per_batch)
-                    return self.quantize(f32, geglu_q, label + ".geglu.q", act=2, out_cols=f32.cols // 2)
-                wa = torch.floor(ws / 2)
-                wb = ws - 2 * wa
-                kw = dict(conv_bhw=conv_bhw, k_pad=k_pad, cols=cols, suffix=suffix, zx=zx, dx=dx, rows_per_batch=rows_per_batch)
-                first_target = accumulate_into if accumulate_into is not None else out
-                part = self.gemm(qm, a, label + ".w8hi", out=first_target, out_cols_offset=out_cols_offset, rowvec=rowvec,
-                                 residual=residual if accumulate_into is None else None,
-                                 accumulate_into=accumulate_into, out_scale=out_scale, use_bias=use_bias,
-                                 _ws=(wa, delta_w), _wscale=2.0, **kw)
-                return self.gemm(qm, a, label, out_q=out_q, accumulate_into=part, out_scale=out_scale, use_bias=False,
-                                 _ws=(wb, delta_w), _wscale=1.0, out_q_head=out_q_head, **kw)
-        else:
-            ws, delta_w = _ws
+        Returns a dict: w8 (the layer needs the two-part W8 form and `part` was None), w_dev (s8 [N, K] or packed
+        4-bit), w_zero, delta_w [N], N, taps, Cred, K, wsum ([N] or [N,3,3] double: zero-point correction sums)."""
+        key = (self.dev.index or 0, label, cols, suffix, k_pad, bool(geglu), part, bool(conv), self.w4_packed)
+        ent = self.wcache.get(key)
+        if ent is not None and (not self.want_specs or ent.get("w8") or "ws_cpu" in ent):
+            return ent
+        ws, delta_w = self._fold(qm, cols, suffix)
+        if part is None and float(ws.abs().max()) > 127:
+            ent = dict(w8=True)
+            self.wcache[key] = ent
+            return ent
+        if part is not None:
+            wa = torch.floor(ws / 2)
+            ws = wa if part == "hi" else ws - 2 * wa
         N = ws.shape[0]
         perm = None
-        if geglu_q is not None:
+        if geglu:
             # GEGLU fused into the epilogue: interleave rows [4 x-features, 4 gate-features] (qd_gemm_desc.geglu)
             r = torch.arange(N, device=ws.device)
             f = 4 * (r // 8) + (r % 8) % 4
             perm = torch.where((r % 8) < 4, f, N // 2 + f)
             ws, delta_w = ws[perm], delta_w[perm]
-            out_q = (geglu_q, False)
-        taps = 9 if (ws.dim() == 4 and ws.shape[-1] == 3 and conv_bhw is not None) else 1
-        if zx is None:
-            zx, dx = a.zp[0], a.delta[0]
+        taps = 9 if (ws.dim() == 4 and ws.shape[-1] == 3 and conv) else 1
         wk = fold.to_k_major(ws) if ws.dim() > 2 else ws
         Cred = wk.shape[1] // taps
         if k_pad is not None and k_pad != wk.shape[1]:
@@ -320,19 +400,61 @@ class Builder:
             pk = ops.pack_int4(wk.reshape(wk.shape[0], -1))
             if pk is not None:
                 w_dev, w_zero = pk[0].to(self.dev), pk[1].to(self.dev)
-                self.keep.append(w_zero)
-                self.packed_layers += 1
         if w_dev is None:
             w_dev = wk.to(torch.int8).contiguous()
+        wsum = ws.to(torch.float64).sum(dim=1) if taps == 9 else ws.reshape(N, -1).to(torch.float64).sum(dim=1)
+        ent = dict(w8=False, w_dev=w_dev, w_zero=w_zero, delta_w=delta_w.contiguous(), N=N, taps=taps, Cred=Cred,
+                   w_rows=wk.shape[0], wsum=wsum, perm=perm)
+        if self.want_specs:
+            ent["ws_cpu"] = ws.detach().to("cpu", torch.float32)
+        self.wcache[key] = ent
+        return ent
+
+    def gemm(self, qm, a, label, *, conv_bhw=None, out=None, out_cols_offset=0, rowvec=None, residual=None,
+             out_q=None, out_scale=1.0, k_pad=None, cols=None, suffix="", zx=None, dx=None, accumulate_into=None,
+             rows_per_batch=0, use_bias=True, geglu_q=None, _part=None, _wscale=1.0, out_q_head=None):
+        """Record one INT8 GEMM for QuantModule `qm` on activation codes `a`.
+
+        W8 (SURVEY H3): wq - zw spans [-255, 255] and does not fit the s8 operand.  Such layers run as TWO exact s8
+        GEMMs, ws = 2*a + b with a = floor(ws/2) in [-128,127], b in {0,1}:  y = 2s(acc_a - corr_a) + s(acc_b - corr_b) + bias,
+        the second one accumulating into the first one's fp32 output and carrying the requantising epilogue.
+
+        cols/suffix select a split-shortcut half.  out_q = (quantizer, transposed) requantises in the
+        epilogue.  out_scale multiplies scale and bias (LDM legacy attention q*s, k*s)."""
+        cols = tuple(cols) if cols is not None else None
+        W = self._weights(qm, label, cols=cols, suffix=suffix, k_pad=k_pad, geglu=geglu_q is not None, part=_part,
+                          conv=conv_bhw is not None)
+        if W["w8"]:
+            if geglu_q is not None:     # fused GEGLU has no accumulate form: unfused fallback
+                f32 = self.gemm(qm, a, label, conv_bhw=conv_bhw, k_pad=k_pad, cols=cols, suffix=suffix, zx=zx, dx=dx,
+                                rows_per_batch=rows_per_batch)
+                return self.quantize(f32, geglu_q, label + ".geglu.q", act=2, out_cols=f32.cols // 2)
+            kw = dict(conv_bhw=conv_bhw, k_pad=k_pad, cols=cols, suffix=suffix, zx=zx, dx=dx, rows_per_batch=rows_per_batch)
+            first_target = accumulate_into if accumulate_into is not None else out
+            part = self.gemm(qm, a, label + ".w8hi", out=first_target, out_cols_offset=out_cols_offset, rowvec=rowvec,
+                             residual=residual if accumulate_into is None else None,
+                             accumulate_into=accumulate_into, out_scale=out_scale, use_bias=use_bias,
+                             _part="hi", _wscale=2.0, **kw)
+            return self.gemm(qm, a, label, out_q=out_q, accumulate_into=part, out_scale=out_scale, use_bias=False,
+                             _part="lo", _wscale=1.0, out_q_head=out_q_head, **kw)
+        N, taps, Cred, delta_w, perm = W["N"], W["taps"], W["Cred"], W["delta_w"], W["perm"]
+        w_dev, w_zero = W["w_dev"], W["w_zero"]
+        if w_zero is not None:
+            self.packed_layers += 1
+            self.keep.append(w_zero)
+        if geglu_q is not None:
+            out_q = (geglu_q, False)
+        if zx is None:
+            zx, dx = a.zp[0], a.delta[0]
         self.keep.append(w_dev)
         scale = (delta_w.double() * float(dx) * out_scale * _wscale).to(torch.float32).contiguous()
         self.keep.append(scale)
         corr = None
         if zx != 0:
             if taps == 9:
-                corr = fold.border_corr(ws, zx).to(self.dev).contiguous()
+                corr = fold.border_corr_from_tapsum(W["wsum"], zx).to(self.dev).contiguous()
             else:
-                corr = (ws.reshape(N, -1).double().sum(dim=1) * zx).to(torch.int32).contiguous()
+                corr = (W["wsum"] * zx).to(torch.int32).contiguous()
             self.keep.append(corr)
         bias = None
         if use_bias and qm.bias is not None:
@@ -378,7 +500,7 @@ class Builder:
                           ldq=(oq_act.t_pad if transposed else oq_act.ld) if oq_act is not None else 0,
                           oq=oq_params, out_q_transposed=transposed, geglu=geglu_q is not None,
                           out_q_head=out_q_head if (out_q is not None and not transposed) else None, w_zero=w_zero,
-                          w_rows=wk.shape[0])
+                          w_rows=W["w_rows"])
         d.a = a.ptr + (cols[0] if cols is not None else 0)
         if rowvec is not None:
             d.rowvec = rowvec.ptr
@@ -386,7 +508,17 @@ class Builder:
             d.residual = res.ptr
         if o is not None:
             d.out = o.ptr + 4 * out_cols_offset
-        self.add(_lib.QD_OP_GEMM, d, label, flops=2 * M * N * Cred * taps)
+        spec = None
+        if self.want_specs:
+            spec = dict(kind="gemm", key=self.key(qm) if id(qm) in self.names else self.key(qm.qm), a=a,
+                        a_cols=(cols[0] if cols is not None else 0), C=Cred, taps=taps, conv_bhw=conv_bhw,
+                        ws=W["ws_cpu"], scale=scale.detach().cpu(),
+                        bias=None if bias is None else bias.detach().cpu(), zx=int(zx), rowvec=rowvec, residual=res,
+                        rows_per_batch=rows_per_batch, out=o, out_cols_offset=out_cols_offset if o is not None else 0,
+                        N=N, out_q=oq_act, oq=_qt(oq_params), transposed=transposed, geglu=geglu_q is not None,
+                        out_q_head=out_q_head if (out_q is not None and not transposed) else None,
+                        packed=w_zero is not None)
+        self.add(_lib.QD_OP_GEMM, d, label, flops=2 * M * N * Cred * taps, spec=spec)
         if o is not None:
             self.layer_traces[label] = o
         return oq_act if out_q is not None else o
@@ -409,7 +541,9 @@ class Builder:
         patches = self.new_codes(self.B * Ho * Wo, k_to, a.signed)
         d = ops.im2col_desc(a.t, patches.t, B=self.B, H=H, W=W, C_=Cin, Ho=Ho, Wo=Wo, stride=stride,
                             pad_top=pad_tl[0], pad_left=pad_tl[1], pad_code=a.zp[0] & 0xFF, ld_dst=k_to)
-        self.add(_lib.QD_OP_IM2COL, d, label + ".im2col")
+        self.add(_lib.QD_OP_IM2COL, d, label + ".im2col",
+                 spec=dict(kind="im2col", src=a, dst=patches, B=self.B, H=H, W=W, Ho=Ho, Wo=Wo, stride=stride, pad_tl=pad_tl,
+                           pad_code=a.zp[0] & 0xFF, k_to=k_to))
         patches.zp, patches.delta = a.zp, a.delta
         return self.gemm(qm, patches, label, k_pad=k_to, **kw)
 
@@ -427,7 +561,7 @@ class Builder:
         out = None
         if consumer is None:
             out = self.new_f32(self.B * Tq, heads * d)
-        qpw, _ = self.qp(qw)
+        qpw, _ = self.qp(qw, wide_ok=True)
         a = AttentionDesc()
         a.q, a.k, a.vt = qc.ptr, kc.ptr, vt.ptr
         a.ld_q, a.ld_k = qc.ld, kc.ld
@@ -455,7 +589,10 @@ class Builder:
             ws = torch.empty(self.B * heads * ((Tk + 127) // 128 * 128), dtype=torch.int32, device=self.dev)
             self.keep.append(ws)
             a.ws = ws.data_ptr()
-        self.add(_lib.QD_OP_ATTENTION, a, label, flops=4 * self.B * heads * Tq * Tk * d)
+        spec = dict(kind="attention", q=qc, k=kc, vt=vt, B=self.B, heads=heads, d=d, Tq=Tq, Tk=Tk, q_layout=q_layout,
+                    k_layout=k_layout, v_layout=v_layout, scale_extra=sim_scale_extra, qw=_qt(qpw),
+                    out=out, oq=_qt(a.oq) if consumer is not None else None)
+        self.add(_lib.QD_OP_ATTENTION, a, label, flops=4 * self.B * heads * Tq * Tk * d, spec=spec)
         return out
 
     # ================================================================== LDM / SD family
@@ -464,7 +601,8 @@ class Builder:
         if x.ld == x.cols and x.col0 == 0:
             return x
         out = self.new_f32(x.rows, x.cols)
-        self.misc(_lib.QD_OP_COPY2D, x.ptr, out.ptr, x.rows, x.cols, ld_src=x.ld, ld_dst=out.ld, label=label + ".dense")
+        self.misc(_lib.QD_OP_COPY2D, x.ptr, out.ptr, x.rows, x.cols, ld_src=x.ld, ld_dst=out.ld, label=label + ".dense",
+                  spec=dict(kind="copy2d", src=x, dst=out))
         return out
 
     def ldm_resblock(self, blk, x, emb, hw, split, out=None):
@@ -503,20 +641,24 @@ class Builder:
                 oh, ow = 2 * H, 2 * W
                 a1 = self.quantize(hf, conv1.act_quantizer, k + ".h_upd.q", upsample=(self.B, H, W))
                 x_res = self.new_f32(self.B * oh * ow, x.cols)
-                self.misc(_lib.QD_OP_UPSAMPLE2X, x.ptr, x_res.ptr, self.B, H, W, x.cols, label=k + ".x_upd")
+                self.misc(_lib.QD_OP_UPSAMPLE2X, x.ptr, x_res.ptr, self.B, H, W, x.cols, label=k + ".x_upd",
+                          spec=dict(kind="upsample2x", src=x, dst=x_res, B=self.B, H=H, W=W))
             else:
                 oh, ow = H // 2, W // 2
                 hp = self.new_f32(self.B * oh * ow, x.cols)
-                self.misc(_lib.QD_OP_AVGPOOL2X, hf.ptr, hp.ptr, self.B, H, W, x.cols, label=k + ".h_upd")
+                self.misc(_lib.QD_OP_AVGPOOL2X, hf.ptr, hp.ptr, self.B, H, W, x.cols, label=k + ".h_upd",
+                          spec=dict(kind="avgpool2x", src=hf, dst=hp, B=self.B, H=H, W=W))
                 a1 = self.quantize(hp, conv1.act_quantizer, k + ".h_upd.q")
                 x_res = self.new_f32(self.B * oh * ow, x.cols)
-                self.misc(_lib.QD_OP_AVGPOOL2X, x.ptr, x_res.ptr, self.B, H, W, x.cols, label=k + ".x_upd")
+                self.misc(_lib.QD_OP_AVGPOOL2X, x.ptr, x_res.ptr, self.B, H, W, x.cols, label=k + ".x_upd",
+                          spec=dict(kind="avgpool2x", src=x, dst=x_res, B=self.B, H=H, W=W))
         emb_out = self.qlinear(lin, emb, k + ".emb_layers.1", act=1)
         oc = conv2.weight.shape[0]
         if getattr(blk, "use_scale_shift_norm", False):
             h = self.conv3x3_s1(conv1, a1, (oh, ow), k + ".in_layers.2")
             ss = (emb_out.t, _Offset(emb_out.t, 4 * oc), emb_out.ld)
-            (a2,), _ = self.groupnorm(h, norm2, oh * ow, [conv2.act_quantizer], True, k + ".out_layers.0", ss=ss)
+            (a2,), _ = self.groupnorm(h, norm2, oh * ow, [conv2.act_quantizer], True, k + ".out_layers.0", ss=ss,
+                                      ss_src=(emb_out, oc))
         else:
             h = self.conv3x3_s1(conv1, a1, (oh, ow), k + ".in_layers.2", rowvec=emb_out)
             (a2,), _ = self.groupnorm(h, norm2, oh * ow, [conv2.act_quantizer], True, k + ".out_layers.0")
@@ -540,7 +682,7 @@ class Builder:
         out = self.conv3x3_s1(conv2, a2, (oh, ow), k + ".out_layers.3", residual=s, out=out)
         return out, (oh, ow)
 
-    def sd_cross_attention(self, attn, x_codes_q, kv_codes, h_res, Tq, Tk, label):
+    def sd_cross_attention(self, attn, x_codes_q, kv_codes, h_res, Tq, Tk, label, static_kv=False):
         """cross_attn_forward, qdiff/quant_block.py:190-221: to_q/to_k/to_v GEMMs requantise straight
         into the attention operand layouts; softmax quantizer = act_quantizer_w (sm_abit, zero point 0)."""
         heads = attn.heads
@@ -548,8 +690,14 @@ class Builder:
         d = inner // heads
         P = self.head_pitch(d)
         qc = self.gemm(attn.to_q, x_codes_q, label + ".to_q", out_q=(attn.act_quantizer_q, False), out_q_head=(d, P))
-        kc = self.gemm(attn.to_k, kv_codes[0], label + ".to_k", out_q=(attn.act_quantizer_k, False), out_q_head=(d, P))
-        vt = self.gemm(attn.to_v, kv_codes[1], label + ".to_v", out_q=(attn.act_quantizer_v, True), rows_per_batch=Tk)
+        if static_kv:
+            self._static_depth += 1      # K / V of the context: step-invariant (static_scope)
+        try:
+            kc = self.gemm(attn.to_k, kv_codes[0], label + ".to_k", out_q=(attn.act_quantizer_k, False), out_q_head=(d, P))
+            vt = self.gemm(attn.to_v, kv_codes[1], label + ".to_v", out_q=(attn.act_quantizer_v, True), rows_per_batch=Tk)
+        finally:
+            if static_kv:
+                self._static_depth -= 1
         o = self.attention(qc, kc, vt, heads=heads, d=d, Tq=Tq, Tk=Tk, q_layout=(0, P), k_layout=(0, P),
                            v_layout=(0, d), sim_scale_extra=float(attn.scale), qw=attn.act_quantizer_w,
                            label=label + ".attn", consumer=attn.to_out[0])
@@ -573,9 +721,10 @@ class Builder:
             if ctx is None:
                 raise ValueError("SpatialTransformer needs a context tensor")
             ctx_act, Tk = ctx
-            kk = self.quantize(ctx_act, a2.to_k.act_quantizer, bk + ".attn2.ctx_k.q")
-            kv = self.quantize(ctx_act, a2.to_v.act_quantizer, bk + ".attn2.ctx_v.q")
-            h = self.sd_cross_attention(a2, cq2, (kk, kv), h, T, Tk, bk + ".attn2")
+            with self.static_scope():
+                kk = self.quantize(ctx_act, a2.to_k.act_quantizer, bk + ".attn2.ctx_k.q")
+                kv = self.quantize(ctx_act, a2.to_v.act_quantizer, bk + ".attn2.ctx_v.q")
+            h = self.sd_cross_attention(a2, cq2, (kk, kv), h, T, Tk, bk + ".attn2", static_kv=self.hoist_ctx)
             proj, ff_out = blk.ff.net[0].proj, blk.ff.net[2]
             (cf,) = self.layernorm(h, blk.norm3, [proj.act_quantizer], bk + ".norm3")
             a_ff = self.gemm(proj, cf, bk + ".ff.net.0.proj", geglu_q=ff_out.act_quantizer)
@@ -624,14 +773,15 @@ class Builder:
         mc = model.model_channels
         temb = self.new_f32(B, mc)
         self.misc(_lib.QD_OP_TIMESTEP_EMB, t_in.data_ptr(), temb.ptr, B, mc, 0, label="timestep_embedding",
-                  aux=ops.timestep_freqs(mc, 0).to(self.dev))
+                  aux=ops.timestep_freqs(mc, 0).to(self.dev), spec=dict(kind="timestep_emb", t=t_in, dst=temb, mode=0))
         e = self.qlinear(model.time_embed[0], temb, "time_embed.0")
         emb = self.qlinear(model.time_embed[2], e, "time_embed.2", act=1)
         ctx = None
         if ctx_in is not None:
             ctx = (Act(ctx_in, ctx_shape[0] * ctx_shape[1], ctx_shape[2]), ctx_shape[1])
         xh = self.new_f32(B * H * W, Cin)
-        self.misc(_lib.QD_OP_NCHW_TO_NHWC, x_in.data_ptr(), xh.ptr, B, Cin, H * W, label="x.nhwc")
+        self.misc(_lib.QD_OP_NCHW_TO_NHWC, x_in.data_ptr(), xh.ptr, B, Cin, H * W, label="x.nhwc",
+                  spec=dict(kind="nchw_to_nhwc", src=x_in, dst=xh))
         h, hw = xh, (H, W)
         hs = []
 
@@ -741,7 +891,8 @@ class Builder:
         o = self.conv3x3_s1(conv, a, hw, "out.2")
         out = torch.zeros((B, o.cols, hw[0], hw[1]), dtype=torch.float32, device=self.dev)
         self.keep.append(out)
-        self.misc(_lib.QD_OP_NHWC_TO_NCHW, o.ptr, out.data_ptr(), B, o.cols, hw[0] * hw[1], label="eps.nchw")
+        self.misc(_lib.QD_OP_NHWC_TO_NCHW, o.ptr, out.data_ptr(), B, o.cols, hw[0] * hw[1], label="eps.nchw",
+                  spec=dict(kind="nhwc_to_nchw", src=o, dst=out))
         return x_in, t_in, ctx_in, out
 
     # ================================================================== DDIM (CIFAR) family
@@ -793,11 +944,12 @@ class Builder:
         split_on = bool(getattr(model.config, "split_shortcut", False))
         temb0 = self.new_f32(B, model.ch)
         self.misc(_lib.QD_OP_TIMESTEP_EMB, t_in.data_ptr(), temb0.ptr, B, model.ch, 1, label="timestep_embedding",
-                  aux=ops.timestep_freqs(model.ch, 1).to(self.dev))
+                  aux=ops.timestep_freqs(model.ch, 1).to(self.dev), spec=dict(kind="timestep_emb", t=t_in, dst=temb0, mode=1))
         e = self.qlinear(model.temb.dense[0], temb0, "temb.dense.0")
         temb = self.qlinear(model.temb.dense[1], e, "temb.dense.1", act=1)
         xh = self.new_f32(B * H * W, Cin)
-        self.misc(_lib.QD_OP_NCHW_TO_NHWC, x_in.data_ptr(), xh.ptr, B, Cin, H * W, label="x.nhwc")
+        self.misc(_lib.QD_OP_NCHW_TO_NHWC, x_in.data_ptr(), xh.ptr, B, Cin, H * W, label="x.nhwc",
+                  spec=dict(kind="nchw_to_nhwc", src=x_in, dst=xh))
         a = self.quantize(xh, model.conv_in.act_quantizer, "conv_in.q")
         hw = (H, W)
         h = self.conv_im2col(model.conv_in, a, hw, "conv_in", 1, (1, 1), hw, (9 * Cin + 31) // 32 * 32)
@@ -841,7 +993,8 @@ class Builder:
         o = self.conv3x3_s1(model.conv_out, a, hw, "conv_out")
         out = torch.zeros((B, o.cols, hw[0], hw[1]), dtype=torch.float32, device=self.dev)
         self.keep.append(out)
-        self.misc(_lib.QD_OP_NHWC_TO_NCHW, o.ptr, out.data_ptr(), B, o.cols, hw[0] * hw[1], label="eps.nchw")
+        self.misc(_lib.QD_OP_NHWC_TO_NCHW, o.ptr, out.data_ptr(), B, o.cols, hw[0] * hw[1], label="eps.nchw",
+                  spec=dict(kind="nhwc_to_nchw", src=o, dst=out))
         return x_in, t_in, None, out
 
 
@@ -898,9 +1051,11 @@ def compile_unet(qnn, x_shape, ctx_shape, device, use_cuda_graph=True):
             x_in, t_in, ctx_in, out = b.lower_ddim(model, x_shape)
         else:
             raise NotImplementedError(f"unknown UNet type {_name(model)}")
+    b.flush()
     check(lib().qd_engine_finalize(b.engine), "qd_engine_finalize")
-    prog = Program(b.engine, b.keep, x_in, t_in, ctx_in, out, b.nops, b.traces, use_cuda_graph)
+    prog = Program(b.engine, b.keep, x_in, t_in, ctx_in, out, b.nops, b.traces, use_cuda_graph, n_static=b.n_static)
     prog.op_names, prog.op_kinds, prog.op_flops = b.op_names, b.op_kinds, b.op_flops
-    prog.kernel_launches = sum(3 if k == _lib.QD_OP_GROUPNORM else 1 for k in b.op_kinds)   # until the first run
+    prog.kernel_launches = sum(3 if k == _lib.QD_OP_GROUPNORM else 1 for k in b.op_kinds[b.n_static:])   # until the first run
     prog.layer_traces = b.layer_traces
+    prog.op_specs = b.op_specs
     return prog

@@ -24,7 +24,10 @@ class QuantModel(nn.Module):
         self.specials = get_specials(act_quant_params['leaf_param'])
         self.quant_module_refactor(self.model, weight_quant_params, act_quant_params)
         self.quant_block_refactor(self.model, weight_quant_params, act_quant_params)
-        self._programs = {}
+        self._programs = {}          # compiled engine programs, keyed by input shape; bounded LRU (max_programs)
+        self._wcache = {}            # folded integer weight operands, shared by all programs (graph.Builder._weights)
+        self.max_programs = int(kwargs.get('max_programs', 4))
+        self.record_op_specs = False  # tests: keep a host-side description of every op for the in-situ parity check
         self.use_cuda_graph = kwargs.get('cuda_graph', True)
 
     # ---- tree rewriting (same traversal order as the reference so nested names coincide)
@@ -56,7 +59,7 @@ class QuantModel(nn.Module):
         for m in self.model.modules():
             if isinstance(m, (QuantModule, BaseQuantBlock)):
                 m.set_quant_state(weight_quant, act_quant)
-        self._programs = {}
+        self._programs = {}     # programs depend on the state; the folded weights (self._wcache) do not
 
     def set_running_stat(self, running_stat: bool, sm_only=False):
         for m in self.model.modules():
@@ -76,17 +79,20 @@ class QuantModel(nn.Module):
 
     # ---- the hot path
     def invalidate(self):
-        """Drop compiled engine programs (call after changing quantizer parameters or weights)."""
+        """Drop compiled engine programs AND the folded weights (call after changing quantizer parameters or weights)."""
         self._programs = {}
+        self._wcache = {}
 
     def program(self, x, context=None):
         from . import graph
         key = (tuple(x.shape), None if context is None else tuple(context.shape), x.device.index)
-        prog = self._programs.get(key)
+        prog = self._programs.pop(key, None)
         if prog is None:
+            while len(self._programs) >= max(self.max_programs, 1):    # least recently used program first
+                self._programs.pop(next(iter(self._programs)))
             prog = graph.compile_unet(self, tuple(x.shape), None if context is None else tuple(context.shape),
                                       x.device, use_cuda_graph=self.use_cuda_graph)
-            self._programs[key] = prog
+        self._programs[key] = prog      # (re)insert at the most-recently-used end
         return prog
 
     def forward(self, x, timesteps=None, context=None):

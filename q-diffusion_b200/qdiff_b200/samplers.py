@@ -101,8 +101,13 @@ class _LatentSampler:
             return self.unet(x, t, cond), 0.0
         x_in = torch.cat([x] * 2)
         t_in = torch.cat([t] * 2)
-        c_in = torch.cat([uc, cond])
-        return self.unet(x_in, t_in, c_in), float(scale)
+        # the conditioning is the same tensor on every step: concatenate once, so the engine sees an unchanged context
+        # object and skips the (step-invariant) context K/V projections (graph.Builder.static_scope)
+        src = getattr(self, "_cin_src", None)
+        if src is None or src[0] is not uc or src[1] is not cond or src[2] != (uc._version, cond._version):
+            self._cin = torch.cat([uc, cond])
+            self._cin_src = (uc, cond, (uc._version, cond._version))
+        return self.unet(x_in, t_in, self._cin), float(scale)
 
 
 class DDIMSampler(_LatentSampler):

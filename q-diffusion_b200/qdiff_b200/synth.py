@@ -23,7 +23,7 @@ SPECS = {
                   in_shape=(4, 64, 64), ctx=(77, 768)),
     "lsun_bedroom": dict(family="ldm", weight_bit=4, act_bit=8, a_sym=True, sm_abit=8, split=False, seed=0,
                          in_shape=(3, 64, 64), ctx=None),
-    "lsun_church": dict(family="ldm", weight_bit=4, act_bit=8, a_sym=False, sm_abit=8, split=False, seed=0,
+    "lsun_church": dict(family="ldm", weight_bit=8, act_bit=8, a_sym=False, sm_abit=8, split=False, seed=0,
                         in_shape=(4, 32, 32), ctx=None),
 }
 

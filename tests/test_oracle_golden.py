@@ -102,3 +102,16 @@ def test_sampler_oracle_matches_reference_samplers():
     out2 = S.generalized_steps(lambda x, t: toy_eps(x, t), q["x"], q["seq"], q["betas"], eta=0.0)
     err2 = (out2 - q["out"]).abs().max().item()
     assert err2 <= 2e-5 * max(1.0, q["out"].abs().max().item()), err2
+    # DDIMSampler.sample with eta = 1 + classifier-free guidance, fed the noise the reference drew (ddim.py:170-220)
+    d = g["ddim"]
+    ac = S.ldm_schedule(1000, d["linear_start"], d["linear_end"])
+    out3 = S.ddim_sample(lambda x, t, c: toy_eps(x, t, c), d["x_T"], d["cond"], d["uc"], d["scale"], ac, d["S"],
+                         eta=d["eta"], noises=d["noises"])
+    err3 = (out3 - d["out"]).abs().max().item()
+    assert len(d["noises"]) == d["S"] and err3 <= 2e-5 * max(1.0, d["out"].abs().max().item()), err3
+    # generalized_steps on the quadratic schedule (cfg 2) with eta = 1 (denoising.py:25-29)
+    q2 = g["generalized_quad"]
+    out4 = S.generalized_steps(lambda x, t: toy_eps(x, t), q2["x"], q2["seq"], q2["betas"], eta=q2["eta"],
+                               noises=q2["noises"])
+    err4 = (out4 - q2["out"]).abs().max().item()
+    assert err4 <= 2e-5 * max(1.0, q2["out"].abs().max().item()), err4

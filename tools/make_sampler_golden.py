@@ -29,6 +29,7 @@ def toy_eps(x, t, context=None):
 def main():
     _import_reference()
     from ldm.models.diffusion.plms import PLMSSampler
+    from ldm.models.diffusion import ddim as ref_ddim
     from ddim.functions.denoising import generalized_steps
 
     from oracle.sampler_oracle import ldm_schedule
@@ -63,6 +64,31 @@ def main():
                                      unconditional_guidance_scale=scale, unconditional_conditioning=uc, eta=0.0,
                                      x_T=x_T)
 
+    # DDIM with eta = 1 and classifier-free guidance (cfg 3 runs `-e 1.0`): the per-step noise draws are recorded by
+    # wrapping the reference's noise_like (util.py:264-267) so the oracle / engine can be fed the same noise
+    class CpuDDIM(ref_ddim.DDIMSampler):
+        def register_buffer(self, name, attr):
+            setattr(self, name, attr)
+
+    ddim_noises = []
+    real_noise_like = ref_ddim.noise_like
+
+    def recording_noise_like(shape, device, repeat=False):
+        n = real_noise_like(shape, device, repeat)
+        ddim_noises.append(n.clone())
+        return n
+
+    ref_ddim.noise_like = recording_noise_like
+    x_T2 = torch.randn(B, *shape, generator=g)
+    torch.manual_seed(11)
+    try:
+        with torch.no_grad():
+            ddim_out, _ = CpuDDIM(ToyLDM()).sample(S=8, batch_size=B, shape=shape, conditioning=cond, verbose=False,
+                                                   unconditional_guidance_scale=2.0, unconditional_conditioning=uc,
+                                                   eta=1.0, x_T=x_T2)
+    finally:
+        ref_ddim.noise_like = real_noise_like
+
     # ddim (CIFAR path): linear beta schedule of the cifar10 config, 20 uniform steps, eta = 0
     betas_c = torch.linspace(0.0001, 0.02, 1000, dtype=torch.float64).float()
     seq = list(range(0, 1000, 50))
@@ -78,12 +104,35 @@ def main():
     try:
         with torch.no_grad():
             xs, _ = generalized_steps(x0, seq, lambda x, t: toy_eps(x, t), betas_c, eta=0.0)
+        # cfg 2 style: quadratic timestep schedule (sample_diffusion_ddim.py:294-301) with eta = 1; the per-step
+        # torch.randn_like draws (denoising.py:28) are recorded
+        import numpy as np
+        seq_q = [int(s) for s in list(np.linspace(0, np.sqrt(1000 * 0.8), 12) ** 2)]
+        gs_noises = []
+        real_randn_like = torch.randn_like
+
+        def recording_randn_like(t, *a, **k):
+            n = real_randn_like(t, *a, **k)
+            gs_noises.append(n.clone())
+            return n
+
+        x1 = torch.randn(B, 3, 8, 8, generator=g)
+        torch.manual_seed(13)
+        torch.randn_like = recording_randn_like
+        try:
+            with torch.no_grad():
+                xs_q, _ = generalized_steps(x1, seq_q, lambda x, t: toy_eps(x, t), betas_c, eta=1.0)
+        finally:
+            torch.randn_like = real_randn_like
     finally:
         torch.Tensor.to = real_to
     os.makedirs(OUT, exist_ok=True)
     torch.save(dict(plms=dict(x_T=x_T, cond=cond, uc=uc, scale=scale, S=S, out=plms_out,
                               linear_start=0.00085, linear_end=0.0120),
-                    generalized=dict(x=x0, seq=seq, betas=betas_c, out=xs[-1])),
+                    generalized=dict(x=x0, seq=seq, betas=betas_c, out=xs[-1]),
+                    ddim=dict(x_T=x_T2, cond=cond, uc=uc, scale=2.0, S=8, eta=1.0, noises=ddim_noises, out=ddim_out,
+                              linear_start=0.00085, linear_end=0.0120),
+                    generalized_quad=dict(x=x1, seq=seq_q, betas=betas_c, eta=1.0, noises=gs_noises, out=xs_q[-1])),
                os.path.join(OUT, "samplers.pt"))
     print("samplers.pt:", tuple(plms_out.shape), float(plms_out.std()), tuple(xs[-1].shape), float(xs[-1].std()))
 
