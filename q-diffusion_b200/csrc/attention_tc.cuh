@@ -19,29 +19,37 @@
 #pragma once
 #include "attention.cuh"
 #include "ptx.cuh"
+#include <type_traits>
 
 namespace qd {
 
-constexpr int ATC_SOFTMAX_WARPS = 16;   // 4 warps per TMEM lane quarter, 32 key columns of a tile each
-constexpr int ATC_THREADS = 64 + 32 * ATC_SOFTMAX_WARPS;
+// Two configurations of the same kernel (template parameter NSW = softmax warps):
+//   NSW = 16: one CTA per SM, 4 softmax warps per TMEM lane quarter (32 key columns of a tile each), S double-buffered in
+//             TMEM (512 columns), 4-stage K/V ring.
+//   NSW =  8: TWO CTAs per SM (d <= 64): 2 softmax warps per lane quarter (64 key columns each), one S slot + O in 256 TMEM
+//             columns, 2-stage K/V ring, <= 102 registers.  The two co-resident CTAs are independent pipelines: one CTA's
+//             prologue (TMEM allocation, Q/K loads), barrier round trips and epilogue are covered by the other's
+//             arithmetic (profiles/r01_attention_tc_final.txt: 13 % of the warp samples sat in mbarrier spins).
 constexpr int ATC_BM = 128, ATC_BN = 128;
-
-constexpr int ATC_STAGES = 4;
+__host__ __device__ constexpr int atc_threads(int NSW) { return 64 + 32 * NSW; }
+__host__ __device__ constexpr int atc_stages(int NSW) { return NSW == 16 ? 4 : 2; }
+__host__ __device__ constexpr int atc_sslots(int NSW) { return NSW == 16 ? 2 : 1; }
 
 struct AtcSmem {
   int q_off, k_off, v_off, p_off, zrk_off, stat_off, bar_off, total, v_stage, k_stage;
 };
-__host__ __device__ inline AtcSmem atc_smem_layout(int NV, int P) {
+__host__ __device__ inline AtcSmem atc_smem_layout(int NV, int P, int NSW = 16) {
+  const int stages = atc_stages(NSW);
   AtcSmem l;
   l.q_off = 0;
-  l.k_off = 16384;
+  l.k_off = (128 * P + 1023) / 1024 * 1024;  // Q tile: 128 rows x P bytes
   l.k_stage = 128 * P;                       // 128 keys x P bytes (P = swizzle span)
   l.v_stage = NV * 128;
-  l.v_off = l.k_off + ATC_STAGES * l.k_stage;
-  l.p_off = (l.v_off + ATC_STAGES * l.v_stage + 1023) / 1024 * 1024;
+  l.v_off = l.k_off + stages * l.k_stage;
+  l.p_off = (l.v_off + stages * l.v_stage + 1023) / 1024 * 1024;
   l.zrk_off = l.p_off + 4 * 16384;          // [buffer][plane]
-  l.stat_off = l.zrk_off + ATC_STAGES * 512;
-  l.bar_off = l.stat_off + 4 * 128 * 8;
+  l.stat_off = l.zrk_off + stages * 512;
+  l.bar_off = l.stat_off + (NSW / 4) * 128 * 8;
   l.total = l.bar_off + 256 + 1024;
   return l;
 }
@@ -57,14 +65,21 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw(uint32_t smem_addr, int P)
   return d;
 }
 
-template <bool SM16, bool MAGIC>
-__global__ void __launch_bounds__(ATC_THREADS, 1)
+template <bool SM16, bool MAGIC, int NSW>
+__global__ void __launch_bounds__(atc_threads(NSW), NSW == 16 ? 1 : 2)
 qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const qd_attention_desc p, const int NV, const int P) {
   extern __shared__ uint8_t atc_raw[];
   const uint32_t raw_addr = smem_u32(atc_raw);
   uint8_t* smem = atc_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  const AtcSmem L = atc_smem_layout(NV, P);
+  constexpr int ATC_SOFTMAX_WARPS = NSW;
+  constexpr int ATC_THREADS = atc_threads(NSW);
+  constexpr int ATC_STAGES = atc_stages(NSW);
+  constexpr int SSLOTS = atc_sslots(NSW);
+  constexpr int NPART = NSW / 4;             // softmax warps per TMEM lane quarter
+  constexpr int CPT = 4 / NPART;             // 32-column chunks of a tile per softmax thread
+  constexpr uint32_t TMEM_COLS = NSW == 16 ? 512 : 256;
+  const AtcSmem L = atc_smem_layout(NV, P, NSW);
   uint8_t* sQ = smem + L.q_off;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* kv_full = bars;        // [ATC_STAGES]
@@ -112,7 +127,7 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
   if (warp == 0) {
     if (lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
-    tmem_alloc(tmem_ptr, 512);
+    tmem_alloc(tmem_ptr, TMEM_COLS);
     tmem_relinquish();
   }
   fence_proxy_async();   // generic-proxy writes of Q / constant rows -> visible to the tensor-core (async) proxy
@@ -120,9 +135,9 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tm_s = tmem_base;             // S slots: columns [0,128) and [128,256)
-  const uint32_t tm_olo = tmem_base + 256;     // O_lo: NV columns
-  const uint32_t tm_ohi = tmem_base + 256 + 128;
+  const uint32_t tm_s = tmem_base;             // S slots: columns [0,128) (and [128,256) when double-buffered)
+  const uint32_t tm_olo = tmem_base + SSLOTS * 128;                          // O_lo: NV columns
+  const uint32_t tm_ohi = tmem_base + SSLOTS * 128 + (NSW == 16 ? 128 : 64);  // O_hi (NV <= 64 in the 256-column layout)
 
   if (warp == 0) {
     // ===================== loader =====================
@@ -169,7 +184,7 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         umma_commit(&s_full[sb]);
         umma_commit(&kv_empty[st]);
         if (++st == ATC_STAGES) { st = 0; ph_kv ^= 1; }
-        if (++sb == 2) { sb = 0; ph_s ^= 1; }
+        if (++sb == SSLOTS) { sb = 0; ph_s ^= 1; }
       }
       // ---- pass 2: S(t+1) is issued before PV(t) so the softmax of t+1 overlaps the PV MMAs of t
       auto issue_s = [&](int st_, int sb_) {
@@ -186,7 +201,7 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int t = 0; t < ntiles; ++t) {
         const int st_cur = st_s;
         if (++st_s == ATC_STAGES) { st_s = 0; ph_kv_s ^= 1; }
-        if (++sb_s == 2) { sb_s = 0; ph_s_s ^= 1; }
+        if (++sb_s == SSLOTS) { sb_s = 0; ph_s_s ^= 1; }
         if (t + 1 < ntiles) {
           mbar_wait(&kv_full[st_s], ph_kv_s);
           mbar_wait(&s_empty[sb_s], ph_s_s ^ 1);
@@ -226,17 +241,23 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     constexpr int BIAS = MAGIC ? 0x4B400000 : 0;
     constexpr int MASKED = MAGIC ? BIAS - (1 << 22) + 1 : INT_MIN / 2;
     auto tof = [](int t) -> float { return MAGIC ? __int_as_float(t) - 12582912.0f : (float)t; };
+    auto tof2 = [](int t0, int t1) -> float2 {
+      return MAGIC ? fadd2(make_float2(__int_as_float(t0), __int_as_float(t1)), make_float2(-12582912.0f, -12582912.0f))
+                   : make_float2((float)t0, (float)t1);
+    };
     int mi = INT_MIN;
     float l = 0.f;
     // ---- pass 1
     for (int t = 0; t < ntiles; ++t) {
-      const int j0 = t * ATC_BN + part * 32;
       mbar_wait(&s_full[sb], ph_s);
       tc_fence_after();
-      const int* zr = reinterpret_cast<const int*>(smem + L.zrk_off + st * 512) + part * 32;
-      {
+#pragma unroll 1
+      for (int cc = 0; cc < CPT; ++cc) {
+        const int col0 = (part * CPT + cc) * 32;          // this thread's 32 key columns of the tile
+        const int j0 = t * ATC_BN + col0;
+        const int* zr = reinterpret_cast<const int*>(smem + L.zrk_off + st * 512) + col0;
         uint32_t v[32];
-        tmem_ld_32x32(tm_s + t_lane + sb * 128 + part * 32, v);
+        tmem_ld_32x32(tm_s + t_lane + sb * 128 + col0, v);
         tmem_ld_wait();
         int s[32];
 #pragma unroll
@@ -258,13 +279,15 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           for (int j = 1; j < 32; ++j) tm = max(tm, s[j]);
           if (tm > mi) { l *= (mi == INT_MIN) ? 0.f : ex2_approx((float)(mi - tm) * c); mi = tm; }
           const float b0 = -(float)(mi - BIAS) * c;
-          float a0 = 0.f, a1 = 0.f;
+          // packed fp32 (FADD2 / FFMA2): same IEEE results as the scalar form, half the issue slots
+          const float2 c2 = make_float2(c, c), b2 = make_float2(b0, b0);
+          float2 acc2 = make_float2(0.f, 0.f);
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            a0 += ex2_approx(fmaf(tof(s[j]), c, b0));
-            a1 += ex2_approx(fmaf(tof(s[j + 1]), c, b0));
+            const float2 x = ffma2(tof2(s[j], s[j + 1]), c2, b2);
+            acc2 = fadd2(acc2, make_float2(ex2_approx(x.x), ex2_approx(x.y)));
           }
-          l += a0 + a1;
+          l += acc2.x + acc2.y;
         }
       }
       tc_fence_before();
@@ -273,52 +296,71 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_arrive(&s_empty[sb]);
         mbar_arrive(&kv_empty[st]);
       }
-      if (++sb == 2) { sb = 0; ph_s ^= 1; }
+      if (++sb == SSLOTS) { sb = 0; ph_s ^= 1; }
       if (++st == ATC_STAGES) { st = 0; ph_kv ^= 1; }
     }
-    // ---- combine the four column quarters of every row (named barrier over the 16 softmax warps)
+    // ---- combine the column parts of every row (named barrier over the softmax warps)
     stat[part * 128 + row] = make_float2(__int_as_float(mi), l);
-    asm volatile("bar.sync 1, 512;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * NSW) : "memory");
     float off;
+    bool row_clamps;
     {
       int mm = INT_MIN;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) mm = max(mm, __float_as_int(stat[k * 128 + row].x));
+      for (int k = 0; k < NPART; ++k) mm = max(mm, __float_as_int(stat[k * 128 + row].x));
       float lt = 0.f;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < NPART; ++k) {
         const float2 o = stat[k * 128 + row];
         const int mo = __float_as_int(o.x);
         lt += o.y * ((mo == INT_MIN) ? 0.f : ex2_approx((float)(mo - mm) * c));
       }
-      off = -(float)(mm - BIAS) * c + log2f(1.0f / (lt * p.delta_w));
+      const float inv = 1.0f / (lt * p.delta_w);     // the row's largest possible P code (score == row max)
+      off = -(float)(mm - BIAS) * c + log2f(inv);
+      row_clamps = !(inv <= pmax);
     }
+    const bool warp_clamps = __any_sync(0xffffffffu, row_clamps);
     // ---- pass 2
     int pb = 0;
     uint32_t ph_p = 0;
     for (int t = 0; t < ntiles; ++t) {
-      const int j0 = t * ATC_BN + part * 32;
       mbar_wait(&s_full[sb], ph_s);
       mbar_wait(&p_empty[pb], ph_p ^ 1);
       tc_fence_after();
-      const int* zr = reinterpret_cast<const int*>(smem + L.zrk_off + st * 512) + part * 32;
       uint8_t* pl = smem + L.p_off + (pb * 2) * 16384 + row * 128;
       uint8_t* phh = pl + 16384;
-      {
+#pragma unroll 1
+      for (int cc = 0; cc < CPT; ++cc) {
+        const int col0 = (part * CPT + cc) * 32;
+        const int j0 = t * ATC_BN + col0;
+        const int* zr = reinterpret_cast<const int*>(smem + L.zrk_off + st * 512) + col0;
         uint32_t v[32];
-        tmem_ld_32x32(tm_s + t_lane + sb * 128 + part * 32, v);
+        tmem_ld_32x32(tm_s + t_lane + sb * 128 + col0, v);
         tmem_ld_wait();
         uint32_t cd[32];
+        const float2 c2 = make_float2(c, c), off2 = make_float2(off, off), k2 = make_float2(12582912.0f, 12582912.0f);
+        // code = rne(min(exp2(c*s + off), pmax)) through the 1.5*2^23 constant; the min is skipped (warp-uniformly) when no
+        // row of this warp can exceed pmax: its largest code is 1 / (l * delta_w), known after pass 1
+        auto codes = [&](auto clamp_tag) {
+          constexpr bool CLAMP = decltype(clamp_tag)::value;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          int4 z = make_int4(BIAS, BIAS, BIAS, BIAS);
-          if (has_zq) z = *reinterpret_cast<const int4*>(zr + j);
-          const int s0 = (int)v[j] + z.x, s1 = (int)v[j + 1] + z.y, s2 = (int)v[j + 2] + z.z, s3 = (int)v[j + 3] + z.w;
-          cd[j] = __float_as_uint(fminf(ex2_approx(fmaf(tof(s0), c, off)), pmax) + 12582912.0f);
-          cd[j + 1] = __float_as_uint(fminf(ex2_approx(fmaf(tof(s1), c, off)), pmax) + 12582912.0f);
-          cd[j + 2] = __float_as_uint(fminf(ex2_approx(fmaf(tof(s2), c, off)), pmax) + 12582912.0f);
-          cd[j + 3] = __float_as_uint(fminf(ex2_approx(fmaf(tof(s3), c, off)), pmax) + 12582912.0f);
-        }
+          for (int j = 0; j < 32; j += 4) {
+            int4 z = make_int4(BIAS, BIAS, BIAS, BIAS);
+            if (has_zq) z = *reinterpret_cast<const int4*>(zr + j);
+            const float2 x0 = ffma2(tof2((int)v[j] + z.x, (int)v[j + 1] + z.y), c2, off2);
+            const float2 x1 = ffma2(tof2((int)v[j + 2] + z.z, (int)v[j + 3] + z.w), c2, off2);
+            float2 e0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+            float2 e1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+            if (CLAMP) {
+              e0.x = fminf(e0.x, pmax); e0.y = fminf(e0.y, pmax);
+              e1.x = fminf(e1.x, pmax); e1.y = fminf(e1.y, pmax);
+            }
+            const float2 r0 = fadd2(e0, k2), r1 = fadd2(e1, k2);
+            cd[j] = __float_as_uint(r0.x); cd[j + 1] = __float_as_uint(r0.y);
+            cd[j + 2] = __float_as_uint(r1.x); cd[j + 3] = __float_as_uint(r1.y);
+          }
+        };
+        if (warp_clamps) codes(std::true_type{}); else codes(std::false_type{});
         if (j0 + 32 > p.Tk) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -337,7 +379,7 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             lo[bq] = __byte_perm(u, w, 0x6420);
             if (SM16) hi[bq] = __byte_perm(u, w, 0x7531);
           }
-          const int chunk = part * 2 + gq;                         // 16-byte chunk of the 128-key row
+          const int chunk = (col0 >> 4) + gq;                      // 16-byte chunk of the 128-key row
           const int sw = (chunk ^ (row & 7)) << 4;
           *reinterpret_cast<uint4*>(pl + sw) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           if (SM16) *reinterpret_cast<uint4*>(phh + sw) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -351,7 +393,7 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_arrive(&kv_empty[st]);
         mbar_arrive(&p_full[pb]);
       }
-      if (++sb == 2) { sb = 0; ph_s ^= 1; }
+      if (++sb == SSLOTS) { sb = 0; ph_s ^= 1; }
       if (++st == ATC_STAGES) { st = 0; ph_kv ^= 1; }
       if (++pb == 2) { pb = 0; ph_p ^= 1; }
     }
@@ -407,7 +449,7 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 0) tmem_dealloc(tmem_base, 512);
+  if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 }  // namespace qd

@@ -133,82 +133,75 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const double* __restri
   }
 }
 // Pass 3: normalise + affine (+scale-shift) (+SiLU) + quantise for each consumer.
-// grid (row chunks, B); a thread owns fixed channel quads, folds mean/rstd/gamma/beta(/scale-shift) into
-// y = a*x + b once, then streams GN_ROWS pixels: no integer division and no table lookups in the loop.
-constexpr int GN_MAXQ = 4;   // channel quads per thread: C <= 4 * 256 * GN_MAXQ
+// Block = TX channel quads x TY rows (TX * TY <= 256); grid (channel slabs, row chunks, B).  A thread owns ONE channel
+// quad: it folds mean / rstd / gamma / beta (/ scale-shift) into y = a*x + b once (8 registers) and then streams its rows,
+// GN_BATCH independent 16-byte loads in flight before the first store.  The first version (one block of C/4 threads per
+// 32 rows, up to 4 quads per thread) needed 118 registers and ran 96-thread blocks at 21 % occupancy: every warp sat
+// on its first FFMA waiting for DRAM (profiles/r02_gn_apply_before.txt: 1.8-3 TB/s).  The consumer count and the raw
+// output are template parameters so that the common single-consumer case carries one quantizer's constants only.
+constexpr int GN_BATCH = 8;
+template <int NOUT, bool RAW>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const qd_groupnorm_desc p, const float* __restrict__ stats,
-                                                       int rows_per_block) {
-  const int b = blockIdx.y;
+                                                       int rows_per_block, int TX) {
+  const int b = blockIdx.z;
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const int TY = blockDim.x / TX;
+  const int q = blockIdx.x * TX + tx;                 // channel quad
   const int cq = p.C >> 2;
+  if (q >= cq || ty >= TY) return;
+  const int c = q << 2;
   const int cpg = p.C / p.groups;
-  const int r0 = blockIdx.x * rows_per_block;
-  const int r1 = min(p.HW, r0 + rows_per_block);
-  float ca[GN_MAXQ][4], cb[GN_MAXQ][4];
-  const QuantK qk[3] = {make_quantk(p.q[0]), make_quantk(p.q[1]), make_quantk(p.q[2])};
-  const QuantK qraw[2] = {make_quantk(p.q_raw[0]), make_quantk(p.q_raw[1])};
-  int nq = 0;
-  for (int q = threadIdx.x; q < cq && nq < GN_MAXQ; q += blockDim.x, ++nq) {
+  float ca[4], cb[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int ch = (q << 2) + j;
-      const int g = ch / cpg;
-      const float mean = stats[((long long)b * p.groups + g) * 2];
-      const float rstd = stats[((long long)b * p.groups + g) * 2 + 1];
-      float a = rstd * p.gamma[ch];
-      float bb = p.beta[ch] - mean * a;
-      if (p.ss_scale) {
-        const float s1 = 1.0f + p.ss_scale[(long long)b * p.ld_ss + ch];
-        a *= s1;
-        bb = bb * s1 + p.ss_shift[(long long)b * p.ld_ss + ch];
-      }
-      ca[nq][j] = a;
-      cb[nq][j] = bb;
+  for (int j = 0; j < 4; ++j) {
+    const int ch = c + j;
+    const int g = ch / cpg;
+    const float mean = stats[((long long)b * p.groups + g) * 2];
+    const float rstd = stats[((long long)b * p.groups + g) * 2 + 1];
+    float a = rstd * p.gamma[ch];
+    float bb = p.beta[ch] - mean * a;
+    if (p.ss_scale) {
+      const float s1 = 1.0f + p.ss_scale[(long long)b * p.ld_ss + ch];
+      a *= s1;
+      bb = bb * s1 + p.ss_shift[(long long)b * p.ld_ss + ch];
     }
+    ca[j] = a;
+    cb[j] = bb;
   }
+  QuantK qk[NOUT > 0 ? NOUT : 1];
 #pragma unroll
-  for (int k = 0; k < GN_MAXQ; ++k) {
-    if (k < nq) {
-      const int c = (threadIdx.x + k * blockDim.x) << 2;
-      const float* xp = p.x + ((long long)b * p.HW + r0) * p.ld_x + c;
-      // Rows go in batches of GN_BATCH: all loads of a batch are issued before its first store.  The outputs may
-      // alias x as far as the compiler knows, so in a plain row loop every load waited for the previous row's
-      // stores - one DRAM round trip per row, 1.9 TB/s where gn_partial reads the same tensor at 4.1 TB/s
-      // (profiles/r01_launches_step_final.summary.txt).
-      constexpr int GN_BATCH = 8;
-      for (int rb = r0; rb < r1; rb += GN_BATCH) {
-        float4 vv[GN_BATCH];
+  for (int o = 0; o < NOUT; ++o) qk[o] = make_quantk(p.q[o]);
+  QuantK kr = make_quantk(p.q_raw[0]);
+  if (RAW && c >= p.raw_split) kr = make_quantk(p.q_raw[1]);
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(p.HW, r0 + rows_per_block);
+  const long long step = (long long)TY * p.ld_x;
+  for (int rb = r0 + ty; rb < r1; rb += GN_BATCH * TY) {
+    const float* xp = p.x + ((long long)b * p.HW + rb) * p.ld_x + c;
+    float4 vv[GN_BATCH];
 #pragma unroll
-        for (int i = 0; i < GN_BATCH; ++i)
-          if (rb + i < r1) vv[i] = *reinterpret_cast<const float4*>(xp + (long long)i * p.ld_x);
-        xp += (long long)GN_BATCH * p.ld_x;
+    for (int i = 0; i < GN_BATCH; ++i)
+      if (rb + i * TY < r1) vv[i] = *reinterpret_cast<const float4*>(xp + i * step);
 #pragma unroll
-        for (int i = 0; i < GN_BATCH; ++i) {
-          const int r = rb + i;
-          if (r >= r1) break;
-          const float4 v = vv[i];
-          const long long row = (long long)b * p.HW + r;
-          if (p.raw_q) {
-            const QuantK& kr = qraw[c < p.raw_split ? 0 : 1];
-            *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.raw_q) + row * p.ld_raw + c) =
-                pack4(quant_code(v.x, kr), quant_code(v.y, kr), quant_code(v.z, kr), quant_code(v.w, kr));
-          }
-          float y[4] = {fmaf(v.x, ca[k][0], cb[k][0]), fmaf(v.y, ca[k][1], cb[k][1]), fmaf(v.z, ca[k][2], cb[k][2]),
-                        fmaf(v.w, ca[k][3], cb[k][3])};
-          if (p.silu) {
+    for (int i = 0; i < GN_BATCH; ++i) {
+      const int r = rb + i * TY;
+      if (r >= r1) break;
+      const float4 v = vv[i];
+      const long long row = (long long)b * p.HW + r;
+      if (RAW)
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.raw_q) + row * p.ld_raw + c) =
+            pack4(quant_code(v.x, kr), quant_code(v.y, kr), quant_code(v.z, kr), quant_code(v.w, kr));
+      float y[4] = {fmaf(v.x, ca[0], cb[0]), fmaf(v.y, ca[1], cb[1]), fmaf(v.z, ca[2], cb[2]), fmaf(v.w, ca[3], cb[3])};
+      if (p.silu) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) y[j] = silu_f(y[j]);
-          }
-          if (p.out_f) *reinterpret_cast<float4*>(p.out_f + row * p.ld_f + c) = make_float4(y[0], y[1], y[2], y[3]);
-#pragma unroll
-          for (int o = 0; o < 3; ++o) {
-            if (o < p.n_out) {
-              const uint32_t code = pack4(quant_code_fast(y[0], qk[o]), quant_code_fast(y[1], qk[o]),
-                                          quant_code_fast(y[2], qk[o]), quant_code_fast(y[3], qk[o]));
-              *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.out_q[o]) + row * p.ld_q[o] + c) = code;
-            }
-          }
-        }
+        for (int j = 0; j < 4; ++j) y[j] = silu_f(y[j]);
       }
+      if (p.out_f) *reinterpret_cast<float4*>(p.out_f + row * p.ld_f + c) = make_float4(y[0], y[1], y[2], y[3]);
+#pragma unroll
+      for (int o = 0; o < NOUT; ++o)
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.out_q[o]) + row * p.ld_q[o] + c) =
+            pack4(quant_code_fast(y[0], qk[o]), quant_code_fast(y[1], qk[o]), quant_code_fast(y[2], qk[o]),
+                  quant_code_fast(y[3], qk[o]));
     }
   }
 }

@@ -127,22 +127,38 @@ int encode_u8_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* 
 
 // ------------------------------------------------------------------ GEMM plan
 struct GemmPlan {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmR;   // tmR: residual as bytes [M][N*4], 128 B x 32 row boxes (plain GEMMs with a residual)
   qd::GemmArgs args;
   int grid, mode;
 };
 
-int pick_bn(int N, int tiles_m, int sms, int hint, int step = 16) {
+// N-tile width.  Model (cycles per 128 x BN tile on one SM; constants fitted to tools/sweep_bn.py on B200):
+//   main loop  per 128-byte k-block: max(tensor time ~ 2.1*BN, L2->SM operand delivery ~ 3.0*(128 + BN)) -- with one CTA per SM
+//              the big-K convs are bound by the operand bytes (128 + BN)*128 per k-block (profiles/r01_gemm_conv_final.txt), so wide
+//              tiles (more reuse of the A rows) win even when they leave the last wave less full;
+//   epilogue   ~ BN columns (overlaps the next tile's main loop through the double-buffered accumulators);
+//   waves      = ceil(tiles / SMs).
+// QDIFF_BN_MODEL=wave selects the round-1 rule (waves * (BN + 24)), kept for A/B comparisons.
+int pick_bn(int N, int tiles_m, int sms, int hint, int step, long long K) {
   if (hint > 0) return hint;
+  static const int wave_model = [] { const char* e = getenv("QDIFF_BN_MODEL"); return (e && !strcmp(e, "wave")) ? 1 : 0; }();
   int best = step;
-  long long best_cost = -1;
+  double best_cost = -1.0;
   const int n16 = (N + step - 1) / step * step;
+  const double kb = (double)((K + 127) / 128);
   for (int bn = step; bn <= 256; bn += step) {
     if (bn > n16) break;
     const long long tiles = (long long)tiles_m * ((N + bn - 1) / bn);
     const long long waves = (tiles + sms - 1) / sms;
-    const long long cost = waves * (bn + 24);
-    if (best_cost < 0 || cost < best_cost || (cost == best_cost && bn > best)) {
+    double cost;
+    if (wave_model) {
+      cost = (double)waves * (bn + 24);
+    } else {
+      const double main_loop = kb * (2.1 * bn > 3.0 * (128 + bn) ? 2.1 * bn : 3.0 * (128 + bn));
+      const double epilogue = 6.0 * bn + 300.0;
+      cost = (double)waves * ((main_loop > epilogue ? main_loop : epilogue) + 200.0);
+    }
+    if (best_cost < 0 || cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && bn > best)) {
       best_cost = cost;
       best = bn;
     }
@@ -170,7 +186,7 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
     if ((d->N & 7) || !d->out_q || d->out || d->rowvec || d->residual || d->out_q_transposed || (d->ldq & 3) || d->taps != 1)
       return fail(QD_ERR_BAD_ARG, "gemm: geglu needs N %% 8 == 0, out_q only, plain GEMM");
   }
-  a.BN = pick_bn(d->N, a.tiles_m, sms, d->bn_hint, d->geglu ? 32 : 16);
+  a.BN = pick_bn(d->N, a.tiles_m, sms, d->bn_hint, d->geglu ? 32 : 16, (long long)d->C * d->taps);
   if (a.BN % 16 || a.BN < 16 || a.BN > 256) return fail(QD_ERR_BAD_ARG, "gemm: bad BN %d", a.BN);
   a.tiles_n = (d->N + a.BN - 1) / a.BN;
   a.a_signed = d->a_signed; a.b_signed = 1;
@@ -243,6 +259,14 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
   const int tiles = a.tiles_m * a.tiles_n;
   pl->grid = tiles < sms ? tiles : sms;
   pl->mode = gemm_mode(a);
+  memset(&pl->tmR, 0, sizeof(pl->tmR));
+  if (qd::gemm_res_tma(pl->mode)) {
+    cuuint64_t rd[2] = {(cuuint64_t)d->N * 4, (cuuint64_t)d->M};
+    cuuint64_t rs[1] = {(cuuint64_t)d->ldr * 4};
+    cuuint32_t rb[2] = {128, 32};
+    rc = encode_u8_map(&pl->tmR, d->residual, 2, rd, rs, rb);
+    if (rc) return rc;
+  }
   return QD_OK;
 }
 
@@ -253,12 +277,13 @@ int launch_gemm_mode_w(const GemmPlan& pl, cudaStream_t s) {
   constexpr int epi_warps = qd::gemm_epi_warps(MODE);
   qd::GemmArgs a = pl.args;
   const int stage_bytes = qd::gemm_stage_footprint(a.BN, W4 ? 1 : 0);
-  int stages = (232448 - 256 - epi_warps * qd::GEMM_EPI_TILE_BYTES - 1024 - 1024) / stage_bytes;
+  constexpr int res_bytes = qd::gemm_res_bytes(MODE);
+  int stages = (232448 - 512 - epi_warps * qd::GEMM_EPI_TILE_BYTES - res_bytes - 1024 - 1024) / stage_bytes;
   if (stages > qd::GEMM_MAX_STAGES) stages = qd::GEMM_MAX_STAGES;
   if (stages < 2) stages = 2;
   a.stages = stages;
-  const int smem = qd::gemm_smem_layout(a.BN, stages, epi_warps, W4 ? 1 : 0).total;
-  qd::gemm_i8_kernel<MODE, W4><<<pl.grid, qd::gemm_threads(MODE), smem, s>>>(pl.tmA, pl.tmB, a);
+  const int smem = qd::gemm_smem_layout(a.BN, stages, epi_warps, W4 ? 1 : 0, res_bytes).total;
+  qd::gemm_i8_kernel<MODE, W4><<<pl.grid, qd::gemm_threads(MODE), smem, s>>>(pl.tmA, pl.tmB, pl.tmR, a);
   return check_launch("gemm_i8_kernel");
 }
 
@@ -280,8 +305,9 @@ int gemm_mode(const qd::GemmArgs& a) {
   if (f && (a.ldo & 3)) return -1;
   if (q && (a.ldq & 3)) return -1;
   if (a.residual && (a.ldr & 3)) return -1;
+  if (a.residual && a.taps == 1 && (reinterpret_cast<uintptr_t>(a.residual) & 15)) return -1;   // residual goes through TMA
   if (a.rowvec && (a.ld_rowvec & 3)) return -1;
-  return (a.corr ? qd::EPI_CORR : 0) | ((a.corr && a.taps == 9) ? qd::EPI_CONV : 0) | (a.rowvec ? qd::EPI_ROWVEC : 0) |
+  return (a.corr ? qd::EPI_CORR : 0) | ((a.taps == 9) ? qd::EPI_CONV : 0) | (a.rowvec ? qd::EPI_ROWVEC : 0) |
          (a.residual ? qd::EPI_RESIDUAL : 0) | (f ? qd::EPI_OUT_F32 : qd::EPI_OUT_Q);
 }
 
@@ -298,6 +324,11 @@ int launch_gemm(const GemmPlan& pl, cudaStream_t s) {
     case EPI_OUT_F32 | EPI_ROWVEC | EPI_CORR | EPI_CONV: return launch_gemm_mode<EPI_OUT_F32 | EPI_ROWVEC | EPI_CORR | EPI_CONV>(pl, s);
     case EPI_OUT_F32 | EPI_RESIDUAL | EPI_CORR | EPI_CONV: return launch_gemm_mode<EPI_OUT_F32 | EPI_RESIDUAL | EPI_CORR | EPI_CONV>(pl, s);
     case EPI_OUT_Q | EPI_CORR | EPI_CONV: return launch_gemm_mode<EPI_OUT_Q | EPI_CORR | EPI_CONV>(pl, s);
+    // 3x3 convs on symmetric activation codes (zero point 0: no correction table): CIFAR-10, LSUN-bedroom
+    case EPI_OUT_F32 | EPI_CONV: return launch_gemm_mode<EPI_OUT_F32 | EPI_CONV>(pl, s);
+    case EPI_OUT_F32 | EPI_ROWVEC | EPI_CONV: return launch_gemm_mode<EPI_OUT_F32 | EPI_ROWVEC | EPI_CONV>(pl, s);
+    case EPI_OUT_F32 | EPI_RESIDUAL | EPI_CONV: return launch_gemm_mode<EPI_OUT_F32 | EPI_RESIDUAL | EPI_CONV>(pl, s);
+    case EPI_OUT_Q | EPI_CONV: return launch_gemm_mode<EPI_OUT_Q | EPI_CONV>(pl, s);
     case EPI_OUT_Q: return launch_gemm_mode<EPI_OUT_Q>(pl, s);
     case EPI_OUT_Q | EPI_CORR: return launch_gemm_mode<EPI_OUT_Q | EPI_CORR>(pl, s);
     case EPI_OUT_Q | EPI_RESIDUAL: return launch_gemm_mode<EPI_OUT_Q | EPI_RESIDUAL>(pl, s);
@@ -386,11 +417,29 @@ int launch_groupnorm(const qd_groupnorm_desc& d, cudaStream_t s) {
   qd::gn_finalize_kernel<<<d.B, 256, 0, s>>>(part, d.HW, d.C, d.groups, nslab, d.eps, stats);
   rc = check_launch("gn_finalize_kernel");
   if (rc) return rc;
-  if (d.C > 4 * 256 * qd::GN_MAXQ) return fail(QD_ERR_UNSUPPORTED, "groupnorm: C=%d too large", d.C);
-  int at = ((d.C / 4) + 31) / 32 * 32;
-  if (at > 256) at = 256;
-  const int rows = slab < 32 ? slab : 32;
-  qd::gn_apply_kernel<<<dim3((d.HW + rows - 1) / rows, d.B), at, 0, s>>>(d, stats, rows);
+  // apply: block = TX channel quads x TY rows, 256 threads; rows per block sized so that the grid fills the GPU ~4x over
+  const int cq = d.C / 4;
+  const int slabs_x = (cq + 255) / 256;
+  const int TX = (cq + slabs_x - 1) / slabs_x;
+  int TY = 256 / TX;
+  if (TY < 1) TY = 1;
+  const int athreads = TX * TY;
+  int rows = qd::GN_BATCH * TY;
+  while ((long long)((d.HW + rows - 1) / rows) * slabs_x * d.B > 8LL * num_sms() && rows < 8 * qd::GN_BATCH * TY) rows += qd::GN_BATCH * TY;
+  const dim3 grid(slabs_x, (d.HW + rows - 1) / rows, d.B);
+  const bool raw = d.raw_q != nullptr;
+#define QD_GN_APPLY(NOUT, RAW) qd::gn_apply_kernel<NOUT, RAW><<<grid, athreads, 0, s>>>(d, stats, rows, TX)
+  switch (d.n_out * 2 + (raw ? 1 : 0)) {
+    case 0: QD_GN_APPLY(0, false); break;
+    case 1: QD_GN_APPLY(0, true); break;
+    case 2: QD_GN_APPLY(1, false); break;
+    case 3: QD_GN_APPLY(1, true); break;
+    case 4: QD_GN_APPLY(2, false); break;
+    case 5: QD_GN_APPLY(2, true); break;
+    case 6: QD_GN_APPLY(3, false); break;
+    default: QD_GN_APPLY(3, true); break;
+  }
+#undef QD_GN_APPLY
   return check_launch("gn_apply_kernel");
 }
 
@@ -484,16 +533,16 @@ int launch_attention_smallk(const qd_attention_desc& d, cudaStream_t s) {
 }
 
 // tcgen05 path (attention_tc.cuh): d <= 112, Q/K codes in the per-head padded layout (pitch 32/64/128), dense V^T
-template <bool S16, bool MAGIC>
+template <bool S16, bool MAGIC, int NSW>
 int launch_attention_tc_inst(const qd_attention_desc& d, const CUtensorMap& tmQ, const CUtensorMap& tmK,
                              const CUtensorMap& tmV, int NV, int P, cudaStream_t s) {
-  auto kern = qd::qattention_tc_kernel<S16, MAGIC>;
+  auto kern = qd::qattention_tc_kernel<S16, MAGIC, NSW>;
   static std::atomic<unsigned long long> optin{0};
-  if (int rc = ensure_smem_optin(kern, 227 * 1024, optin, "attention_tc")) return rc;
-  const qd::AtcSmem lay = qd::atc_smem_layout(NV, P);
-  if (lay.total > 227 * 1024) return fail(QD_ERR_UNSUPPORTED, "attention_tc: %d B of shared memory", lay.total);
+  if (int rc = ensure_smem_optin(kern, NSW == 16 ? 227 * 1024 : 113 * 1024, optin, "attention_tc")) return rc;
+  const qd::AtcSmem lay = qd::atc_smem_layout(NV, P, NSW);
+  if (lay.total > (NSW == 16 ? 227 : 113) * 1024) return fail(QD_ERR_UNSUPPORTED, "attention_tc: %d B of shared memory", lay.total);
   dim3 grid((d.Tq + qd::ATC_BM - 1) / qd::ATC_BM, d.B * d.heads);
-  kern<<<grid, qd::ATC_THREADS, lay.total, s>>>(tmQ, tmK, tmV, d, NV, P);
+  kern<<<grid, qd::atc_threads(NSW), lay.total, s>>>(tmQ, tmK, tmV, d, NV, P);
   return check_launch("qattention_tc_kernel");
 }
 
@@ -543,10 +592,18 @@ int launch_attention_tc(const qd_attention_desc& d, cudaStream_t s) {
     if (rc) return rc;
   }
   const bool s16 = d.sm_bits > 8, magic = d.d <= 64;
-  if (s16 && magic) return launch_attention_tc_inst<true, true>(d, tmQ, tmK, tmV, NV, P, s);
-  if (s16 && !magic) return launch_attention_tc_inst<true, false>(d, tmQ, tmK, tmV, NV, P, s);
-  if (!s16 && magic) return launch_attention_tc_inst<false, true>(d, tmQ, tmK, tmV, NV, P, s);
-  return launch_attention_tc_inst<false, false>(d, tmQ, tmK, tmV, NV, P, s);
+  // two co-resident CTAs per SM (8 softmax warps each) when the 256-column TMEM layout and 113 KB of shared memory suffice;
+  // QDIFF_ATTN_2CTA=0 forces the one-CTA (16 softmax warps) configuration (A/B comparisons)
+  static const int two_cta = [] { const char* e = getenv("QDIFF_ATTN_2CTA"); return (e && !strcmp(e, "0")) ? 0 : 1; }();
+  const bool small = two_cta && P <= 64 && NV <= 64 && magic && qd::atc_smem_layout(NV, P, 8).total <= 113 * 1024;
+  if (small) {
+    if (s16) return launch_attention_tc_inst<true, true, 8>(d, tmQ, tmK, tmV, NV, P, s);
+    return launch_attention_tc_inst<false, true, 8>(d, tmQ, tmK, tmV, NV, P, s);
+  }
+  if (s16 && magic) return launch_attention_tc_inst<true, true, 16>(d, tmQ, tmK, tmV, NV, P, s);
+  if (s16 && !magic) return launch_attention_tc_inst<true, false, 16>(d, tmQ, tmK, tmV, NV, P, s);
+  if (!s16 && magic) return launch_attention_tc_inst<false, true, 16>(d, tmQ, tmK, tmV, NV, P, s);
+  return launch_attention_tc_inst<false, false, 16>(d, tmQ, tmK, tmV, NV, P, s);
 }
 
 int launch_attention(const qd_attention_desc& d, cudaStream_t s) {

@@ -32,8 +32,26 @@ constexpr int GEMM_BK = 128;  // bytes == int8 elements per k-block (one 128B sw
 // quarter, taking 32-column chunks round-robin.  The instruction-bound epilogues whose register footprint
 // allows it (GEGLU, transposed V^T: <= 102 registers at 640 threads) run with 16 warps = 4 per scheduler.
 __host__ __device__ constexpr int gemm_epi_warps(int MODE) {
-  // EPI_GEGLU | EPI_TRANS, and plain requantising epilogues (EPI_OUT_Q without residual / rowvec)
-  return (MODE >= 0 && ((MODE & (32 | 64)) != 0 || ((MODE & 16) != 0 && (MODE & (2 | 4)) == 0))) ? 16 : 8;
+  // 16 warps: EPI_GEGLU | EPI_TRANS, plain requantising epilogues (EPI_OUT_Q without residual / rowvec), and - round 2 -
+  // the fp32-output epilogues of the plain GEMMs (to_out / ff.net.2 / proj_out / proj_in: EPI_OUT_F32 without EPI_CONV or
+  // EPI_ROWVEC).  Those are bound by memory latency, not instructions: with 8 warps x 4 rows x 16 B of residual per
+  // thread an SM had 16 KB of loads in flight and the kernels sat at 3.5 TB/s with 17 % issue activity
+  // (profiles/r02_gemm_smallk_before.txt); twice the warps = twice the bytes in flight.
+  if (MODE < 0) return 8;
+  if ((MODE & (32 | 64)) != 0) return 16;
+  if ((MODE & 16) != 0 && (MODE & (2 | 4)) == 0) return 16;
+  if ((MODE & 8) != 0 && (MODE & (2 | 4 | 128)) == 0) return 16;
+  return 8;
+}
+// Residual operand through TMA (round 2): the plain-GEMM epilogues that add a residual (to_out / ff.net.2 / proj_out:
+// EPI_RESIDUAL without EPI_CONV) were bound by the latency of their residual loads: per 32x32 chunk a warp issued 4 rows
+// of LDG.128, waited a DRAM round trip, stored, issued the next 4 rows, waited again (3.3-3.5 TB/s, 17 % issue activity).
+// Now every epilogue warp owns a ring of GEMM_RES_NBUF 4 KB buffers and keeps the residual sub-tiles of its NEXT work items
+// (tile, chunk) in flight as cp.async.bulk.tensor loads while it finalises the current one.
+constexpr int GEMM_RES_NBUF = 3;
+__host__ __device__ constexpr bool gemm_res_tma(int MODE) { return MODE >= 0 && (MODE & 4) != 0 && (MODE & 128) == 0; }
+__host__ __device__ constexpr int gemm_res_bytes(int MODE) {
+  return gemm_res_tma(MODE) ? gemm_epi_warps(MODE) * GEMM_RES_NBUF * 4096 : 0;
 }
 __host__ __device__ constexpr int gemm_threads(int MODE) { return (4 + gemm_epi_warps(MODE)) * 32; }
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK;
@@ -48,7 +66,7 @@ constexpr int EPI_OUT_F32 = 8;    // fp32 output
 constexpr int EPI_OUT_Q = 16;     // requantised code output (row-major)
 constexpr int EPI_GEGLU = 32;     // columns interleaved [4 x, 4 gate]: out_q = Q(x * gelu(gate)), N/2 columns
 constexpr int EPI_TRANS = 64;     // requantised code output, transposed [img][n][token'] (V^T operand of qattention)
-constexpr int EPI_CONV = 128;     // with EPI_CORR: 3x3 conv, correction table indexed by border class (else one row)
+constexpr int EPI_CONV = 128;     // 3x3 conv (taps == 9); with EPI_CORR the correction table is indexed by border class
 
 struct GemmArgs {
   int M, N;            // logical output rows / columns (columns >= N are masked)
@@ -88,7 +106,8 @@ struct GemmSmemLayout {
   int stage_bytes;
   int pack_off;   // packed-INT4 B tiles, stages x BN x 64 bytes (w4 only)
   int bar_offset;
-  int stage_off;  // epilogue staging tiles (4 warps)
+  int stage_off;  // epilogue staging tiles (one per epilogue warp)
+  int res_off;    // residual ring (GEMM_RES_NBUF x 4 KB per epilogue warp; residual-by-TMA modes only)
   int total;
 };
 
@@ -96,13 +115,14 @@ __host__ __device__ inline int gemm_stage_footprint(int BN, int w4) {
   return GEMM_A_STAGE_BYTES + BN * GEMM_BK + (w4 ? BN * (GEMM_BK / 2) : 0);
 }
 
-__host__ __device__ inline GemmSmemLayout gemm_smem_layout(int BN, int stages, int epi_warps, int w4 = 0) {
+__host__ __device__ inline GemmSmemLayout gemm_smem_layout(int BN, int stages, int epi_warps, int w4 = 0, int res_bytes = 0) {
   GemmSmemLayout l;
   l.stage_bytes = GEMM_A_STAGE_BYTES + BN * GEMM_BK;
   l.pack_off = l.stage_bytes * stages;
   l.bar_offset = l.pack_off + (w4 ? stages * BN * (GEMM_BK / 2) : 0);
-  l.stage_off = l.bar_offset + 256;
-  l.total = l.stage_off + epi_warps * GEMM_EPI_TILE_BYTES + 1024;  // + alignment slack
+  l.stage_off = l.bar_offset + 512;
+  l.res_off = l.stage_off + epi_warps * GEMM_EPI_TILE_BYTES;
+  l.total = l.res_off + res_bytes + 1024;  // + alignment slack
   return l;
 }
 
@@ -272,7 +292,8 @@ __device__ __forceinline__ void gemm_finalise4(const GemmArgs& p, const QuantK& 
 // run-time flag the register allocation of the epilogue changed and the default path lost 8 %).
 template <int MODE, bool W4 = false>
 __global__ void __launch_bounds__(gemm_threads(MODE), 1)
-gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmR, const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
@@ -280,7 +301,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   constexpr int EPI_WARPS = gemm_epi_warps(MODE);
   constexpr int CSTEP = 32 * (EPI_WARPS / 4);   // column stride between the chunks of one epilogue warp
-  const GemmSmemLayout lay = gemm_smem_layout(p.BN, p.stages, EPI_WARPS, W4 ? 1 : 0);
+  constexpr bool RES_TMA = gemm_res_tma(MODE);
+  const GemmSmemLayout lay = gemm_smem_layout(p.BN, p.stages, EPI_WARPS, W4 ? 1 : 0, gemm_res_bytes(MODE));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_offset);
   uint64_t* full_bar = bars;                          // [stages]
   uint64_t* empty_bar = bars + GEMM_MAX_STAGES;       // [stages]
@@ -288,6 +310,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_empty = tmem_full + 2;               // [2]
   uint64_t* ready_bar = tmem_empty + 2;               // [stages] (w4: B tile unpacked, stage ready for the MMA)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ready_bar + GEMM_MAX_STAGES);
+  uint64_t* res_bar = ready_bar + GEMM_MAX_STAGES + 1;   // [EPI_WARPS][GEMM_RES_NBUF] (residual ring, RES_TMA only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -298,6 +321,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if constexpr (RES_TMA) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -309,6 +333,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], EPI_WARPS);
     }
+    if constexpr (RES_TMA)
+      for (int s = 0; s < EPI_WARPS * GEMM_RES_NBUF; ++s) mbar_init(&res_bar[s], 1);
     fence_mbar_init();
     fence_proxy_async();
   }
@@ -457,6 +483,29 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool conv = MODE < 0 ? (p.taps == 9) : ((MODE & EPI_CONV) != 0);
     int acc = 0;
     uint32_t acc_phase = 0;
+    // ---- residual ring (RES_TMA): work items of this warp = (tile, chunk) in processing order; `pf_*` is the prefetch
+    // cursor, GEMM_RES_NBUF - 1 items ahead of the item being finalised
+    uint8_t* rring = smem + lay.res_off + (warp - 4) * (GEMM_RES_NBUF * 4096);
+    uint64_t* rbar = res_bar + (warp - 4) * GEMM_RES_NBUF;
+    int pf_tile = blockIdx.x, pf_c = half * 32, pf_buf = 0;
+    int rd_buf = 0;
+    uint32_t rd_phase = 0;
+    auto res_issue = [&]() {          // issue the load of the cursor's item (if any) and advance the cursor
+      if (pf_tile >= num_tiles) return;
+      if (lane == 0) {
+        const int ptm = pf_tile / p.tiles_n, ptn = pf_tile - ptm * p.tiles_n;
+        mbar_arrive_expect_tx(&rbar[pf_buf], 4096u);
+        tma_load_2d(rring + pf_buf * 4096, &tmR, &rbar[pf_buf], (ptn * p.BN + pf_c) * 4, ptm * GEMM_BM + q * 32);
+      }
+      if (++pf_buf == GEMM_RES_NBUF) pf_buf = 0;
+      pf_c += CSTEP;
+      if (pf_c >= p.BN) { pf_c = half * 32; pf_tile += gridDim.x; }
+    };
+    if constexpr (RES_TMA) {
+      if (half * 32 >= p.BN) pf_tile = num_tiles;      // this warp owns no chunk (BN narrower than its first column)
+#pragma unroll 1
+      for (int i = 0; i < GEMM_RES_NBUF - 1; ++i) res_issue();
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tm = tile / p.tiles_n;
       const int tn = tile - tm * p.tiles_n;
@@ -608,6 +657,12 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
           __syncwarp();
+          const uint8_t* rbuf = nullptr;
+          if constexpr (RES_TMA) {
+            res_issue();                              // keep GEMM_RES_NBUF - 1 loads in flight
+            mbar_wait(&rbar[rd_buf], rd_phase);       // this item's residual sub-tile (32 rows x 128 B, 128B-swizzled)
+            rbuf = rring + rd_buf * 4096;
+          }
           const int n = n_base + c + cq * 4;
           if (cq * 4 < ncols && n < p.N) {
             float sc[4], bi[4];
@@ -656,7 +711,10 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   [[maybe_unused]] const int m = m_warp + it * 4 + rsub;
                   rpre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                   cpre[i] = corr4;
-                  if constexpr (MODE >= 0 && (MODE & EPI_RESIDUAL) != 0) {
+                  if constexpr (RES_TMA) {
+                    const int row = it * 4 + rsub;    // rows beyond M were zero-filled by the TMA unit
+                    rpre[i] = *reinterpret_cast<const float4*>(rbuf + row * 128 + ((cq ^ (row & 7)) << 4));
+                  } else if constexpr (MODE >= 0 && (MODE & EPI_RESIDUAL) != 0) {
                     if (FULL || m < p.M) rpre[i] = *reinterpret_cast<const float4*>(res0 + it * res_step);
                   }
                   if constexpr (MODE >= 0 && (MODE & EPI_CORR) != 0 && (MODE & EPI_CONV) != 0)
@@ -676,6 +734,10 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             };
             if (m_warp + 32 <= p.M) rows(std::true_type{}); else rows(std::false_type{});
+          }
+          if constexpr (RES_TMA) {
+            fence_proxy_async();      // this buffer's generic-proxy reads are ordered before the TMA write that reuses it
+            if (++rd_buf == GEMM_RES_NBUF) { rd_buf = 0; rd_phase ^= 1; }
           }
           __syncwarp();
         }

@@ -150,6 +150,25 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---------------------------------------------------------------- packed fp32 (sm_100: FFMA2 / FADD2, one issue slot for two lanes of work)
+__device__ __forceinline__ unsigned long long pack_f2(float x, float y) {
+  return ((unsigned long long)__float_as_uint(y) << 32) | (unsigned long long)__float_as_uint(x);
+}
+__device__ __forceinline__ float2 unpack_f2(unsigned long long v) {
+  return make_float2(__uint_as_float((uint32_t)v), __uint_as_float((uint32_t)(v >> 32)));
+}
+// d = a * b + c on both halves (IEEE round-to-nearest: bit-identical to two scalar fmaf)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pack_f2(a.x, a.y)), "l"(pack_f2(b.x, b.y)), "l"(pack_f2(c.x, c.y)));
+  return unpack_f2(d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack_f2(a.x, a.y)), "l"(pack_f2(b.x, b.y)));
+  return unpack_f2(d);
+}
+
 // ---------------------------------------------------------------- UMMA descriptors
 // Shared-memory matrix descriptor, K-major operand tile stored as rows of 128 bytes with the
 // 128-byte swizzle (what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B):

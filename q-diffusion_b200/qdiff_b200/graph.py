@@ -39,7 +39,8 @@ class Act:
 
     def logical(self):
         """The [rows, cols] tensor this Act denotes (a strided view when it lives inside a wider buffer)."""
-        return self.t[:self.rows, self.col0:self.col0 + self.cols]
+        t = self.t if self.t.dim() == 2 else self.t.view(-1, self.ld)      # transposed V^T codes are allocated flat
+        return t[:self.rows, self.col0:self.col0 + self.cols]
 
 
 def _qt(qp):
