@@ -87,6 +87,21 @@ typedef struct qd_gemm_desc {
   int32_t w_int4_packed; /* 1: w holds packed unsigned 4-bit codes, see above */
   int32_t reserved3;
   const int8_t* w_zero;  /* [n_rows] zero points of the packed codes (w_int4_packed only) */
+  /* Optional, for requantising GEMMs (out_q set, out NULL, geglu 0): the epilogue constants pre-divided by the consumer's
+   * step, scale_q[n] = scale[n] / oq.delta and bias_q[n] = bias[n] / oq.delta + oq.zero_point (computed in double by the
+   * caller).  With them the epilogue emits  code = clamp(rne(acc * scale_q + bias_q [+ residual / oq.delta]), qmin, qmax)
+   * with ONE fused multiply-add per element (the quotient differs from the two-step y / delta by <= 1 ulp, i.e. a code can
+   * differ from quant_layer.py:82-87 applied to the fp32 y only where y / delta sits within an ulp of a rounding
+   * boundary - the same class as the fused GroupNorm / SiLU / GELU quantizers).  NULL: the exact two-step form. */
+  const float* scale_q;
+  const float* bias_q;
+  /* Optional (fp32 output only): per-column partial sums for a GroupNorm that consumes `out`.  gn_stats[(m / 32) * ld_stats
+   * + n] = (sum, sum of squares) of out[m0 .. m0+31, n] over the 32-row slab of row m (only rows < M), written by the
+   * epilogue warp that owns the slab: no atomics, deterministic.  gn_stats points at the column of out's first column;
+   * ld_stats is the row pitch in float2 units.  qd_groupnorm_quant turns the slabs into per-(image, group) mean / rstd
+   * (stats_in), replacing its own pass over the fp32 tensor (GroupNorm32: ldm util.py:214-216). */
+  float* gn_stats;
+  long long ld_stats;
 } qd_gemm_desc;
 
 int qd_qgemm_i8(const qd_gemm_desc* d, qd_stream_t stream);
@@ -148,6 +163,10 @@ typedef struct qd_groupnorm_desc {
   int32_t raw_split;
   int32_t reserved2;
   qd_qparams q_raw[2];
+  /* optional: 32-row slab sums written by the producing GEMM(s) (qd_gemm_desc.gn_stats), float2 [B*HW/32][ld_stats_in],
+   * pointing at x's first column; needs HW % 32 == 0.  When set, the statistics pass over x is skipped. */
+  const float* stats_in;
+  long long ld_stats_in;
 } qd_groupnorm_desc;
 
 int qd_groupnorm_quant(const qd_groupnorm_desc* d, qd_stream_t stream);

@@ -132,6 +132,43 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const double* __restri
     stats[((long long)b * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
   }
 }
+// Statistics from the producing GEMMs' epilogues (qd_gemm_desc.gn_stats): per 32-row slab and channel (sum, sum of squares).
+// One block per image, one warp per group (8 warps x 4 rounds for 32 groups): lanes stride over the group's
+// (slab, channel) items, accumulate in double, shuffle-reduce in a fixed order.  Replaces gn_partial + gn_finalize, i.e.
+// one full read of the fp32 tensor (SD: 2.5 GB per step, profiles/r01_launches_step_final.summary.txt).
+__global__ void __launch_bounds__(256) gn_finalize_from_stats_kernel(const float2* __restrict__ slabs, long long ld_stats,
+                                                                    int HW, int C, int groups, float eps,
+                                                                    float* __restrict__ stats) {
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int cpg = C / groups;
+  const int nsl = HW >> 5;
+  const float2* base = slabs + (long long)b * nsl * ld_stats;
+  for (int g = warp; g < groups; g += nwarps) {
+    double s = 0.0, ss = 0.0;
+    const int items = nsl * cpg;
+    for (int i = lane; i < items; i += 32) {
+      const int sl = i / cpg, ch = i - sl * cpg;
+      const float2 v = base[(long long)sl * ld_stats + g * cpg + ch];
+      s += (double)v.x;
+      ss += (double)v.y;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, off);
+      ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    }
+    if (lane == 0) {
+      const double cnt = (double)HW * cpg;
+      const double mean = s / cnt;
+      double var = ss / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      stats[((long long)b * groups + g) * 2] = (float)mean;
+      stats[((long long)b * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  }
+}
+
 // Pass 3: normalise + affine (+scale-shift) (+SiLU) + quantise for each consumer.
 // Block = TX channel quads x TY rows (TX * TY <= 256); grid (channel slabs, row chunks, B).  A thread owns ONE channel
 // quad: it folds mean / rstd / gamma / beta (/ scale-shift) into y = a*x + b once (8 registers) and then streams its rows,

@@ -254,6 +254,11 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
     return fail(QD_ERR_UNSUPPORTED, "gemm: the epilogue emits 8-bit codes; quantizer range [%d, %d] is wider", d->oq.qmin, d->oq.qmax);
   a.q_delta = d->oq.delta; a.q_zp = d->oq.zero_point; a.q_lo = d->oq.qmin; a.q_hi = d->oq.qmax;
   a.scale = d->scale; a.bias = d->bias; a.corr = d->corr;
+  a.scale_q = d->scale_q; a.bias_q = d->bias_q;
+  a.gn_stats = reinterpret_cast<float2*>(d->gn_stats); a.ld_stats = d->ld_stats;
+  if (d->gn_stats && (!d->out || (d->ld_stats & 1) || (reinterpret_cast<uintptr_t>(d->gn_stats) & 15)))
+    return fail(QD_ERR_BAD_ARG, "gemm: gn_stats needs an fp32 output, an even ld_stats and 16-byte alignment");
+  if ((d->scale_q == nullptr) != (d->bias_q == nullptr)) return fail(QD_ERR_BAD_ARG, "gemm: scale_q and bias_q come together");
   a.rowvec = d->rowvec; a.ld_rowvec = d->ld_rowvec;
   a.residual = d->residual; a.ldr = d->ldr;
   const int tiles = a.tiles_m * a.tiles_n;
@@ -296,6 +301,7 @@ int launch_gemm_mode(const GemmPlan& pl, cudaStream_t s) {
 int gemm_mode(const qd::GemmArgs& a) {
   const bool f = a.out != nullptr, q = a.out_q != nullptr;
   if (a.geglu) return qd::EPI_GEGLU | qd::EPI_OUT_Q | (a.corr ? qd::EPI_CORR : 0);
+  if (q && !f && !a.geglu && !a.scale_q) return -1;     // specialised requantising epilogues take pre-divided constants
   if (a.out_q_transposed && q && !f && !a.rowvec && !a.residual && a.taps == 1 && a.oq_d == 0 &&
       a.rows_per_batch % 32 == 0 && (a.ldq & 15) == 0 && (reinterpret_cast<uintptr_t>(a.out_q) & 15) == 0)
     return qd::EPI_TRANS | qd::EPI_OUT_Q | (a.corr ? qd::EPI_CORR : 0);
@@ -305,10 +311,15 @@ int gemm_mode(const qd::GemmArgs& a) {
   if (f && (a.ldo & 3)) return -1;
   if (q && (a.ldq & 3)) return -1;
   if (a.residual && (a.ldr & 3)) return -1;
-  if (a.residual && a.taps == 1 && (reinterpret_cast<uintptr_t>(a.residual) & 15)) return -1;   // residual goes through TMA
   if (a.rowvec && (a.ld_rowvec & 3)) return -1;
+  // short-K plain GEMMs with a residual (to_out / proj_out at the 64x64 and 32x32 levels, split-shortcut second halves):
+  // the epilogue is the critical path and its residual loads are latency-bound -> TMA ring.  Longer K: the ring's shared
+  // memory would cost pipeline stages (tools/sweep_bn.py: K = 1280 lost 10 % with 2 stages), registers-prefetch path.
+  static const int ring_kb = [] { const char* e = getenv("QDIFF_RES_RING_KB"); return e ? atoi(e) : 5; }();
+  const int num_kb = ((a.C + qd::GEMM_BK - 1) / qd::GEMM_BK) * a.taps;
+  const bool ring = a.residual && a.taps == 1 && num_kb <= ring_kb && !(reinterpret_cast<uintptr_t>(a.residual) & 15);
   return (a.corr ? qd::EPI_CORR : 0) | ((a.taps == 9) ? qd::EPI_CONV : 0) | (a.rowvec ? qd::EPI_ROWVEC : 0) |
-         (a.residual ? qd::EPI_RESIDUAL : 0) | (f ? qd::EPI_OUT_F32 : qd::EPI_OUT_Q);
+         (a.residual ? qd::EPI_RESIDUAL : 0) | (f ? qd::EPI_OUT_F32 : qd::EPI_OUT_Q) | (ring ? qd::EPI_RESTMA : 0);
 }
 
 int launch_gemm(const GemmPlan& pl, cudaStream_t s) {
@@ -333,6 +344,10 @@ int launch_gemm(const GemmPlan& pl, cudaStream_t s) {
     case EPI_OUT_Q | EPI_CORR: return launch_gemm_mode<EPI_OUT_Q | EPI_CORR>(pl, s);
     case EPI_OUT_Q | EPI_RESIDUAL: return launch_gemm_mode<EPI_OUT_Q | EPI_RESIDUAL>(pl, s);
     case EPI_OUT_Q | EPI_RESIDUAL | EPI_CORR: return launch_gemm_mode<EPI_OUT_Q | EPI_RESIDUAL | EPI_CORR>(pl, s);
+    case EPI_OUT_F32 | EPI_RESIDUAL | EPI_RESTMA: return launch_gemm_mode<EPI_OUT_F32 | EPI_RESIDUAL | EPI_RESTMA>(pl, s);
+    case EPI_OUT_F32 | EPI_RESIDUAL | EPI_CORR | EPI_RESTMA: return launch_gemm_mode<EPI_OUT_F32 | EPI_RESIDUAL | EPI_CORR | EPI_RESTMA>(pl, s);
+    case EPI_OUT_Q | EPI_RESIDUAL | EPI_RESTMA: return launch_gemm_mode<EPI_OUT_Q | EPI_RESIDUAL | EPI_RESTMA>(pl, s);
+    case EPI_OUT_Q | EPI_RESIDUAL | EPI_CORR | EPI_RESTMA: return launch_gemm_mode<EPI_OUT_Q | EPI_RESIDUAL | EPI_CORR | EPI_RESTMA>(pl, s);
     case EPI_TRANS | EPI_OUT_Q: return launch_gemm_mode<EPI_TRANS | EPI_OUT_Q>(pl, s);
     case EPI_TRANS | EPI_OUT_Q | EPI_CORR: return launch_gemm_mode<EPI_TRANS | EPI_OUT_Q | EPI_CORR>(pl, s);
     case EPI_GEGLU | EPI_OUT_Q: return launch_gemm_mode<EPI_GEGLU | EPI_OUT_Q>(pl, s);
@@ -410,13 +425,24 @@ int launch_groupnorm(const qd_groupnorm_desc& d, cudaStream_t s) {
   threads = (threads + 31) / 32 * 32;
   if (threads > 256) threads = 256;
   if (threads < 2 * d.groups) threads = (2 * d.groups + 31) / 32 * 32;
-  qd::gn_partial_kernel<<<dim3(nslab, d.B), threads, 2 * d.C * sizeof(float), s>>>(d.x, d.ld_x, d.HW, d.C, d.groups, slab,
-                                                                                   nslab, part);
-  int rc = check_launch("gn_partial_kernel");
-  if (rc) return rc;
-  qd::gn_finalize_kernel<<<d.B, 256, 0, s>>>(part, d.HW, d.C, d.groups, nslab, d.eps, stats);
-  rc = check_launch("gn_finalize_kernel");
-  if (rc) return rc;
+  int rc;
+  static const int use_stats = [] { const char* e = getenv("QDIFF_GN_STATS"); return (e && !strcmp(e, "0")) ? 0 : 1; }();
+  if (d.stats_in && use_stats) {
+    // the producing GEMMs left per-slab column sums: no pass over x for the statistics
+    if (d.HW % 32) return fail(QD_ERR_BAD_ARG, "groupnorm: stats_in needs HW %% 32 == 0");
+    qd::gn_finalize_from_stats_kernel<<<d.B, 256, 0, s>>>(reinterpret_cast<const float2*>(d.stats_in), d.ld_stats_in, d.HW,
+                                                         d.C, d.groups, d.eps, stats);
+    rc = check_launch("gn_finalize_from_stats_kernel");
+    if (rc) return rc;
+  } else {
+    qd::gn_partial_kernel<<<dim3(nslab, d.B), threads, 2 * d.C * sizeof(float), s>>>(d.x, d.ld_x, d.HW, d.C, d.groups, slab,
+                                                                                     nslab, part);
+    rc = check_launch("gn_partial_kernel");
+    if (rc) return rc;
+    qd::gn_finalize_kernel<<<d.B, 256, 0, s>>>(part, d.HW, d.C, d.groups, nslab, d.eps, stats);
+    rc = check_launch("gn_finalize_kernel");
+    if (rc) return rc;
+  }
   // apply: block = TX channel quads x TY rows, 256 threads; rows per block sized so that the grid fills the GPU ~4x over
   const int cq = d.C / 4;
   const int slabs_x = (cq + 255) / 256;
@@ -595,7 +621,10 @@ int launch_attention_tc(const qd_attention_desc& d, cudaStream_t s) {
   // two co-resident CTAs per SM (8 softmax warps each) when the 256-column TMEM layout and 113 KB of shared memory suffice;
   // QDIFF_ATTN_2CTA=0 forces the one-CTA (16 softmax warps) configuration (A/B comparisons)
   static const int two_cta = [] { const char* e = getenv("QDIFF_ATTN_2CTA"); return (e && !strcmp(e, "0")) ? 0 : 1; }();
-  const bool small = two_cta && P <= 64 && NV <= 64 && magic && qd::atc_smem_layout(NV, P, 8).total <= 113 * 1024;
+  // measured (tools/prof_attn.py, B=16 x 8 heads, d=40): Tq=Tk=1024: 143 us vs 150 us with one CTA per SM; Tq=Tk=4096: 1845
+  // vs 1750 us (the long problem is throughput-bound on MUFU + issue, the single S slot costs more than co-residency gains)
+  const bool small = two_cta && P <= 64 && NV <= 64 && magic && (long long)d.Tq * d.Tk <= (1LL << 21) &&
+                     qd::atc_smem_layout(NV, P, 8).total <= 113 * 1024;
   if (small) {
     if (s16) return launch_attention_tc_inst<true, true, 8>(d, tmQ, tmK, tmV, NV, P, s);
     return launch_attention_tc_inst<false, true, 8>(d, tmQ, tmK, tmV, NV, P, s);

@@ -228,7 +228,7 @@ extern "C" int probe_gemm_i8_2cta(const void* a, const void* b, int32_t* out, in
   cudaError_t err = cudaDeviceSynchronize();
   if (err != cudaSuccess) { fprintf(stderr, "probe: %s\n", cudaGetErrorString(err)); return -20; }
   float t = 0.f;
-  cudaEventElapsedTime(&t, e0, e1);
+  if (iters > 0) cudaEventElapsedTime(&t, e0, e1);     // e0 is only recorded when there is a timed launch
   if (ms) *ms = iters > 0 ? t / iters : 0.f;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);

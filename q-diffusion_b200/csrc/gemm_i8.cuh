@@ -49,7 +49,7 @@ __host__ __device__ constexpr int gemm_epi_warps(int MODE) {
 // Now every epilogue warp owns a ring of GEMM_RES_NBUF 4 KB buffers and keeps the residual sub-tiles of its NEXT work items
 // (tile, chunk) in flight as cp.async.bulk.tensor loads while it finalises the current one.
 constexpr int GEMM_RES_NBUF = 3;
-__host__ __device__ constexpr bool gemm_res_tma(int MODE) { return MODE >= 0 && (MODE & 4) != 0 && (MODE & 128) == 0; }
+__host__ __device__ constexpr bool gemm_res_tma(int MODE) { return MODE >= 0 && (MODE & 4) != 0 && (MODE & 256) != 0; }
 __host__ __device__ constexpr int gemm_res_bytes(int MODE) {
   return gemm_res_tma(MODE) ? gemm_epi_warps(MODE) * GEMM_RES_NBUF * 4096 : 0;
 }
@@ -67,6 +67,7 @@ constexpr int EPI_OUT_Q = 16;     // requantised code output (row-major)
 constexpr int EPI_GEGLU = 32;     // columns interleaved [4 x, 4 gate]: out_q = Q(x * gelu(gate)), N/2 columns
 constexpr int EPI_TRANS = 64;     // requantised code output, transposed [img][n][token'] (V^T operand of qattention)
 constexpr int EPI_CONV = 128;     // 3x3 conv (taps == 9); with EPI_CORR the correction table is indexed by border class
+constexpr int EPI_RESTMA = 256;   // with EPI_RESIDUAL: residual sub-tiles arrive through the per-warp TMA ring (short-K GEMMs)
 
 struct GemmArgs {
   int M, N;            // logical output rows / columns (columns >= N are masked)
@@ -100,7 +101,15 @@ struct GemmArgs {
   // 128B-swizzled operand tile in shared memory (wq - wzero[n]) before the MMA consumes the stage
   int w4;
   const int8_t* wzero;     // [w_rows]
+  // requantising epilogues (specialised EPI_OUT_Q modes without GEGLU): scale / delta_q and bias / delta_q + zero_point
+  const float* scale_q;
+  const float* bias_q;
+  // GroupNorm slab statistics of the fp32 output (qd_gemm_desc.gn_stats): float2 [M/32][ld_stats]
+  float2* gn_stats;
+  long long ld_stats;
 };
+// Specialised requantising modes take the pre-divided constants (one FFMA per element: quant_math.cuh quant_bits_pre)
+__host__ __device__ constexpr bool gemm_qpre(int MODE) { return MODE >= 0 && (MODE & 16) != 0 && (MODE & 32) == 0; }
 
 struct GemmSmemLayout {
   int stage_bytes;
@@ -121,7 +130,9 @@ __host__ __device__ inline GemmSmemLayout gemm_smem_layout(int BN, int stages, i
   l.pack_off = l.stage_bytes * stages;
   l.bar_offset = l.pack_off + (w4 ? stages * BN * (GEMM_BK / 2) : 0);
   l.stage_off = l.bar_offset + 512;
-  l.res_off = l.stage_off + epi_warps * GEMM_EPI_TILE_BYTES;
+  // the ring buffers are TMA targets with the 128-byte swizzle: the pattern is a function of the shared-memory ADDRESS
+  // (bits 4-6 ^= bits 7-9), so they must start on a 1024-byte boundary for "chunk ^ (row & 7)" to address them
+  l.res_off = (l.stage_off + epi_warps * GEMM_EPI_TILE_BYTES + 1023) / 1024 * 1024;
   l.total = l.res_off + res_bytes + 1024;  // + alignment slack
   return l;
 }
@@ -213,7 +224,7 @@ template <int MODE>
 __device__ __forceinline__ void gemm_finalise4(const GemmArgs& p, const QuantK& qk, const bool conv, const uint4 a4,
                                                const float (&sc)[4], const float (&bi)[4], const int4 corr4,
                                                const float4 rpre, float* of, int8_t* oq, const float* res, int n,
-                                               int cls, int img) {
+                                               int cls, int img, float (&gsum)[4], float (&gsq)[4]) {
   constexpr bool G = MODE < 0;
   const bool has_corr = G ? (p.corr != nullptr) : bool(MODE & EPI_CORR);
   const bool has_rowvec = G ? (p.rowvec != nullptr) : bool(MODE & EPI_ROWVEC);
@@ -250,11 +261,17 @@ __device__ __forceinline__ void gemm_finalise4(const GemmArgs& p, const QuantK& 
         if (n + j < p.N) y[j] += rv[j];
     }
   }
+  constexpr bool QPRE = gemm_qpre(MODE);
   if (has_res && !G) {
     // specialised kernels pre-load the residual of a row group before its first store: `out` may alias
     // `residual` (in-place accumulate), so the compiler cannot hoist these loads itself and they would
     // otherwise serialise one global-memory latency per row
-    y[0] += rpre.x; y[1] += rpre.y; y[2] += rpre.z; y[3] += rpre.w;
+    if constexpr (QPRE) {     // y is in code units (pre-scaled constants): bring the residual there too
+      y[0] = fmaf(rpre.x, qk.rdelta, y[0]); y[1] = fmaf(rpre.y, qk.rdelta, y[1]);
+      y[2] = fmaf(rpre.z, qk.rdelta, y[2]); y[3] = fmaf(rpre.w, qk.rdelta, y[3]);
+    } else {
+      y[0] += rpre.x; y[1] += rpre.y; y[2] += rpre.z; y[3] += rpre.w;
+    }
   } else if (has_res) {
     if (full && ((p.ldr & 3) == 0)) {
       const float4 rv = *reinterpret_cast<const float4*>(res);
@@ -266,6 +283,9 @@ __device__ __forceinline__ void gemm_finalise4(const GemmArgs& p, const QuantK& 
     }
   }
   if (out_f) {
+    // column sums of the values being stored (GroupNorm slab statistics; dead code unless the caller uses them)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { gsum[j] += y[j]; gsq[j] = fmaf(y[j], y[j], gsq[j]); }
     if (full && (G ? ((p.ldo & 3) == 0) : true)) {
       *reinterpret_cast<float4*>(of) = make_float4(y[0], y[1], y[2], y[3]);
     } else {
@@ -274,7 +294,10 @@ __device__ __forceinline__ void gemm_finalise4(const GemmArgs& p, const QuantK& 
         if (n + j < p.N) of[j] = y[j];
     }
   }
-  if (out_q) {
+  if constexpr (QPRE) {
+    *reinterpret_cast<uint32_t*>(oq) = pack4_low_bytes(quant_bits_pre(y[0], qk), quant_bits_pre(y[1], qk),
+                                                       quant_bits_pre(y[2], qk), quant_bits_pre(y[3], qk));
+  } else if (out_q) {
     const uint32_t q0 = quant_code(y[0], qk), q1 = quant_code(y[1], qk);
     const uint32_t q2 = quant_code(y[2], qk), q3 = quant_code(y[3], qk);
     if (full && (G ? ((p.ldq & 3) == 0) : true)) {
@@ -479,7 +502,10 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* stg = smem + lay.stage_off + (warp - 4) * GEMM_EPI_TILE_BYTES;
     const int rsub = lane >> 3;   // row within a group of 4
     const int cq = lane & 7;      // column quad within the 32-column chunk
-    const QuantK qk = make_quantk(p.q_delta, p.q_zp, p.q_lo, p.q_hi);
+    constexpr bool QPRE = gemm_qpre(MODE);
+    const QuantK qk = QPRE ? make_quantk_pre(p.q_delta, p.q_lo, p.q_hi) : make_quantk(p.q_delta, p.q_zp, p.q_lo, p.q_hi);
+    const float* const ep_scale = QPRE ? p.scale_q : p.scale;      // per-column epilogue constants of this mode
+    const float* const ep_bias = QPRE ? p.bias_q : p.bias;
     const bool conv = MODE < 0 ? (p.taps == 9) : ((MODE & EPI_CONV) != 0);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -551,8 +577,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int col = ncols == 32 ? lane : (lane & 15);
           const int n = n_base + c + col;
           if (m_warp < p.M && n < p.N) {
-            const float sc1 = __ldg(p.scale + n);
-            const float bi1 = p.bias ? __ldg(p.bias + n) : 0.f;
+            const float sc1 = __ldg(ep_scale + n);
+            const float bi1 = ep_bias ? __ldg(ep_bias + n) : 0.f;
             int cr = 0;
             if constexpr ((MODE & EPI_CORR) != 0) cr = __ldg(p.corr + n);
             int8_t* o = p.out_q + ((long long)img * p.N + n) * p.ldq + tok0;
@@ -565,7 +591,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int k = 0; k < 16; ++k) {
                 const int r7 = (((k >> 1) & 1) << 3) | (((k >> 2) & 3) << 1) | (k & 1);   // token of byte k
                 const int a = *reinterpret_cast<const int*>(src + (g * 16 + r7) * 128 + ((cj ^ (r7 & 7)) << 4));
-                const uint32_t qv = quant_code((float)(a - cr) * sc1 + bi1, qk);
+                const uint32_t qv = QPRE ? (quant_bits_pre(fmaf((float)(a - cr), sc1, bi1), qk) & 0xFFu)
+                                         : quant_code((float)(a - cr) * sc1 + bi1, qk);
                 w4[k >> 2] = (k & 3) ? (w4[k >> 2] | (qv << (8 * (k & 3)))) : qv;
               }
               *reinterpret_cast<uint4*>(o + g * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
@@ -664,14 +691,16 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             rbuf = rring + rd_buf * 4096;
           }
           const int n = n_base + c + cq * 4;
-          if (cq * 4 < ncols && n < p.N) {
+          const bool col_ok = cq * 4 < ncols && n < p.N;
+          const unsigned cmask = __ballot_sync(0xffffffffu, col_ok);   // lanes ^8 / ^16 share cq: partners are always both in or out
+          if (col_ok) {
             float sc[4], bi[4];
             int4 corr4 = make_int4(0, 0, 0, 0);
             if (MODE >= 0 || n + 3 < p.N) {
-              const float4 s4 = *reinterpret_cast<const float4*>(p.scale + n);
+              const float4 s4 = *reinterpret_cast<const float4*>(ep_scale + n);
               sc[0] = s4.x; sc[1] = s4.y; sc[2] = s4.z; sc[3] = s4.w;
-              if (p.bias) {
-                const float4 b4 = *reinterpret_cast<const float4*>(p.bias + n);
+              if (ep_bias) {
+                const float4 b4 = *reinterpret_cast<const float4*>(ep_bias + n);
                 bi[0] = b4.x; bi[1] = b4.y; bi[2] = b4.z; bi[3] = b4.w;
               } else {
                 bi[0] = bi[1] = bi[2] = bi[3] = 0.f;
@@ -699,6 +728,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int8_t* oq0 = p.out_q ? p.out_q + mrow * p.ldq + nq : nullptr;
             const float* res0 = p.residual ? p.residual + mrow * p.ldr + n : nullptr;
             const long long of_step = 4 * p.ldo, oq_step = 4 * p.ldq, res_step = 4 * p.ldr;
+            float gsum[4] = {0.f, 0.f, 0.f, 0.f}, gsq[4] = {0.f, 0.f, 0.f, 0.f};
             auto rows = [&](auto full_tag) {
               constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
@@ -728,12 +758,34 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   if (FULL || m < p.M) {
                     const uint4 a4 = *reinterpret_cast<const uint4*>(stg + row * 128 + ((cq ^ (row & 7)) << 4));
                     gemm_finalise4<MODE>(p, qk, conv, a4, sc, bi, cpre[i], rpre[i], of0 + it * of_step, oq0 + it * oq_step,
-                                         res0 + it * res_step, n, cls8[it], img8[it]);
+                                         res0 + it * res_step, n, cls8[it], img8[it], gsum, gsq);
                   }
                 }
               }
             };
             if (m_warp + 32 <= p.M) rows(std::true_type{}); else rows(std::false_type{});
+            if ((MODE < 0 || (MODE & EPI_OUT_F32) != 0) && p.gn_stats != nullptr) {
+              // this thread holds 8 of the slab's 32 rows for 4 columns: add the other three row groups (lanes ^ 8, ^ 16),
+              // lanes 0-7 then own the slab's column sums for the chunk's 32 columns
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                gsum[j] += __shfl_xor_sync(cmask, gsum[j], 8);
+                gsq[j] += __shfl_xor_sync(cmask, gsq[j], 8);
+                gsum[j] += __shfl_xor_sync(cmask, gsum[j], 16);
+                gsq[j] += __shfl_xor_sync(cmask, gsq[j], 16);
+              }
+              if (rsub == 0) {
+                float2* st = p.gn_stats + (long long)(m_warp >> 5) * p.ld_stats + n;
+                if (MODE >= 0 || n + 3 < p.N) {
+                  *reinterpret_cast<float4*>(st) = make_float4(gsum[0], gsq[0], gsum[1], gsq[1]);
+                  *reinterpret_cast<float4*>(st + 2) = make_float4(gsum[2], gsq[2], gsum[3], gsq[3]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    if (n + j < p.N) st[j] = make_float2(gsum[j], gsq[j]);
+                }
+              }
+            }
           }
           if constexpr (RES_TMA) {
             fence_proxy_async();      // this buffer's generic-proxy reads are ordered before the TMA write that reuses it

@@ -53,6 +53,25 @@ __device__ __forceinline__ uint32_t quant_code_fast(float y, const QuantK& k) {
   return (uint32_t)(__float_as_int(q + 12582912.0f) - k.bias) & 0xFFu;
 }
 
+// Pre-scaled form (3 instructions + a quarter of the 3-PRMT pack): the caller's value is already t = y / delta + zero_point
+// (qd_gemm_desc.scale_q / bias_q); clamp to the code range, round through the magic constant.  Returns the float's bit
+// pattern: its LOW BYTE is the code (two's complement for signed codes), because 0x4B400000 ends in 0x00.
+__device__ __forceinline__ QuantK make_quantk_pre(float delta, int lo, int hi) {
+  QuantK k;
+  k.delta = delta;
+  k.rdelta = __frcp_rn(delta);     // multiplies a residual into code units
+  k.bias = 0x4B400000;
+  k.flo = (float)lo;
+  k.fhi = (float)hi;
+  return k;
+}
+__device__ __forceinline__ uint32_t quant_bits_pre(float t, const QuantK& k) {
+  return __float_as_uint(fminf(fmaxf(t, k.flo), k.fhi) + 12582912.0f);
+}
+__device__ __forceinline__ uint32_t pack4_low_bytes(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  return __byte_perm(__byte_perm(r0, r1, 0x0040), __byte_perm(r2, r3, 0x0040), 0x5410);
+}
+
 // x * sigmoid(x) with 2 XU operations (ex2, rcp); ~2 ulp, inside the reference's own fp32 noise band.
 __device__ __forceinline__ float silu_fast(float x) {
   float e;

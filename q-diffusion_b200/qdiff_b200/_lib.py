@@ -37,6 +37,8 @@ class GemmDesc(C.Structure):
         ("oq", QParams),
         ("bn_hint", c_i32), ("out_q_head_dim", c_i32), ("out_q_head_pitch", c_i32), ("geglu", c_i32),
         ("w_int4_packed", c_i32), ("reserved3", c_i32), ("w_zero", c_vp),
+        ("scale_q", c_vp), ("bias_q", c_vp),
+        ("gn_stats", c_vp), ("ld_stats", c_ll),
     ]
 
 
@@ -59,6 +61,7 @@ class GroupNormDesc(C.Structure):
         ("out_q", c_vp * 3), ("ld_q", c_ll * 3), ("q", QParams * 3),
         ("out_f", c_vp), ("ld_f", c_ll), ("ws", c_vp),
         ("raw_q", c_vp), ("ld_raw", c_ll), ("raw_split", c_i32), ("reserved2", c_i32), ("q_raw", QParams * 2),
+        ("stats_in", c_vp), ("ld_stats_in", c_ll),
     ]
 
 

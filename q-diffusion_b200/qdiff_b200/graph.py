@@ -166,6 +166,7 @@ class Builder:
         if not hasattr(qnn, "_wcache"):
             qnn._wcache = {}
         self.wcache = qnn._wcache   # folded weight operands, shared by every program of this QuantModel
+        self.gn_slabs = {}          # id(backing fp32 tensor) -> [slab-sum tensor [rows/32, ld, 2], covered column ranges]
         self._pending = []          # (kind, desc, label, flops, spec, static) in recording order; see flush()
         self._static_depth = 0
         self.n_static = 0
@@ -227,6 +228,18 @@ class Builder:
             self.op_flops.append(flops)
             self.op_specs.append(spec)
         self._pending = []
+
+    @staticmethod
+    def _covered(ranges, lo, hi):
+        """True when the union of the (lo, hi) column ranges covers [lo, hi)."""
+        pos = lo
+        for a, b in sorted(ranges):
+            if a > pos:
+                break
+            pos = max(pos, b)
+            if pos >= hi:
+                return True
+        return pos >= hi
 
     def key(self, m):
         n = self.names[id(m)]
@@ -301,6 +314,11 @@ class Builder:
                                groups=norm.num_groups, ss=ss, out_f=out_f.t if out_f else None,
                                ld_f=out_f.ld if out_f else 0, raw=raw_arg)
         d.x = x.ptr
+        slabs = self.gn_slabs.get(id(x.t))
+        if slabs is not None and hw % 32 == 0 and self._covered(slabs[1], x.col0, x.col0 + x.cols):
+            # every column of x was written by GEMMs that left slab sums: the statistics pass over x is skipped
+            d.stats_in = slabs[0].data_ptr() + 8 * x.col0
+            d.ld_stats_in = x.ld
         self.add(_lib.QD_OP_GROUPNORM, d, label,
                  spec=dict(kind="groupnorm", x=x, B=B, HW=hw, groups=norm.num_groups, eps=norm.eps,
                            gamma=norm.weight.detach().float().cpu(), beta=norm.bias.detach().float().cpu(), silu=silu,
@@ -503,12 +521,26 @@ class Builder:
                           out_q_head=out_q_head if (out_q is not None and not transposed) else None, w_zero=w_zero,
                           w_rows=W["w_rows"])
         d.a = a.ptr + (cols[0] if cols is not None else 0)
+        if getattr(d, "_keep_q", None) is not None:
+            self.keep.extend(d._keep_q)           # pre-divided requantisation constants (ops.gemm_desc)
         if rowvec is not None:
             d.rowvec = rowvec.ptr
         if res is not None:
             d.residual = res.ptr
         if o is not None:
             d.out = o.ptr + 4 * out_cols_offset
+            if M % 32 == 0 and M >= 2048 and o.t.dim() == 2 and os.environ.get("QDIFF_GN_STATS", "1") != "0":
+                # GroupNorm slab statistics of this output (qd_gemm_desc.gn_stats): kept per backing tensor so that the two
+                # producers of a concat buffer fill their own column ranges of the same table
+                ent = self.gn_slabs.get(id(o.t))
+                if ent is None:
+                    ent = [torch.zeros((o.t.shape[0] // 32, o.t.shape[1], 2), dtype=torch.float32, device=self.dev), []]
+                    self.keep.append(ent[0])
+                    self.gn_slabs[id(o.t)] = ent
+                c0 = o.col0 + out_cols_offset
+                d.gn_stats = ent[0].data_ptr() + 8 * c0
+                d.ld_stats = o.t.shape[1]
+                ent[1].append((c0, c0 + N))
         spec = None
         if self.want_specs:
             spec = dict(kind="gemm", key=self.key(qm) if id(qm) in self.names else self.key(qm.qm), a=a,

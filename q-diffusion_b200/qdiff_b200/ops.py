@@ -32,7 +32,8 @@ def _require_cuda(*ts):
 
 def gemm_desc(a, w, scale, *, M, N, C, taps=1, lda=None, conv_bhw=None, a_signed=True, bias=None, corr=None,
               rowvec=None, ld_rowvec=0, rows_per_batch=0, residual=None, ldr=0, out=None, ldo=0, out_q=None, ldq=0,
-              oq=None, out_q_transposed=False, bn_hint=0, w_rows=None, geglu=False, out_q_head=None, w_zero=None):
+              oq=None, out_q_transposed=False, bn_hint=0, w_rows=None, geglu=False, out_q_head=None, w_zero=None,
+              prescale=True, gn_stats=None, ld_stats=0):
     d = GemmDesc()
     d.a, d.w = ptr(a), ptr(w)
     d.lda = int(lda if lda is not None else C)
@@ -54,6 +55,15 @@ def gemm_desc(a, w, scale, *, M, N, C, taps=1, lda=None, conv_bhw=None, a_signed
         d.out_q_head_dim, d.out_q_head_pitch = int(out_q_head[0]), int(out_q_head[1])
     if w_zero is not None:      # w = packed unsigned 4-bit codes [rows][K/2], w_zero = per-row zero points (int8)
         d.w_int4_packed, d.w_zero = 1, ptr(w_zero)
+    if gn_stats is not None:
+        d.gn_stats, d.ld_stats = (gn_stats if isinstance(gn_stats, int) else ptr(gn_stats)), int(ld_stats)
+    if out_q is not None and out is None and not geglu and prescale:
+        # requantising epilogue constants pre-divided by the consumer's step (qd_gemm_desc.scale_q / bias_q)
+        sq = (scale.double() / float(d.oq.delta)).to(torch.float32).contiguous()
+        b0 = bias.double() if bias is not None else torch.zeros(scale.shape, dtype=torch.float64, device=scale.device)
+        bq = (b0 / float(d.oq.delta) + int(d.oq.zero_point)).to(torch.float32).contiguous()
+        d.scale_q, d.bias_q = ptr(sq), ptr(bq)
+        d._keep_q = (sq, bq)      # the descriptor holds raw pointers: keep the tensors alive with it
     return d
 
 
@@ -100,7 +110,7 @@ def gn_workspace_floats(B, HW, C_, groups=32):
 
 
 def groupnorm_desc(x, gamma, beta, ws, *, B, HW, C_, ld_x, eps, silu, outs, groups=32, ss=None, out_f=None, ld_f=0,
-                   raw=None):
+                   raw=None, stats_in=None, ld_stats_in=0):
     """outs: list of (tensor, ld, QParams).  raw: (tensor, ld, split, QParams, QParams) = codes of the un-normalised
     input for the block's skip_connection (channels < split use the first quantizer)."""
     d = GroupNormDesc()
@@ -121,6 +131,8 @@ def groupnorm_desc(x, gamma, beta, ws, *, B, HW, C_, ld_x, eps, silu, outs, grou
         t, ld, split, q0, q1 = raw
         d.raw_q, d.ld_raw, d.raw_split = t.data_ptr(), int(ld), int(split)
         d.q_raw[0], d.q_raw[1] = q0, q1
+    if stats_in is not None:
+        d.stats_in, d.ld_stats_in = (stats_in if isinstance(stats_in, int) else ptr(stats_in)), int(ld_stats_in)
     return d
 
 

@@ -186,6 +186,45 @@ def test_qgemm_epilogue_variants(cuda):
     assert torch.equal(out_t.cpu().long()[:, :, pos], codes2.long())
 
 
+@pytest.mark.parametrize("M,N,C,asym,alias,want_q", [
+    (4096, 320, 320, True, True, False),     # to_out / proj_out: short K -> residual through the TMA ring, in-place accumulate
+    (1000, 320, 320, True, False, False),    # ragged M (the ring's last rows are zero-filled), separate residual
+    (2048, 96, 64, False, True, False),      # symmetric codes (no correction), BN with a 16-column tail chunk
+    (4096, 320, 1280, True, True, False),    # ff.net.2: long K -> register-prefetch path
+    (2048, 320, 320, True, False, True),     # requantised output + residual (last ff.net.2 of a transformer)
+    (2048, 640, 2560, True, False, True),    # ... long K
+])
+def test_qgemm_residual_modes(cuda, M, N, C, asym, alias, want_q):
+    """Specialised residual epilogues (EPI_RESIDUAL with / without the TMA ring, fp32 or requantised output)."""
+    ops, fold = _ops()
+    gen = torch.Generator().manual_seed(99 + M + C)
+    L = _make_layer(N, C, 1, 4, gen, asym)
+    lo, hi = (0, 255) if asym else (-128, 127)
+    a = torch.randint(lo, hi + 1, (M, C), generator=gen)
+    res = torch.randn(M, N, generator=gen) * 3.0
+    ref = O.int_linear(a, L["zx"], L["ws"], L["scale"], L["bias"]) + res.double()
+    a_dev = (a.to(torch.uint8) if asym else a.to(torch.int8)).to(cuda)
+    w_dev = L["ws"].to(torch.int8).to(cuda)
+    corr = (L["zx"] * L["ws"].double().sum(dim=1)).to(torch.int32).to(cuda) if asym else None
+    res_dev = res.to(cuda)
+    kw = dict(a_signed=not asym, bias=L["bias"].to(cuda), corr=corr, residual=res_dev, ldr=N)
+    if want_q:
+        oq = ops.act_qparams(0.07, 121, 8, False)
+        out_q = torch.zeros(M, N, dtype=torch.uint8, device=cuda)
+        d = ops.gemm_desc(a_dev, w_dev, L["scale"].to(cuda), M=M, N=N, C=C, out_q=out_q, ldq=N, oq=oq, **kw)
+        ops.qgemm(d)
+        torch.cuda.synchronize()
+        codes_ref = O.uaq_codes(ref.float(), 0.07, 121, 8, False)
+        diff = (out_q.cpu().long() - codes_ref.long()).abs()
+        assert diff.max() <= 1 and (diff > 0).float().mean() < 1e-3, (int(diff.max()), float((diff > 0).float().mean()))
+    else:
+        out = res_dev if alias else torch.full((M, N), float("nan"), device=cuda)
+        d = ops.gemm_desc(a_dev, w_dev, L["scale"].to(cuda), M=M, N=N, C=C, out=out, ldo=N, **kw)
+        ops.qgemm(d)
+        torch.cuda.synchronize()
+        _report(f"qgemm+residual {M}x{N}x{C}", out, ref, atol=1e-4, rtol=2e-6)
+
+
 @pytest.mark.parametrize("act,split,sym", [(0, 0, False), (1, 0, True), (2, 0, False), (0, 64, False)])
 def test_quantize(cuda, act, split, sym):
     ops, _ = _ops()
@@ -264,6 +303,52 @@ def test_groupnorm_quant(cuda, C, HW, silu, n_out):
         ref = O.uaq_codes(y.reshape(B * HW, C), q.delta, q.zero_point, 8, False)
         diff = (t.cpu().long() - ref.long()).abs()
         assert diff.max() <= 1 and (diff > 0).float().mean() < 2e-3, (int(diff.max()), float((diff > 0).float().mean()))
+
+
+@pytest.mark.parametrize("B,HW,C,K,asym", [(2, 1024, 320, 320, True), (3, 256, 640, 128, False), (2, 4096, 96, 64, True)])
+def test_groupnorm_from_gemm_slab_stats(cuda, B, HW, C, K, asym):
+    """GroupNorm statistics from the producing GEMM's epilogue (qd_gemm_desc.gn_stats -> qd_groupnorm_desc.stats_in): the slab
+    sums must equal the column sums of the fp32 output, and the GroupNorm that consumes them must emit the same codes as
+    the one that reads the tensor itself."""
+    ops, fold = _ops()
+    gen = torch.Generator().manual_seed(11 + C)
+    M = B * HW
+    L = _make_layer(C, K, 1, 4, gen, asym)
+    lo, hi = (0, 255) if asym else (-128, 127)
+    a = torch.randint(lo, hi + 1, (M, K), generator=gen)
+    a_dev = (a.to(torch.uint8) if asym else a.to(torch.int8)).to(cuda)
+    corr = (L["zx"] * L["ws"].double().sum(dim=1)).to(torch.int32).to(cuda) if asym else None
+    res = torch.randn(M, C, generator=gen).to(cuda)
+    out = res.clone()
+    slabs = torch.full((M // 32, C, 2), float("nan"), device=cuda)
+    d = ops.gemm_desc(a_dev, L["ws"].to(torch.int8).to(cuda), (L["scale"] * 30).to(cuda), M=M, N=C, C=K, a_signed=not asym,
+                      bias=L["bias"].to(cuda), corr=corr, residual=out, ldr=C, out=out, ldo=C, gn_stats=slabs, ld_stats=C)
+    ops.qgemm(d)
+    torch.cuda.synchronize()
+    o64 = out.double().cpu().reshape(M // 32, 32, C)
+    ref_s, ref_ss = o64.sum(dim=1), (o64 * o64).sum(dim=1)
+    got = slabs.double().cpu()
+    assert torch.isfinite(got).all()
+    assert (got[..., 0] - ref_s).abs().max() <= 1e-5 * max(1.0, ref_s.abs().max().item())
+    assert (got[..., 1] - ref_ss).abs().max() <= 1e-5 * max(1.0, ref_ss.abs().max().item())
+    gamma = (torch.randn(C, generator=gen) * 0.2 + 1.0).to(cuda)
+    beta = (torch.randn(C, generator=gen) * 0.1).to(cuda)
+    q = ops.act_qparams(0.03, 117, 8, False)
+    codes = []
+    for use_stats in (False, True):
+        t = torch.zeros(M, C, dtype=torch.uint8, device=cuda)
+        ws = torch.zeros(ops.gn_workspace_floats(B, HW, C), device=cuda)
+        dg = ops.groupnorm_desc(out, gamma, beta, ws, B=B, HW=HW, C_=C, ld_x=C, eps=1e-5, silu=True, outs=[(t, C, q)],
+                                stats_in=slabs if use_stats else None, ld_stats_in=C)
+        ops.groupnorm_quant(dg)
+        torch.cuda.synchronize()
+        codes.append(t.cpu().long())
+    diff = (codes[0] - codes[1]).abs()
+    assert diff.max() <= 1 and (diff > 0).float().mean() < 1e-3, (int(diff.max()), float((diff > 0).float().mean()))
+    y = F.group_norm(out.cpu().reshape(B, HW, C).permute(0, 2, 1).contiguous(), 32, gamma.cpu(), beta.cpu(), 1e-5).permute(0, 2, 1)
+    ref = O.uaq_codes(O.silu(y).reshape(M, C), q.delta, q.zero_point, 8, False).long()
+    d2 = (codes[1] - ref).abs()
+    assert d2.max() <= 1 and (d2 > 0).float().mean() < 2e-3
 
 
 @pytest.mark.parametrize("C,n_out", [(320, 3), (1280, 1), (64, 2)])

@@ -57,7 +57,7 @@ def main():
             print("  first mismatches (row, col):", bad[:8].tolist())
             return 1
     # ---- timing: the 64x64 conv shapes as plain GEMMs with K = 9*C (rounded to 128), next to the shipped kernel
-    for (M, N, K, BN) in [(65536, 320, 8704, 160), (65536, 320, 2944, 160), (16384, 640, 5760, 256), (4096, 1280, 11520, 256)]:
+    for (M, N, K, BN) in [(65536, 320, 8704, 160), (65536, 320, 2944, 160), (16384, 640, 5760, 160), (16384, 1280, 11520, 256), (4096, 1280, 11520, 256)]:
         rc, a, b, out, ms = run(M, N, K, BN, 10)
         assert rc == 0, rc
         tops2 = 2.0 * M * N * K / (ms * 1e-3) / 1e12
