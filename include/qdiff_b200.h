@@ -102,6 +102,15 @@ typedef struct qd_gemm_desc {
    * (stats_in), replacing its own pass over the fp32 tensor (GroupNorm32: ldm util.py:214-216). */
   float* gn_stats;
   long long ld_stats;
+  /* Weight-only layers (set_quant_state(True, False): quantised weights, fp32 activations; BASELINE configs[0]):
+   * a_bf16 = 1: `a` holds the activation as THREE bfloat16 planes per pixel, [M][3][Cp] (hi, mid, lo with
+   * x = hi + mid + lo to 2^-24 relative, written by qd_split_bf16x3), `w` the zero-point-free weight codes as bfloat16
+   * [n_rows][taps][3][Cp] (the codes repeated for the three planes: |code| <= 255 is exact in bfloat16), C = BYTES per
+   * tap = 6 * Cp, lda in bytes.  The contraction runs on tcgen05.mma kind::f16 with fp32 accumulation, so
+   * y = scale[n] * sum_k x[m,k] * ws[n,k] + bias (+ rowvec, + residual) carries fp32-level rounding only
+   * (qdiff/quant_layer.py:263-279 with use_act_quant False).  No corr, no out_q, no geglu. */
+  int32_t a_bf16;
+  int32_t reserved4;
 } qd_gemm_desc;
 
 int qd_qgemm_i8(const qd_gemm_desc* d, qd_stream_t stream);
@@ -170,6 +179,44 @@ typedef struct qd_groupnorm_desc {
 } qd_groupnorm_desc;
 
 int qd_groupnorm_quant(const qd_groupnorm_desc* d, qd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Weight-only mode (quant_act False): activations stay fp32.
+ * qd_split_bf16x3 -- dst[m][p][c] = plane p of f(src[m][c]) as bfloat16 (p = 0 hi, 1 mid, 2 lo), c < C; columns C..Cp-1 of
+ *   every plane must be zero (allocate dst zeroed).  f: act 0 none, 1 SiLU; upsample2x as in qd_quantize.  ld_dst = 3*Cp.
+ * qd_attention_fp32 -- softmax(scale * q k^T) v per (batch, head) in fp32: QuantAttnBlock.forward with use_act_quant
+ *   False (qdiff/quant_block.py:360-386) and QKVAttentionLegacy (openaimodel.py:384-406; scale = 1/sqrt(ch) applied to
+ *   the product).  q: [B*Tq, ld_q], head h at columns q_off + h*head_stride_q (k, v likewise); out [B*Tq, ld_out].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct qd_split_desc {
+  const float* src;
+  long long ld_src;
+  void* dst;             /* bfloat16 */
+  long long ld_dst;      /* elements: 3 * Cp */
+  int32_t M, C, Cp;
+  int32_t act;
+  int32_t upsample2x, B, H, W;
+} qd_split_desc;
+
+typedef struct qd_attention_fp_desc {
+  const float* q;
+  const float* k;
+  const float* v;
+  long long ld_q, ld_k, ld_v;
+  int32_t B, heads, d, Tq, Tk;
+  int32_t q_off, k_off, v_off;
+  int32_t head_stride_q, head_stride_k, head_stride_v;
+  float scale;
+  float* out;
+  long long ld_out;
+} qd_attention_fp_desc;
+
+/* out[i] = a*x[i] + b*y[i] + c*z[i] (y / z may be NULL): the DPM-Solver++ multistep update
+ * x_t = (sigma_t/sigma_s) x - alpha_t (e^-h - 1) m0 - 0.5 alpha_t (e^-h - 1) D1   (dpm_solver.py:504-527, 755-795). */
+int qd_lincomb3(float* out, float a, const float* x, float b, const float* y, float c, const float* z, long long n,
+                qd_stream_t stream);
+int qd_split_bf16x3(const qd_split_desc* d, qd_stream_t stream);
+int qd_attention_fp32(const qd_attention_fp_desc* d, qd_stream_t stream);
 long long qd_groupnorm_workspace_floats(int B, int HW, int C, int groups);
 
 /* ------------------------------------------------------------------------------------------
@@ -312,7 +359,9 @@ enum qd_op_kind {
   QD_OP_NCHW_TO_NHWC = 9,
   QD_OP_NHWC_TO_NCHW = 10,
   QD_OP_AVGPOOL2X = 11,
-  QD_OP_UPSAMPLE2X = 12
+  QD_OP_UPSAMPLE2X = 12,
+  QD_OP_SPLIT3 = 13,
+  QD_OP_ATTENTION_FP = 14
 };
 
 /* generic argument block for the small helpers when recorded into an engine */

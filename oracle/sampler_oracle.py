@@ -109,3 +109,82 @@ def generalized_steps(model, x, seq, betas, eta=0.0, noises=None):
         noise = noises[k] if noises is not None else torch.zeros_like(x)
         xt = at_next.sqrt() * x0_t + c1 * noise + c2 * et
     return xt
+
+
+# ------------------------------------------------------------------------------------------- DPM-Solver++ (2M)
+class _DiscreteVP:
+    """NoiseScheduleVP('discrete', alphas_cumprod=...) (ldm/models/diffusion/dpm_solver/dpm_solver.py:96-108,125-156):
+    log(alpha_t) is piecewise linear in t over t_n = n / N, n = 1..N; fp32 like the reference."""
+
+    def __init__(self, alphas_cumprod):
+        self.log_alpha = 0.5 * torch.log(alphas_cumprod)
+        self.total_N = self.log_alpha.shape[0]
+        self.t_array = torch.linspace(0., 1., self.total_N + 1, dtype=alphas_cumprod.dtype)[1:]
+
+    def marginal_log_mean_coeff(self, t):
+        """interpolate_fn (:1132-1170): linear interpolation, the outermost segments extended beyond the key points."""
+        K = self.total_N
+        idx = torch.searchsorted(self.t_array, t.reshape(-1)).clamp(1, K - 1)
+        x0, x1 = self.t_array[idx - 1], self.t_array[idx]
+        y0, y1 = self.log_alpha[idx - 1], self.log_alpha[idx]
+        return (y0 + (t.reshape(-1) - x0) * (y1 - y0) / (x1 - x0)).reshape(t.shape)
+
+    def marginal_alpha(self, t):
+        return torch.exp(self.marginal_log_mean_coeff(t))
+
+    def marginal_std(self, t):
+        return torch.sqrt(1. - torch.exp(2. * self.marginal_log_mean_coeff(t)))
+
+    def marginal_lambda(self, t):
+        lm = self.marginal_log_mean_coeff(t)
+        return lm - 0.5 * torch.log(1. - torch.exp(2. * lm))
+
+
+def dpm_solver_sample(model, x_T, cond, uc, scale, alphas_cumprod, S):
+    """DPMSolverSampler.sample (ldm/models/diffusion/dpm_solver/sampler.py:24-82): DPM-Solver++ with data prediction
+    (predict_x0=True), multistep order 2, uniform time steps, lower_order_final, classifier-free guidance
+    (dpm_solver.py:321-345 model_fn, :386-399 data prediction, :504-527 first-order update, :755-795 second-order update,
+    :1077-1105 the multistep loop).  model(x, t_model, context) -> eps, t_model = (t - 1/N) * 1000 (:278-287)."""
+    ns = _DiscreteVP(alphas_cumprod)
+    dt = x_T.dtype
+    b = x_T.shape[0]
+    t_0, t_T = 1. / ns.total_N, 1.
+    timesteps = torch.linspace(t_T, t_0, S + 1, dtype=dt)
+
+    def data_pred(x, t):
+        vec_t = t.expand(b)
+        t_in = (vec_t - 1. / ns.total_N) * 1000.
+        if uc is None or scale == 1.0:
+            noise = model(x, t_in, cond)
+        else:
+            e_u, e_c = model(torch.cat([x] * 2), torch.cat([t_in] * 2), torch.cat([uc, cond])).chunk(2)
+            noise = e_u + scale * (e_c - e_u)
+        a, sg = ns.marginal_alpha(vec_t), ns.marginal_std(vec_t)
+        return (x - sg.reshape(-1, 1, 1, 1) * noise) / a.reshape(-1, 1, 1, 1)
+
+    def first(x, s, t, m_s):
+        h = ns.marginal_lambda(t) - ns.marginal_lambda(s)
+        return (ns.marginal_std(t) / ns.marginal_std(s)) * x - (ns.marginal_alpha(t) * torch.expm1(-h)) * m_s
+
+    def second(x, m1, m0, t1, t0, t):
+        l1, l0, lt = ns.marginal_lambda(t1), ns.marginal_lambda(t0), ns.marginal_lambda(t)
+        h_0, h = l0 - l1, lt - l0
+        r0 = h_0 / h
+        D1 = (1. / r0) * (m0 - m1)
+        k = ns.marginal_alpha(t) * (torch.exp(-h) - 1.)
+        return (ns.marginal_std(t) / ns.marginal_std(t0)) * x - k * m0 - 0.5 * k * D1
+
+    x = x_T.clone()
+    ms, ts = [data_pred(x, timesteps[0])], [timesteps[0]]
+    x = first(x, ts[-1], timesteps[1], ms[-1])                # init_order = 1
+    ms.append(data_pred(x, timesteps[1]))
+    ts.append(timesteps[1])
+    for step in range(2, S + 1):
+        t = timesteps[step]
+        order = min(2, S + 1 - step) if S < 15 else 2
+        x = first(x, ts[-1], t, ms[-1]) if order == 1 else second(x, ms[0], ms[1], ts[0], ts[1], t)
+        ms[0], ts[0] = ms[1], ts[1]
+        ts[1] = t
+        if step < S:
+            ms[1] = data_pred(x, t)
+    return x

@@ -70,6 +70,121 @@ __global__ void quantize_scalar_kernel(const qd_quantize_desc p) {
   }
 }
 
+// ------------------------------------------------------------------------------------ weight-only operands
+// fp32 activation -> three bfloat16 planes (hi, mid, lo): x = hi + mid + lo up to 2^-24 |x|, so that a bfloat16 tensor-core
+// contraction against integer weight codes (exact in bfloat16) with fp32 accumulation reproduces the fp32 conv of the
+// reference's weight-only path (quant_layer.py:263-279, use_act_quant False).  One thread = 4 channels of one row.
+__device__ __forceinline__ uint32_t bf16_bits(float x) { return __float_as_uint(x) >> 16; }   // x already on the bf16 grid
+__device__ __forceinline__ float bf16_rn(float x) {       // round-to-nearest-even to the bfloat16 grid, kept as float
+  const uint32_t u = __float_as_uint(x);
+  const uint32_t r = u + 0x7FFFu + ((u >> 16) & 1u);
+  return __uint_as_float(r & 0xFFFF0000u);
+}
+__global__ void split_bf16x3_kernel(const qd_split_desc p) {
+  const int cq = p.C >> 2;
+  const long long rows_out = p.upsample2x ? (long long)p.B * (2 * p.H) * (2 * p.W) : (long long)p.M;
+  const long long total = rows_out * cq;
+  uint16_t* dst = reinterpret_cast<uint16_t*>(p.dst);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long ro = i / cq;
+    const int c = (int)(i - ro * cq) << 2;
+    long long rs = ro;
+    if (p.upsample2x) {
+      const int W2 = 2 * p.W, H2 = 2 * p.H;
+      const int w2 = (int)(ro % W2);
+      const long long t = ro / W2;
+      const int h2 = (int)(t % H2);
+      const long long b = t / H2;
+      rs = (b * p.H + (h2 >> 1)) * p.W + (w2 >> 1);
+    }
+    const float4 v4 = *reinterpret_cast<const float4*>(p.src + rs * p.ld_src + c);
+    float v[4] = {v4.x, v4.y, v4.z, v4.w};
+    uint32_t pl[3][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x = v[j];
+      if (p.act == 1) x = x / (1.0f + __expf(-x));          // SiLU with the accurate exponential (this path is fp32-faithful)
+      const float h = bf16_rn(x);
+      const float r1 = x - h;
+      const float m = bf16_rn(r1);
+      const float l = bf16_rn(r1 - m);
+      pl[0][j] = bf16_bits(h); pl[1][j] = bf16_bits(m); pl[2][j] = bf16_bits(l);
+    }
+    uint16_t* o = dst + ro * p.ld_dst + c;
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      *reinterpret_cast<uint2*>(o + (long long)q * p.Cp) = make_uint2(pl[q][0] | (pl[q][1] << 16), pl[q][2] | (pl[q][3] << 16));
+  }
+}
+
+// element-wise variant for C % 4 != 0 (conv_in with 3 input channels)
+__global__ void split_bf16x3_scalar_kernel(const qd_split_desc p) {
+  const long long total = (long long)p.M * p.C;
+  uint16_t* dst = reinterpret_cast<uint16_t*>(p.dst);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / p.C;
+    const int c = (int)(i - r * p.C);
+    float x = p.src[r * p.ld_src + c];
+    if (p.act == 1) x = x / (1.0f + __expf(-x));
+    const float h = bf16_rn(x);
+    const float r1 = x - h;
+    const float m = bf16_rn(r1);
+    const float l = bf16_rn(r1 - m);
+    uint16_t* o = dst + r * p.ld_dst + c;
+    o[0] = (uint16_t)bf16_bits(h);
+    o[p.Cp] = (uint16_t)bf16_bits(m);
+    o[2 * p.Cp] = (uint16_t)bf16_bits(l);
+  }
+}
+
+// fp32 attention of the weight-only path: one block per (query row, batch*head).  Scores of the row live in shared
+// memory (Tk <= 8192), exact expf, fp32 accumulation in a fixed order.  Small problems only (CIFAR 16x16, LDM latents):
+// correctness path of BASELINE configs[0], not a throughput kernel.
+__global__ void __launch_bounds__(128) attention_fp32_kernel(const qd_attention_fp_desc p) {
+  extern __shared__ float afp_sh[];
+  float* qs = afp_sh;                 // [d]
+  float* sc = afp_sh + p.d;           // [Tk]
+  __shared__ float red[4];
+  const int bh = blockIdx.y, b = bh / p.heads, h = bh - b * p.heads;
+  const int r = blockIdx.x;
+  const float* q = p.q + ((long long)b * p.Tq + r) * p.ld_q + p.q_off + h * p.head_stride_q;
+  for (int i = threadIdx.x; i < p.d; i += blockDim.x) qs[i] = q[i];
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < p.Tk; j += blockDim.x) {
+    const float* k = p.k + ((long long)b * p.Tk + j) * p.ld_k + p.k_off + h * p.head_stride_k;
+    float acc = 0.f;
+    for (int i = 0; i < p.d; ++i) acc = fmaf(qs[i], k[i], acc);
+    acc *= p.scale;
+    sc[j] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < p.Tk; j += blockDim.x) {
+    const float e = expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  const float inv = 1.0f / (red[0] + red[1] + red[2] + red[3]);
+  float* o = p.out + ((long long)b * p.Tq + r) * p.ld_out + h * p.d;
+  for (int c = threadIdx.x; c < p.d; c += blockDim.x) {
+    const float* v = p.v + (long long)b * p.Tk * p.ld_v + p.v_off + h * p.head_stride_v + c;
+    float acc = 0.f;
+    for (int j = 0; j < p.Tk; ++j) acc = fmaf(sc[j] * inv, v[(long long)j * p.ld_v], acc);
+    o[c] = acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------ groupnorm
 // Three-kernel path (large feature maps).  Pass 1: a block reduces `slab` pixels x all channels to per-GROUP
 // partial sums (fp32 per thread over the slab, then double, in a fixed order: results are run-to-run
@@ -133,39 +248,42 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const double* __restri
   }
 }
 // Statistics from the producing GEMMs' epilogues (qd_gemm_desc.gn_stats): per 32-row slab and channel (sum, sum of squares).
-// One block per image, one warp per group (8 warps x 4 rounds for 32 groups): lanes stride over the group's
-// (slab, channel) items, accumulate in double, shuffle-reduce in a fixed order.  Replaces gn_partial + gn_finalize, i.e.
-// one full read of the fp32 tensor (SD: 2.5 GB per step, profiles/r01_launches_step_final.summary.txt).
-__global__ void __launch_bounds__(256) gn_finalize_from_stats_kernel(const float2* __restrict__ slabs, long long ld_stats,
+// One block per (group, image): 128 threads stride over the group's (slab, channel) items, accumulate in double, reduce
+// in a fixed order (warp shuffles, then the 4 warps through shared memory).  Replaces gn_partial + gn_finalize, i.e. one
+// full read of the fp32 tensor (SD: 2.5 GB per step, profiles/r01_launches_step_final.summary.txt).  (The first version
+// used one block per IMAGE: 16 blocks walking 330 KB each were slower than the pass they replaced.)
+__global__ void __launch_bounds__(128) gn_finalize_from_stats_kernel(const float2* __restrict__ slabs, long long ld_stats,
                                                                     int HW, int C, int groups, float eps,
                                                                     float* __restrict__ stats) {
-  const int b = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  __shared__ double sh[2][4];
+  const int g = blockIdx.x, b = blockIdx.y;
   const int cpg = C / groups;
   const int nsl = HW >> 5;
-  const float2* base = slabs + (long long)b * nsl * ld_stats;
-  for (int g = warp; g < groups; g += nwarps) {
-    double s = 0.0, ss = 0.0;
-    const int items = nsl * cpg;
-    for (int i = lane; i < items; i += 32) {
-      const int sl = i / cpg, ch = i - sl * cpg;
-      const float2 v = base[(long long)sl * ld_stats + g * cpg + ch];
-      s += (double)v.x;
-      ss += (double)v.y;
-    }
+  const float2* base = slabs + (long long)b * nsl * ld_stats + g * cpg;
+  double s = 0.0, ss = 0.0;
+  const int items = nsl * cpg;
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int sl = i / cpg, ch = i - sl * cpg;
+    const float2 v = base[(long long)sl * ld_stats + ch];
+    s += (double)v.x;
+    ss += (double)v.y;
+  }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, off);
-      ss += __shfl_xor_sync(0xffffffffu, ss, off);
-    }
-    if (lane == 0) {
-      const double cnt = (double)HW * cpg;
-      const double mean = s / cnt;
-      double var = ss / cnt - mean * mean;
-      if (var < 0.0) var = 0.0;
-      stats[((long long)b * groups + g) * 2] = (float)mean;
-      stats[((long long)b * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
-    }
+  for (int off = 16; off > 0; off >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, off);
+    ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = ss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s = (sh[0][0] + sh[0][1]) + (sh[0][2] + sh[0][3]);
+    ss = (sh[1][0] + sh[1][1]) + (sh[1][2] + sh[1][3]);
+    const double cnt = (double)HW * cpg;
+    const double mean = s / cnt;
+    double var = ss / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[((long long)b * groups + g) * 2] = (float)mean;
+    stats[((long long)b * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
   }
 }
 
@@ -572,6 +690,16 @@ __global__ void upsample2x_f32_kernel(const float* __restrict__ src, float* __re
 }
 
 // ------------------------------------------------------------------------------------ sampler
+__global__ void lincomb3_kernel(float* __restrict__ out, float a, const float* __restrict__ x, float b,
+                                const float* __restrict__ y, float c, const float* __restrict__ z, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = a * x[i];
+    if (y) v = fmaf(b, y[i], v);
+    if (z) v = fmaf(c, z[i], v);
+    out[i] = v;
+  }
+}
+
 __global__ void sampler_step_kernel(const qd_sampler_desc p) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n;
        i += (long long)gridDim.x * blockDim.x) {

@@ -172,6 +172,8 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
   if (!d || !d->a || !d->w || !d->scale) return fail(QD_ERR_BAD_ARG, "gemm: null operand");
   if (d->taps != 1 && d->taps != 9) return fail(QD_ERR_UNSUPPORTED, "gemm: taps must be 1 or 9 (got %d)", d->taps);
   if (d->C <= 0 || (d->C % 32) != 0) return fail(QD_ERR_UNSUPPORTED, "gemm: C=%d must be a positive multiple of 32", d->C);
+  if (d->a_bf16 && (d->corr || d->out_q || d->geglu || d->w_int4_packed || !d->out))
+    return fail(QD_ERR_BAD_ARG, "gemm: a_bf16 (weight-only) layers take no corr / out_q / geglu / packed weights and write fp32");
   if (d->M <= 0 || d->N <= 0) return fail(QD_ERR_BAD_ARG, "gemm: bad M/N");
   if (!d->out && !d->out_q) return fail(QD_ERR_BAD_ARG, "gemm: no output");
   const int sms = num_sms();
@@ -256,6 +258,7 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
   a.scale = d->scale; a.bias = d->bias; a.corr = d->corr;
   a.scale_q = d->scale_q; a.bias_q = d->bias_q;
   a.gn_stats = reinterpret_cast<float2*>(d->gn_stats); a.ld_stats = d->ld_stats;
+  a.bf16 = d->a_bf16;
   if (d->gn_stats && (!d->out || (d->ld_stats & 1) || (reinterpret_cast<uintptr_t>(d->gn_stats) & 15)))
     return fail(QD_ERR_BAD_ARG, "gemm: gn_stats needs an fp32 output, an even ld_stats and 16-byte alignment");
   if ((d->scale_q == nullptr) != (d->bias_q == nullptr)) return fail(QD_ERR_BAD_ARG, "gemm: scale_q and bias_q come together");
@@ -264,6 +267,8 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
   const int tiles = a.tiles_m * a.tiles_n;
   pl->grid = tiles < sms ? tiles : sms;
   pl->mode = gemm_mode(a);
+  if (a.bf16 && pl->mode < 0)
+    return fail(QD_ERR_UNSUPPORTED, "gemm: weight-only (a_bf16) layer needs a specialised epilogue (N %% 4 == 0, aligned leading dimensions)");
   memset(&pl->tmR, 0, sizeof(pl->tmR));
   if (qd::gemm_res_tma(pl->mode)) {
     cuuint64_t rd[2] = {(cuuint64_t)d->N * 4, (cuuint64_t)d->M};
@@ -315,6 +320,10 @@ int gemm_mode(const qd::GemmArgs& a) {
   // short-K plain GEMMs with a residual (to_out / proj_out at the 64x64 and 32x32 levels, split-shortcut second halves):
   // the epilogue is the critical path and its residual loads are latency-bound -> TMA ring.  Longer K: the ring's shared
   // memory would cost pipeline stages (tools/sweep_bn.py: K = 1280 lost 10 % with 2 stages), registers-prefetch path.
+  if (a.bf16) {      // weight-only: fp32 output with an optional per-image vector or residual; no ring (long byte-K)
+    return qd::EPI_BF16 | qd::EPI_OUT_F32 | ((a.taps == 9) ? qd::EPI_CONV : 0) | (a.rowvec ? qd::EPI_ROWVEC : 0) |
+           (a.residual ? qd::EPI_RESIDUAL : 0);
+  }
   static const int ring_kb = [] { const char* e = getenv("QDIFF_RES_RING_KB"); return e ? atoi(e) : 5; }();
   const int num_kb = ((a.C + qd::GEMM_BK - 1) / qd::GEMM_BK) * a.taps;
   const bool ring = a.residual && a.taps == 1 && num_kb <= ring_kb && !(reinterpret_cast<uintptr_t>(a.residual) & 15);
@@ -348,6 +357,13 @@ int launch_gemm(const GemmPlan& pl, cudaStream_t s) {
     case EPI_OUT_F32 | EPI_RESIDUAL | EPI_CORR | EPI_RESTMA: return launch_gemm_mode<EPI_OUT_F32 | EPI_RESIDUAL | EPI_CORR | EPI_RESTMA>(pl, s);
     case EPI_OUT_Q | EPI_RESIDUAL | EPI_RESTMA: return launch_gemm_mode<EPI_OUT_Q | EPI_RESIDUAL | EPI_RESTMA>(pl, s);
     case EPI_OUT_Q | EPI_RESIDUAL | EPI_CORR | EPI_RESTMA: return launch_gemm_mode<EPI_OUT_Q | EPI_RESIDUAL | EPI_CORR | EPI_RESTMA>(pl, s);
+    // weight-only layers (bfloat16 x3 planes, fp32 accumulators)
+    case EPI_BF16 | EPI_OUT_F32: return launch_gemm_mode_w<EPI_BF16 | EPI_OUT_F32, false>(pl, s);
+    case EPI_BF16 | EPI_OUT_F32 | EPI_ROWVEC: return launch_gemm_mode_w<EPI_BF16 | EPI_OUT_F32 | EPI_ROWVEC, false>(pl, s);
+    case EPI_BF16 | EPI_OUT_F32 | EPI_RESIDUAL: return launch_gemm_mode_w<EPI_BF16 | EPI_OUT_F32 | EPI_RESIDUAL, false>(pl, s);
+    case EPI_BF16 | EPI_OUT_F32 | EPI_CONV: return launch_gemm_mode_w<EPI_BF16 | EPI_OUT_F32 | EPI_CONV, false>(pl, s);
+    case EPI_BF16 | EPI_OUT_F32 | EPI_ROWVEC | EPI_CONV: return launch_gemm_mode_w<EPI_BF16 | EPI_OUT_F32 | EPI_ROWVEC | EPI_CONV, false>(pl, s);
+    case EPI_BF16 | EPI_OUT_F32 | EPI_RESIDUAL | EPI_CONV: return launch_gemm_mode_w<EPI_BF16 | EPI_OUT_F32 | EPI_RESIDUAL | EPI_CONV, false>(pl, s);
     case EPI_TRANS | EPI_OUT_Q: return launch_gemm_mode<EPI_TRANS | EPI_OUT_Q>(pl, s);
     case EPI_TRANS | EPI_OUT_Q | EPI_CORR: return launch_gemm_mode<EPI_TRANS | EPI_OUT_Q | EPI_CORR>(pl, s);
     case EPI_GEGLU | EPI_OUT_Q: return launch_gemm_mode<EPI_GEGLU | EPI_OUT_Q>(pl, s);
@@ -430,8 +446,8 @@ int launch_groupnorm(const qd_groupnorm_desc& d, cudaStream_t s) {
   if (d.stats_in && use_stats) {
     // the producing GEMMs left per-slab column sums: no pass over x for the statistics
     if (d.HW % 32) return fail(QD_ERR_BAD_ARG, "groupnorm: stats_in needs HW %% 32 == 0");
-    qd::gn_finalize_from_stats_kernel<<<d.B, 256, 0, s>>>(reinterpret_cast<const float2*>(d.stats_in), d.ld_stats_in, d.HW,
-                                                         d.C, d.groups, d.eps, stats);
+    qd::gn_finalize_from_stats_kernel<<<dim3(d.groups, d.B), 128, 0, s>>>(reinterpret_cast<const float2*>(d.stats_in),
+                                                                         d.ld_stats_in, d.HW, d.C, d.groups, d.eps, stats);
     rc = check_launch("gn_finalize_from_stats_kernel");
     if (rc) return rc;
   } else {
@@ -492,6 +508,29 @@ int launch_layernorm(const qd_layernorm_desc& d, cudaStream_t s) {
     case 11: case 12: case 13: case 14: case 15: case 16: return launch_layernorm_t<16>(d, s);
     default: return fail(QD_ERR_UNSUPPORTED, "layernorm: C=%d exceeds 2048", d.C);
   }
+}
+
+int launch_split3(const qd_split_desc& d, cudaStream_t s) {
+  if (!d.src || !d.dst || d.M <= 0 || d.C <= 0) return fail(QD_ERR_BAD_ARG, "split: bad args");
+  if ((d.Cp & 3) || d.Cp < d.C || d.ld_dst < 3LL * d.Cp || (d.ld_dst & 3))
+    return fail(QD_ERR_UNSUPPORTED, "split: Cp=%d must be a multiple of 4, >= C, with ld_dst >= 3*Cp", d.Cp);
+  if ((d.C & 3) || (d.ld_src & 3)) {
+    if (d.upsample2x) return fail(QD_ERR_UNSUPPORTED, "split: upsample needs C %% 4 == 0");
+    qd::split_bf16x3_scalar_kernel<<<grid_for((long long)d.M * d.C, 256), 256, 0, s>>>(d);
+    return check_launch("split_bf16x3_scalar_kernel");
+  }
+  const long long rows = d.upsample2x ? (long long)d.B * 4 * d.H * d.W : d.M;
+  qd::split_bf16x3_kernel<<<grid_for(rows * (d.C / 4), 256), 256, 0, s>>>(d);
+  return check_launch("split_bf16x3_kernel");
+}
+
+int launch_attention_fp(const qd_attention_fp_desc& d, cudaStream_t s) {
+  if (!d.q || !d.k || !d.v || !d.out || d.B <= 0 || d.heads <= 0 || d.d <= 0 || d.Tq <= 0 || d.Tk <= 0)
+    return fail(QD_ERR_BAD_ARG, "attention_fp32: bad args");
+  const size_t smem = (size_t)(d.d + d.Tk) * sizeof(float);
+  if (smem > 48 * 1024) return fail(QD_ERR_UNSUPPORTED, "attention_fp32: d + Tk = %d exceeds 12288 floats of shared memory", d.d + d.Tk);
+  qd::attention_fp32_kernel<<<dim3(d.Tq, d.B * d.heads), 128, smem, s>>>(d);
+  return check_launch("attention_fp32_kernel");
 }
 
 int launch_im2col(const qd_im2col_desc& d, cudaStream_t s) {
@@ -704,6 +743,8 @@ struct Op {
     qd_im2col_desc im2col;
     qd_attention_desc att;
     qd_misc_desc misc;
+    qd_split_desc split;
+    qd_attention_fp_desc attfp;
   };
   Op() : kind(0) { memset(&gemm, 0, sizeof(gemm)); memset(&gn, 0, sizeof(gn)); }
 };
@@ -716,6 +757,8 @@ int run_op(const Op& op, cudaStream_t s) {
     case QD_OP_LAYERNORM: return launch_layernorm(op.ln, s);
     case QD_OP_IM2COL: return launch_im2col(op.im2col, s);
     case QD_OP_ATTENTION: return launch_attention(op.att, s);
+    case QD_OP_SPLIT3: return launch_split3(op.split, s);
+    case QD_OP_ATTENTION_FP: return launch_attention_fp(op.attfp, s);
     default: return launch_misc(op.kind, op.misc, s);
   }
 }
@@ -764,6 +807,20 @@ int qd_im2col_i8(const qd_im2col_desc* d, qd_stream_t s) {
 int qd_qattention(const qd_attention_desc* d, qd_stream_t s) {
   if (!d) return fail(QD_ERR_BAD_ARG, "null desc");
   return launch_attention(*d, (cudaStream_t)s);
+}
+int qd_lincomb3(float* out, float a, const float* x, float b, const float* y, float c, const float* z, long long n,
+                qd_stream_t s) {
+  if (!out || !x || n <= 0) return fail(QD_ERR_BAD_ARG, "lincomb3: bad args");
+  qd::lincomb3_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)s>>>(out, a, x, b, y, c, z, n);
+  return check_launch("lincomb3_kernel");
+}
+int qd_split_bf16x3(const qd_split_desc* d, qd_stream_t s) {
+  if (!d) return fail(QD_ERR_BAD_ARG, "null desc");
+  return launch_split3(*d, (cudaStream_t)s);
+}
+int qd_attention_fp32(const qd_attention_fp_desc* d, qd_stream_t s) {
+  if (!d) return fail(QD_ERR_BAD_ARG, "null desc");
+  return launch_attention_fp(*d, (cudaStream_t)s);
 }
 int qd_timestep_embedding(const float* t, const float* freqs, int32_t B, int32_t dim, int32_t mode, float* out,
                           qd_stream_t s) {
@@ -828,6 +885,8 @@ int qd_engine_add_op(qd_engine* e, int kind, const void* desc) {
     case QD_OP_LAYERNORM: op.ln = *reinterpret_cast<const qd_layernorm_desc*>(desc); break;
     case QD_OP_IM2COL: op.im2col = *reinterpret_cast<const qd_im2col_desc*>(desc); break;
     case QD_OP_ATTENTION: op.att = *reinterpret_cast<const qd_attention_desc*>(desc); break;
+    case QD_OP_SPLIT3: op.split = *reinterpret_cast<const qd_split_desc*>(desc); break;
+    case QD_OP_ATTENTION_FP: op.attfp = *reinterpret_cast<const qd_attention_fp_desc*>(desc); break;
     case QD_OP_TIMESTEP_EMB: case QD_OP_COPY2D: case QD_OP_NCHW_TO_NHWC: case QD_OP_NHWC_TO_NCHW:
     case QD_OP_AVGPOOL2X: case QD_OP_UPSAMPLE2X:
       op.misc = *reinterpret_cast<const qd_misc_desc*>(desc);

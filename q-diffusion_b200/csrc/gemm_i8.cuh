@@ -68,6 +68,7 @@ constexpr int EPI_GEGLU = 32;     // columns interleaved [4 x, 4 gate]: out_q = 
 constexpr int EPI_TRANS = 64;     // requantised code output, transposed [img][n][token'] (V^T operand of qattention)
 constexpr int EPI_CONV = 128;     // 3x3 conv (taps == 9); with EPI_CORR the correction table is indexed by border class
 constexpr int EPI_RESTMA = 256;   // with EPI_RESIDUAL: residual sub-tiles arrive through the per-warp TMA ring (short-K GEMMs)
+constexpr int EPI_BF16 = 512;     // weight-only layers: bfloat16 x3 activation planes x bfloat16 weight codes, fp32 accumulators
 
 struct GemmArgs {
   int M, N;            // logical output rows / columns (columns >= N are masked)
@@ -107,6 +108,7 @@ struct GemmArgs {
   // GroupNorm slab statistics of the fp32 output (qd_gemm_desc.gn_stats): float2 [M/32][ld_stats]
   float2* gn_stats;
   long long ld_stats;
+  int bf16;            // weight-only layer: bfloat16 operands, fp32 accumulators (EPI_BF16 modes)
 };
 // Specialised requantising modes take the pre-divided constants (one FFMA per element: quant_math.cuh quant_bits_pre)
 __host__ __device__ constexpr bool gemm_qpre(int MODE) { return MODE >= 0 && (MODE & 16) != 0 && (MODE & 32) == 0; }
@@ -248,8 +250,13 @@ __device__ __forceinline__ void gemm_finalise4(const GemmArgs& p, const QuantK& 
     }
   }
   float y[4];
+  if constexpr (MODE >= 0 && (MODE & EPI_BF16) != 0) {     // fp32 accumulators (weight-only layers)
+    y[0] = __uint_as_float(a4.x) * sc[0] + bi[0]; y[1] = __uint_as_float(a4.y) * sc[1] + bi[1];
+    y[2] = __uint_as_float(a4.z) * sc[2] + bi[2]; y[3] = __uint_as_float(a4.w) * sc[3] + bi[3];
+  } else {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) y[j] = (float)a[j] * sc[j] + bi[j];
+    for (int j = 0; j < 4; ++j) y[j] = (float)a[j] * sc[j] + bi[j];
+  }
   if (has_rowvec) {
     const float* rv = p.rowvec + (long long)img * p.ld_rowvec + n;
     if (full && (G ? ((p.ld_rowvec & 3) == 0) : true)) {
@@ -411,7 +418,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_i8(GEMM_BM, p.BN, p.a_signed, p.b_signed);
+      constexpr bool BF16 = MODE >= 0 && (MODE & EPI_BF16) != 0;
+      const uint32_t idesc = BF16 ? make_idesc_bf16(GEMM_BM, p.BN) : make_idesc_i8(GEMM_BM, p.BN, p.a_signed, p.b_signed);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -431,7 +439,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t db = make_smem_desc_sw128(sa + GEMM_A_STAGE_BYTES);
           for (int j = 0; j < nmma; ++j) {
             // advance 32 bytes (one K=32 slice) inside the 128B swizzle row: +2 in 16-byte units
-            umma_i8(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (kb | j) ? 1u : 0u);
+            if constexpr (BF16) umma_bf16(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (kb | j) ? 1u : 0u);
+            else umma_i8(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (kb | j) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }

@@ -119,6 +119,18 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[smem] * B[smem], bfloat16 operands, fp32 accumulate (weight-only layers: SASS UTCHMMA).
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier when all previously issued tcgen05.mma of this thread complete.
 // (implicitly performs tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -191,6 +203,18 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_i8(int M, int N, int a_s
   d |= 2u << 4;
   d |= (uint32_t)(a_signed ? 1 : 0) << 7;
   d |= (uint32_t)(b_signed ? 1 : 0) << 10;
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
+
+// Instruction descriptor for kind::f16 with bfloat16 operands and fp32 accumulation: c_format F32 (1) at [4,6);
+// a_format / b_format BF16 (1) at [7,10) / [10,13); K-major A and B; N>>3 at [17,23); M>>4 at [24,29).
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;
+  d |= 1u << 7;
+  d |= 1u << 10;
   d |= (uint32_t)(N >> 3) << 17;
   d |= (uint32_t)(M >> 4) << 24;
   return d;

@@ -17,6 +17,7 @@ c_vp = C.c_void_p
 
 QD_OP_GEMM, QD_OP_QUANTIZE, QD_OP_GROUPNORM, QD_OP_LAYERNORM, QD_OP_IM2COL, QD_OP_ATTENTION = 1, 2, 3, 4, 5, 6
 QD_OP_TIMESTEP_EMB, QD_OP_COPY2D, QD_OP_NCHW_TO_NHWC, QD_OP_NHWC_TO_NCHW, QD_OP_AVGPOOL2X, QD_OP_UPSAMPLE2X = 7, 8, 9, 10, 11, 12
+QD_OP_SPLIT3, QD_OP_ATTENTION_FP = 13, 14
 
 
 class QParams(C.Structure):
@@ -39,6 +40,7 @@ class GemmDesc(C.Structure):
         ("w_int4_packed", c_i32), ("reserved3", c_i32), ("w_zero", c_vp),
         ("scale_q", c_vp), ("bias_q", c_vp),
         ("gn_stats", c_vp), ("ld_stats", c_ll),
+        ("a_bf16", c_i32), ("reserved4", c_i32),
     ]
 
 
@@ -98,6 +100,20 @@ class AttentionDesc(C.Structure):
     ]
 
 
+class SplitDesc(C.Structure):
+    _fields_ = [("src", c_vp), ("ld_src", c_ll), ("dst", c_vp), ("ld_dst", c_ll),
+                ("M", c_i32), ("C", c_i32), ("Cp", c_i32), ("act", c_i32),
+                ("upsample2x", c_i32), ("B", c_i32), ("H", c_i32), ("W", c_i32)]
+
+
+class AttentionFpDesc(C.Structure):
+    _fields_ = [("q", c_vp), ("k", c_vp), ("v", c_vp), ("ld_q", c_ll), ("ld_k", c_ll), ("ld_v", c_ll),
+                ("B", c_i32), ("heads", c_i32), ("d", c_i32), ("Tq", c_i32), ("Tk", c_i32),
+                ("q_off", c_i32), ("k_off", c_i32), ("v_off", c_i32),
+                ("head_stride_q", c_i32), ("head_stride_k", c_i32), ("head_stride_v", c_i32),
+                ("scale", c_f), ("out", c_vp), ("ld_out", c_ll)]
+
+
 class MiscDesc(C.Structure):
     _fields_ = [("src", c_vp), ("dst", c_vp), ("ld_src", c_ll), ("ld_dst", c_ll),
                 ("a", c_i32), ("b", c_i32), ("c", c_i32), ("d", c_i32), ("aux", c_vp)]
@@ -115,7 +131,7 @@ class SamplerDesc(C.Structure):
 
 EXPORTS = [
     "qd_qgemm_i8", "qd_quantize", "qd_groupnorm_quant", "qd_groupnorm_workspace_floats", "qd_layernorm_quant",
-    "qd_im2col_i8", "qd_qattention", "qd_timestep_embedding", "qd_copy2d", "qd_nchw_to_nhwc", "qd_nhwc_to_nchw", "qd_avgpool2x", "qd_upsample2x_f32",
+    "qd_im2col_i8", "qd_qattention", "qd_split_bf16x3", "qd_attention_fp32", "qd_lincomb3", "qd_timestep_embedding", "qd_copy2d", "qd_nchw_to_nhwc", "qd_nhwc_to_nchw", "qd_avgpool2x", "qd_upsample2x_f32",
     "qd_sampler_step", "qd_engine_create", "qd_engine_add_op", "qd_engine_num_ops", "qd_engine_finalize",
     "qd_engine_run", "qd_engine_run_range", "qd_engine_destroy", "qd_last_error", "qd_num_sms", "qd_launch_count",
 ]
@@ -138,10 +154,11 @@ def lib():
     L.qd_last_error.restype = C.c_char_p
     L.qd_launch_count.restype = c_ll
     for name in ("qd_qgemm_i8", "qd_quantize", "qd_groupnorm_quant", "qd_layernorm_quant", "qd_im2col_i8",
-                 "qd_qattention", "qd_sampler_step"):
+                 "qd_qattention", "qd_sampler_step", "qd_split_bf16x3", "qd_attention_fp32"):
         getattr(L, name).argtypes = [c_vp, c_vp]
         getattr(L, name).restype = C.c_int
     L.qd_timestep_embedding.argtypes = [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]
+    L.qd_lincomb3.argtypes = [c_vp, c_f, c_vp, c_f, c_vp, c_f, c_vp, c_ll, c_vp]
     L.qd_copy2d.argtypes = [c_vp, c_ll, c_vp, c_ll, c_i32, c_i32, c_vp]
     L.qd_nchw_to_nhwc.argtypes = [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]
     L.qd_nhwc_to_nchw.argtypes = [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]

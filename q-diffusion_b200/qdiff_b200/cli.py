@@ -323,8 +323,9 @@ def run_ldm(args):
     from . import dist as qdist, samplers, unet
     _require_resume(args)
     rank, world, dev = _setup(args.seed)
-    if args.vanilla_sample or args.dpm:
-        raise SystemExit("the engine implements DDIM sampling for this script (vanilla DDPM / DPM-Solver: SURVEY section 8 f3)")
+    if args.vanilla_sample:
+        raise SystemExit("the engine implements DDIM (default) and DPM-Solver++ (--dpm) sampling for this script, not the "
+                         "1000-step ancestral DDPM loop")
     if args.b200_synthetic:
         qnn, spec = _synthetic(args, "ldm")
         ch, size = spec["in_shape"][0], spec["in_shape"][1]
@@ -337,7 +338,8 @@ def run_ldm(args):
         ch, size = cfg["channels"], cfg["image_size"]
         sched = dict(timesteps=cfg.get("timesteps", 1000), linear_start=cfg.get("linear_start", 1e-4),
                      linear_end=cfg.get("linear_end", 2e-2))
-    sampler = samplers.DDIMSampler(qnn, samplers.Schedule("linear", sched["timesteps"], sched["linear_start"], sched["linear_end"]))
+    schedule = samplers.Schedule("linear", sched["timesteps"], sched["linear_start"], sched["linear_end"])
+    sampler = (samplers.DPMSolverSampler if args.dpm else samplers.DDIMSampler)(qnn, schedule)
     per = _shard(args.batch_size, world)
     outs, t0, r = [], time.time(), 0
     while sum(o.shape[0] for o in outs) < args.n_samples:
@@ -347,8 +349,11 @@ def run_ldm(args):
 
         def noise_fn(i, shape, d_, gen=gen, lo=lo):
             return torch.randn(args.batch_size, ch, size, size, generator=gen)[lo:lo + per].to(d_)
-        z, _ = sampler.sample(S=args.custom_steps, batch_size=per, shape=(ch, size, size), eta=args.eta, x_T=x_T,
-                              noise_fn=noise_fn)
+        if args.dpm:      # convsample_dpm (sample_diffusion_ldm.py:96-103): deterministic, eta is not used
+            z, _ = sampler.sample(S=args.custom_steps, batch_size=per, shape=(ch, size, size), x_T=x_T)
+        else:
+            z, _ = sampler.sample(S=args.custom_steps, batch_size=per, shape=(ch, size, size), eta=args.eta, x_T=x_T,
+                                  noise_fn=noise_fn)
         outs.append(qdist.gather_latents(z, world))
         r += 1
     z = torch.cat(outs)[:args.n_samples]

@@ -1031,6 +1031,233 @@ class Builder:
         return x_in, t_in, None, out
 
 
+# ====================================================================== weight-only lowering (quant_act False)
+class WeightOnlyBuilder(Builder):
+    """set_quant_state(True, False): quantised weights, fp32 activations (BASELINE configs[0], qdiff/utils.py:407).
+
+    Every QuantModule becomes  y = delta_w[n] * sum_k x[m,k] * ws[n,k] + bias  with the fp32 activation split into three
+    bfloat16 planes (qd_split_bf16x3) and the integer weight codes held exactly in bfloat16: a tcgen05 kind::f16
+    contraction with fp32 accumulation, i.e. the reference's fp32 conv up to summation order.  Norms emit fp32 (+SiLU),
+    attention runs in fp32 (qd_attention_fp32).  Families: ddim (CIFAR) and LDM UNets without SpatialTransformer."""
+
+    def split3(self, src, label, act=0, upsample=None):
+        C_ = src.cols
+        Cp = (C_ + 15) // 16 * 16
+        rows = src.rows * (4 if upsample is not None else 1)
+        t = torch.zeros((rows, 3 * Cp), dtype=torch.bfloat16, device=self.dev)
+        self.keep.append(t)
+        a = Act(t, rows, 3 * Cp)
+        a.bf16, a.C, a.Cp = True, C_, Cp
+        d = ops.split_desc(src.t, t, M=src.rows, C_=C_, Cp=Cp, ld_src=src.ld, act=act, upsample=upsample)
+        d.src = src.ptr
+        self.add(_lib.QD_OP_SPLIT3, d, label, spec=dict(kind="split3", src=src, dst=a, act=act, upsample=upsample, C=C_, Cp=Cp))
+        return a
+
+    def gemm_wo(self, qm, a, label, *, conv_bhw=None, rowvec=None, residual=None, out=None, rows_per_batch=0, cols=None,
+                suffix="", accumulate_into=None, use_bias=True, im2col=None):
+        """One weight-only GEMM.  a: bfloat16 plane Act from split3.  im2col = (hw, stride, pad_tl, out_hw): explicit patch
+        gather first (strided convs, conv_in)."""
+        cols = tuple(cols) if cols is not None else None
+        key = (self.dev.index or 0, "wo", label, cols, suffix, conv_bhw is not None or im2col is not None)
+        ent = self.wcache.get(key)
+        if ent is None or (self.want_specs and "ws_cpu" not in ent):
+            ws, delta_w = self._fold(qm, cols, suffix)
+            N = ws.shape[0]
+            taps = 9 if (ws.dim() == 4 and ws.shape[-1] == 3) else 1
+            w3 = ws.reshape(N, ws.shape[1], taps).permute(0, 2, 1)                  # [N, taps, C]
+            Np = (N + 3) // 4 * 4          # the specialised epilogues store 4 columns at a time: pad conv_out (3 channels)
+            wk = torch.zeros((Np, taps, 3, a.Cp), dtype=torch.bfloat16, device=self.dev)
+            wk[:N, :, :, :ws.shape[1]] = w3.to(torch.bfloat16)[:, :, None, :]
+            dw = torch.ones(Np, dtype=torch.float32, device=self.dev)
+            dw[:N] = delta_w.to(torch.float32)
+            ent = dict(w_dev=wk.reshape(Np, -1).contiguous(), delta_w=dw, N=Np, N_real=N, taps=taps)
+            if self.want_specs:
+                wpad = torch.zeros((Np,) + tuple(ws.shape[1:]), dtype=torch.float32)
+                wpad[:N] = ws.detach().to("cpu", torch.float32)
+                ent["ws_cpu"] = wpad
+            self.wcache[key] = ent
+        N, taps, w_dev, scale = ent["N"], ent["taps"], ent["w_dev"], ent["delta_w"]
+        self.keep += [w_dev, scale]
+        bias = None
+        if use_bias and qm.bias is not None:
+            bias = torch.zeros(N, dtype=torch.float32, device=self.dev)
+            bias[:ent["N_real"]] = qm.bias.detach().to(self.dev, torch.float32)
+            self.keep.append(bias)
+        cbytes = 6 * a.Cp
+        src_act = a
+        if im2col is not None:
+            (H, W), stride, pad_tl, (Ho, Wo) = im2col
+            patches = torch.zeros((self.B * Ho * Wo, 9 * cbytes), dtype=torch.uint8, device=self.dev)
+            self.keep.append(patches)
+            di = ops.im2col_desc(a.t, patches, B=self.B, H=H, W=W, C_=cbytes, Ho=Ho, Wo=Wo, stride=stride,
+                                 pad_top=pad_tl[0], pad_left=pad_tl[1], pad_code=0, ld_dst=9 * cbytes)
+            pa = Act(patches, self.B * Ho * Wo, 9 * cbytes)
+            pa.bf16, pa.C, pa.Cp = True, a.C, a.Cp
+            self.add(_lib.QD_OP_IM2COL, di, label + ".im2col",
+                     spec=dict(kind="im2col_bytes", src=a, dst=pa, B=self.B, H=H, W=W, Ho=Ho, Wo=Wo, stride=stride,
+                               pad_tl=pad_tl, cbytes=cbytes))
+            src_act, gemm_taps, gemm_c, conv_bhw = pa, 1, 9 * cbytes, None
+        elif taps == 9:
+            gemm_taps, gemm_c = 9, cbytes
+        else:
+            gemm_taps, gemm_c = 1, cbytes
+        M = src_act.rows
+        o = accumulate_into if accumulate_into is not None else (out if out is not None else self.new_f32(M, N))
+        res = accumulate_into if accumulate_into is not None else residual
+        d = ops.gemm_desc(src_act.t, w_dev, scale, M=M, N=N, C=gemm_c, taps=gemm_taps, lda=src_act.ld * src_act.t.element_size(),
+                          conv_bhw=conv_bhw, a_signed=False, bias=bias,
+                          rowvec=rowvec.t if rowvec is not None else None, ld_rowvec=rowvec.ld if rowvec is not None else 0,
+                          rows_per_batch=rows_per_batch, residual=res.t if res is not None else None,
+                          ldr=res.ld if res is not None else 0, out=o.t, ldo=o.ld)
+        d.a_bf16 = 1
+        d.a = src_act.ptr
+        if rowvec is not None:
+            d.rowvec = rowvec.ptr
+        if res is not None:
+            d.residual = res.ptr
+        d.out = o.ptr
+        spec = None
+        if self.want_specs:
+            spec = dict(kind="gemm_wo", key=self.key(qm) if id(qm) in self.names else self.key(qm.qm), a=src_act, Cp=a.Cp,
+                        C=a.C, taps=9 if (taps == 9) else 1, im2col=im2col is not None, conv_bhw=conv_bhw, ws=ent["ws_cpu"],
+                        scale=scale.detach().cpu(), bias=None if bias is None else bias.detach().cpu(), rowvec=rowvec,
+                        residual=res, rows_per_batch=rows_per_batch, out=o, N=N)
+        self.add(_lib.QD_OP_GEMM, d, label, flops=2 * M * N * (gemm_c // 6) * gemm_taps, spec=spec)
+        self.layer_traces[label] = o
+        return o
+
+    def lin(self, qm, x_f32, label, act=0, **kw):
+        return self.gemm_wo(qm, self.split3(x_f32, label + ".split", act=act), label, **kw)
+
+    def gn_f32(self, x, norm, hw, silu, label, ss=None, ss_src=None):
+        _, out_f = self.groupnorm(x, norm, hw, [], silu, label, ss=ss, want_f32=True, ss_src=ss_src)
+        return out_f
+
+    def attention_fp(self, q, k, v, *, heads, d, Tq, Tk, q_layout, k_layout, v_layout, scale, label):
+        out = self.new_f32(self.B * Tq, heads * d)
+        a = _lib.AttentionFpDesc()
+        a.q, a.k, a.v = q.ptr, k.ptr, v.ptr
+        a.ld_q, a.ld_k, a.ld_v = q.ld, k.ld, v.ld
+        a.B, a.heads, a.d, a.Tq, a.Tk = self.B, heads, d, Tq, Tk
+        a.q_off, a.head_stride_q = q_layout
+        a.k_off, a.head_stride_k = k_layout
+        a.v_off, a.head_stride_v = v_layout
+        a.scale = float(scale)
+        a.out, a.ld_out = out.ptr, out.ld
+        self.add(_lib.QD_OP_ATTENTION_FP, a, label, flops=4 * self.B * heads * Tq * Tk * d,
+                 spec=dict(kind="attention_fp", q=q, k=k, v=v, B=self.B, heads=heads, d=d, Tq=Tq, Tk=Tk, q_layout=q_layout,
+                           k_layout=k_layout, v_layout=v_layout, scale=float(scale), out=out))
+        return out
+
+    # ------------------------------------------------------------------ shortcut convs (with or without split)
+    def shortcut(self, qm, x, label, split):
+        if split:
+            if qm.split == 0:
+                raise RuntimeError(f"{label}: split is set but the checkpoint has no split quantizers")
+            s = self.gemm_wo(qm, self.split3(x.view(0, split), label + ".split0"), label + ".half0", cols=(0, split))
+            self.gemm_wo(qm, self.split3(x.view(split, x.cols - split), label + ".split1"), label, cols=(split, x.cols),
+                         suffix="_0", accumulate_into=s, use_bias=False)
+            return s
+        return self.lin(qm, x, label)
+
+    # ================================================================== DDIM (CIFAR) family
+    def ddim_resnet(self, blk, x, temb, hw, split):
+        """QuantResnetBlock.forward (qdiff/quant_block.py:307-330) with use_act_quant False."""
+        k = self.key(blk)
+        H, W = hw
+        h1 = self.gn_f32(x, blk.norm1, H * W, True, k + ".norm1")
+        tp = self.lin(blk.temb_proj, temb, k + ".temb_proj", act=1)
+        h = self.gemm_wo(blk.conv1, self.split3(h1, k + ".conv1.split"), k + ".conv1", conv_bhw=(self.B, H, W),
+                         rows_per_batch=H * W, rowvec=tp)
+        h2 = self.gn_f32(h, blk.norm2, H * W, True, k + ".norm2")
+        s = x
+        if blk.in_channels != blk.out_channels:
+            if getattr(blk, "use_conv_shortcut", False):
+                raise NotImplementedError("conv_shortcut=True is not used by the reference configs")
+            s = self.shortcut(blk.nin_shortcut, x, k + ".nin_shortcut", split)
+        return self.gemm_wo(blk.conv2, self.split3(h2, k + ".conv2.split"), k + ".conv2", conv_bhw=(self.B, H, W),
+                            rows_per_batch=H * W, residual=s)
+
+    def ddim_attn(self, blk, x, hw):
+        """QuantAttnBlock.forward (qdiff/quant_block.py:354-386) with use_act_quant False: plain fp32 attention."""
+        k = self.key(blk)
+        T = hw[0] * hw[1]
+        C_ = x.cols
+        hn = self.gn_f32(x, blk.norm, T, False, k + ".norm")
+        a = self.split3(hn, k + ".qkv.split")
+        q = self.gemm_wo(blk.q, a, k + ".q")
+        kk = self.gemm_wo(blk.k, a, k + ".k")
+        v = self.gemm_wo(blk.v, a, k + ".v")
+        o = self.attention_fp(q, kk, v, heads=1, d=C_, Tq=T, Tk=T, q_layout=(0, C_), k_layout=(0, C_), v_layout=(0, C_),
+                              scale=float(int(C_) ** (-0.5)), label=k + ".attn")
+        return self.lin(blk.proj_out, o, k + ".proj_out", residual=x)
+
+    def lower_ddim(self, model, x_shape):
+        B, Cin, H, W = x_shape
+        x_in = torch.zeros(x_shape, dtype=torch.float32, device=self.dev)
+        t_in = torch.zeros(B, dtype=torch.float32, device=self.dev)
+        self.keep += [x_in, t_in]
+        split_on = bool(getattr(model.config, "split_shortcut", False))
+        temb0 = self.new_f32(B, model.ch)
+        self.misc(_lib.QD_OP_TIMESTEP_EMB, t_in.data_ptr(), temb0.ptr, B, model.ch, 1, label="timestep_embedding",
+                  aux=ops.timestep_freqs(model.ch, 1).to(self.dev), spec=dict(kind="timestep_emb", t=t_in, dst=temb0, mode=1))
+        e = self.lin(model.temb.dense[0], temb0, "temb.dense.0")
+        temb = self.lin(model.temb.dense[1], e, "temb.dense.1", act=1)
+        xh = self.new_f32(B * H * W, Cin)
+        self.misc(_lib.QD_OP_NCHW_TO_NHWC, x_in.data_ptr(), xh.ptr, B, Cin, H * W, label="x.nhwc",
+                  spec=dict(kind="nchw_to_nhwc", src=x_in, dst=xh))
+        hw = (H, W)
+        h = self.gemm_wo(model.conv_in, self.split3(xh, "conv_in.split"), "conv_in", im2col=(hw, 1, (1, 1), hw))
+        hs = [(h, hw)]
+        nres = model.num_resolutions
+        for lv in range(nres):
+            st = model.down[lv]
+            for ib in range(model.num_res_blocks):
+                h = self.ddim_resnet(st.block[ib], hs[-1][0], temb, hw, 0)
+                if len(st.attn) > 0:
+                    h = self.ddim_attn(st.attn[ib], h, hw)
+                hs.append((h, hw))
+            if lv != nres - 1:
+                conv = st.downsample.conv
+                ohw = (hw[0] // 2, hw[1] // 2)
+                # F.pad (0,1,0,1) then 3x3 stride 2, padding 0 (ddim/models/diffusion.py:67-71)
+                h = self.gemm_wo(conv, self.split3(hs[-1][0], self.key(conv) + ".split"), self.key(conv),
+                                 im2col=(hw, 2, (0, 0), ohw))
+                hw = ohw
+                hs.append((h, hw))
+        h = hs[-1][0]
+        h = self.ddim_resnet(model.mid.block_1, h, temb, hw, 0)
+        h = self.ddim_attn(model.mid.attn_1, h, hw)
+        h = self.ddim_resnet(model.mid.block_2, h, temb, hw, 0)
+        self.traces["mid"] = (h, hw)
+        for lv in reversed(range(nres)):
+            st = model.up[lv]
+            for ib in range(model.num_res_blocks + 1):
+                split = h.cols if (lv < 4 and split_on) else 0
+                skip_t, _ = hs.pop()
+                cat = self.concat(h, skip_t, f"up.{lv}.block.{ib}")
+                h = self.ddim_resnet(st.block[ib], cat, temb, hw, split)
+                if len(st.attn) > 0:
+                    h = self.ddim_attn(st.attn[ib], h, hw)
+            if lv != 0:
+                conv = st.upsample.conv
+                a = self.split3(h, self.key(conv) + ".split", upsample=(B, hw[0], hw[1]))
+                hw = (2 * hw[0], 2 * hw[1])
+                h = self.gemm_wo(conv, a, self.key(conv), conv_bhw=(B, hw[0], hw[1]), rows_per_batch=hw[0] * hw[1])
+        hn = self.gn_f32(h, model.norm_out, hw[0] * hw[1], True, "norm_out")
+        o = self.gemm_wo(model.conv_out, self.split3(hn, "conv_out.split"), "conv_out", conv_bhw=(B, hw[0], hw[1]),
+                         rows_per_batch=hw[0] * hw[1])
+        out = torch.zeros((B, o.cols, hw[0], hw[1]), dtype=torch.float32, device=self.dev)   # o.cols: out_ch padded to 4
+        self.keep.append(out)
+        self.misc(_lib.QD_OP_NHWC_TO_NCHW, o.ptr, out.data_ptr(), B, o.cols, hw[0] * hw[1], label="eps.nchw",
+                  spec=dict(kind="nhwc_to_nchw", src=o, dst=out))
+        return x_in, t_in, None, out[:, :int(model.conv_out.weight.shape[0])]
+
+    def lower_ldm(self, model, x_shape, ctx_shape):
+        raise NotImplementedError("weight-only sampling is lowered for the DDIM (CIFAR) family (BASELINE configs[0]); the "
+                                  "LDM / Stable Diffusion UNets run with --quant_act (W4A8 / W8A8) on this engine")
+
+
 class _RowView:
     """A QuantModule restricted to a subset of its output rows (regrouping the fused qkv conv)."""
 
@@ -1071,11 +1298,14 @@ def compile_unet(qnn, x_shape, ctx_shape, device, use_cuda_graph=True):
     if not torch.cuda.is_available():
         raise RuntimeError("qdiff_b200: no CUDA device; the engine has no CPU fallback")
     states = {(m.use_weight_quant, m.use_act_quant) for m in qnn.model.modules() if _name(m) == "QuantModule"}
-    if states != {(True, True)}:
+    if states == {(True, True)}:
+        b = Builder(qnn, device, x_shape[0])
+    elif states == {(True, False)}:
+        b = WeightOnlyBuilder(qnn, device, x_shape[0])      # quant_act False: fp32 activations, integer weights
+    else:
         raise NotImplementedError(
-            f"engine realises set_quant_state(True, True) (W4A8-style) only; got states {states}. "
-            "Weight-only sampling (cfg 1) is the next hot-path row.")
-    b = Builder(qnn, device, x_shape[0])
+            f"the engine realises set_quant_state(True, True) and (True, False); got states {states}. The full-precision "
+            "state (False, False) is the reference's own path (calibration data / FP baselines).")
     model = qnn.model
     with torch.no_grad():
         if _name(model) == "UNetModel":

@@ -8,8 +8,8 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (AttentionDesc, GemmDesc, GroupNormDesc, Im2colDesc, LayerNormDesc, MiscDesc, QParams,
-                   QuantizeDesc, SamplerDesc, check, lib, ptr, stream_ptr)
+from ._lib import (AttentionDesc, AttentionFpDesc, GemmDesc, GroupNormDesc, Im2colDesc, LayerNormDesc, MiscDesc, QParams,
+                   QuantizeDesc, SamplerDesc, SplitDesc, check, lib, ptr, stream_ptr)
 
 
 def qparams(delta, zero_point, qmin, qmax):
@@ -169,12 +169,36 @@ def im2col(desc):
     check(lib().qd_im2col_i8(C.byref(desc), stream_ptr()), "qd_im2col_i8")
 
 
+def split_desc(src, dst, *, M, C_, Cp, ld_src, act=0, upsample=None):
+    """fp32 [M, C] -> bfloat16 [M, 3, Cp] planes (weight-only operands, qd_split_bf16x3)."""
+    d = SplitDesc()
+    d.src, d.ld_src, d.dst, d.ld_dst = ptr(src), int(ld_src), ptr(dst), 3 * int(Cp)
+    d.M, d.C, d.Cp, d.act = int(M), int(C_), int(Cp), int(act)
+    if upsample is not None:
+        d.upsample2x = 1
+        d.B, d.H, d.W = [int(v) for v in upsample]
+    return d
+
+
+def split_bf16x3(desc):
+    check(lib().qd_split_bf16x3(C.byref(desc), stream_ptr()), "qd_split_bf16x3")
+
+
+def attention_fp32(desc):
+    check(lib().qd_attention_fp32(C.byref(desc), stream_ptr()), "qd_attention_fp32")
+
+
 def attention(desc):
     check(lib().qd_qattention(C.byref(desc), stream_ptr()), "qd_qattention")
 
 
 def sampler_step(desc):
     check(lib().qd_sampler_step(C.byref(desc), stream_ptr()), "qd_sampler_step")
+
+
+def lincomb3(out, a, x, b=0.0, y=None, c=0.0, z=None):
+    check(lib().qd_lincomb3(ptr(out), float(a), ptr(x), float(b), ptr(y), float(c), ptr(z), x.numel(), stream_ptr()),
+          "qd_lincomb3")
 
 
 def timestep_freqs(dim, mode):

@@ -179,6 +179,90 @@ class PLMSSampler(_LatentSampler):
         return img, {}
 
 
+class DPMSolverSampler(_LatentSampler):
+    """DPMSolverSampler.sample (ldm/models/diffusion/dpm_solver/sampler.py:24-82; `--dpm` of sample_diffusion_ldm.py):
+    DPM-Solver++ with data prediction, multistep order 2, uniform time steps, lower-order final steps for S < 15
+    (dpm_solver.py:386-399, 504-527, 755-795, 1077-1105).  Per step: one UNet replay, one fused kernel that turns the
+    (guided) eps into the data prediction x0 (qd_sampler_step: CFG combine + (x - sigma eps) / alpha), one 3-term linear
+    combination kernel for the update.  The UNet receives the solver's fractional timesteps (t - 1/N) * 1000."""
+
+    def _schedule(self, dev):
+        ac = self.schedule.alphas_cumprod.to(torch.float32)
+        self._log_alpha = 0.5 * torch.log(ac)
+        self._N = ac.shape[0]
+        self._t_array = torch.linspace(0., 1., self._N + 1)[1:]
+
+    def _lm(self, t):                  # marginal_log_mean_coeff: piecewise linear in t (interpolate_fn)
+        t = torch.as_tensor(t, dtype=torch.float32).reshape(1)
+        idx = torch.searchsorted(self._t_array, t).clamp(1, self._N - 1)
+        x0, x1 = self._t_array[idx - 1], self._t_array[idx]
+        y0, y1 = self._log_alpha[idx - 1], self._log_alpha[idx]
+        return (y0 + (t - x0) * (y1 - y0) / (x1 - x0))[0]
+
+    def _alpha_sigma_lambda(self, t):
+        lm = self._lm(t)
+        sg = torch.sqrt(1. - torch.exp(2. * lm))
+        return torch.exp(lm), sg, lm - 0.5 * torch.log(1. - torch.exp(2. * lm))
+
+    @torch.no_grad()
+    def sample(self, S, batch_size, shape, conditioning=None, x_T=None, unconditional_guidance_scale=1.,
+               unconditional_conditioning=None, verbose=False, **kwargs):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self._schedule(dev)
+        size = (batch_size,) + tuple(shape)
+        x = torch.randn(size, device=dev) if x_T is None else x_T.to(dev, torch.float32).clone()
+        nxt, scratch = torch.empty_like(x), torch.empty_like(x)
+        ts = torch.linspace(1., 1. / self._N, S + 1)
+        uc, sc = unconditional_conditioning, unconditional_guidance_scale
+
+        def data_pred(x, t, out):
+            a, sg, _ = self._alpha_sigma_lambda(t)
+            t_in = torch.full((batch_size,), float((t - 1. / self._N) * 1000.), device=dev, dtype=torch.float32)
+            eps, s = self._model_eps(x, t_in, conditioning, uc, sc)
+            # x0 = (x - sigma_t eps) / alpha_t through the fused kernel (alphas_cumprod notation: sqrt_at = alpha_t)
+            _step(x, eps, scratch, a_t=float(a) ** 2, a_prev=1.0, sigma=0.0, sqrt_one_minus_at=float(sg), cfg_scale=s,
+                  pred_x0=out)
+            return out
+
+        def first(x, s_, t, m, out):
+            a_t, sg_t, l_t = self._alpha_sigma_lambda(t)
+            _, sg_s, l_s = self._alpha_sigma_lambda(s_)
+            h = l_t - l_s
+            ops.lincomb3(out, float(sg_t / sg_s), x, float(-(a_t * torch.expm1(-h))), m)
+
+        def second(x, m1, m0, t1, t0, t, out):
+            a_t, sg_t, l_t = self._alpha_sigma_lambda(t)
+            _, sg_0, l_0 = self._alpha_sigma_lambda(t0)
+            _, _, l_1 = self._alpha_sigma_lambda(t1)
+            h_0, h = l_0 - l_1, l_t - l_0
+            r0 = h_0 / h
+            k = a_t * (torch.exp(-h) - 1.)
+            # x_t = (sg_t/sg_0) x - k m0 - 0.5 k (m0 - m1) / r0
+            ops.lincomb3(out, float(sg_t / sg_0), x, float(-k - 0.5 * k / r0), m0, float(0.5 * k / r0), m1)
+
+        bufs = [torch.empty_like(x), torch.empty_like(x)]
+        ms, tt = [data_pred(x, ts[0], bufs[0])], [ts[0]]
+        first(x, tt[-1], ts[1], ms[-1], nxt)
+        x, nxt = nxt, x
+        ms.append(data_pred(x, ts[1], bufs[1]))
+        tt.append(ts[1])
+        for step in range(2, S + 1):
+            t = ts[step]
+            order = min(2, S + 1 - step) if S < 15 else 2
+            if order == 1:
+                first(x, tt[-1], t, ms[-1], nxt)
+            else:
+                second(x, ms[0], ms[1], tt[0], tt[1], t, nxt)
+            x, nxt = nxt, x
+            ms[0], ms[1] = ms[1], ms[0]          # the older prediction's buffer is recycled for the next one
+            tt[0], tt[1] = tt[1], t
+            if step < S:
+                data_pred(x, t, ms[1])
+            else:
+                ms[1] = ms[0]
+        return x, None
+
+
 @torch.no_grad()
 def generalized_steps(x, seq, model, b, eta=0.0, noise_fn=None):
     """DDIM loop of the CIFAR script (ddim/functions/denoising.py:10-32).  x: [n,C,H,W] on CUDA, seq: list of

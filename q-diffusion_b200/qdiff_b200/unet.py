@@ -149,6 +149,14 @@ class UNetModel(_NoForward):
                  use_scale_shift_norm=False, resblock_updown=False, use_new_attention_order=False,
                  use_spatial_transformer=False, transformer_depth=1, context_dim=None, n_embed=None, legacy=True):
         super().__init__()
+        # constructor arguments, recorded for the engine-native checkpoint (qdiff_b200/packed.py)
+        self._ctor = dict(image_size=image_size, in_channels=in_channels, model_channels=model_channels,
+                          out_channels=out_channels, num_res_blocks=num_res_blocks,
+                          attention_resolutions=list(attention_resolutions), channel_mult=list(channel_mult),
+                          num_heads=num_heads, num_head_channels=num_head_channels, num_heads_upsample=num_heads_upsample,
+                          use_scale_shift_norm=use_scale_shift_norm, resblock_updown=resblock_updown,
+                          use_spatial_transformer=use_spatial_transformer, transformer_depth=transformer_depth,
+                          context_dim=context_dim, legacy=legacy)
         if dims != 2 or num_classes is not None or n_embed is not None or use_new_attention_order:
             raise NotImplementedError("qdiff_b200.UNetModel: only the 2-D, unconditional-label, legacy-attention-order "
                                       "variants used by the reference's configs are realised")

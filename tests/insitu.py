@@ -99,7 +99,8 @@ def _cmp_f32(rep, idx, label, kind, got, ref, tol, what="fp32"):
 
 
 # ----------------------------------------------------------------------------------------------- snapshots
-_INPUTS = {"quantize": ["src"], "groupnorm": ["x"], "layernorm": ["x"], "gemm": ["a", "rowvec", "residual"],
+_INPUTS = {"split3": ["src"], "gemm_wo": ["rowvec", "residual"], "attention_fp": ["q", "k", "v"],
+           "quantize": ["src"], "groupnorm": ["x"], "layernorm": ["x"], "gemm": ["a", "rowvec", "residual"],
            "attention": ["q", "k", "vt"], "im2col": ["src"], "copy2d": ["src"], "upsample2x": ["src"],
            "avgpool2x": ["src"], "nhwc_to_nchw": ["src"]}
 
@@ -111,6 +112,9 @@ def snapshot(spec):
         a = spec.get(name)
         if a is not None:
             pre[name] = rd_codes(a) if a.signed is not None else rd_f32(a)
+    if spec["kind"] in ("gemm_wo", "im2col_bytes"):        # bfloat16 planes (or gathered patches of them), raw
+        a = spec["a"] if spec["kind"] == "gemm_wo" else spec["src"]
+        pre["a_raw"] = a.t.detach().cpu()
     if spec["kind"] == "groupnorm" and spec.get("ss") is not None:
         pre["ss"] = rd_f32(spec["ss"][0])
     if spec["kind"] == "timestep_emb":
@@ -327,7 +331,95 @@ def check_misc(rep, i, label, s, pre):
         rep.add(i, label, k, "unchecked", 0, 0, 0.0, False, note="op kind without an in-situ check")
 
 
-CHECKS = {"quantize": check_quantize, "groupnorm": check_groupnorm, "layernorm": check_layernorm, "im2col": check_im2col,
+def _planes_to_f64(t, Cp, C):
+    """bfloat16 [rows, 3*Cp] planes -> float64 [rows, C] (exact sum hi + mid + lo)."""
+    p = t.to(torch.float64).reshape(t.shape[0], 3, Cp)
+    return p.sum(dim=1)[:, :C]
+
+
+def check_split3(rep, i, label, s, pre):
+    x = pre["src"].to(torch.float32)
+    if s["act"] == 1:
+        x = O.silu(x)
+    if s["upsample"] is not None:
+        B, H, W = s["upsample"]
+        x = x.reshape(B, H, W, -1).repeat_interleave(2, dim=1).repeat_interleave(2, dim=2).reshape(-1, x.shape[1])
+    got = _planes_to_f64(s["dst"].t.detach().cpu(), s["Cp"], s["C"])
+    ref = x.double()
+    tol = (2e-7 if s["act"] == 0 else 4e-6) * ref.abs() + 1e-30       # 3 planes carry 24 bits; SiLU adds expf rounding
+    _cmp_f32(rep, i, label, "split3", got, ref, tol + 1e-12)
+
+
+def check_im2col_bytes(rep, i, label, s, pre):
+    B, H, W, Ho, Wo, cb = s["B"], s["H"], s["W"], s["Ho"], s["Wo"], s["cbytes"]
+    src = pre["a_raw"].view(torch.uint8).reshape(B, H, W, cb).to(torch.int64)
+    pt, pl = s["pad_tl"]
+    xp = torch.zeros((B, H + 3, W + 3, cb), dtype=torch.int64)
+    xp[:, pt:pt + H, pl:pl + W] = src
+    st = s["stride"]
+    ref = torch.zeros(B, Ho, Wo, 9 * cb, dtype=torch.int64)
+    for ky in range(3):
+        for kx in range(3):
+            ref[..., (ky * 3 + kx) * cb:(ky * 3 + kx + 1) * cb] = xp[:, ky:ky + st * Ho:st, kx:kx + st * Wo:st][:, :Ho, :Wo]
+    got = s["dst"].t.detach().cpu().to(torch.int64)
+    _cmp_codes(rep, i, label, "im2col", got, ref.reshape(-1, 9 * cb), exact=True)
+
+
+def check_gemm_wo(rep, i, label, s, pre):
+    N, Cp, C = s["N"], s["Cp"], s["C"]
+    ws = s["ws"].double()
+    raw = pre["a_raw"]
+    if s["im2col"]:                                   # patches: [rows, 9 taps x (3 planes x Cp) bf16]
+        a = raw.view(torch.bfloat16).reshape(raw.shape[0], 9, 3, Cp).to(torch.float64).sum(dim=2)[:, :, :C]      # [rows, 9, C]
+        w2 = ws.reshape(N, C, 9).permute(0, 2, 1)                                                               # [N, 9, C]
+        acc = torch.einsum("mtc,ntc->mn", a, w2)
+    else:
+        x = _planes_to_f64(raw, Cp, C)
+        M = x.shape[0]
+        if s["taps"] == 9:
+            B, H, W = s["conv_bhw"]
+            acc = F.conv2d(x.reshape(B, H, W, C).permute(0, 3, 1, 2), ws, None, stride=1, padding=1).permute(0, 2, 3, 1).reshape(M, N)
+        else:
+            acc = x @ ws.reshape(N, -1).t()
+    M = acc.shape[0]
+    t_main = acc * s["scale"].double()[None, :]
+    y, mag = t_main.clone(), t_main.abs()
+    # |acc| can hide cancellation: bound the fp32 accumulation error by the sum of |products| scale (coarse: use |x| |w|)
+    if s["bias"] is not None:
+        y += s["bias"].double()[None, :]
+        mag += s["bias"].double().abs()[None, :]
+    if s["rowvec"] is not None:
+        rv = pre["rowvec"][:, :N]
+        img = torch.arange(M) // s["rows_per_batch"]
+        y += rv[img]
+        mag += rv[img].abs()
+    if s["residual"] is not None:
+        r = pre["residual"][:, :N]
+        y += r
+        mag += r.abs()
+    got = rd_f32(s["out"])[:, :N]
+    # fp32 accumulation over K terms: tolerance relative to the output scale of the layer, not to each element
+    tol = 2e-5 * mag + 2e-5 * float(t_main.abs().max())
+    _cmp_f32(rep, i, label, "gemm_wo", got, y, tol, what="fp32acc")
+
+
+def check_attention_fp(rep, i, label, s, pre):
+    B, heads, d, Tq, Tk = s["B"], s["heads"], s["d"], s["Tq"], s["Tk"]
+    h = torch.arange(heads)[:, None]
+    c = torch.arange(d)[None, :]
+
+    def take(name, layout, T):
+        cols = (layout[0] + h * layout[1] + c).reshape(-1)
+        return pre[name][:, cols].reshape(B, T, heads, d).permute(0, 2, 1, 3)
+    q, k, v = take("q", s["q_layout"], Tq), take("k", s["k_layout"], Tk), take("v", s["v_layout"], Tk)
+    p = torch.softmax((torch.einsum("bhid,bhjd->bhij", q, k) * s["scale"]).to(torch.float32), dim=-1).double()
+    ref = torch.einsum("bhij,bhjd->bhid", p, v).permute(0, 2, 1, 3).reshape(B * Tq, heads * d)
+    got = rd_f32(s["out"])
+    _cmp_f32(rep, i, label, "attention", got, ref, 2e-5 * ref.abs() + 2e-5 * float(ref.abs().max()), what="fp32acc")
+
+
+CHECKS = {"split3": check_split3, "im2col_bytes": check_im2col_bytes, "gemm_wo": check_gemm_wo, "attention_fp": check_attention_fp,
+          "quantize": check_quantize, "groupnorm": check_groupnorm, "layernorm": check_layernorm, "im2col": check_im2col,
           "gemm": check_gemm, "attention": check_attention}
 
 

@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from tests import insitu
-from tests.test_oracle_golden import CASES, load_case
+from tests.test_oracle_golden import CASES, ORACLE_ONLY, load_case
 from tests.test_unet_gpu import build_qnn
 
 pytestmark = pytest.mark.gpu
@@ -41,7 +41,7 @@ def _run(name, qnn, x, t, ctx, cuda):
     return prog, rep
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + ORACLE_ONLY)      # ORACLE_ONLY: the weight-only fixture (BASELINE configs[0])
 def test_every_op_matches_oracle_on_golden_unets(cuda, name):
     g = load_case(name)
     qnn = build_qnn(g, cuda)
@@ -55,7 +55,7 @@ def test_every_op_matches_oracle_on_golden_unets(cuda, name):
     assert not fails, "\n".join(f"op {r['idx']} {r['kind']} {r['label']} {r['what']} bad={r['nbad']}/{r['n']} max={r['maxdiff']}"
                                 for r in fails[:20])
     # every QuantModule of the model is covered by at least one checked GEMM op
-    covered = {s["key"] for s in prog.op_specs if s["kind"] == "gemm"}
+    covered = {s["key"] for s in prog.op_specs if s["kind"] in ("gemm", "gemm_wo")}
     modules = {k for k, m in qnn.model.named_modules() if type(m).__name__ == "QuantModule"}
     assert modules <= covered, sorted(modules - covered)[:10]
 

@@ -10,8 +10,8 @@ from oracle import unet_oracle as U
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["ddim_w4a8_split", "ldm_legacy_w4a8", "ldm_updown_w4a8", "sd_tiny_w4a8_sm16", "ldm_updown_w8a8"]
-# BASELINE configs[0] (weight-only W8, the reference's own CPU-runnable case): the oracle is pinned against the
-# reference for it; the CUDA engine does not realise weight-only sampling yet
+# BASELINE configs[0] (weight-only W8, the reference's own CPU-runnable case): kept in a separate list because the name
+# says what it pins first - the oracle against the reference; the GPU tests run the engine's weight-only lowering on it too
 ORACLE_ONLY = ["ddim_w8_weightonly"]
 
 
@@ -115,3 +115,10 @@ def test_sampler_oracle_matches_reference_samplers():
                                noises=q2["noises"])
     err4 = (out4 - q2["out"]).abs().max().item()
     assert err4 <= 2e-5 * max(1.0, q2["out"].abs().max().item()), err4
+    # DPM-Solver++ (2M) as DPMSolverSampler drives it (--dpm): 6 steps (lower_order_final active) and 20 steps
+    dp = g["dpm"]
+    ac = S.ldm_schedule(1000, dp["linear_start"], dp["linear_end"])
+    for steps, ref in dp["out"].items():
+        out5 = S.dpm_solver_sample(lambda x, t, c: toy_eps(x, t, c), dp["x_T"], dp["cond"], dp["uc"], dp["scale"], ac, steps)
+        err5 = (out5 - ref).abs().max().item()
+        assert err5 <= 5e-5 * max(1.0, ref.abs().max().item()), (steps, err5)

@@ -46,7 +46,7 @@ class RecordingOracle:
 
     def __call__(self, x, t, c=None):
         gg = dict(self.g)
-        gg["x"], gg["t"], gg["context"] = x, t.long(), c
+        gg["x"], gg["t"], gg["context"] = x, (t if t.is_floating_point() else t.long()), c   # DPM-Solver feeds fractional t
         e = oracle_forward(gg, dtype=self.dtype).to(torch.float32 if self.dtype == torch.float32 else torch.float64)
         if self.record:
             self.calls.append((x.clone(), t.clone(), None if c is None else c.clone(), e.clone()))
@@ -60,7 +60,7 @@ def _teacher_forced(qnn, g, calls, cuda):
     for k, (x, t, c, e_ref) in enumerate(calls):
         e_eng = qnn(x.to(cuda), t.to(cuda), c.to(cuda) if c is not None else None).cpu()
         e_hi = hi(x.double(), t, c.double() if c is not None else None)
-        rows.append(dict(call=k, t=int(t[0]), mse=_mse(e_eng, e_ref), band=_mse(e_hi, e_ref), var=float(e_ref.double().var())))
+        rows.append(dict(call=k, t=float(t[0]), mse=_mse(e_eng, e_ref), band=_mse(e_hi, e_ref), var=float(e_ref.double().var())))
     return rows
 
 
@@ -68,7 +68,7 @@ def _report(name, rows, final):
     worst = max(r["mse"] for r in rows)
     print(f"\n[{name}] per-step eps MSE (teacher-forced, engine vs oracle) and fp32 noise band of the reference algorithm:")
     for r in rows:
-        print(f"   call {r['call']:2d} t={r['t']:4d}  mse {r['mse']:.3e}  band {r['band']:.3e}  (eps var {r['var']:.3e})"
+        print(f"   call {r['call']:2d} t={r['t']:7.2f}  mse {r['mse']:.3e}  band {r['band']:.3e}  (eps var {r['var']:.3e})"
               f"  north-star 1e-4 {'met' if r['mse'] <= 1e-4 else 'NOT met'}")
     print(f"   final latent: cosine {final['cos']:.6f} (band {final['cos_band']:.6f}), mse {final['mse']:.3e} "
           f"(band {final['mse_band']:.3e}), latent std {final['std']:.3f}; worst per-step eps mse {worst:.3e}")
@@ -218,3 +218,42 @@ def test_sampler_step_matches_oracle_update(cuda):
         S=6, batch_size=B, shape=shape, conditioning=cond.to(cuda), x_T=x, unconditional_guidance_scale=2.5,
         unconditional_conditioning=uc.to(cuda))
     assert (out2.cpu() - ref2).abs().max().item() <= 2e-5 * max(1.0, ref2.abs().max().item())
+
+
+@pytest.mark.parametrize("S", [6, 20])
+def test_dpm_solver_matches_oracle(cuda, S):
+    """DPM-Solver++ (2M) behind --dpm: engine sampler vs oracle/sampler_oracle.dpm_solver_sample (pinned to
+    the reference's DPMSolverSampler) around one shared eps-model, then around the quantised UNet with the band gate."""
+    from oracle import sampler_oracle as SO
+    from qdiff_b200 import samplers
+    from tools.make_sampler_golden import toy_eps
+    gen = torch.Generator().manual_seed(17)
+    B, shape = 2, (4, 16, 16)
+    ac = SO.ldm_schedule(1000, 0.00085, 0.0120)
+    x = torch.randn(B, *shape, generator=gen)
+    cond = torch.randn(B, 7, 64, generator=gen)
+    uc = torch.randn(1, 7, 64, generator=gen).expand(B, 7, 64).contiguous()
+
+    class Eng:
+        def __call__(self, xx, tt, cc=None):
+            return toy_eps(xx.cpu(), tt.cpu(), cc.cpu()).to(xx.device)
+
+    ref = SO.dpm_solver_sample(lambda a, t, c: toy_eps(a, t, c), x, cond, uc, 2.5, ac, S)
+    sched = samplers.Schedule("linear", 1000, 0.00085, 0.0120)
+    out, _ = samplers.DPMSolverSampler(Eng(), sched).sample(S=S, batch_size=B, shape=shape, conditioning=cond.to(cuda), x_T=x,
+                                                           unconditional_guidance_scale=2.5, unconditional_conditioning=uc.to(cuda))
+    assert (out.cpu() - ref).abs().max().item() <= 5e-5 * max(1.0, ref.abs().max().item())
+    if S != 6:
+        return
+    g = load_case("sd_tiny_w4a8_sm16")
+    qnn = build_qnn(g, cuda)
+    lo = RecordingOracle(g)
+    ref = SO.dpm_solver_sample(lo, x, cond, uc, 2.5, ac, S)
+    ref_hi = SO.dpm_solver_sample(RecordingOracle(g, torch.float64, record=False), x.double(), cond.double(), uc.double(), 2.5,
+                                  ac.double(), S).float()
+    out, _ = samplers.DPMSolverSampler(qnn, sched).sample(S=S, batch_size=B, shape=shape, conditioning=cond.to(cuda), x_T=x,
+                                                         unconditional_guidance_scale=2.5, unconditional_conditioning=uc.to(cuda))
+    rows = _teacher_forced(qnn, g, lo.calls, cuda)
+    final = _final(out.cpu(), ref, ref_hi)
+    _report("dpm_solver_sd_tiny_cfg2p5", rows, final)
+    _gate(rows, final)

@@ -89,6 +89,21 @@ def main():
     finally:
         ref_ddim.noise_like = real_noise_like
 
+    # DPM-Solver++ (2M) through the reference's DPMSolverSampler (--dpm); its register_buffer also forces "cuda"
+    from ldm.models.diffusion.dpm_solver import DPMSolverSampler
+
+    class CpuDPM(DPMSolverSampler):
+        def register_buffer(self, name, attr):
+            setattr(self, name, attr)
+
+    x_T3 = torch.randn(B, *shape, generator=g)
+    dpm_out = {}
+    for S_dpm in (6, 20):          # 6: lower_order_final active (steps < 15); 20: plain second order
+        with torch.no_grad():
+            o, _ = CpuDPM(ToyLDM()).sample(S=S_dpm, batch_size=B, shape=shape, conditioning=cond, verbose=False,
+                                           unconditional_guidance_scale=2.5, unconditional_conditioning=uc, x_T=x_T3)
+        dpm_out[S_dpm] = o
+
     # ddim (CIFAR path): linear beta schedule of the cifar10 config, 20 uniform steps, eta = 0
     betas_c = torch.linspace(0.0001, 0.02, 1000, dtype=torch.float64).float()
     seq = list(range(0, 1000, 50))
@@ -132,7 +147,8 @@ def main():
                     generalized=dict(x=x0, seq=seq, betas=betas_c, out=xs[-1]),
                     ddim=dict(x_T=x_T2, cond=cond, uc=uc, scale=2.0, S=8, eta=1.0, noises=ddim_noises, out=ddim_out,
                               linear_start=0.00085, linear_end=0.0120),
-                    generalized_quad=dict(x=x1, seq=seq_q, betas=betas_c, eta=1.0, noises=gs_noises, out=xs_q[-1])),
+                    generalized_quad=dict(x=x1, seq=seq_q, betas=betas_c, eta=1.0, noises=gs_noises, out=xs_q[-1]),
+                    dpm=dict(x_T=x_T3, cond=cond, uc=uc, scale=2.5, out=dpm_out, linear_start=0.00085, linear_end=0.0120)),
                os.path.join(OUT, "samplers.pt"))
     print("samplers.pt:", tuple(plms_out.shape), float(plms_out.std()), tuple(xs[-1].shape), float(xs[-1].std()))
 
