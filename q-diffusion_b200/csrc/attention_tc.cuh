@@ -65,7 +65,12 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw(uint32_t smem_addr, int P)
   return d;
 }
 
-template <bool SM16, bool MAGIC, int NSW>
+// GRP = 2 (with NSW = 16): the softmax warps form two groups of 8 that take ALTERNATE key tiles (tile T -> S slot T & 1 ->
+// group T & 1), group 1 starting half a tile period late.  With one group all four warps of a scheduler are in the same
+// phase of the per-tile work - TMEM load + integer max, then 32 x {FADD2, FFMA2, MUFU}, then packing - so the XU pipe
+// (54 % busy, profiles/r02_attention_ncu.txt) idles while the ALU phase runs and vice versa; two phase-shifted groups let
+// one group's exp2 stream overlap the other's integer / packing work.
+template <bool SM16, bool MAGIC, int NSW, int GRP>
 __global__ void __launch_bounds__(atc_threads(NSW), NSW == 16 ? 1 : 2)
 qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const qd_attention_desc p, const int NV, const int P) {
@@ -76,8 +81,10 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   constexpr int ATC_THREADS = atc_threads(NSW);
   constexpr int ATC_STAGES = atc_stages(NSW);
   constexpr int SSLOTS = atc_sslots(NSW);
+  static_assert(GRP == 1 || (GRP == 2 && NSW == 16), "two softmax groups need the 16-warp configuration");
   constexpr int NPART = NSW / 4;             // softmax warps per TMEM lane quarter
-  constexpr int CPT = 4 / NPART;             // 32-column chunks of a tile per softmax thread
+  constexpr int CPT = 4 * GRP / NPART;       // 32-column chunks of a tile per softmax thread
+  constexpr int WPG = NSW / GRP;             // softmax warps that work on one tile
   constexpr uint32_t TMEM_COLS = NSW == 16 ? 512 : 256;
   const AtcSmem L = atc_smem_layout(NV, P, NSW);
   uint8_t* sQ = smem + L.q_off;
@@ -113,13 +120,13 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < ATC_STAGES; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1 + ATC_SOFTMAX_WARPS);    // MMA commit + softmax warps (they read the zq*rowsum(k) slice of the stage)
+      mbar_init(&kv_empty[i], 1 + WPG);    // MMA commit + the softmax warps of the tile (they read the zq*rowsum(k) slice of the stage)
     }
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], ATC_SOFTMAX_WARPS);
-      mbar_init(&p_full[i], ATC_SOFTMAX_WARPS);
+      mbar_init(&s_empty[i], WPG);
+      mbar_init(&p_full[i], WPG);
       mbar_init(&p_empty[i], 1);
     }
     mbar_init(o_done, 1);
@@ -233,8 +240,12 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const float c = p.sim_scale * 1.4426950408889634f;
     const float pmax = (float)p.p_qmax;
     float2* stat = reinterpret_cast<float2*>(smem + L.stat_off);
-    int sb = 0, st = 0;
-    uint32_t ph_s = 0, ph_kv = 0;
+    const int grp = GRP == 2 ? (part >> 1) : 0;          // softmax group of this warp
+    const int sub = GRP == 2 ? (part & 1) : part;        // column part inside the group
+    // Tile counters: T = pass * ntiles + t is the global index of a key tile in MMA issue order.  Everything follows from
+    // it: S slot T & 1 (phase (T >> 1) & 1; one slot: phase T & 1), K/V stage T % stages, P buffer t & 1 (phase (t >> 1) & 1).
+    auto s_slot = [](int T) { return SSLOTS == 2 ? (T & 1) : 0; };
+    auto s_phase = [](int T) -> uint32_t { return SSLOTS == 2 ? ((T >> 1) & 1) : (T & 1); };
     // Scores are handled in BIASED integer form t = S_raw - zq*rowsum(k) + BIAS (one IADD against the staged
     // "BIAS - zq*rowsum" table): with BIAS = 0x4B400000 (d <= 64, |S| < 2^22) the same register is the score for the
     // integer row max AND the bit pattern of the float 1.5*2^23 + S, so the int->float conversion is a single FADD.
@@ -248,12 +259,15 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     int mi = INT_MIN;
     float l = 0.f;
     // ---- pass 1
-    for (int t = 0; t < ntiles; ++t) {
-      mbar_wait(&s_full[sb], ph_s);
+    if (GRP == 2 && grp == 1) __nanosleep(500);             // phase shift between the two groups (about half a tile period)
+    for (int t = (GRP == 2 ? grp : 0); t < ntiles; t += GRP) {
+      const int T = t;
+      const int sb = s_slot(T), st = T % ATC_STAGES;
+      mbar_wait(&s_full[sb], s_phase(T));
       tc_fence_after();
 #pragma unroll 1
       for (int cc = 0; cc < CPT; ++cc) {
-        const int col0 = (part * CPT + cc) * 32;          // this thread's 32 key columns of the tile
+        const int col0 = (sub * CPT + cc) * 32;           // this thread's 32 key columns of the tile
         const int j0 = t * ATC_BN + col0;
         const int* zr = reinterpret_cast<const int*>(smem + L.zrk_off + st * 512) + col0;
         uint32_t v[32];
@@ -296,8 +310,6 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_arrive(&s_empty[sb]);
         mbar_arrive(&kv_empty[st]);
       }
-      if (++sb == SSLOTS) { sb = 0; ph_s ^= 1; }
-      if (++st == ATC_STAGES) { st = 0; ph_kv ^= 1; }
     }
     // ---- combine the column parts of every row (named barrier over the softmax warps)
     stat[part * 128 + row] = make_float2(__int_as_float(mi), l);
@@ -320,18 +332,20 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       row_clamps = !(inv <= pmax);
     }
     const bool warp_clamps = __any_sync(0xffffffffu, row_clamps);
-    // ---- pass 2
-    int pb = 0;
-    uint32_t ph_p = 0;
-    for (int t = 0; t < ntiles; ++t) {
-      mbar_wait(&s_full[sb], ph_s);
+    // ---- pass 2 (group g takes the tiles whose global index ntiles + t has parity g)
+    if (GRP == 2 && grp == 1) __nanosleep(500);
+    for (int t = (GRP == 2 ? ((grp + ntiles) & 1) : 0); t < ntiles; t += GRP) {
+      const int T = ntiles + t;
+      const int sb = s_slot(T), st = T % ATC_STAGES, pb = t & 1;
+      const uint32_t ph_p = (t >> 1) & 1;
+      mbar_wait(&s_full[sb], s_phase(T));
       mbar_wait(&p_empty[pb], ph_p ^ 1);
       tc_fence_after();
       uint8_t* pl = smem + L.p_off + (pb * 2) * 16384 + row * 128;
       uint8_t* phh = pl + 16384;
 #pragma unroll 1
       for (int cc = 0; cc < CPT; ++cc) {
-        const int col0 = (part * CPT + cc) * 32;
+        const int col0 = (sub * CPT + cc) * 32;
         const int j0 = t * ATC_BN + col0;
         const int* zr = reinterpret_cast<const int*>(smem + L.zrk_off + st * 512) + col0;
         uint32_t v[32];
@@ -393,9 +407,6 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_arrive(&kv_empty[st]);
         mbar_arrive(&p_full[pb]);
       }
-      if (++sb == SSLOTS) { sb = 0; ph_s ^= 1; }
-      if (++st == ATC_STAGES) { st = 0; ph_kv ^= 1; }
-      if (++pb == 2) { pb = 0; ph_p ^= 1; }
     }
     // ---- epilogue: O = (256*hi + lo - zv*rowsum) * out_scale
     mbar_wait(o_done, 0);

@@ -598,10 +598,10 @@ int launch_attention_smallk(const qd_attention_desc& d, cudaStream_t s) {
 }
 
 // tcgen05 path (attention_tc.cuh): d <= 112, Q/K codes in the per-head padded layout (pitch 32/64/128), dense V^T
-template <bool S16, bool MAGIC, int NSW>
+template <bool S16, bool MAGIC, int NSW, int GRP = 1>
 int launch_attention_tc_inst(const qd_attention_desc& d, const CUtensorMap& tmQ, const CUtensorMap& tmK,
                              const CUtensorMap& tmV, int NV, int P, cudaStream_t s) {
-  auto kern = qd::qattention_tc_kernel<S16, MAGIC, NSW>;
+  auto kern = qd::qattention_tc_kernel<S16, MAGIC, NSW, GRP>;
   static std::atomic<unsigned long long> optin{0};
   if (int rc = ensure_smem_optin(kern, NSW == 16 ? 227 * 1024 : 113 * 1024, optin, "attention_tc")) return rc;
   const qd::AtcSmem lay = qd::atc_smem_layout(NV, P, NSW);
@@ -667,6 +667,12 @@ int launch_attention_tc(const qd_attention_desc& d, cudaStream_t s) {
   if (small) {
     if (s16) return launch_attention_tc_inst<true, true, 8>(d, tmQ, tmK, tmV, NV, P, s);
     return launch_attention_tc_inst<false, true, 8>(d, tmQ, tmK, tmV, NV, P, s);
+  }
+  // two phase-shifted softmax groups (attention_tc.cuh): QDIFF_ATTN_GROUPS=1 keeps all 16 warps on the same tile
+  static const int groups = [] { const char* e = getenv("QDIFF_ATTN_GROUPS"); return (e && !strcmp(e, "1")) ? 1 : 2; }();
+  if (magic && groups == 2 && d.Tk > 256) {
+    if (s16) return launch_attention_tc_inst<true, true, 16, 2>(d, tmQ, tmK, tmV, NV, P, s);
+    return launch_attention_tc_inst<false, true, 16, 2>(d, tmQ, tmK, tmV, NV, P, s);
   }
   if (s16 && magic) return launch_attention_tc_inst<true, true, 16>(d, tmQ, tmK, tmV, NV, P, s);
   if (s16 && !magic) return launch_attention_tc_inst<true, false, 16>(d, tmQ, tmK, tmV, NV, P, s);

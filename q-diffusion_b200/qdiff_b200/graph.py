@@ -529,7 +529,8 @@ class Builder:
             d.residual = res.ptr
         if o is not None:
             d.out = o.ptr + 4 * out_cols_offset
-            if M % 32 == 0 and M >= 2048 and o.t.dim() == 2 and os.environ.get("QDIFF_GN_STATS", "1") != "0":
+            if (M % 32 == 0 and M >= 2048 and o.t.dim() == 2 and o.t.shape[1] % 4 == 0 and (o.col0 + out_cols_offset) % 4 == 0
+                    and os.environ.get("QDIFF_GN_STATS", "1") != "0"):
                 # GroupNorm slab statistics of this output (qd_gemm_desc.gn_stats): kept per backing tensor so that the two
                 # producers of a concat buffer fill their own column ranges of the same table
                 ent = self.gn_slabs.get(id(o.t))
@@ -1283,13 +1284,26 @@ class _Sel:
 
 
 class _WQView:
+    """Row subset of a weight quantizer.  Lazy: with an engine-native checkpoint (packed.py) the folded operands come from the
+    cache and the quantizer tensors are never read."""
+
     def __init__(self, wq, rows):
-        self.n_bits = wq.n_bits
-        r = rows.to(wq.delta.device)
-        self.delta = wq.delta.detach().reshape(wq.delta.shape[0], -1)[r]
-        self.zero_point = wq.zero_point.detach().reshape(wq.zero_point.shape[0], -1)[r]
-        alpha = getattr(wq, "alpha", None)
-        self.alpha = alpha.detach()[rows.to(alpha.device)] if alpha is not None else None
+        self.wq, self.rows, self.n_bits = wq, rows, wq.n_bits
+
+    @property
+    def delta(self):
+        d = self.wq.delta.detach()
+        return d.reshape(d.shape[0], -1)[self.rows.to(d.device)]
+
+    @property
+    def zero_point(self):
+        z = self.wq.zero_point.detach()
+        return z.reshape(z.shape[0], -1)[self.rows.to(z.device)]
+
+    @property
+    def alpha(self):
+        alpha = getattr(self.wq, "alpha", None)
+        return alpha.detach()[self.rows.to(alpha.device)] if alpha is not None else None
 
 
 def compile_unet(qnn, x_shape, ctx_shape, device, use_cuda_graph=True):

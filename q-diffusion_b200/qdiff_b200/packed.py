@@ -135,6 +135,11 @@ def load_packed(path, device="cuda", cuda_graph=True):
     aqp = {'n_bits': q["act_bit"], 'symmetric': q["a_sym"], 'channel_wise': False, 'scale_method': 'max',
            'leaf_param': q["quant_act"]}
     qnn = QuantModel(model=model, weight_quant_params=wqp, act_quant_params=aqp, sm_abit=q["sm_abit"], cuda_graph=cuda_graph)
+    # split-shortcut layers first: set_split() creates the `_0` quantizer sub-modules the other tables refer to
+    for n, s in blob["splits"].items():
+        m = dict(qnn.model.named_modules())[n]
+        m.split = int(s)
+        m.set_split()
     mods = dict(qnn.model.named_modules())
     # ---- small fp32 parameters (biases, norm scales) become real tensors; the big weights stay on `meta` (shapes only)
     for n, t in blob["small"].items():
@@ -144,9 +149,6 @@ def load_packed(path, device="cuda", cuda_graph=True):
             m.bias = torch.nn.Parameter(t.clone(), requires_grad=False)
         else:
             m._parameters[leaf] = torch.nn.Parameter(t.clone(), requires_grad=False)
-    for n, s in blob["splits"].items():
-        mods[n].split = int(s)
-        mods[n].set_split()
     for n, (delta, zp) in blob["act"].items():
         qz = mods[n]
         qz.delta = torch.nn.Parameter(torch.tensor(float(delta)), requires_grad=False)

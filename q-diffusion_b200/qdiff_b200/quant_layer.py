@@ -163,6 +163,9 @@ class QuantModule(nn.Module):
 
     @property
     def org_weight(self):
+        """The FP weight.  The reference keeps a clone() taken at construction (quant_layer.py:228-231); here it is the live
+        tensor - the engine never modifies weights (they are folded into separate integer operands), and a clone would
+        double the 3.4 GB of SD weights on the host."""
         return self.weight.data
 
     def forward(self, input, split: int = 0):
@@ -178,6 +181,12 @@ class QuantModule(nn.Module):
             self.act_quantizer_0 = UniformAffineQuantizer(**self.act_quant_params)
 
     def set_running_stat(self, running_stat: bool):
+        if running_stat:
+            # the reference updates (x_min, x_max) with momentum inside UniformAffineQuantizer.forward
+            # (quant_layer.py:68-80, act_momentum_update :91-110) during CALIBRATION; the engine only consumes calibrated
+            # checkpoints, so switching the statistics on would silently do nothing
+            raise NotImplementedError("running statistics belong to calibration, which is not part of the sampling engine: "
+                                      "calibrate with the reference and load the result with resume_cali_model")
         if self.act_quant_mode == 'qdiff':
             self.act_quantizer.running_stat = running_stat
             if self.split != 0:

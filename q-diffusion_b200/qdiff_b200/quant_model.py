@@ -1,5 +1,13 @@
 """Host-side mirror of qdiff/quant_model.py -- the drop-in API boundary (reference :12-97).
 
+Quantisation states the engine realises (set_quant_state, reference :52-55):
+    (True, True)   weights and activations quantised (W4A8 / W8A8): INT8 tcgen05 GEMMs, all four UNet configurations;
+    (True, False)  weight-only (what resume_cali_model(..., quant_act=False) leaves, qdiff/utils.py:407): fp32 activations
+                   as bfloat16 x3 planes against exact bfloat16 weight codes, fp32 accumulation; DDIM (CIFAR) family;
+    (False, False) full precision: NOT realised (it is the reference's own path for FP baselines / calibration data).
+Activation quantizers must be per-tensor and at most 8 bits (16 for the softmax quantizer); graph.Builder.qp refuses
+anything else instead of wrapping codes.
+
 QuantModel(model, weight_quant_params, act_quant_params, sm_abit=8) wraps a UNet module tree
 in place exactly like the reference (layers -> QuantModule, blocks -> Quant*Block) so state-dict
 keys match `ckpt.pth`; `forward(x, timesteps, context)` lowers the tree once per input shape to an
