@@ -85,7 +85,10 @@ typedef struct qd_gemm_desc {
   int32_t geglu;         /* 1: rows of w (and scale/bias/corr) are interleaved [4 x-features, 4 gate-features]...;
                             out_q receives Q(x * gelu_erf(gate)) with N/2 columns (ldm/modules/attention.py:42-44) */
   int32_t w_int4_packed; /* 1: w holds packed unsigned 4-bit codes, see above */
-  int32_t reserved3;
+  int32_t k_dup;         /* 0 / 1: plain.  2: the reduction runs TWICE over the activation against two weight segments, w is
+                          * [n_rows][2][taps*C]: y = scale * sum_k x_k (wa_k + wb_k).  8-bit weights: wq - zw spans [-255, 255] and
+                          * does not fit one s8 operand; wa = floor(ws/2), wb = ws - wa do (unless ws = 255), and ONE launch with
+                          * a doubled K replaces two accumulating GEMMs.  corr / scale refer to the sum wa + wb. */
   const int8_t* w_zero;  /* [n_rows] zero points of the packed codes (w_int4_packed only) */
   /* Optional, for requantising GEMMs (out_q set, out NULL, geglu 0): the epilogue constants pre-divided by the consumer's
    * step, scale_q[n] = scale[n] / oq.delta and bias_q[n] = bias[n] / oq.delta + oq.zero_point (computed in double by the
@@ -188,6 +191,7 @@ int qd_groupnorm_quant(const qd_groupnorm_desc* d, qd_stream_t stream);
  *   False (qdiff/quant_block.py:360-386) and QKVAttentionLegacy (openaimodel.py:384-406; scale = 1/sqrt(ch) applied to
  *   the product).  q: [B*Tq, ld_q], head h at columns q_off + h*head_stride_q (k, v likewise); out [B*Tq, ld_out].
  * ------------------------------------------------------------------------------------------ */
+/* qd_split_desc.act: 0 none, 1 SiLU, 2 GEGLU (src has 2*C columns: value = src[:, c] * gelu_erf(src[:, C + c])) */
 typedef struct qd_split_desc {
   const float* src;
   long long ld_src;
@@ -234,6 +238,8 @@ typedef struct qd_layernorm_desc {
   void* out_q[3];
   long long ld_q[3];
   qd_qparams q[3];
+  float* out_f;          /* optional fp32 output (weight-only state: the consumers take fp32); n_out may then be 0 */
+  long long ld_f;
 } qd_layernorm_desc;
 
 int qd_layernorm_quant(const qd_layernorm_desc* d, qd_stream_t stream);

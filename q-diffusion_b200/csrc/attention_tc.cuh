@@ -69,7 +69,9 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw(uint32_t smem_addr, int P)
 // group T & 1), group 1 starting half a tile period late.  With one group all four warps of a scheduler are in the same
 // phase of the per-tile work - TMEM load + integer max, then 32 x {FADD2, FFMA2, MUFU}, then packing - so the XU pipe
 // (54 % busy, profiles/r02_attention_ncu.txt) idles while the ALU phase runs and vice versa; two phase-shifted groups let
-// one group's exp2 stream overlap the other's integer / packing work.
+// one group's exp2 stream overlap the other's integer / packing work.  MEASURED: 9 % slower than one group (1938 vs 1775 us,
+// B=16 x 8 heads, T=4096): a thread then walks two 32-column chunks per tile back to back and the groups' tile hand-offs
+// serialise on the in-order MMA issue.  Not the default (engine.cu: QDIFF_ATTN_GROUPS=2 enables it).
 template <bool SM16, bool MAGIC, int NSW, int GRP>
 __global__ void __launch_bounds__(atc_threads(NSW), NSW == 16 ? 1 : 2)
 qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,

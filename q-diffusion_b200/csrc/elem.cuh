@@ -100,6 +100,10 @@ __global__ void split_bf16x3_kernel(const qd_split_desc p) {
     }
     const float4 v4 = *reinterpret_cast<const float4*>(p.src + rs * p.ld_src + c);
     float v[4] = {v4.x, v4.y, v4.z, v4.w};
+    if (p.act == 2) {       // GEGLU (ldm/modules/attention.py:42-44) with the exact-erf GELU
+      const float4 g4 = *reinterpret_cast<const float4*>(p.src + rs * p.ld_src + p.C + c);
+      v[0] *= gelu_erf_f(g4.x); v[1] *= gelu_erf_f(g4.y); v[2] *= gelu_erf_f(g4.z); v[3] *= gelu_erf_f(g4.w);
+    }
     uint32_t pl[3][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -128,6 +132,7 @@ __global__ void split_bf16x3_scalar_kernel(const qd_split_desc p) {
     const int c = (int)(i - r * p.C);
     float x = p.src[r * p.ld_src + c];
     if (p.act == 1) x = x / (1.0f + __expf(-x));
+    else if (p.act == 2) x *= gelu_erf_f(p.src[r * p.ld_src + p.C + c]);
     const float h = bf16_rn(x);
     const float r1 = x - h;
     const float m = bf16_rn(r1);
@@ -520,6 +525,7 @@ __global__ void __launch_bounds__(256) layernorm_quant_kernel(const qd_layernorm
         const float y1 = (v[k].y - mean) * rstd * g[k].y + be[k].y;
         const float y2 = (v[k].z - mean) * rstd * g[k].z + be[k].z;
         const float y3 = (v[k].w - mean) * rstd * g[k].w + be[k].w;
+        if (p.out_f) *reinterpret_cast<float4*>(p.out_f + row * p.ld_f + c) = make_float4(y0, y1, y2, y3);
 #pragma unroll
         for (int o = 0; o < 3; ++o) {
           if (o < p.n_out) {

@@ -182,13 +182,16 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
   qd::GemmArgs& a = pl->args;
   memset(&a, 0, sizeof(a));
   a.M = d->M; a.N = d->N; a.C = d->C; a.taps = d->taps;
+  a.kdup = d->k_dup == 2 ? 2 : 1;
+  if (d->k_dup != 0 && d->k_dup != 1 && d->k_dup != 2) return fail(QD_ERR_BAD_ARG, "gemm: k_dup must be 0, 1 or 2");
+  if (a.kdup == 2 && d->w_int4_packed) return fail(QD_ERR_BAD_ARG, "gemm: k_dup 2 is for 8-bit weights (not packed INT4)");
   a.tiles_m = (d->M + qd::GEMM_BM - 1) / qd::GEMM_BM;
   a.geglu = d->geglu;
   if (d->geglu) {
     if ((d->N & 7) || !d->out_q || d->out || d->rowvec || d->residual || d->out_q_transposed || (d->ldq & 3) || d->taps != 1)
       return fail(QD_ERR_BAD_ARG, "gemm: geglu needs N %% 8 == 0, out_q only, plain GEMM");
   }
-  a.BN = pick_bn(d->N, a.tiles_m, sms, d->bn_hint, d->geglu ? 32 : 16, (long long)d->C * d->taps);
+  a.BN = pick_bn(d->N, a.tiles_m, sms, d->bn_hint, d->geglu ? 32 : 16, (long long)d->C * d->taps * a.kdup);
   if (a.BN % 16 || a.BN < 16 || a.BN > 256) return fail(QD_ERR_BAD_ARG, "gemm: bad BN %d", a.BN);
   a.tiles_n = (d->N + a.BN - 1) / a.BN;
   a.a_signed = d->a_signed; a.b_signed = 1;
@@ -237,8 +240,8 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
       a.w4 = 1;
       a.wzero = d->w_zero;
     } else {
-      cuuint64_t bd[2] = {(cuuint64_t)d->taps * d->C, (cuuint64_t)w_rows};
-      cuuint64_t bs[1] = {(cuuint64_t)d->taps * d->C};
+      cuuint64_t bd[2] = {(cuuint64_t)d->taps * d->C * a.kdup, (cuuint64_t)w_rows};
+      cuuint64_t bs[1] = {(cuuint64_t)d->taps * d->C * a.kdup};
       cuuint32_t bb[2] = {qd::GEMM_BK, (cuuint32_t)a.BN};
       rc = encode_u8_map(&pl->tmB, d->w, 2, bd, bs, bb);
     }
@@ -325,7 +328,7 @@ int gemm_mode(const qd::GemmArgs& a) {
            (a.residual ? qd::EPI_RESIDUAL : 0);
   }
   static const int ring_kb = [] { const char* e = getenv("QDIFF_RES_RING_KB"); return e ? atoi(e) : 5; }();
-  const int num_kb = ((a.C + qd::GEMM_BK - 1) / qd::GEMM_BK) * a.taps;
+  const int num_kb = ((a.C + qd::GEMM_BK - 1) / qd::GEMM_BK) * a.taps * a.kdup;
   const bool ring = a.residual && a.taps == 1 && num_kb <= ring_kb && !(reinterpret_cast<uintptr_t>(a.residual) & 15);
   return (a.corr ? qd::EPI_CORR : 0) | ((a.taps == 9) ? qd::EPI_CONV : 0) | (a.rowvec ? qd::EPI_ROWVEC : 0) |
          (a.residual ? qd::EPI_RESIDUAL : 0) | (f ? qd::EPI_OUT_F32 : qd::EPI_OUT_Q) | (ring ? qd::EPI_RESTMA : 0);
@@ -495,7 +498,8 @@ int launch_layernorm_t(const qd_layernorm_desc& d, cudaStream_t s) {
 int launch_layernorm(const qd_layernorm_desc& d, cudaStream_t s) {
   if (!d.x || !d.gamma || !d.beta) return fail(QD_ERR_BAD_ARG, "layernorm: null arg");
   if (d.C % 4 || d.ld_x % 4) return fail(QD_ERR_UNSUPPORTED, "layernorm: C=%d", d.C);
-  if (d.n_out < 1 || d.n_out > 3) return fail(QD_ERR_BAD_ARG, "layernorm: n_out");
+  if (d.n_out < 0 || d.n_out > 3 || (d.n_out == 0 && !d.out_f)) return fail(QD_ERR_BAD_ARG, "layernorm: n_out");
+  if (d.out_f && (d.ld_f & 3)) return fail(QD_ERR_UNSUPPORTED, "layernorm: ld_f");
   const int nvec = (d.C / 4 + 31) / 32;
   switch (nvec) {
     case 1: return launch_layernorm_t<1>(d, s);
@@ -668,8 +672,9 @@ int launch_attention_tc(const qd_attention_desc& d, cudaStream_t s) {
     if (s16) return launch_attention_tc_inst<true, true, 8>(d, tmQ, tmK, tmV, NV, P, s);
     return launch_attention_tc_inst<false, true, 8>(d, tmQ, tmK, tmV, NV, P, s);
   }
-  // two phase-shifted softmax groups (attention_tc.cuh): QDIFF_ATTN_GROUPS=1 keeps all 16 warps on the same tile
-  static const int groups = [] { const char* e = getenv("QDIFF_ATTN_GROUPS"); return (e && !strcmp(e, "1")) ? 1 : 2; }();
+  // two phase-shifted softmax groups (attention_tc.cuh), QDIFF_ATTN_GROUPS=2: measured SLOWER (1938 vs 1775 us on the 64x64
+  // self-attention), kept as an experiment switch; the default keeps all 16 warps on the same key tile
+  static const int groups = [] { const char* e = getenv("QDIFF_ATTN_GROUPS"); return (e && !strcmp(e, "2")) ? 2 : 1; }();
   if (magic && groups == 2 && d.Tk > 256) {
     if (s16) return launch_attention_tc_inst<true, true, 16, 2>(d, tmQ, tmK, tmV, NV, P, s);
     return launch_attention_tc_inst<false, true, 16, 2>(d, tmQ, tmK, tmV, NV, P, s);

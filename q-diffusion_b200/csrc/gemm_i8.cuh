@@ -74,6 +74,7 @@ struct GemmArgs {
   int M, N;            // logical output rows / columns (columns >= N are masked)
   int C;               // reduction length per tap (multiple of 32)
   int taps;            // 1 = plain GEMM, 9 = 3x3 conv (stride 1, pad 1)
+  int kdup;            // 1, or 2: two weight segments over the same activation (8-bit weights as wa + wb, qd_gemm_desc.k_dup)
   int BN;              // N tile (multiple of 16, <= 256)
   int tiles_m, tiles_n;
   int stages;
@@ -346,7 +347,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.tiles_m * p.tiles_n;
   const int kb_per_tap = (p.C + GEMM_BK - 1) / GEMM_BK;
-  const int num_kb = kb_per_tap * p.taps;
+  const int num_kb = kb_per_tap * p.taps * p.kdup;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -394,7 +395,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           b0 = m0 / hw;
           h0 = (m0 - b0 * hw) / p.W;
         }
-        for (int tap = 0; tap < p.taps; ++tap) {
+        for (int seg = 0; seg < p.taps * p.kdup; ++seg) {
+          const int tap = seg % p.taps;            // activation geometry of this segment; the weight column offset is seg * C
           const int ky = tap / 3, kx = tap - ky * 3;
           for (int kc = 0; kc < kb_per_tap; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -407,9 +409,9 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_4d(sa, &tmA, &full_bar[stage], kc * GEMM_BK, m0, 0, 0);
             if constexpr (W4)
               tma_load_2d(smem + lay.pack_off + (size_t)stage * p.BN * (GEMM_BK / 2), &tmB, &full_bar[stage],
-                          (tap * p.C + kc * GEMM_BK) / 2, n0);
+                          (seg * p.C + kc * GEMM_BK) / 2, n0);
             else
-              tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.C + kc * GEMM_BK, n0);
+              tma_load_2d(sb, &tmB, &full_bar[stage], seg * p.C + kc * GEMM_BK, n0);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }

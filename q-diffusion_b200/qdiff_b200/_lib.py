@@ -37,7 +37,7 @@ class GemmDesc(C.Structure):
         ("out_q", c_vp), ("ldq", c_ll),
         ("oq", QParams),
         ("bn_hint", c_i32), ("out_q_head_dim", c_i32), ("out_q_head_pitch", c_i32), ("geglu", c_i32),
-        ("w_int4_packed", c_i32), ("reserved3", c_i32), ("w_zero", c_vp),
+        ("w_int4_packed", c_i32), ("k_dup", c_i32), ("w_zero", c_vp),
         ("scale_q", c_vp), ("bias_q", c_vp),
         ("gn_stats", c_vp), ("ld_stats", c_ll),
         ("a_bf16", c_i32), ("reserved4", c_i32),
@@ -72,6 +72,7 @@ class LayerNormDesc(C.Structure):
         ("x", c_vp), ("ld_x", c_ll), ("M", c_i32), ("C", c_i32), ("eps", c_f), ("n_out", c_i32),
         ("gamma", c_vp), ("beta", c_vp),
         ("out_q", c_vp * 3), ("ld_q", c_ll * 3), ("q", QParams * 3),
+        ("out_f", c_vp), ("ld_f", c_ll),
     ]
 
 

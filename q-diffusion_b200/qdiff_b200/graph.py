@@ -167,6 +167,9 @@ class Builder:
             qnn._wcache = {}
         self.wcache = qnn._wcache   # folded weight operands, shared by every program of this QuantModel
         self.gn_slabs = {}          # id(backing fp32 tensor) -> [slab-sum tensor [rows/32, ld, 2], covered column ranges]
+        # classifier-free-guidance prefix (cfg_split): while `prefix` is set the builder works on the FIRST half of the batch
+        # and every buffer is allocated with room for both halves
+        self.B_full, self.prefix, self._prefix_acts, self.cfg_live = batch, False, [], []
         self._pending = []          # (kind, desc, label, flops, spec, static) in recording order; see flush()
         self._static_depth = 0
         self.n_static = 0
@@ -176,15 +179,45 @@ class Builder:
 
     # ------------------------------------------------------------------ helpers
     def new(self, rows, cols, dtype):
-        t = torch.empty((rows, cols), dtype=dtype, device=self.dev)
+        t = torch.empty(((2 if self.prefix else 1) * rows, cols), dtype=dtype, device=self.dev)
         self.keep.append(t)
         return t
 
     def new_f32(self, rows, cols):
-        return Act(self.new(rows, cols, torch.float32), rows, cols)
+        a = Act(self.new(rows, cols, torch.float32), rows, cols)
+        if self.prefix:
+            self._prefix_acts.append(a)
+        return a
 
     def new_codes(self, rows, cols, signed):
         return Act(self.new(rows, cols, torch.int8 if signed else torch.uint8), rows, cols, signed=signed)
+
+    def cfg_split(self, live):
+        """End of the classifier-free-guidance prefix.  The doubled batch [x; x] with one timestep vector makes the two
+        halves IDENTICAL until the first cross-attention reads the (different) contexts (plms.py:185-189 builds exactly
+        that batch), so everything up to and including the first self-attention - conv_in, the first ResBlock, one of SD's
+        five 64x64 self-attentions - was recorded for the first half only.  Here the tensors that live on are copied into
+        the second half of their (double-size) buffers, together with their GroupNorm slab sums, and the builder switches
+        to the full batch.  Bit-identical to running the doubled batch (tests/test_unet_gpu.py::test_cfg_prefix_dedup)."""
+        seen = set()
+        for a in live:
+            if id(a) in seen or a.signed is not None:
+                continue
+            seen.add(id(a))
+            half = a.rows
+            self.misc(_lib.QD_OP_COPY2D, a.ptr, a.ptr + 4 * half * a.ld, half, a.cols, ld_src=a.ld, ld_dst=a.ld,
+                      label="cfg.dup", spec=dict(kind="cfg_dup"))
+            ent = self.gn_slabs.get(id(a.t))
+            if ent is not None and half % 32 == 0 and self._covered(ent[1], a.col0, a.col0 + a.cols):
+                ld2 = 2 * ent[0].shape[1]
+                src = ent[0].data_ptr() + 8 * a.col0
+                self.misc(_lib.QD_OP_COPY2D, src, src + 4 * (half // 32) * ld2, half // 32, 2 * a.cols, ld_src=ld2, ld_dst=ld2,
+                          label="cfg.dup.slabs", spec=dict(kind="cfg_dup"))
+            a.rows = 2 * half
+        for a in self._prefix_acts:          # buffers allocated for both halves: the Act now spans both
+            if id(a) not in seen:
+                a.rows *= 2
+        self.B, self.prefix, self._prefix_acts = self.B_full, False, []
 
     def dev_t(self, t, dtype):
         t = t.detach().to(device=self.dev, dtype=dtype).contiguous()
@@ -393,10 +426,17 @@ class Builder:
         if ent is not None and (not self.want_specs or ent.get("w8") or "ws_cpu" in ent):
             return ent
         ws, delta_w = self._fold(qm, cols, suffix)
+        kdup = 1
         if part is None and float(ws.abs().max()) > 127:
-            ent = dict(w8=True)
-            self.wcache[key] = ent
-            return ent
+            # 8-bit weights: wq - zw spans [-255, 255].  One GEMM whose reduction runs twice over the activation, against
+            # wa = floor(ws/2) and wb = ws - wa (qd_gemm_desc.k_dup = 2): exact unless some ws == 255 (wb would be 128; a row
+            # with zero point 0 and code 255), in which case - or with QDIFF_W8_KDUP=0 - the layer runs as two accumulating
+            # GEMMs (parts "hi" / "lo": y = 2 s acc_a + s acc_b)
+            if float(ws.max()) > 254 or os.environ.get("QDIFF_W8_KDUP", "1") == "0":
+                ent = dict(w8=True)
+                self.wcache[key] = ent
+                return ent
+            kdup = 2
         if part is not None:
             wa = torch.floor(ws / 2)
             ws = wa if part == "hi" else ws - 2 * wa
@@ -414,6 +454,9 @@ class Builder:
         if k_pad is not None and k_pad != wk.shape[1]:
             wk = torch.nn.functional.pad(wk, (0, k_pad - wk.shape[1]))
             Cred = k_pad
+        if kdup == 2:
+            wa = torch.floor(wk / 2)
+            wk = torch.cat([wa, wk - wa], dim=1)          # [N, 2 * taps * C]: segment a, then segment b
         w_dev, w_zero = None, None
         if self.w4_packed:                      # K3: keep 4-bit codes packed in HBM, the GEMM unpacks in shared memory
             pk = ops.pack_int4(wk.reshape(wk.shape[0], -1))
@@ -423,7 +466,7 @@ class Builder:
             w_dev = wk.to(torch.int8).contiguous()
         wsum = ws.to(torch.float64).sum(dim=1) if taps == 9 else ws.reshape(N, -1).to(torch.float64).sum(dim=1)
         ent = dict(w8=False, w_dev=w_dev, w_zero=w_zero, delta_w=delta_w.contiguous(), N=N, taps=taps, Cred=Cred,
-                   w_rows=wk.shape[0], wsum=wsum, perm=perm)
+                   w_rows=wk.shape[0], wsum=wsum, perm=perm, kdup=kdup)
         if self.want_specs:
             ent["ws_cpu"] = ws.detach().to("cpu", torch.float32)
         self.wcache[key] = ent
@@ -521,6 +564,7 @@ class Builder:
                           out_q_head=out_q_head if (out_q is not None and not transposed) else None, w_zero=w_zero,
                           w_rows=W["w_rows"])
         d.a = a.ptr + (cols[0] if cols is not None else 0)
+        d.k_dup = W.get("kdup", 1)
         if getattr(d, "_keep_q", None) is not None:
             self.keep.extend(d._keep_q)           # pre-divided requantisation constants (ops.gemm_desc)
         if rowvec is not None:
@@ -552,7 +596,7 @@ class Builder:
                         N=N, out_q=oq_act, oq=_qt(oq_params), transposed=transposed, geglu=geglu_q is not None,
                         out_q_head=out_q_head if (out_q is not None and not transposed) else None,
                         packed=w_zero is not None)
-        self.add(_lib.QD_OP_GEMM, d, label, flops=2 * M * N * Cred * taps, spec=spec)
+        self.add(_lib.QD_OP_GEMM, d, label, flops=2 * M * N * Cred * taps * W.get("kdup", 1), spec=spec)
         if o is not None:
             self.layer_traces[label] = o
         return oq_act if out_q is not None else o
@@ -751,6 +795,8 @@ class Builder:
             cq, ck, cv = self.layernorm(h, blk.norm1, [a1.to_q.act_quantizer, a1.to_k.act_quantizer,
                                                        a1.to_v.act_quantizer], bk + ".norm1")
             h = self.sd_cross_attention(a1, cq, (ck, cv), h, T, T, bk + ".attn1")
+            if self.prefix:                     # first cross-attention ahead: the two guidance halves diverge from here
+                self.cfg_split([h, x] + self.cfg_live)
             (cq2,) = self.layernorm(h, blk.norm2, [a2.to_q.act_quantizer], bk + ".norm2")
             if ctx is None:
                 raise ValueError("SpatialTransformer needs a context tensor")
@@ -798,9 +844,14 @@ class Builder:
                            consumer=blk.proj_out)
         return self.gemm(blk.proj_out, o, k + ".proj_out", residual=x, out=out)
 
-    def lower_ldm(self, model, x_shape, ctx_shape):
+    def lower_ldm(self, model, x_shape, ctx_shape, cfg_dedup=False):
         B, Cin, H, W = x_shape
-        x_in = torch.zeros(x_shape, dtype=torch.float32, device=self.dev)
+        if cfg_dedup:
+            if B % 2 or ctx_shape is None or ctx_shape[0] != B:
+                raise ValueError("cfg_dedup needs an even batch [uncond; cond] with one context row per sample")
+            self.B, self.prefix = B // 2, True        # record the guidance-invariant prefix for the first half only
+            B = self.B
+        x_in = torch.zeros((B,) + tuple(x_shape[1:]), dtype=torch.float32, device=self.dev)
         t_in = torch.zeros(B, dtype=torch.float32, device=self.dev)
         ctx_in = torch.zeros(ctx_shape, dtype=torch.float32, device=self.dev) if ctx_shape is not None else None
         self.keep += [x_in, t_in] + ([ctx_in] if ctx_in is not None else [])
@@ -818,6 +869,7 @@ class Builder:
                   spec=dict(kind="nchw_to_nhwc", src=x_in, dst=xh))
         h, hw = xh, (H, W)
         hs = []
+        self.cfg_live = [emb]             # tensors the prefix hands over to the full batch (plus the skips, appended below)
 
         # torch.cat([h, hs.pop()], dim=1) without copies (openaimodel.py:733): the concat buffer of decoder block j
         # is allocated up front; the encoder block whose output is that skip writes its right-hand columns, the
@@ -853,7 +905,7 @@ class Builder:
             """View for decoder block j's concat: side 'skip' = right-hand columns, 'h' = left-hand ones."""
             if j is None or j < 0 or j >= nblk or cat_total[j] is None:
                 return None
-            rows = B * ohw[0] * ohw[1]
+            rows = self.B * ohw[0] * ohw[1]
             if cat_buf[j] is None:
                 if side != "skip":
                     return None
@@ -863,9 +915,10 @@ class Builder:
             buf = cat_buf[j]
             if buf.rows != rows:
                 return None
-            if side == "skip":
-                return buf.view(buf.cols - cs, cs)
-            return buf.view(0, cs)
+            v = buf.view(buf.cols - cs, cs) if side == "skip" else buf.view(0, cs)
+            if self.prefix:
+                self._prefix_acts.append(v)      # handed out inside the guidance prefix: spans both halves after cfg_split
+            return v
 
         def run(seq, h, hw, split, dest=None):
             """dest = (j, side): the last layer writes its output into decoder block j's concat buffer."""
@@ -895,7 +948,7 @@ class Builder:
                     hw = ohw
                 elif n == "Upsample":
                     conv = layer.conv
-                    a = self.quantize(h, conv.act_quantizer, self.key(conv) + ".q", upsample=(B, hw[0], hw[1]))
+                    a = self.quantize(h, conv.act_quantizer, self.key(conv) + ".q", upsample=(self.B, hw[0], hw[1]))
                     hw = (2 * hw[0], 2 * hw[1])
                     h = self.conv3x3_s1(conv, a, hw, self.key(conv), out=out)
                 else:
@@ -904,9 +957,15 @@ class Builder:
 
         nin_blocks = len(model.input_blocks)
         for i, blk in enumerate(model.input_blocks):
+            B = self.B                    # half batch inside the guidance prefix, full batch after cfg_split
             h, hw = run(blk, h, hw, 0, dest=(nin_blocks - 1 - i, "skip") if nin_blocks == nblk else None)
             hs.append((h, hw))
+            if self.prefix:
+                self.cfg_live.append(h)   # a skip produced inside the prefix: needed by the decoder at full batch
             self.traces[f"input_blocks.{i}"] = (h, hw)
+        if self.prefix:
+            raise NotImplementedError("cfg_dedup: no cross-attention found to end the guidance-invariant prefix")
+        B = self.B
         h, hw = run(model.middle_block, h, hw, 0, dest=(0, "h"))
         self.traces["middle_block"] = (h, hw)
         for i, blk in enumerate(model.output_blocks):
@@ -1306,8 +1365,9 @@ class _WQView:
         return alpha.detach()[self.rows.to(alpha.device)] if alpha is not None else None
 
 
-def compile_unet(qnn, x_shape, ctx_shape, device, use_cuda_graph=True):
-    """Lower `qnn` (QuantModel) for a fixed input shape; returns a Program."""
+def compile_unet(qnn, x_shape, ctx_shape, device, use_cuda_graph=True, cfg_dedup=False):
+    """Lower `qnn` (QuantModel) for a fixed input shape; returns a Program.  cfg_dedup: x_shape / ctx_shape describe the
+    doubled classifier-free-guidance batch, the program takes x and timesteps of HALF that batch (Builder.cfg_split)."""
     lib()  # fail loudly if the CUDA library is missing
     if not torch.cuda.is_available():
         raise RuntimeError("qdiff_b200: no CUDA device; the engine has no CPU fallback")
@@ -1322,8 +1382,11 @@ def compile_unet(qnn, x_shape, ctx_shape, device, use_cuda_graph=True):
             "state (False, False) is the reference's own path (calibration data / FP baselines).")
     model = qnn.model
     with torch.no_grad():
+        if cfg_dedup and (_name(model) != "UNetModel" or type(b) is not Builder):
+            raise NotImplementedError("cfg_dedup applies to the quantised LDM / SD UNets with a cross-attention context")
         if _name(model) == "UNetModel":
-            x_in, t_in, ctx_in, out = b.lower_ldm(model, x_shape, ctx_shape)
+            x_in, t_in, ctx_in, out = b.lower_ldm(model, x_shape, ctx_shape, cfg_dedup) if cfg_dedup else \
+                b.lower_ldm(model, x_shape, ctx_shape)
         elif _name(model) == "Model":
             x_in, t_in, ctx_in, out = b.lower_ddim(model, x_shape)
         else:

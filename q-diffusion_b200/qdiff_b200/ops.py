@@ -140,7 +140,7 @@ def groupnorm_quant(desc):
     check(lib().qd_groupnorm_quant(C.byref(desc), stream_ptr()), "qd_groupnorm_quant")
 
 
-def layernorm_desc(x, gamma, beta, *, M, C_, ld_x, eps, outs):
+def layernorm_desc(x, gamma, beta, *, M, C_, ld_x, eps, outs, out_f=None, ld_f=0):
     d = LayerNormDesc()
     d.x, d.ld_x, d.M, d.C, d.eps = ptr(x), int(ld_x), int(M), int(C_), float(eps)
     d.gamma, d.beta = ptr(gamma), ptr(beta)
@@ -149,6 +149,7 @@ def layernorm_desc(x, gamma, beta, *, M, C_, ld_x, eps, outs):
         d.out_q[i] = t.data_ptr()
         d.ld_q[i] = int(ld)
         d.q[i] = q
+    d.out_f, d.ld_f = ptr(out_f), int(ld_f)
     return d
 
 

@@ -87,7 +87,7 @@ def export_packed(qnn, path, example_inputs=None):
         rec = dict(w8=False, N=ent["N"], taps=ent.get("taps", 1), w_rows=ent.get("w_rows", ent["N"]),
                    delta_w=ent["delta_w"].detach().cpu())
         if "Cred" in ent:                        # INT8-path operand (quantised activations)
-            rec.update(Cred=ent["Cred"], wsum=ent["wsum"].detach().cpu(),
+            rec.update(Cred=ent["Cred"], kdup=ent.get("kdup", 1), wsum=ent["wsum"].detach().cpu(),
                        perm=None if ent["perm"] is None else ent["perm"].detach().cpu())
             if ent["w_zero"] is not None:        # already packed (QDIFF_W4_PACKED=1)
                 rec.update(w=w, w_zero=ent["w_zero"].detach().cpu(), packed=True)
@@ -188,7 +188,7 @@ def load_packed(path, device="cuda", cuda_graph=True):
         else:
             w_dev = rec["w"].to(dev)
         cache[key] = dict(w8=False, w_dev=w_dev, w_zero=w_zero, delta_w=rec["delta_w"].to(dev), N=rec["N"],
-                          taps=rec["taps"], Cred=rec["Cred"], w_rows=rec["w_rows"], wsum=rec["wsum"].to(dev),
+                          taps=rec["taps"], Cred=rec["Cred"], kdup=rec.get("kdup", 1), w_rows=rec["w_rows"], wsum=rec["wsum"].to(dev),
                           perm=None if rec["perm"] is None else rec["perm"].to(dev))
     qnn._wcache = cache
     qnn._packed_source = path

@@ -91,8 +91,19 @@ class QuantModel(nn.Module):
         self._programs = {}
         self._wcache = {}
 
-    def program(self, x, context=None):
+    def program(self, x, context=None, cfg_dedup=False):
         from . import graph
+        if cfg_dedup:       # x: one guidance half; the program is compiled for the doubled batch
+            full = (2 * x.shape[0],) + tuple(x.shape[1:])
+            key = ("cfg", full, tuple(context.shape), x.device.index)
+            prog = self._programs.pop(key, None)
+            if prog is None:
+                while len(self._programs) >= max(self.max_programs, 1):
+                    self._programs.pop(next(iter(self._programs)))
+                prog = graph.compile_unet(self, full, tuple(context.shape), x.device, use_cuda_graph=self.use_cuda_graph,
+                                          cfg_dedup=True)
+            self._programs[key] = prog
+            return prog
         key = (tuple(x.shape), None if context is None else tuple(context.shape), x.device.index)
         prog = self._programs.pop(key, None)
         if prog is None:
@@ -102,6 +113,16 @@ class QuantModel(nn.Module):
                                       x.device, use_cuda_graph=self.use_cuda_graph)
         self._programs[key] = prog      # (re)insert at the most-recently-used end
         return prog
+
+    def forward_cfg(self, x, timesteps, context):
+        """eps of the classifier-free-guidance batch [x; x] with timesteps [t; t] and context [uncond; cond] (what
+        p_sample_plms / p_sample_ddim build, plms.py:185-189) from ONE copy of x and t: the guidance-invariant prefix of the
+        UNet runs once (graph.Builder.cfg_split).  Returns [2B, C, H, W], bit-identical to forward(cat, cat, context)."""
+        if not x.is_cuda:
+            raise RuntimeError("qdiff_b200.QuantModel.forward_cfg needs CUDA tensors: the engine has no CPU fallback")
+        if context is None or context.shape[0] != 2 * x.shape[0]:
+            raise ValueError("forward_cfg: context must hold [uncond; cond] rows for the batch (2 x batch rows)")
+        return self.program(x, context, cfg_dedup=True).run(x, timesteps, context)
 
     def forward(self, x, timesteps=None, context=None):
         if timesteps is None and isinstance(x, (tuple, list)):  # ddim Model.forward accepts (x, t) as one argument

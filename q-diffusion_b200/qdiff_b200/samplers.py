@@ -11,6 +11,7 @@ Restates, with the same argument names:
   schedules                             ldm/modules/diffusionmodules/util.py:21-74, ddpm.py:118-146
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -60,6 +61,9 @@ def make_ddim_sampling_parameters(alphacums, ddim_timesteps, eta):
     return sigmas, alphas, alphas_prev
 
 
+_CFG_DEDUP = os.environ.get("QDIFF_CFG_DEDUP", "1") != "0"     # A/B switch for QuantModel.forward_cfg
+
+
 # ------------------------------------------------------------------------------- fused update
 def _step(x, eps, x_prev, *, a_t, a_prev, sigma, sqrt_one_minus_at=None, cfg_scale=0.0, coef=(1.0, 0, 0, 0),
           olds=(None, None, None), noise=None, pred_x0=None, eps_out=None):
@@ -99,15 +103,15 @@ class _LatentSampler:
         batch [uncond; cond] (plms.py:185-189) and the combine happens inside qd_sampler_step."""
         if uc is None or scale == 1.:
             return self.unet(x, t, cond), 0.0
-        x_in = torch.cat([x] * 2)
-        t_in = torch.cat([t] * 2)
         # the conditioning is the same tensor on every step: concatenate once, so the engine sees an unchanged context
         # object and skips the (step-invariant) context K/V projections (graph.Builder.static_scope)
         src = getattr(self, "_cin_src", None)
         if src is None or src[0] is not uc or src[1] is not cond or src[2] != (uc._version, cond._version):
             self._cin = torch.cat([uc, cond])
             self._cin_src = (uc, cond, (uc._version, cond._version))
-        return self.unet(x_in, t_in, self._cin), float(scale)
+        if hasattr(self.unet, "forward_cfg") and _CFG_DEDUP and getattr(getattr(self.unet, "model", None), "use_spatial_transformer", False):
+            return self.unet.forward_cfg(x, t, self._cin), float(scale)      # engine: the shared prefix runs once
+        return self.unet(torch.cat([x] * 2), torch.cat([t] * 2), self._cin), float(scale)
 
 
 class DDIMSampler(_LatentSampler):

@@ -466,6 +466,8 @@ def _run_attention(cuda, B, heads, d, Tq, Tk, sym, sm_bits, seed):
 
 @pytest.mark.parametrize("B,heads,d,Tq,Tk,sym,sm_bits", [
     (2, 8, 40, 256, 256, False, 16),   # SD self-attention head shape (sm_abit 16, asymmetric)
+    (1, 2, 40, 384, 1100, False, 16),  # several key tiles with a ragged last one (the 64x64 level's code path), Tq != Tk
+    (1, 3, 32, 640, 640, True, 8),     # LDM-legacy head dim, 5 key tiles, symmetric codes, 8-bit softmax
     (2, 8, 40, 200, 77, False, 16),    # SD cross-attention: ragged Tq, 77 context tokens (small-Tk kernel)
     (1, 4, 80, 300, 77, False, 16),    # ... at the 32x32 level (d = 80)
     (1, 2, 40, 2100, 77, True, 8),     # ... several slabs per warp, symmetric, 8-bit softmax codes
