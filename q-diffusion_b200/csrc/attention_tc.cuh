@@ -65,14 +65,20 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw(uint32_t smem_addr, int P)
   return d;
 }
 
-// GRP = 2 (with NSW = 16): the softmax warps form two groups of 8 that take ALTERNATE key tiles (tile T -> S slot T & 1 ->
-// group T & 1), group 1 starting half a tile period late.  With one group all four warps of a scheduler are in the same
-// phase of the per-tile work - TMEM load + integer max, then 32 x {FADD2, FFMA2, MUFU}, then packing - so the XU pipe
-// (54 % busy, profiles/r02_attention_ncu.txt) idles while the ALU phase runs and vice versa; two phase-shifted groups let
-// one group's exp2 stream overlap the other's integer / packing work.  MEASURED: 9 % slower than one group (1938 vs 1775 us,
-// B=16 x 8 heads, T=4096): a thread then walks two 32-column chunks per tile back to back and the groups' tile hand-offs
-// serialise on the in-order MMA issue.  Not the default (engine.cu: QDIFF_ATTN_GROUPS=2 enables it).
-template <bool SM16, bool MAGIC, int NSW, int GRP>
+// What sets the pace (csrc/experimental/tmem_probe.cu, tools/prof_attn.py; B=16 x 8 heads, T=4096, d=40):
+//   * the softmax warps are INSTRUCTION bound, not XU bound: replacing every exp2 by a multiply changes 1765 us to 1667 us, and
+//     the bare pass-1 arithmetic on 16 warps without any MMA or barrier needs 1274 cycles per 128x128 tile against 1024 for
+//     the exp2 alone.  Every instruction per score counts: HZ as a template parameter removes 32 predicated MOVs per chunk
+//     (-5 %), the int->float conversion is folded into the scaling FMA (below, -0.5 instruction per score and pass).
+//   * the S slot goes back to the MMA warp as soon as a warp holds its scores in registers (not after the exp2 work), and
+//     in pass 2 the MMA warp issues S(t + 2) BEFORE P(t) V(t) - both become possible at about the same time and the short S
+//     MMA must not queue behind 8 PV MMAs on the in-order tensor pipe.  Together -7.5 % (either alone: -1.4 % / -2.7 %).
+//   * tried and measured slower or equal: two softmax groups on alternate tiles (+9 %), phase-shifting the four warps of a
+//     scheduler with nanosleep (0), four parallel max chains / two exp2 accumulators (0), a software pipeline that loads the
+//     next 16-column piece during the arithmetic of the current one (+13 %: twice the per-piece overhead instructions),
+//     8-stage K ring + whole-axis zq*rowsum(k) table (0: the loader is not on the critical path).
+// HZ: q has a zero point (scores need the zq*rowsum(k) correction).
+template <bool SM16, bool MAGIC, int NSW, bool HZ>
 __global__ void __launch_bounds__(atc_threads(NSW), NSW == 16 ? 1 : 2)
 qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const qd_attention_desc p, const int NV, const int P) {
@@ -83,10 +89,9 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   constexpr int ATC_THREADS = atc_threads(NSW);
   constexpr int ATC_STAGES = atc_stages(NSW);
   constexpr int SSLOTS = atc_sslots(NSW);
-  static_assert(GRP == 1 || (GRP == 2 && NSW == 16), "two softmax groups need the 16-warp configuration");
   constexpr int NPART = NSW / 4;             // softmax warps per TMEM lane quarter
-  constexpr int CPT = 4 * GRP / NPART;       // 32-column chunks of a tile per softmax thread
-  constexpr int WPG = NSW / GRP;             // softmax warps that work on one tile
+  constexpr int CPT = 4 / NPART;             // 32-column chunks of a tile per softmax thread
+  constexpr int WPG = NSW;                   // softmax warps that work on one tile
   constexpr uint32_t TMEM_COLS = NSW == 16 ? 512 : 256;
   const AtcSmem L = atc_smem_layout(NV, P, NSW);
   uint8_t* sQ = smem + L.q_off;
@@ -108,7 +113,7 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int d = p.d;
   const int nks = (d + 31) >> 5;                 // K=32 slices of QK^T
   const int ntiles = (p.Tk + ATC_BN - 1) / ATC_BN;
-  const bool has_zq = p.zq != 0;
+  constexpr bool has_zq = HZ;
 
   const int* zrk_g = reinterpret_cast<const int*>(p.ws) + (long long)bh * (long long)att_ws_stride(p.Tk);
 
@@ -195,7 +200,7 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (++st == ATC_STAGES) { st = 0; ph_kv ^= 1; }
         if (++sb == SSLOTS) { sb = 0; ph_s ^= 1; }
       }
-      // ---- pass 2: S(t+1) is issued before PV(t) so the softmax of t+1 overlaps the PV MMAs of t
+      // ---- pass 2: SSLOTS score tiles are kept in flight ahead of the PV MMAs (S(t + SSLOTS) is issued BEFORE P(t) V(t))
       auto issue_s = [&](int st_, int sb_) {
         const uint64_t dk = make_smem_desc_sw(smem_u32(smem + L.k_off + st_ * L.k_stage), P);
         for (int j = 0; j < nks; ++j) umma_i8(tm_s + sb_ * 128, dq + 2 * j, dk + 2 * j, idesc_s, j ? 1u : 0u);
@@ -207,17 +212,23 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tc_fence_after();
       issue_s(st_s, sb_s);
       umma_commit(&s_full[sb_s]);
-      for (int t = 0; t < ntiles; ++t) {
-        const int st_cur = st_s;
+      int st_v = st;            // K/V stage of the tile whose P V is issued next
+      auto next_s = [&](int tnext) {
         if (++st_s == ATC_STAGES) { st_s = 0; ph_kv_s ^= 1; }
         if (++sb_s == SSLOTS) { sb_s = 0; ph_s_s ^= 1; }
-        if (t + 1 < ntiles) {
+        if (tnext < ntiles) {
           mbar_wait(&kv_full[st_s], ph_kv_s);
           mbar_wait(&s_empty[sb_s], ph_s_s ^ 1);
           tc_fence_after();
           issue_s(st_s, sb_s);
           umma_commit(&s_full[sb_s]);
         }
+      };
+      if (SSLOTS == 2) next_s(1);
+      for (int t = 0; t < ntiles; ++t) {
+        const int st_cur = st_v;
+        if (++st_v == ATC_STAGES) st_v = 0;
+        next_s(t + SSLOTS);
         mbar_wait(&p_full[pb], ph_p);
         tc_fence_after();
         const uint64_t dv = make_smem_desc_sw128(smem_u32(smem + L.v_off + st_cur * L.v_stage));
@@ -242,8 +253,6 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const float c = p.sim_scale * 1.4426950408889634f;
     const float pmax = (float)p.p_qmax;
     float2* stat = reinterpret_cast<float2*>(smem + L.stat_off);
-    const int grp = GRP == 2 ? (part >> 1) : 0;          // softmax group of this warp
-    const int sub = GRP == 2 ? (part & 1) : part;        // column part inside the group
     // Tile counters: T = pass * ntiles + t is the global index of a key tile in MMA issue order.  Everything follows from
     // it: S slot T & 1 (phase (T >> 1) & 1; one slot: phase T & 1), K/V stage T % stages, P buffer t & 1 (phase (t >> 1) & 1).
     auto s_slot = [](int T) { return SSLOTS == 2 ? (T & 1) : 0; };
@@ -253,7 +262,6 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // integer row max AND the bit pattern of the float 1.5*2^23 + S, so the int->float conversion is a single FADD.
     constexpr int BIAS = MAGIC ? 0x4B400000 : 0;
     constexpr int MASKED = MAGIC ? BIAS - (1 << 22) + 1 : INT_MIN / 2;
-    auto tof = [](int t) -> float { return MAGIC ? __int_as_float(t) - 12582912.0f : (float)t; };
     auto tof2 = [](int t0, int t1) -> float2 {
       return MAGIC ? fadd2(make_float2(__int_as_float(t0), __int_as_float(t1)), make_float2(-12582912.0f, -12582912.0f))
                    : make_float2((float)t0, (float)t1);
@@ -261,20 +269,24 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     int mi = INT_MIN;
     float l = 0.f;
     // ---- pass 1
-    if (GRP == 2 && grp == 1) __nanosleep(500);             // phase shift between the two groups (about half a tile period)
-    for (int t = (GRP == 2 ? grp : 0); t < ntiles; t += GRP) {
+    for (int t = 0; t < ntiles; ++t) {
       const int T = t;
       const int sb = s_slot(T), st = T % ATC_STAGES;
       mbar_wait(&s_full[sb], s_phase(T));
       tc_fence_after();
 #pragma unroll 1
       for (int cc = 0; cc < CPT; ++cc) {
-        const int col0 = (sub * CPT + cc) * 32;           // this thread's 32 key columns of the tile
+        const int col0 = (part * CPT + cc) * 32;          // this thread's 32 key columns of the tile
         const int j0 = t * ATC_BN + col0;
         const int* zr = reinterpret_cast<const int*>(smem + L.zrk_off + st * 512) + col0;
         uint32_t v[32];
         tmem_ld_32x32(tm_s + t_lane + sb * 128 + col0, v);
         tmem_ld_wait();
+        if (cc == CPT - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[sb]);
+        }
         int s[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -294,29 +306,43 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
           for (int j = 1; j < 32; ++j) tm = max(tm, s[j]);
           if (tm > mi) { l *= (mi == INT_MIN) ? 0.f : ex2_approx((float)(mi - tm) * c); mi = tm; }
-          const float b0 = -(float)(mi - BIAS) * c;
           // packed fp32 (FADD2 / FFMA2): same IEEE results as the scalar form, half the issue slots
-          const float2 c2 = make_float2(c, c), b2 = make_float2(b0, b0);
+          const float2 c2 = make_float2(c, c);
           float2 acc2 = make_float2(0.f, 0.f);
+          if (MAGIC) {
+            // F = float pattern of the biased score = K + S, Fm = K + max: c * (S - max) = fma(F, c, -c * Fm).  -c * Fm is
+            // split exactly into hi + lo (lo = the FMA residual), the chunk is summed against hi alone - one FFMA2 per
+            // two scores instead of FADD2 + FFMA2 - and the sum is multiplied by 2^lo afterwards (|lo| <= ulp(c * Fm) / 2)
+            const float Fm = __int_as_float(mi);
+            const float hi = -c * Fm, lo = fmaf(-c, Fm, -hi);
+            const float2 h2 = make_float2(hi, hi);
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float2 x = ffma2(tof2(s[j], s[j + 1]), c2, b2);
-            acc2 = fadd2(acc2, make_float2(ex2_approx(x.x), ex2_approx(x.y)));
+            for (int j = 0; j < 32; j += 2) {
+              const float2 x = ffma2(make_float2(__int_as_float(s[j]), __int_as_float(s[j + 1])), c2, h2);
+              acc2 = fadd2(acc2, make_float2(ex2_approx(x.x), ex2_approx(x.y)));
+            }
+            const float tl = lo * 0.6931471805599453f;
+            l = fmaf(acc2.x + acc2.y, fmaf(tl, fmaf(tl, 0.5f, 1.0f), 1.0f), l);
+          } else {
+            const float b0 = -(float)(mi - BIAS) * c;
+            const float2 b2 = make_float2(b0, b0);
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float2 x = ffma2(tof2(s[j], s[j + 1]), c2, b2);
+              acc2 = fadd2(acc2, make_float2(ex2_approx(x.x), ex2_approx(x.y)));
+            }
+            l += acc2.x + acc2.y;
           }
-          l += acc2.x + acc2.y;
         }
       }
-      tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&s_empty[sb]);
-        mbar_arrive(&kv_empty[st]);
-      }
+      if (lane == 0) mbar_arrive(&kv_empty[st]);
     }
     // ---- combine the column parts of every row (named barrier over the softmax warps)
     stat[part * 128 + row] = make_float2(__int_as_float(mi), l);
     asm volatile("bar.sync 1, %0;" ::"n"(32 * NSW) : "memory");
-    float off;
+    float off;          // code = exp2(c * S + off)
+    float off_hi, g_lo; // MAGIC: c * S + off = fma(F, c, off_hi) + lo with F = K + S; g_lo = 2^lo multiplies the exponential
     bool row_clamps;
     {
       int mm = INT_MIN;
@@ -330,13 +356,23 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         lt += o.y * ((mo == INT_MIN) ? 0.f : ex2_approx((float)(mo - mm) * c));
       }
       const float inv = 1.0f / (lt * p.delta_w);     // the row's largest possible P code (score == row max)
-      off = -(float)(mm - BIAS) * c + log2f(inv);
+      const float lg = log2f(inv);
+      off = -(float)(mm - BIAS) * c + lg;
+      {
+        // -c * (K + max) + lg = h1 + l1 + lg exactly (FMA residual), then TwoSum(h1, lg) = off_hi + err
+        const float Fm = __int_as_float(mm);
+        const float h1 = -c * Fm, l1 = fmaf(-c, Fm, -h1);
+        off_hi = h1 + lg;
+        const float bb = off_hi - h1;
+        const float err = (h1 - (off_hi - bb)) + (lg - bb);
+        const float tl = (err + l1) * 0.6931471805599453f;
+        g_lo = fmaf(tl, fmaf(tl, 0.5f, 1.0f), 1.0f);
+      }
       row_clamps = !(inv <= pmax);
     }
     const bool warp_clamps = __any_sync(0xffffffffu, row_clamps);
-    // ---- pass 2 (group g takes the tiles whose global index ntiles + t has parity g)
-    if (GRP == 2 && grp == 1) __nanosleep(500);
-    for (int t = (GRP == 2 ? ((grp + ntiles) & 1) : 0); t < ntiles; t += GRP) {
+    // ---- pass 2
+    for (int t = 0; t < ntiles; ++t) {
       const int T = ntiles + t;
       const int sb = s_slot(T), st = T % ATC_STAGES, pb = t & 1;
       const uint32_t ph_p = (t >> 1) & 1;
@@ -347,14 +383,20 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       uint8_t* phh = pl + 16384;
 #pragma unroll 1
       for (int cc = 0; cc < CPT; ++cc) {
-        const int col0 = (sub * CPT + cc) * 32;
+        const int col0 = (part * CPT + cc) * 32;
         const int j0 = t * ATC_BN + col0;
         const int* zr = reinterpret_cast<const int*>(smem + L.zrk_off + st * 512) + col0;
         uint32_t v[32];
         tmem_ld_32x32(tm_s + t_lane + sb * 128 + col0, v);
         tmem_ld_wait();
+        if (cc == CPT - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[sb]);
+        }
         uint32_t cd[32];
         const float2 c2 = make_float2(c, c), off2 = make_float2(off, off), k2 = make_float2(12582912.0f, 12582912.0f);
+        const float2 oh2 = make_float2(off_hi, off_hi), g2 = make_float2(g_lo, g_lo);
         // code = rne(min(exp2(c*s + off), pmax)) through the 1.5*2^23 constant; the min is skipped (warp-uniformly) when no
         // row of this warp can exceed pmax: its largest code is 1 / (l * delta_w), known after pass 1
         auto codes = [&](auto clamp_tag) {
@@ -363,15 +405,31 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           for (int j = 0; j < 32; j += 4) {
             int4 z = make_int4(BIAS, BIAS, BIAS, BIAS);
             if (has_zq) z = *reinterpret_cast<const int4*>(zr + j);
-            const float2 x0 = ffma2(tof2((int)v[j] + z.x, (int)v[j + 1] + z.y), c2, off2);
-            const float2 x1 = ffma2(tof2((int)v[j + 2] + z.z, (int)v[j + 3] + z.w), c2, off2);
-            float2 e0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
-            float2 e1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
-            if (CLAMP) {
-              e0.x = fminf(e0.x, pmax); e0.y = fminf(e0.y, pmax);
-              e1.x = fminf(e1.x, pmax); e1.y = fminf(e1.y, pmax);
+            float2 r0, r1;
+            if (MAGIC) {
+              // fma(F, c, off_hi) replaces {F - K, fma(., c, off)}; the 2^lo factor rides on the rounding add: fma(e, g, K)
+              const float2 x0 = ffma2(make_float2(__int_as_float((int)v[j] + z.x), __int_as_float((int)v[j + 1] + z.y)), c2, oh2);
+              const float2 x1 = ffma2(make_float2(__int_as_float((int)v[j + 2] + z.z), __int_as_float((int)v[j + 3] + z.w)), c2, oh2);
+              float2 e0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+              float2 e1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+              if (CLAMP) {
+                e0.x = fminf(e0.x * g_lo, pmax); e0.y = fminf(e0.y * g_lo, pmax);
+                e1.x = fminf(e1.x * g_lo, pmax); e1.y = fminf(e1.y * g_lo, pmax);
+                r0 = fadd2(e0, k2); r1 = fadd2(e1, k2);
+              } else {
+                r0 = ffma2(e0, g2, k2); r1 = ffma2(e1, g2, k2);
+              }
+            } else {
+              const float2 x0 = ffma2(tof2((int)v[j] + z.x, (int)v[j + 1] + z.y), c2, off2);
+              const float2 x1 = ffma2(tof2((int)v[j + 2] + z.z, (int)v[j + 3] + z.w), c2, off2);
+              float2 e0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+              float2 e1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+              if (CLAMP) {
+                e0.x = fminf(e0.x, pmax); e0.y = fminf(e0.y, pmax);
+                e1.x = fminf(e1.x, pmax); e1.y = fminf(e1.y, pmax);
+              }
+              r0 = fadd2(e0, k2); r1 = fadd2(e1, k2);
             }
-            const float2 r0 = fadd2(e0, k2), r1 = fadd2(e1, k2);
             cd[j] = __float_as_uint(r0.x); cd[j + 1] = __float_as_uint(r0.y);
             cd[j + 2] = __float_as_uint(r1.x); cd[j + 3] = __float_as_uint(r1.y);
           }
@@ -402,10 +460,8 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
       fence_proxy_async();       // P bytes (generic proxy) -> visible to the MMA (async proxy)
-      tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&s_empty[sb]);
         mbar_arrive(&kv_empty[st]);
         mbar_arrive(&p_full[pb]);
       }

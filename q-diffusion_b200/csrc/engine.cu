@@ -602,10 +602,10 @@ int launch_attention_smallk(const qd_attention_desc& d, cudaStream_t s) {
 }
 
 // tcgen05 path (attention_tc.cuh): d <= 112, Q/K codes in the per-head padded layout (pitch 32/64/128), dense V^T
-template <bool S16, bool MAGIC, int NSW, int GRP = 1>
+template <bool S16, bool MAGIC, int NSW, bool HZ>
 int launch_attention_tc_inst(const qd_attention_desc& d, const CUtensorMap& tmQ, const CUtensorMap& tmK,
                              const CUtensorMap& tmV, int NV, int P, cudaStream_t s) {
-  auto kern = qd::qattention_tc_kernel<S16, MAGIC, NSW, GRP>;
+  auto kern = qd::qattention_tc_kernel<S16, MAGIC, NSW, HZ>;
   static std::atomic<unsigned long long> optin{0};
   if (int rc = ensure_smem_optin(kern, NSW == 16 ? 227 * 1024 : 113 * 1024, optin, "attention_tc")) return rc;
   const qd::AtcSmem lay = qd::atc_smem_layout(NV, P, NSW);
@@ -613,6 +613,12 @@ int launch_attention_tc_inst(const qd_attention_desc& d, const CUtensorMap& tmQ,
   dim3 grid((d.Tq + qd::ATC_BM - 1) / qd::ATC_BM, d.B * d.heads);
   kern<<<grid, qd::atc_threads(NSW), lay.total, s>>>(tmQ, tmK, tmV, d, NV, P);
   return check_launch("qattention_tc_kernel");
+}
+template <bool S16, bool MAGIC, int NSW>
+int launch_attention_tc_hz(const qd_attention_desc& d, const CUtensorMap& tmQ, const CUtensorMap& tmK,
+                           const CUtensorMap& tmV, int NV, int P, cudaStream_t s) {
+  if (d.zq != 0) return launch_attention_tc_inst<S16, MAGIC, NSW, true>(d, tmQ, tmK, tmV, NV, P, s);
+  return launch_attention_tc_inst<S16, MAGIC, NSW, false>(d, tmQ, tmK, tmV, NV, P, s);
 }
 
 bool attention_tc_eligible(const qd_attention_desc& d) {
@@ -669,20 +675,13 @@ int launch_attention_tc(const qd_attention_desc& d, cudaStream_t s) {
   const bool small = two_cta && P <= 64 && NV <= 64 && magic && (long long)d.Tq * d.Tk <= (1LL << 21) &&
                      qd::atc_smem_layout(NV, P, 8).total <= 113 * 1024;
   if (small) {
-    if (s16) return launch_attention_tc_inst<true, true, 8>(d, tmQ, tmK, tmV, NV, P, s);
-    return launch_attention_tc_inst<false, true, 8>(d, tmQ, tmK, tmV, NV, P, s);
+    if (s16) return launch_attention_tc_hz<true, true, 8>(d, tmQ, tmK, tmV, NV, P, s);
+    return launch_attention_tc_hz<false, true, 8>(d, tmQ, tmK, tmV, NV, P, s);
   }
-  // two phase-shifted softmax groups (attention_tc.cuh), QDIFF_ATTN_GROUPS=2: measured SLOWER (1938 vs 1775 us on the 64x64
-  // self-attention), kept as an experiment switch; the default keeps all 16 warps on the same key tile
-  static const int groups = [] { const char* e = getenv("QDIFF_ATTN_GROUPS"); return (e && !strcmp(e, "2")) ? 2 : 1; }();
-  if (magic && groups == 2 && d.Tk > 256) {
-    if (s16) return launch_attention_tc_inst<true, true, 16, 2>(d, tmQ, tmK, tmV, NV, P, s);
-    return launch_attention_tc_inst<false, true, 16, 2>(d, tmQ, tmK, tmV, NV, P, s);
-  }
-  if (s16 && magic) return launch_attention_tc_inst<true, true, 16>(d, tmQ, tmK, tmV, NV, P, s);
-  if (s16 && !magic) return launch_attention_tc_inst<true, false, 16>(d, tmQ, tmK, tmV, NV, P, s);
-  if (!s16 && magic) return launch_attention_tc_inst<false, true, 16>(d, tmQ, tmK, tmV, NV, P, s);
-  return launch_attention_tc_inst<false, false, 16>(d, tmQ, tmK, tmV, NV, P, s);
+  if (s16 && magic) return launch_attention_tc_hz<true, true, 16>(d, tmQ, tmK, tmV, NV, P, s);
+  if (s16 && !magic) return launch_attention_tc_hz<true, false, 16>(d, tmQ, tmK, tmV, NV, P, s);
+  if (!s16 && magic) return launch_attention_tc_hz<false, true, 16>(d, tmQ, tmK, tmV, NV, P, s);
+  return launch_attention_tc_hz<false, false, 16>(d, tmQ, tmK, tmV, NV, P, s);
 }
 
 int launch_attention(const qd_attention_desc& d, cudaStream_t s) {

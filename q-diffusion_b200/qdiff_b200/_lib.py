@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqdiff_b200.so")
+# QDIFF_B200_LIB: another build of the same library (A/B timing of kernel variants); the default is the in-tree build
+LIB_PATH = os.environ.get("QDIFF_B200_LIB") or os.path.join(_HERE, "libqdiff_b200.so")
 
 c_ll = C.c_longlong
 c_i32 = C.c_int32
