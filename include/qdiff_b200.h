@@ -113,7 +113,11 @@ typedef struct qd_gemm_desc {
    * y = scale[n] * sum_k x[m,k] * ws[n,k] + bias (+ rowvec, + residual) carries fp32-level rounding only
    * (qdiff/quant_layer.py:263-279 with use_act_quant False).  No corr, no out_q, no geglu. */
   int32_t a_bf16;
-  int32_t reserved4;
+  /* out_q_f16 = 1 (row-major out_q only): out_q receives fp16 values (code - zero_point) instead of 8-bit codes; ldq and
+   * out_q_head_pitch then count fp16 elements.  Operand format of qd_attention_desc.qk_f16 (the attention's QK^T on
+   * tcgen05.mma kind::f16: the same integers, no zero-point correction pass).  The centred code is an integer of
+   * magnitude <= 255, exact in fp16. */
+  int32_t out_q_f16;
 } qd_gemm_desc;
 
 int qd_qgemm_i8(const qd_gemm_desc* d, qd_stream_t stream);
@@ -295,6 +299,11 @@ typedef struct qd_attention_desc {
   void* out_q;           /* optional: codes of the consumer's activation quantizer `oq` (to_out / proj_out input) */
   long long ld_out_q;
   qd_qparams oq;
+  /* qk_f16 = 1: q and k hold fp16 values (code - zero_point) in the per-head padded layout (head_stride_q = head_stride_k
+   * = 128 BYTES, d <= 64; ld_q / ld_k / offsets in bytes as always); zq / zk / q_signed / k_signed / ws are ignored.
+   * Same result as the code path (exact integer arithmetic in fp32); tcgen05 kernel only. */
+  int32_t qk_f16;
+  int32_t reserved5;
 } qd_attention_desc;
 
 int qd_qattention(const qd_attention_desc* d, qd_stream_t stream);

@@ -31,12 +31,17 @@ namespace qd {
 //             prologue (TMEM allocation, Q/K loads), barrier round trips and epilogue are covered by the other's
 //             arithmetic (profiles/r01_attention_tc_final.txt: 13 % of the warp samples sat in mbarrier spins).
 constexpr int ATC_BM = 128, ATC_BN = 128;
+#ifndef ATC_PBUFS
+#define ATC_PBUFS 2         // P buffers (lo + hi plane each); 3 (when shared memory allows) measured slower: 1541 vs 1461 us
+#endif
+
 __host__ __device__ constexpr int atc_threads(int NSW) { return 64 + 32 * NSW; }
 __host__ __device__ constexpr int atc_stages(int NSW) { return NSW == 16 ? 4 : 2; }
 __host__ __device__ constexpr int atc_sslots(int NSW) { return NSW == 16 ? 2 : 1; }
 
 struct AtcSmem {
   int q_off, k_off, v_off, p_off, zrk_off, stat_off, bar_off, total, v_stage, k_stage;
+  int npb;      // P buffers
 };
 __host__ __device__ inline AtcSmem atc_smem_layout(int NV, int P, int NSW = 16) {
   const int stages = atc_stages(NSW);
@@ -47,7 +52,10 @@ __host__ __device__ inline AtcSmem atc_smem_layout(int NV, int P, int NSW = 16) 
   l.v_stage = NV * 128;
   l.v_off = l.k_off + stages * l.k_stage;
   l.p_off = (l.v_off + stages * l.v_stage + 1023) / 1024 * 1024;
-  l.zrk_off = l.p_off + 4 * 16384;          // [buffer][plane]
+  l.npb = 2;
+  if (NSW == 16 && ATC_PBUFS > 2 && l.p_off + ATC_PBUFS * 32768 + stages * 512 + (NSW / 4) * 128 * 8 + 256 + 1024 <= 227 * 1024)
+    l.npb = ATC_PBUFS;
+  l.zrk_off = l.p_off + l.npb * 2 * 16384;          // [buffer][plane]
   l.stat_off = l.zrk_off + stages * 512;
   l.bar_off = l.stat_off + (NSW / 4) * 128 * 8;
   l.total = l.bar_off + 256 + 1024;
@@ -73,12 +81,24 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw(uint32_t smem_addr, int P)
 //   * the S slot goes back to the MMA warp as soon as a warp holds its scores in registers (not after the exp2 work), and
 //     in pass 2 the MMA warp issues S(t + 2) BEFORE P(t) V(t) - both become possible at about the same time and the short S
 //     MMA must not queue behind 8 PV MMAs on the in-order tensor pipe.  Together -7.5 % (either alone: -1.4 % / -2.7 %).
-//   * tried and measured slower or equal: two softmax groups on alternate tiles (+9 %), phase-shifting the four warps of a
-//     scheduler with nanosleep (0), four parallel max chains / two exp2 accumulators (0), a software pipeline that loads the
-//     next 16-column piece during the arithmetic of the current one (+13 %: twice the per-piece overhead instructions),
-//     8-stage K ring + whole-axis zq*rowsum(k) table (0: the loader is not on the critical path).
+//   * tried and measured slower or equal (profiles/r02_attention_variants.txt): two softmax groups on alternate tiles
+//     (+9 %), phase-shifting the four warps of a scheduler with nanosleep (0), four parallel max chains / two exp2
+//     accumulators (0), software pipelines that load the next 16- or 32-column piece during the arithmetic of the current
+//     one, with the exp2 stream referenced to the previous pieces' maximum (integer path +13 %, fp16 path +7 % / +14 %),
+//     8-stage K ring + whole-axis zq*rowsum(k) table (0: the loader is not on the critical path), a third P buffer (+5 %),
+//     a third or a quarter of the exp2 as a degree-6 polynomial on the FMA pipe (+1..+12 %: with four warps per scheduler
+//     the softmax is bound by each warp's serial instruction stream, so every added instruction costs time even on an idle
+//     pipe, while removing the exp2 altogether only gains 13 %).
 // HZ: q has a zero point (scores need the zq*rowsum(k) correction).
-template <bool SM16, bool MAGIC, int NSW, bool HZ>
+// F16: Q and K arrive as fp16 values (code - zero_point), written that way by the to_q / to_k GEMM epilogues
+// (qd_gemm_desc.out_q_f16), and S = Q K^T runs as tcgen05.mma kind::f16 with fp32 accumulation: products and sums of
+// integers below 2^24 are exact in fp32, so S is the SAME integer (q - zq).(k - zk) the integer path produces after its
+// zero-point correction - but it needs no correction (no zq*rowsum(k) kernel, table, LDS or IADD per score), no int->float
+// conversion, and the row maximum is a 3-input FMNMX.  Per score: pass 1 = {FMNMX3/2, FFMA2/2, EX2, FADD2/2}, pass 2 =
+// {FFMA2/2, EX2, FFMA2/2, PRMT, STS/16} - about 5.6 instructions over both passes against 9.8 on the integer path.  The
+// tensor pipe runs kind::f16 at half the kind::i8 rate, which does not matter at ~12 % utilisation.  d <= 64 (one 128-byte
+// swizzle span per row).
+template <bool SM16, bool MAGIC, int NSW, bool HZ, bool F16 = false>
 __global__ void __launch_bounds__(atc_threads(NSW), NSW == 16 ? 1 : 2)
 qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const qd_attention_desc p, const int NV, const int P) {
@@ -100,19 +120,31 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* kv_empty = bars + 4;   // [ATC_STAGES]
   uint64_t* s_full = bars + 8;     // [2]
   uint64_t* s_empty = bars + 10;   // [2]
-  uint64_t* p_full = bars + 12;    // [2]
-  uint64_t* p_empty = bars + 14;   // [2]
-  uint64_t* o_done = bars + 16;    // [1]
-  uint64_t* q_full = bars + 17;    // [1]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* p_full = bars + 12;    // [4]
+  uint64_t* p_empty = bars + 16;   // [4]
+  uint64_t* o_done = bars + 20;    // [1]
+  uint64_t* q_full = bars + 21;    // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 22);
+  const int npb = L.npb;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
   const int b = bh / p.heads, h = bh - b * p.heads;
   const int row_base = blockIdx.x * ATC_BM;
   const int d = p.d;
-  const int nks = (d + 31) >> 5;                 // K=32 slices of QK^T
+  const int nks = F16 ? (d + 15) >> 4 : (d + 31) >> 5;   // 32-byte K slices of QK^T (32 codes, or 16 fp16 values)
   const int ntiles = (p.Tk + ATC_BN - 1) / ATC_BN;
+  // timing experiments (-DATC_DBG_SKIP1 / -DATC_DBG_SKIP2: one pass only, results wrong)
+#ifdef ATC_DBG_SKIP1
+  const int n1 = 0;
+#else
+  const int n1 = ntiles;
+#endif
+#ifdef ATC_DBG_SKIP2
+  const int n2 = 0;
+#else
+  const int n2 = ntiles;
+#endif
   constexpr bool has_zq = HZ;
 
   const int* zrk_g = reinterpret_cast<const int*>(p.ws) + (long long)bh * (long long)att_ws_stride(p.Tk);
@@ -127,12 +159,14 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < ATC_STAGES; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1 + WPG);    // MMA commit + the softmax warps of the tile (they read the zq*rowsum(k) slice of the stage)
+      mbar_init(&kv_empty[i], F16 ? 1 : 1 + WPG);    // MMA commit (+ the softmax warps of the tile: they read the zq*rowsum(k) slice of the stage)
     }
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], WPG);
+    }
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&p_full[i], WPG);
       mbar_init(&p_empty[i], 1);
     }
@@ -162,7 +196,7 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tma_load_2d(sQ, &tmQ, q_full, h * P, b * p.Tq + row_base);
     }
     for (int pass = 0; pass < 2; ++pass) {
-      for (int t = 0; t < ntiles; ++t) {
+      for (int t = 0; t < (pass == 0 ? n1 : n2); ++t) {
         const int j0 = t * ATC_BN;
         mbar_wait(&kv_empty[st], ph ^ 1);
         if (has_zq) {
@@ -182,19 +216,22 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_i8(128, 128, p.q_signed, p.k_signed);
+      const uint32_t idesc_s = F16 ? make_idesc_f16(128, 128) : make_idesc_i8(128, 128, p.q_signed, p.k_signed);
       const uint32_t idesc_o = make_idesc_i8(128, NV, 0, p.v_signed);
       const uint64_t dq = make_smem_desc_sw(smem_u32(sQ), P);
       mbar_wait(q_full, 0);
       int st = 0, sb = 0, pb = 0;
       uint32_t ph_kv = 0, ph_s = 0, ph_p = 0;
       // ---- pass 1: S only
-      for (int t = 0; t < ntiles; ++t) {
+      for (int t = 0; t < n1; ++t) {
         mbar_wait(&kv_full[st], ph_kv);
         mbar_wait(&s_empty[sb], ph_s ^ 1);
         tc_fence_after();
         const uint64_t dk = make_smem_desc_sw(smem_u32(smem + L.k_off + st * L.k_stage), P);
-        for (int j = 0; j < nks; ++j) umma_i8(tm_s + sb * 128, dq + 2 * j, dk + 2 * j, idesc_s, j ? 1u : 0u);
+        for (int j = 0; j < nks; ++j) {
+          if (F16) umma_bf16(tm_s + sb * 128, dq + 2 * j, dk + 2 * j, idesc_s, j ? 1u : 0u);     // kind::f16, fp16 operands
+          else umma_i8(tm_s + sb * 128, dq + 2 * j, dk + 2 * j, idesc_s, j ? 1u : 0u);
+        }
         umma_commit(&s_full[sb]);
         umma_commit(&kv_empty[st]);
         if (++st == ATC_STAGES) { st = 0; ph_kv ^= 1; }
@@ -203,10 +240,14 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // ---- pass 2: SSLOTS score tiles are kept in flight ahead of the PV MMAs (S(t + SSLOTS) is issued BEFORE P(t) V(t))
       auto issue_s = [&](int st_, int sb_) {
         const uint64_t dk = make_smem_desc_sw(smem_u32(smem + L.k_off + st_ * L.k_stage), P);
-        for (int j = 0; j < nks; ++j) umma_i8(tm_s + sb_ * 128, dq + 2 * j, dk + 2 * j, idesc_s, j ? 1u : 0u);
+        for (int j = 0; j < nks; ++j) {
+          if (F16) umma_bf16(tm_s + sb_ * 128, dq + 2 * j, dk + 2 * j, idesc_s, j ? 1u : 0u);
+          else umma_i8(tm_s + sb_ * 128, dq + 2 * j, dk + 2 * j, idesc_s, j ? 1u : 0u);
+        }
       };
       int st_s = st, sb_s = sb;
       uint32_t ph_kv_s = ph_kv, ph_s_s = ph_s;
+      if (n2 > 0) {
       mbar_wait(&kv_full[st_s], ph_kv_s);
       mbar_wait(&s_empty[sb_s], ph_s_s ^ 1);
       tc_fence_after();
@@ -216,7 +257,7 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       auto next_s = [&](int tnext) {
         if (++st_s == ATC_STAGES) { st_s = 0; ph_kv_s ^= 1; }
         if (++sb_s == SSLOTS) { sb_s = 0; ph_s_s ^= 1; }
-        if (tnext < ntiles) {
+        if (tnext < n2) {
           mbar_wait(&kv_full[st_s], ph_kv_s);
           mbar_wait(&s_empty[sb_s], ph_s_s ^ 1);
           tc_fence_after();
@@ -225,7 +266,7 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       };
       if (SSLOTS == 2) next_s(1);
-      for (int t = 0; t < ntiles; ++t) {
+      for (int t = 0; t < n2; ++t) {
         const int st_cur = st_v;
         if (++st_v == ATC_STAGES) st_v = 0;
         next_s(t + SSLOTS);
@@ -240,7 +281,8 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         umma_commit(&p_empty[pb]);
         umma_commit(&kv_empty[st_cur]);
-        if (++pb == 2) { pb = 0; ph_p ^= 1; }
+        if (++pb == npb) { pb = 0; ph_p ^= 1; }
+      }
       }
       umma_commit(o_done);
     }
@@ -260,16 +302,25 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // Scores are handled in BIASED integer form t = S_raw - zq*rowsum(k) + BIAS (one IADD against the staged
     // "BIAS - zq*rowsum" table): with BIAS = 0x4B400000 (d <= 64, |S| < 2^22) the same register is the score for the
     // integer row max AND the bit pattern of the float 1.5*2^23 + S, so the int->float conversion is a single FADD.
+    // F16: the TMEM word already IS the float score; `mi` then holds float bits and NONE / MASKED are -inf.
     constexpr int BIAS = MAGIC ? 0x4B400000 : 0;
-    constexpr int MASKED = MAGIC ? BIAS - (1 << 22) + 1 : INT_MIN / 2;
+    constexpr int NONE = F16 ? (int)0xFF800000 : INT_MIN;
+    constexpr int MASKED = F16 ? (int)0xFF800000 : (MAGIC ? BIAS - (1 << 22) + 1 : INT_MIN / 2);
+    constexpr bool FOLD = MAGIC || F16;      // scores are float bit patterns F: exponent = fma(F, c, hi)
+    auto s_gt = [](int a, int b) { return F16 ? __int_as_float(a) > __int_as_float(b) : a > b; };
+    auto s_max = [](int a, int b) { return F16 ? __float_as_int(fmaxf(__int_as_float(a), __int_as_float(b))) : max(a, b); };
+    auto s_diff = [](int a, int b) { return F16 ? __int_as_float(a) - __int_as_float(b) : (float)(a - b); };   // a - b in score units
+#if defined(ATC_DBG_NOXU)
+#define ex2_approx(x) ((x) * 0.5f)       /* timing experiment: no XU work (results wrong) */
+#endif
     auto tof2 = [](int t0, int t1) -> float2 {
       return MAGIC ? fadd2(make_float2(__int_as_float(t0), __int_as_float(t1)), make_float2(-12582912.0f, -12582912.0f))
                    : make_float2((float)t0, (float)t1);
     };
-    int mi = INT_MIN;
+    int mi = NONE;
     float l = 0.f;
     // ---- pass 1
-    for (int t = 0; t < ntiles; ++t) {
+    for (int t = 0; t < n1; ++t) {
       const int T = t;
       const int sb = s_slot(T), st = T % ATC_STAGES;
       mbar_wait(&s_full[sb], s_phase(T));
@@ -290,9 +341,13 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         int s[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          int4 z = make_int4(BIAS, BIAS, BIAS, BIAS);
-          if (has_zq) z = *reinterpret_cast<const int4*>(zr + j);
-          s[j] = (int)v[j] + z.x; s[j + 1] = (int)v[j + 1] + z.y; s[j + 2] = (int)v[j + 2] + z.z; s[j + 3] = (int)v[j + 3] + z.w;
+          if (F16) {
+            s[j] = (int)v[j]; s[j + 1] = (int)v[j + 1]; s[j + 2] = (int)v[j + 2]; s[j + 3] = (int)v[j + 3];
+          } else {
+            int4 z = make_int4(BIAS, BIAS, BIAS, BIAS);
+            if (has_zq) z = *reinterpret_cast<const int4*>(zr + j);
+            s[j] = (int)v[j] + z.x; s[j + 1] = (int)v[j + 1] + z.y; s[j + 2] = (int)v[j + 2] + z.z; s[j + 3] = (int)v[j + 3] + z.w;
+          }
         }
         bool any_valid = true;
         if (j0 + 32 > p.Tk) {     // ragged last tile: masked keys drop out of the max and of the sum
@@ -304,13 +359,13 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (any_valid) {
           int tm = s[0];
 #pragma unroll
-          for (int j = 1; j < 32; ++j) tm = max(tm, s[j]);
-          if (tm > mi) { l *= (mi == INT_MIN) ? 0.f : ex2_approx((float)(mi - tm) * c); mi = tm; }
+          for (int j = 1; j < 32; ++j) tm = s_max(tm, s[j]);
+          if (s_gt(tm, mi)) { l *= (mi == NONE) ? 0.f : ex2_approx(s_diff(mi, tm) * c); mi = tm; }
           // packed fp32 (FADD2 / FFMA2): same IEEE results as the scalar form, half the issue slots
           const float2 c2 = make_float2(c, c);
           float2 acc2 = make_float2(0.f, 0.f);
-          if (MAGIC) {
-            // F = float pattern of the biased score = K + S, Fm = K + max: c * (S - max) = fma(F, c, -c * Fm).  -c * Fm is
+          if (FOLD) {
+            // F = float pattern of the biased score = K + S (F16: the score itself, K = 0), Fm = K + max: c * (S - max) = fma(F, c, -c * Fm).  -c * Fm is
             // split exactly into hi + lo (lo = the FMA residual), the chunk is summed against hi alone - one FFMA2 per
             // two scores instead of FADD2 + FFMA2 - and the sum is multiplied by 2^lo afterwards (|lo| <= ulp(c * Fm) / 2)
             const float Fm = __int_as_float(mi);
@@ -336,7 +391,7 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&kv_empty[st]);
+      if (!F16 && lane == 0) mbar_arrive(&kv_empty[st]);
     }
     // ---- combine the column parts of every row (named barrier over the softmax warps)
     stat[part * 128 + row] = make_float2(__int_as_float(mi), l);
@@ -345,19 +400,19 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     float off_hi, g_lo; // MAGIC: c * S + off = fma(F, c, off_hi) + lo with F = K + S; g_lo = 2^lo multiplies the exponential
     bool row_clamps;
     {
-      int mm = INT_MIN;
+      int mm = NONE;
 #pragma unroll
-      for (int k = 0; k < NPART; ++k) mm = max(mm, __float_as_int(stat[k * 128 + row].x));
+      for (int k = 0; k < NPART; ++k) mm = s_max(mm, __float_as_int(stat[k * 128 + row].x));
       float lt = 0.f;
 #pragma unroll
       for (int k = 0; k < NPART; ++k) {
         const float2 o = stat[k * 128 + row];
         const int mo = __float_as_int(o.x);
-        lt += o.y * ((mo == INT_MIN) ? 0.f : ex2_approx((float)(mo - mm) * c));
+        lt += o.y * ((mo == NONE) ? 0.f : ex2_approx(s_diff(mo, mm) * c));
       }
       const float inv = 1.0f / (lt * p.delta_w);     // the row's largest possible P code (score == row max)
       const float lg = log2f(inv);
-      off = -(float)(mm - BIAS) * c + lg;
+      off = (F16 ? -__int_as_float(mm) : -(float)(mm - BIAS)) * c + lg;
       {
         // -c * (K + max) + lg = h1 + l1 + lg exactly (FMA residual), then TwoSum(h1, lg) = off_hi + err
         const float Fm = __int_as_float(mm);
@@ -372,10 +427,11 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     const bool warp_clamps = __any_sync(0xffffffffu, row_clamps);
     // ---- pass 2
-    for (int t = 0; t < ntiles; ++t) {
-      const int T = ntiles + t;
-      const int sb = s_slot(T), st = T % ATC_STAGES, pb = t & 1;
-      const uint32_t ph_p = (t >> 1) & 1;
+    int pb = 0;
+    uint32_t ph_p = 0;
+    for (int t = 0; t < n2; ++t) {
+      const int T = n1 + t;
+      const int sb = s_slot(T), st = T % ATC_STAGES;
       mbar_wait(&s_full[sb], s_phase(T));
       mbar_wait(&p_empty[pb], ph_p ^ 1);
       tc_fence_after();
@@ -404,9 +460,10 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             int4 z = make_int4(BIAS, BIAS, BIAS, BIAS);
-            if (has_zq) z = *reinterpret_cast<const int4*>(zr + j);
+            if (F16) z = make_int4(0, 0, 0, 0);
+            else if (has_zq) z = *reinterpret_cast<const int4*>(zr + j);
             float2 r0, r1;
-            if (MAGIC) {
+            if (FOLD) {
               // fma(F, c, off_hi) replaces {F - K, fma(., c, off)}; the 2^lo factor rides on the rounding add: fma(e, g, K)
               const float2 x0 = ffma2(make_float2(__int_as_float((int)v[j] + z.x), __int_as_float((int)v[j + 1] + z.y)), c2, oh2);
               const float2 x1 = ffma2(make_float2(__int_as_float((int)v[j + 2] + z.z), __int_as_float((int)v[j + 3] + z.w)), c2, oh2);
@@ -462,9 +519,10 @@ qattention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       fence_proxy_async();       // P bytes (generic proxy) -> visible to the MMA (async proxy)
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&kv_empty[st]);
+        if (!F16) mbar_arrive(&kv_empty[st]);
         mbar_arrive(&p_full[pb]);
       }
+      if (++pb == npb) { pb = 0; ph_p ^= 1; }
     }
     // ---- epilogue: O = (256*hi + lo - zv*rowsum) * out_scale
     mbar_wait(o_done, 0);

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "../../include/qdiff_b200.h"
@@ -38,6 +39,20 @@ int check_launch(const char* what) {
   if (e != cudaSuccess) return fail(QD_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return QD_OK;
+}
+
+// Every kernel launch of the library goes through here.
+// Programmatic dependent launch (cudaLaunchAttributeProgrammaticStreamSerialization on every launch + griddepcontrol.wait /
+// launch_dependents in every kernel) was built and MEASURED in round 2: SD step 20.93 vs 20.68 ms, CIFAR 11.94 vs 11.26 ms,
+// church 7.69 vs 7.71 ms - no gain inside the CUDA graphs, so the launches stay plain.
+template <typename... KArgs, typename... Args>
+void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
 }
 
 int current_device() {
@@ -253,6 +268,9 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
   a.rows_per_batch = d->rows_per_batch;
   if ((d->rowvec || d->out_q_transposed) && d->rows_per_batch <= 0) return fail(QD_ERR_BAD_ARG, "gemm: rows_per_batch required");
   a.oq_d = d->out_q_head_dim; a.oq_pitch = d->out_q_head_pitch;
+  a.oq_f16 = d->out_q_f16 ? 1 : 0;
+  if (a.oq_f16 && (!d->out_q || d->out_q_transposed || d->geglu || (d->ldq & 3) || (((uintptr_t)d->out_q) & 7)))
+    return fail(QD_ERR_BAD_ARG, "gemm: out_q_f16 needs a row-major out_q with ldq %% 4 == 0");
   if (a.oq_d > 0 && ((a.oq_d & 3) || (a.oq_pitch & 3) || a.oq_pitch < a.oq_d || d->out_q_transposed || !d->out_q))
     return fail(QD_ERR_BAD_ARG, "gemm: bad out_q head layout");
   if (d->out_q && d->oq.qmax - d->oq.qmin > 255)
@@ -296,7 +314,7 @@ int launch_gemm_mode_w(const GemmPlan& pl, cudaStream_t s) {
   if (stages < 2) stages = 2;
   a.stages = stages;
   const int smem = qd::gemm_smem_layout(a.BN, stages, epi_warps, W4 ? 1 : 0, res_bytes).total;
-  qd::gemm_i8_kernel<MODE, W4><<<pl.grid, qd::gemm_threads(MODE), smem, s>>>(pl.tmA, pl.tmB, pl.tmR, a);
+  launch_k(qd::gemm_i8_kernel<MODE, W4>, pl.grid, qd::gemm_threads(MODE), smem, s, pl.tmA, pl.tmB, pl.tmR, a);
   return check_launch("gemm_i8_kernel");
 }
 
@@ -384,9 +402,9 @@ int launch_quantize(const qd_quantize_desc& d, cudaStream_t s) {
   if (d.upsample2x && !vec) return fail(QD_ERR_UNSUPPORTED, "quantize: upsample needs C %% 4 == 0");
   if (vec) {
     const long long rows = d.upsample2x ? (long long)d.B * 4 * d.H * d.W : d.M;
-    qd::quantize_kernel<<<grid_for(rows * (d.C / 4), 256), 256, 0, s>>>(d);
+    launch_k(qd::quantize_kernel, grid_for(rows * (d.C / 4), 256), 256, 0, s, d);
   } else {
-    qd::quantize_scalar_kernel<<<grid_for((long long)d.M * d.C, 256), 256, 0, s>>>(d);
+    launch_k(qd::quantize_scalar_kernel, grid_for((long long)d.M * d.C, 256), 256, 0, s, d);
   }
   return check_launch("quantize_kernel");
 }
@@ -430,7 +448,7 @@ int launch_groupnorm(const qd_groupnorm_desc& d, cudaStream_t s) {
       int threads = units <= 256LL * qd::GN_NU ? 256 : 512;
       if (units < 256) threads = (int)((units + 31) / 32 * 32);
       if (threads < cpg / 2) threads = (cpg / 2 + 31) / 32 * 32;
-      qd::gn_fused_small_kernel<<<dim3(d.groups, d.B), threads, 0, s>>>(d);
+      launch_k(qd::gn_fused_small_kernel, dim3(d.groups, d.B), threads, 0, s, d);
       return check_launch("gn_fused_small_kernel");
     }
   }
@@ -449,16 +467,16 @@ int launch_groupnorm(const qd_groupnorm_desc& d, cudaStream_t s) {
   if (d.stats_in && use_stats) {
     // the producing GEMMs left per-slab column sums: no pass over x for the statistics
     if (d.HW % 32) return fail(QD_ERR_BAD_ARG, "groupnorm: stats_in needs HW %% 32 == 0");
-    qd::gn_finalize_from_stats_kernel<<<dim3(d.groups, d.B), 128, 0, s>>>(reinterpret_cast<const float2*>(d.stats_in),
+    launch_k(qd::gn_finalize_from_stats_kernel, dim3(d.groups, d.B), 128, 0, s, reinterpret_cast<const float2*>(d.stats_in),
                                                                          d.ld_stats_in, d.HW, d.C, d.groups, d.eps, stats);
     rc = check_launch("gn_finalize_from_stats_kernel");
     if (rc) return rc;
   } else {
-    qd::gn_partial_kernel<<<dim3(nslab, d.B), threads, 2 * d.C * sizeof(float), s>>>(d.x, d.ld_x, d.HW, d.C, d.groups, slab,
+    launch_k(qd::gn_partial_kernel, dim3(nslab, d.B), threads, 2 * d.C * sizeof(float), s, d.x, d.ld_x, d.HW, d.C, d.groups, slab,
                                                                                      nslab, part);
     rc = check_launch("gn_partial_kernel");
     if (rc) return rc;
-    qd::gn_finalize_kernel<<<d.B, 256, 0, s>>>(part, d.HW, d.C, d.groups, nslab, d.eps, stats);
+    launch_k(qd::gn_finalize_kernel, d.B, 256, 0, s, part, d.HW, d.C, d.groups, nslab, d.eps, stats);
     rc = check_launch("gn_finalize_kernel");
     if (rc) return rc;
   }
@@ -473,7 +491,7 @@ int launch_groupnorm(const qd_groupnorm_desc& d, cudaStream_t s) {
   while ((long long)((d.HW + rows - 1) / rows) * slabs_x * d.B > 8LL * num_sms() && rows < 8 * qd::GN_BATCH * TY) rows += qd::GN_BATCH * TY;
   const dim3 grid(slabs_x, (d.HW + rows - 1) / rows, d.B);
   const bool raw = d.raw_q != nullptr;
-#define QD_GN_APPLY(NOUT, RAW) qd::gn_apply_kernel<NOUT, RAW><<<grid, athreads, 0, s>>>(d, stats, rows, TX)
+#define QD_GN_APPLY(NOUT, RAW) launch_k(qd::gn_apply_kernel<NOUT, RAW>, grid, athreads, 0, s, d, stats, rows, TX)
   switch (d.n_out * 2 + (raw ? 1 : 0)) {
     case 0: QD_GN_APPLY(0, false); break;
     case 1: QD_GN_APPLY(0, true); break;
@@ -491,7 +509,7 @@ int launch_groupnorm(const qd_groupnorm_desc& d, cudaStream_t s) {
 template <int NVEC>
 int launch_layernorm_t(const qd_layernorm_desc& d, cudaStream_t s) {
   const int wpb = 8;
-  qd::layernorm_quant_kernel<NVEC><<<grid_for((long long)d.M * 32, wpb * 32, 8), wpb * 32, 0, s>>>(d);
+  launch_k(qd::layernorm_quant_kernel<NVEC>, grid_for((long long)d.M * 32, wpb * 32, 8), wpb * 32, 0, s, d);
   return check_launch("layernorm_quant_kernel");
 }
 
@@ -520,11 +538,11 @@ int launch_split3(const qd_split_desc& d, cudaStream_t s) {
     return fail(QD_ERR_UNSUPPORTED, "split: Cp=%d must be a multiple of 4, >= C, with ld_dst >= 3*Cp", d.Cp);
   if ((d.C & 3) || (d.ld_src & 3)) {
     if (d.upsample2x) return fail(QD_ERR_UNSUPPORTED, "split: upsample needs C %% 4 == 0");
-    qd::split_bf16x3_scalar_kernel<<<grid_for((long long)d.M * d.C, 256), 256, 0, s>>>(d);
+    launch_k(qd::split_bf16x3_scalar_kernel, grid_for((long long)d.M * d.C, 256), 256, 0, s, d);
     return check_launch("split_bf16x3_scalar_kernel");
   }
   const long long rows = d.upsample2x ? (long long)d.B * 4 * d.H * d.W : d.M;
-  qd::split_bf16x3_kernel<<<grid_for(rows * (d.C / 4), 256), 256, 0, s>>>(d);
+  launch_k(qd::split_bf16x3_kernel, grid_for(rows * (d.C / 4), 256), 256, 0, s, d);
   return check_launch("split_bf16x3_kernel");
 }
 
@@ -533,7 +551,7 @@ int launch_attention_fp(const qd_attention_fp_desc& d, cudaStream_t s) {
     return fail(QD_ERR_BAD_ARG, "attention_fp32: bad args");
   const size_t smem = (size_t)(d.d + d.Tk) * sizeof(float);
   if (smem > 48 * 1024) return fail(QD_ERR_UNSUPPORTED, "attention_fp32: d + Tk = %d exceeds 12288 floats of shared memory", d.d + d.Tk);
-  qd::attention_fp32_kernel<<<dim3(d.Tq, d.B * d.heads), 128, smem, s>>>(d);
+  launch_k(qd::attention_fp32_kernel, dim3(d.Tq, d.B * d.heads), 128, smem, s, d);
   return check_launch("attention_fp32_kernel");
 }
 
@@ -541,11 +559,11 @@ int launch_im2col(const qd_im2col_desc& d, cudaStream_t s) {
   if (!d.src || !d.dst) return fail(QD_ERR_BAD_ARG, "im2col: null arg");
   if (d.ld_dst < 9 * d.C) return fail(QD_ERR_BAD_ARG, "im2col: ld_dst too small");
   if ((d.C % 16) == 0 && d.ld_dst == 9 * d.C && (d.ld_dst % 16) == 0) {
-    qd::im2col_vec_kernel<<<grid_for((long long)d.B * d.Ho * d.Wo * 9 * (d.C / 16), 256), 256, 0, s>>>(d);
+    launch_k(qd::im2col_vec_kernel, grid_for((long long)d.B * d.Ho * d.Wo * 9 * (d.C / 16), 256), 256, 0, s, d);
     return check_launch("im2col_vec_kernel");
   }
   const long long total = (long long)d.B * d.Ho * d.Wo * d.ld_dst;
-  qd::im2col_kernel<<<grid_for(total, 256), 256, 0, s>>>(d);
+  launch_k(qd::im2col_kernel, grid_for(total, 256), 256, 0, s, d);
   return check_launch("im2col_kernel");
 }
 
@@ -560,12 +578,12 @@ int launch_attention_inst(const qd_attention_desc& d, cudaStream_t s) {
   if (d.zq != 0) {
     if (!d.ws) return fail(QD_ERR_BAD_ARG, "attention: workspace required when zq != 0");
     const int tk_pad = qd::att_ws_stride(d.Tk);
-    qd::att_krowsum_kernel<QS><<<grid_for((long long)d.B * d.heads * tk_pad, 256), 256, 0, s>>>(d, tk_pad);
+    launch_k(qd::att_krowsum_kernel<QS>, grid_for((long long)d.B * d.heads * tk_pad, 256), 256, 0, s, d, tk_pad, 0, 0);
     int rc = check_launch("att_krowsum_kernel");
     if (rc) return rc;
   }
   dim3 grid((d.Tq + qd::ATT_BM - 1) / qd::ATT_BM, d.B * d.heads);
-  kern<<<grid, qd::ATT_WARPS * 32, lay.total, s>>>(d);
+  launch_k(kern, grid, qd::ATT_WARPS * 32, lay.total, s, d);
   return check_launch("qattention_kernel");
 }
 
@@ -587,7 +605,7 @@ int launch_attention_smallk_inst(const qd_attention_desc& d, cudaStream_t s) {
   const int spw = d.Tq >= 2048 ? 4 : (d.Tq >= 512 ? 2 : 1);
   const int slabs = (d.Tq + 15) / 16;
   dim3 grid((slabs + spw * qd::ATS_WARPS - 1) / (spw * qd::ATS_WARPS), d.B * d.heads);
-  kern<<<grid, qd::ATS_WARPS * 32, qd::ats_smem_bytes<DQ, DV, NKV>(), s>>>(d, spw);
+  launch_k(kern, grid, qd::ATS_WARPS * 32, qd::ats_smem_bytes<DQ, DV, NKV>(), s, d, spw);
   return check_launch("qattention_smallk_kernel");
 }
 
@@ -602,16 +620,16 @@ int launch_attention_smallk(const qd_attention_desc& d, cudaStream_t s) {
 }
 
 // tcgen05 path (attention_tc.cuh): d <= 112, Q/K codes in the per-head padded layout (pitch 32/64/128), dense V^T
-template <bool S16, bool MAGIC, int NSW, bool HZ>
+template <bool S16, bool MAGIC, int NSW, bool HZ, bool F16 = false>
 int launch_attention_tc_inst(const qd_attention_desc& d, const CUtensorMap& tmQ, const CUtensorMap& tmK,
                              const CUtensorMap& tmV, int NV, int P, cudaStream_t s) {
-  auto kern = qd::qattention_tc_kernel<S16, MAGIC, NSW, HZ>;
+  auto kern = qd::qattention_tc_kernel<S16, MAGIC, NSW, HZ, F16>;
   static std::atomic<unsigned long long> optin{0};
   if (int rc = ensure_smem_optin(kern, NSW == 16 ? 227 * 1024 : 113 * 1024, optin, "attention_tc")) return rc;
   const qd::AtcSmem lay = qd::atc_smem_layout(NV, P, NSW);
   if (lay.total > (NSW == 16 ? 227 : 113) * 1024) return fail(QD_ERR_UNSUPPORTED, "attention_tc: %d B of shared memory", lay.total);
   dim3 grid((d.Tq + qd::ATC_BM - 1) / qd::ATC_BM, d.B * d.heads);
-  kern<<<grid, qd::atc_threads(NSW), lay.total, s>>>(tmQ, tmK, tmV, d, NV, P);
+  launch_k(kern, grid, qd::atc_threads(NSW), lay.total, s, tmQ, tmK, tmV, d, NV, P);
   return check_launch("qattention_tc_kernel");
 }
 template <bool S16, bool MAGIC, int NSW>
@@ -630,7 +648,7 @@ bool attention_tc_eligible(const qd_attention_desc& d) {
   if (!mode) return false;
   const int P = d.head_stride_q;
   if (d.d > 112 || (d.d & 7)) return false;
-  if ((P != 32 && P != 64 && P != 128) || P < d.d || d.head_stride_k != P) return false;
+  if ((P != 32 && P != 64 && P != 128) || P < d.d * (d.qk_f16 ? 2 : 1) || d.head_stride_k != P) return false;
   if (d.q_off != 0 || d.k_off != 0 || d.ld_q != (long long)d.heads * P || d.ld_k != (long long)d.heads * P) return false;
   if (d.v_off != 0 || d.head_stride_v != d.d || d.v_batch_stride != (long long)d.heads * d.d * d.ld_vt) return false;
   if (d.out && ((d.ld_out & 3) || (((uintptr_t)d.out) & 15))) return false;
@@ -657,19 +675,29 @@ int launch_attention_tc(const qd_attention_desc& d, cudaStream_t s) {
   cuuint32_t box[2] = {128, (cuuint32_t)d.d};
   int rc = encode_u8_map(&tmV, d.vt, 2, dims, strides, box);
   if (rc) return rc;
+  static const int two_cta = [] { const char* e = getenv("QDIFF_ATTN_2CTA"); return (e && !strcmp(e, "0")) ? 0 : 1; }();
+  if (d.qk_f16) {      // fp16 (code - zero_point) operands: no zero-point correction pass
+    const bool small16 = two_cta && P <= 64 && NV <= 64 && (long long)d.Tq * d.Tk <= (1LL << 21) &&
+                         qd::atc_smem_layout(NV, P, 8).total <= 113 * 1024;
+    if (small16) {
+      if (d.sm_bits > 8) return launch_attention_tc_inst<true, true, 8, false, true>(d, tmQ, tmK, tmV, NV, P, s);
+      return launch_attention_tc_inst<false, true, 8, false, true>(d, tmQ, tmK, tmV, NV, P, s);
+    }
+    if (d.sm_bits > 8) return launch_attention_tc_inst<true, true, 16, false, true>(d, tmQ, tmK, tmV, NV, P, s);
+    return launch_attention_tc_inst<false, true, 16, false, true>(d, tmQ, tmK, tmV, NV, P, s);
+  }
   if (d.zq != 0) {
     if (!d.ws) return fail(QD_ERR_BAD_ARG, "attention: workspace required when zq != 0");
     const int tk_pad = qd::att_ws_stride(d.Tk);
     const int bias = d.d <= 64 ? 0x4B400000 : 0;   // MAGIC variant of the kernel (see attention_tc.cuh)
-    if (d.q_signed) qd::att_krowsum_kernel<true><<<grid_for((long long)d.B * d.heads * tk_pad, 256), 256, 0, s>>>(d, tk_pad, 1, bias);
-    else qd::att_krowsum_kernel<false><<<grid_for((long long)d.B * d.heads * tk_pad, 256), 256, 0, s>>>(d, tk_pad, 1, bias);
+    if (d.q_signed) launch_k(qd::att_krowsum_kernel<true>, grid_for((long long)d.B * d.heads * tk_pad, 256), 256, 0, s, d, tk_pad, 1, bias);
+    else launch_k(qd::att_krowsum_kernel<false>, grid_for((long long)d.B * d.heads * tk_pad, 256), 256, 0, s, d, tk_pad, 1, bias);
     rc = check_launch("att_krowsum_kernel");
     if (rc) return rc;
   }
   const bool s16 = d.sm_bits > 8, magic = d.d <= 64;
   // two co-resident CTAs per SM (8 softmax warps each) when the 256-column TMEM layout and 113 KB of shared memory suffice;
   // QDIFF_ATTN_2CTA=0 forces the one-CTA (16 softmax warps) configuration (A/B comparisons)
-  static const int two_cta = [] { const char* e = getenv("QDIFF_ATTN_2CTA"); return (e && !strcmp(e, "0")) ? 0 : 1; }();
   // measured (tools/prof_attn.py, B=16 x 8 heads, d=40): Tq=Tk=1024: 143 us vs 150 us with one CTA per SM; Tq=Tk=4096: 1845
   // vs 1750 us (the long problem is throughput-bound on MUFU + issue, the single S slot costs more than co-residency gains)
   const bool small = two_cta && P <= 64 && NV <= 64 && magic && (long long)d.Tq * d.Tk <= (1LL << 21) &&
@@ -694,6 +722,11 @@ int launch_attention(const qd_attention_desc& d, cudaStream_t s) {
   if ((d.q_off | d.head_stride_q | (int)d.ld_q) & 3) return fail(QD_ERR_UNSUPPORTED, "attention: q needs 4-byte alignment");
   if ((d.k_off | d.head_stride_k | (int)d.ld_k | d.d) & 7) return fail(QD_ERR_UNSUPPORTED, "attention: k rows need 8-byte alignment");
   if (d.out && (d.ld_out % 2)) return fail(QD_ERR_UNSUPPORTED, "attention: ld_out");
+  if (d.qk_f16) {
+    if (d.d > 64 || !attention_tc_eligible(d))
+      return fail(QD_ERR_UNSUPPORTED, "attention: qk_f16 needs the tcgen05 layout (d <= 64, per-head pitch 32/64/128 bytes >= 2 * d)");
+    return launch_attention_tc(d, s);
+  }
   if (d.Tk <= 96 && (d.d == 40 || d.d == 80)) {
     static const bool off = [] { const char* e = getenv("QDIFF_ATTENTION"); return e && !strcmp(e, "nosmallk"); }();
     if (!off) return d.d == 40 ? launch_attention_smallk<64, 40>(d, s) : launch_attention_smallk<96, 80>(d, s);
@@ -718,25 +751,25 @@ int launch_misc(int kind, const qd_misc_desc& m, cudaStream_t s) {
   switch (kind) {
     case QD_OP_TIMESTEP_EMB:
       if (!m.aux) return fail(QD_ERR_BAD_ARG, "timestep_embedding: missing frequency table");
-      qd::timestep_embedding_kernel<<<grid_for((long long)m.a * (m.b / 2), 128), 128, 0, s>>>(m.src, m.aux, m.a, m.b, m.c, m.dst);
+      launch_k(qd::timestep_embedding_kernel, grid_for((long long)m.a * (m.b / 2), 128), 128, 0, s, m.src, m.aux, m.a, m.b, m.c, m.dst);
       return check_launch("timestep_embedding_kernel");
     case QD_OP_COPY2D:
       if (m.b % 4 || m.ld_src % 4 || m.ld_dst % 4) return fail(QD_ERR_UNSUPPORTED, "copy2d: alignment");
-      qd::copy2d_kernel<<<grid_for((long long)m.a * (m.b / 4), 256), 256, 0, s>>>(m.src, m.ld_src, m.dst, m.ld_dst, m.a, m.b);
+      launch_k(qd::copy2d_kernel, grid_for((long long)m.a * (m.b / 4), 256), 256, 0, s, m.src, m.ld_src, m.dst, m.ld_dst, m.a, m.b);
       return check_launch("copy2d_kernel");
     case QD_OP_NCHW_TO_NHWC:
-      qd::nchw_to_nhwc_kernel<<<grid_for((long long)m.a * m.b * m.c, 256), 256, 0, s>>>(m.src, m.dst, m.a, m.b, m.c);
+      launch_k(qd::nchw_to_nhwc_kernel, grid_for((long long)m.a * m.b * m.c, 256), 256, 0, s, m.src, m.dst, m.a, m.b, m.c);
       return check_launch("nchw_to_nhwc_kernel");
     case QD_OP_NHWC_TO_NCHW:
-      qd::nhwc_to_nchw_kernel<<<grid_for((long long)m.a * m.b * m.c, 256), 256, 0, s>>>(m.src, m.dst, m.a, m.b, m.c);
+      launch_k(qd::nhwc_to_nchw_kernel, grid_for((long long)m.a * m.b * m.c, 256), 256, 0, s, m.src, m.dst, m.a, m.b, m.c);
       return check_launch("nhwc_to_nchw_kernel");
     case QD_OP_AVGPOOL2X:
       if (m.d % 4) return fail(QD_ERR_UNSUPPORTED, "avgpool: C %% 4");
-      qd::avgpool2x_kernel<<<grid_for((long long)m.a * (m.b / 2) * (m.c / 2) * (m.d / 4), 256), 256, 0, s>>>(m.src, m.dst, m.a, m.b, m.c, m.d);
+      launch_k(qd::avgpool2x_kernel, grid_for((long long)m.a * (m.b / 2) * (m.c / 2) * (m.d / 4), 256), 256, 0, s, m.src, m.dst, m.a, m.b, m.c, m.d);
       return check_launch("avgpool2x_kernel");
     case QD_OP_UPSAMPLE2X:
       if (m.d % 4) return fail(QD_ERR_UNSUPPORTED, "upsample: C %% 4");
-      qd::upsample2x_f32_kernel<<<grid_for((long long)m.a * m.b * m.c * m.d, 256), 256, 0, s>>>(m.src, m.dst, m.a, m.b, m.c, m.d);
+      launch_k(qd::upsample2x_f32_kernel, grid_for((long long)m.a * m.b * m.c * m.d, 256), 256, 0, s, m.src, m.dst, m.a, m.b, m.c, m.d);
       return check_launch("upsample2x_f32_kernel");
     default:
       return fail(QD_ERR_BAD_ARG, "misc: unknown kind %d", kind);
@@ -821,7 +854,7 @@ int qd_qattention(const qd_attention_desc* d, qd_stream_t s) {
 int qd_lincomb3(float* out, float a, const float* x, float b, const float* y, float c, const float* z, long long n,
                 qd_stream_t s) {
   if (!out || !x || n <= 0) return fail(QD_ERR_BAD_ARG, "lincomb3: bad args");
-  qd::lincomb3_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)s>>>(out, a, x, b, y, c, z, n);
+  launch_k(qd::lincomb3_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)s, out, a, x, b, y, c, z, n);
   return check_launch("lincomb3_kernel");
 }
 int qd_split_bf16x3(const qd_split_desc* d, qd_stream_t s) {
@@ -859,7 +892,7 @@ int qd_upsample2x_f32(const float* src, float* dst, int32_t B, int32_t H, int32_
 }
 int qd_sampler_step(const qd_sampler_desc* d, qd_stream_t s) {
   if (!d || !d->x || !d->eps || !d->x_prev || d->n <= 0) return fail(QD_ERR_BAD_ARG, "sampler: bad args");
-  qd::sampler_step_kernel<<<grid_for(d->n, 256), 256, 0, (cudaStream_t)s>>>(*d);
+  launch_k(qd::sampler_step_kernel, grid_for(d->n, 256), 256, 0, (cudaStream_t)s, *d);
   return check_launch("sampler_step_kernel");
 }
 

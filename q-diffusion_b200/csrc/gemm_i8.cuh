@@ -22,6 +22,7 @@
 #pragma once
 #include "ptx.cuh"
 #include "quant_math.cuh"
+#include <cuda_fp16.h>
 #include <type_traits>
 
 namespace qd {
@@ -99,6 +100,7 @@ struct GemmArgs {
   long long ldr;
   int geglu;
   int oq_d, oq_pitch;      // > 0: per-head padded code layout for row-major out_q
+  int oq_f16;              // out_q receives fp16 (code - zero_point) instead of 8-bit codes (ldq / oq_pitch in fp16 elements)
   // packed INT4 weights (K3): the B tile arrives as BN x 64 packed bytes and warps 2-3 expand it to the s8
   // 128B-swizzled operand tile in shared memory (wq - wzero[n]) before the MMA consumes the stage
   int w4;
@@ -303,8 +305,27 @@ __device__ __forceinline__ void gemm_finalise4(const GemmArgs& p, const QuantK& 
     }
   }
   if constexpr (QPRE) {
-    *reinterpret_cast<uint32_t*>(oq) = pack4_low_bytes(quant_bits_pre(y[0], qk), quant_bits_pre(y[1], qk),
-                                                       quant_bits_pre(y[2], qk), quant_bits_pre(y[3], qk));
+    if (p.oq_f16) {      // centred codes as fp16: float(K + code) - (K + zero_point), exact
+      const float kz = 12582912.0f + (float)p.q_zp;
+      const __half2 h01 = __floats2half2_rn(__uint_as_float(quant_bits_pre(y[0], qk)) - kz, __uint_as_float(quant_bits_pre(y[1], qk)) - kz);
+      const __half2 h23 = __floats2half2_rn(__uint_as_float(quant_bits_pre(y[2], qk)) - kz, __uint_as_float(quant_bits_pre(y[3], qk)) - kz);
+      *reinterpret_cast<uint2*>(oq) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    } else {
+      *reinterpret_cast<uint32_t*>(oq) = pack4_low_bytes(quant_bits_pre(y[0], qk), quant_bits_pre(y[1], qk),
+                                                         quant_bits_pre(y[2], qk), quant_bits_pre(y[3], qk));
+    }
+  } else if (out_q && p.oq_f16) {
+    float cz[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cz[j] = quant_centered(y[j], qk);
+    if (full) {
+      const __half2 h01 = __floats2half2_rn(cz[0], cz[1]), h23 = __floats2half2_rn(cz[2], cz[3]);
+      *reinterpret_cast<uint2*>(oq) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n + j < p.N) reinterpret_cast<__half*>(oq)[j] = __float2half_rn(cz[j]);
+    }
   } else if (out_q) {
     const uint32_t q0 = quant_code(y[0], qk), q1 = quant_code(y[1], qk);
     const uint32_t q2 = quant_code(y[2], qk), q3 = quant_code(y[3], qk);
@@ -736,9 +757,10 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // per scheduler the resulting dependent-issue chains (stall_wait) bounded the small-K GEMMs.
             const long long mrow = m_warp + rsub;
             float* of0 = p.out ? p.out + mrow * p.ldo + n : nullptr;
-            int8_t* oq0 = p.out_q ? p.out_q + mrow * p.ldq + nq : nullptr;
+            const int oq_es = p.oq_f16 ? 2 : 1;      // bytes per emitted code
+            int8_t* oq0 = p.out_q ? p.out_q + (mrow * p.ldq + nq) * oq_es : nullptr;
             const float* res0 = p.residual ? p.residual + mrow * p.ldr + n : nullptr;
-            const long long of_step = 4 * p.ldo, oq_step = 4 * p.ldq, res_step = 4 * p.ldr;
+            const long long of_step = 4 * p.ldo, oq_step = 4 * p.ldq * oq_es, res_step = 4 * p.ldr;
             float gsum[4] = {0.f, 0.f, 0.f, 0.f}, gsq[4] = {0.f, 0.f, 0.f, 0.f};
             auto rows = [&](auto full_tag) {
               constexpr bool FULL = decltype(full_tag)::value;

@@ -218,6 +218,14 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_i8(int M, int N, int a_s
 
 // Instruction descriptor for kind::f16 with bfloat16 operands and fp32 accumulation: c_format F32 (1) at [4,6);
 // a_format / b_format BF16 (1) at [7,10) / [10,13); K-major A and B; N>>3 at [17,23); M>>4 at [24,29).
+// kind::f16 with fp16 operands (a_format = b_format = 0), fp32 accumulate
+__host__ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
 __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N) {
   uint32_t d = 0;
   d |= 1u << 4;

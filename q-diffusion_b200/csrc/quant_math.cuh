@@ -45,6 +45,14 @@ __device__ __forceinline__ uint32_t quant_code(float y, const QuantK& k) {
   return (uint32_t)(__float_as_int(q + 12582912.0f) - k.bias) & 0xFFu;   // rne(q) + zero_point
 }
 
+// rne(y / delta) clamped to [qmin - zp, qmax - zp]: the code minus its zero point, as a float (fp16 attention operands)
+__device__ __forceinline__ float quant_centered(float y, const QuantK& k) {
+  const float q0 = y * k.rdelta;
+  float q = fmaf(fmaf(-q0, k.delta, y), k.rdelta, q0);
+  q = fminf(fmaxf(q, k.flo), k.fhi);
+  return (q + 12582912.0f) - 12582912.0f;
+}
+
 // Fast form (5 instructions, reciprocal multiply without the Newton step): y*r differs from y/delta by <= 1 ulp,
 // which can move a code only when the quotient sits within 1 ulp of a rounding boundary (~1e-5 of elements).
 // Used behind SiLU / GELU / normalisation, whose inputs already differ from the reference by ulps.

@@ -41,7 +41,7 @@ class GemmDesc(C.Structure):
         ("w_int4_packed", c_i32), ("k_dup", c_i32), ("w_zero", c_vp),
         ("scale_q", c_vp), ("bias_q", c_vp),
         ("gn_stats", c_vp), ("ld_stats", c_ll),
-        ("a_bf16", c_i32), ("reserved4", c_i32),
+        ("a_bf16", c_i32), ("out_q_f16", c_i32),
     ]
 
 
@@ -99,6 +99,7 @@ class AttentionDesc(C.Structure):
         ("sim_scale", c_f), ("delta_w", c_f), ("out_scale", c_f),
         ("out", c_vp), ("ld_out", c_ll), ("ws", c_vp),
         ("out_q", c_vp), ("ld_out_q", c_ll), ("oq", QParams),
+        ("qk_f16", c_i32), ("reserved5", c_i32),
     ]
 
 

@@ -543,11 +543,14 @@ class Builder:
                 oq_act = Act(t, M // T * N, t_pad, signed=signed)
                 oq_act.t_pad = t_pad
             elif out_q_head is not None:
-                # per-head padded layout (pads stay zero: the epilogue never writes them)
+                # per-head padded layout (pads stay zero: the epilogue never writes them); f16 = centred codes as fp16
                 cols_p = (N // out_q_head[0]) * out_q_head[1]
-                tz = torch.zeros((M, cols_p), dtype=torch.int8 if signed else torch.uint8, device=self.dev)
+                f16 = len(out_q_head) > 2 and out_q_head[2]
+                tz = torch.zeros((M, cols_p), dtype=torch.float16 if f16 else (torch.int8 if signed else torch.uint8),
+                                 device=self.dev)
                 self.keep.append(tz)
                 oq_act = Act(tz, M, cols_p, signed=signed)
+                oq_act.f16 = bool(f16)
             else:
                 oq_act = self.new_codes(M, N // 2 if geglu_q is not None else N, signed)
             oq_act.zp, oq_act.delta = (oq_params.zero_point, None), (oq_params.delta, None)
@@ -561,7 +564,8 @@ class Builder:
                           out_q=oq_act.t if oq_act is not None else None,
                           ldq=(oq_act.t_pad if transposed else oq_act.ld) if oq_act is not None else 0,
                           oq=oq_params, out_q_transposed=transposed, geglu=geglu_q is not None,
-                          out_q_head=out_q_head if (out_q is not None and not transposed) else None, w_zero=w_zero,
+                          out_q_head=out_q_head[:2] if (out_q is not None and not transposed and out_q_head is not None) else None,
+                          out_q_f16=bool(oq_act is not None and getattr(oq_act, "f16", False)), w_zero=w_zero,
                           w_rows=W["w_rows"])
         d.a = a.ptr + (cols[0] if cols is not None else 0)
         d.k_dup = W.get("kdup", 1)
@@ -594,7 +598,7 @@ class Builder:
                         bias=None if bias is None else bias.detach().cpu(), zx=int(zx), rowvec=rowvec, residual=res,
                         rows_per_batch=rows_per_batch, out=o, out_cols_offset=out_cols_offset if o is not None else 0,
                         N=N, out_q=oq_act, oq=_qt(oq_params), transposed=transposed, geglu=geglu_q is not None,
-                        out_q_head=out_q_head if (out_q is not None and not transposed) else None,
+                        out_q_head=out_q_head[:2] if (out_q is not None and not transposed and out_q_head is not None) else None,
                         packed=w_zero is not None)
         self.add(_lib.QD_OP_GEMM, d, label, flops=2 * M * N * Cred * taps * W.get("kdup", 1), spec=spec)
         if o is not None:
@@ -630,6 +634,15 @@ class Builder:
         """Per-head pitch of the Q/K code layout: the tcgen05 attention kernel wants d padded to the TMA swizzle span."""
         return 32 if d <= 32 else 64 if d <= 64 else 128 if d <= 112 else d
 
+    @staticmethod
+    def qk_head(d, Tk):
+        """out_q_head of the to_q / to_k GEMMs: (d, pitch) in 8-bit codes, or (d, pitch, True) with the pitch in fp16
+        elements when the attention runs its QK^T on fp16 centred codes (qd_attention_desc.qk_f16: d <= 64, key axes
+        beyond the small-Tk kernel's range; QDIFF_ATTN_F16=0 keeps 8-bit codes)."""
+        if d <= 64 and d % 8 == 0 and Tk > 96 and os.environ.get("QDIFF_ATTN_F16", "1") != "0":
+            return (d, 16 if d <= 16 else 32 if d <= 32 else 64, True)
+        return (d, Builder.head_pitch(d))
+
     # ------------------------------------------------------------------ attention recorder
     def attention(self, qc, kc, vt, *, heads, d, Tq, Tk, q_layout, k_layout, v_layout, sim_scale_extra, qw, label,
                   consumer=None):
@@ -642,12 +655,16 @@ class Builder:
         qpw, _ = self.qp(qw, wide_ok=True)
         a = AttentionDesc()
         a.q, a.k, a.vt = qc.ptr, kc.ptr, vt.ptr
-        a.ld_q, a.ld_k = qc.ld, kc.ld
+        f16 = bool(getattr(qc, "f16", False))
+        assert f16 == bool(getattr(kc, "f16", False)), "q and k operand formats differ"
+        es = 2 if f16 else 1                     # the descriptor counts bytes
+        a.qk_f16 = int(f16)
+        a.ld_q, a.ld_k = qc.ld * es, kc.ld * es
         a.ld_vt = vt.t_pad
         a.v_batch_stride = (vt.rows // self.B) * vt.t_pad
         a.B, a.heads, a.d, a.Tq, a.Tk = self.B, heads, d, Tq, Tk
-        a.q_off, a.head_stride_q = q_layout
-        a.k_off, a.head_stride_k = k_layout
+        a.q_off, a.head_stride_q = q_layout[0] * es, q_layout[1] * es
+        a.k_off, a.head_stride_k = k_layout[0] * es, k_layout[1] * es
         a.v_off, a.head_stride_v = v_layout
         a.q_signed, a.k_signed, a.v_signed, a.p_signed = int(qc.signed), int(kc.signed), int(vt.signed), 0
         a.zq, a.zk, a.zv, a.zw = qc.zp[0], kc.zp[0], vt.zp[0], qpw.zero_point
@@ -663,7 +680,7 @@ class Builder:
             out = self.new_codes(self.B * Tq, heads * d, osigned)
             out.zp, out.delta = (oqp.zero_point, None), (oqp.delta, None)
             a.out_q, a.ld_out_q, a.oq = out.ptr, out.ld, oqp
-        if a.zq != 0:
+        if a.zq != 0 and not f16:
             ws = torch.empty(self.B * heads * ((Tk + 127) // 128 * 128), dtype=torch.int32, device=self.dev)
             self.keep.append(ws)
             a.ws = ws.data_ptr()
@@ -766,12 +783,13 @@ class Builder:
         heads = attn.heads
         inner = attn.to_q.weight.shape[0]
         d = inner // heads
-        P = self.head_pitch(d)
-        qc = self.gemm(attn.to_q, x_codes_q, label + ".to_q", out_q=(attn.act_quantizer_q, False), out_q_head=(d, P))
+        qkh = self.qk_head(d, Tk)
+        P = qkh[1]
+        qc = self.gemm(attn.to_q, x_codes_q, label + ".to_q", out_q=(attn.act_quantizer_q, False), out_q_head=qkh)
         if static_kv:
             self._static_depth += 1      # K / V of the context: step-invariant (static_scope)
         try:
-            kc = self.gemm(attn.to_k, kv_codes[0], label + ".to_k", out_q=(attn.act_quantizer_k, False), out_q_head=(d, P))
+            kc = self.gemm(attn.to_k, kv_codes[0], label + ".to_k", out_q=(attn.act_quantizer_k, False), out_q_head=qkh)
             vt = self.gemm(attn.to_v, kv_codes[1], label + ".to_v", out_q=(attn.act_quantizer_v, True), rows_per_batch=Tk)
         finally:
             if static_kv:
@@ -836,9 +854,9 @@ class Builder:
             rows = idx[:, j, :].reshape(-1)
             view = _RowView(blk.qkv, rows)
             parts.append(self.gemm(view, a, f"{k}.qkv.{'qkv'[j]}", out_q=(quantizer, transposed), out_scale=sc,
-                                   rows_per_batch=T, out_q_head=None if transposed else (ch, self.head_pitch(ch))))
+                                   rows_per_batch=T, out_q_head=None if transposed else self.qk_head(ch, T)))
         qc, kc, vt = parts
-        Pq = self.head_pitch(ch)
+        Pq = self.qk_head(ch, T)[1]
         o = self.attention(qc, kc, vt, heads=heads, d=ch, Tq=T, Tk=T, q_layout=(0, Pq), k_layout=(0, Pq),
                            v_layout=(0, ch), sim_scale_extra=1.0, qw=smv.act_quantizer_w, label=k + ".attention",
                            consumer=blk.proj_out)

@@ -33,7 +33,7 @@ def _require_cuda(*ts):
 def gemm_desc(a, w, scale, *, M, N, C, taps=1, lda=None, conv_bhw=None, a_signed=True, bias=None, corr=None,
               rowvec=None, ld_rowvec=0, rows_per_batch=0, residual=None, ldr=0, out=None, ldo=0, out_q=None, ldq=0,
               oq=None, out_q_transposed=False, bn_hint=0, w_rows=None, geglu=False, out_q_head=None, w_zero=None,
-              prescale=True, gn_stats=None, ld_stats=0):
+              prescale=True, gn_stats=None, ld_stats=0, out_q_f16=False):
     d = GemmDesc()
     d.a, d.w = ptr(a), ptr(w)
     d.lda = int(lda if lda is not None else C)
@@ -51,6 +51,7 @@ def gemm_desc(a, w, scale, *, M, N, C, taps=1, lda=None, conv_bhw=None, a_signed
     d.oq = oq if oq is not None else qparams(1.0, 0, 0, 0)
     d.bn_hint = int(bn_hint)
     d.geglu = 1 if geglu else 0
+    d.out_q_f16 = 1 if out_q_f16 else 0      # out_q = fp16 (code - zero_point); ldq / head pitch in fp16 elements
     if out_q_head is not None:
         d.out_q_head_dim, d.out_q_head_pitch = int(out_q_head[0]), int(out_q_head[1])
     if w_zero is not None:      # w = packed unsigned 4-bit codes [rows][K/2], w_zero = per-row zero points (int8)

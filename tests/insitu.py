@@ -32,7 +32,10 @@ def rd_f32(act):
 
 
 def rd_codes(act):
-    return act.logical().detach().cpu().to(torch.int64)       # uint8 -> 0..255, int8 -> -128..127
+    t = act.logical().detach().cpu()
+    if getattr(act, "f16", False):         # attention Q/K operands as fp16 (code - zero_point): back to codes
+        return t.to(torch.float64).round().to(torch.int64) + int(act.zp[0])
+    return t.to(torch.int64)               # uint8 -> 0..255, int8 -> -128..127
 
 
 def vt_positions(T):

@@ -400,7 +400,7 @@ def test_im2col(cuda, stride, pad_tl, pad_total, C):
     assert torch.equal(dst.cpu().reshape(B, Ho, Wo, ld), ref)
 
 
-def _run_attention(cuda, B, heads, d, Tq, Tk, sym, sm_bits, seed):
+def _run_attention(cuda, B, heads, d, Tq, Tk, sym, sm_bits, seed, f16=False):
     """q,k,v float -> codes (oracle quantizer) -> kernel; oracle = fake-quant attention on the same floats."""
     ops, _ = _ops()
     from qdiff_b200._lib import AttentionDesc, ptr
@@ -427,13 +427,19 @@ def _run_attention(cuda, B, heads, d, Tq, Tk, sym, sm_bits, seed):
     dt = torch.int8 if sym else torch.uint8
     P = 32 if d <= 32 else 64 if d <= 64 else 128 if d <= 112 else d     # per-head pitch of the code layout
 
-    def padded(t, T):
+    def padded(t, T, zp=0):
+        if f16:      # qk_f16 operands: fp16 (code - zero_point), pitch in BYTES = the swizzle span holding 2 * d
+            out = torch.zeros(B, T, heads, P // 2, dtype=torch.float16)
+            out[..., :d] = (t.reshape(B, T, heads, d).to(torch.int32) - zp).to(torch.float16)
+            return out.reshape(B, T, heads * (P // 2)).to(cuda)
         out = torch.zeros(B, T, heads, P, dtype=dt)
         out[..., :d] = t.reshape(B, T, heads, d).to(dt)
         return out.reshape(B, T, heads * P).to(cuda)
 
-    qc = padded(O.uaq_codes(q, *qp_q), Tq)
-    kc = padded(O.uaq_codes(k, *qp_k), Tk)
+    if f16:
+        P = 32 if d <= 16 else 64 if d <= 32 else 128
+    qc = padded(O.uaq_codes(q, *qp_q), Tq, qp_q[1])
+    kc = padded(O.uaq_codes(k, *qp_k), Tk, qp_k[1])
     vc = O.uaq_codes(v, *qp_v).to(dt)
     Tk_pad = (Tk + 15) // 16 * 16
     vt = torch.zeros(B, heads * d, Tk_pad, dtype=dt)
@@ -459,6 +465,7 @@ def _run_attention(cuda, B, heads, d, Tq, Tk, sym, sm_bits, seed):
     a.out_scale = dw * qp_v[0]
     a.out, a.ld_out = ptr(out), heads * d
     a.ws = ptr(ws)
+    a.qk_f16 = 1 if f16 else 0
     ops.attention(a)
     torch.cuda.synchronize()
     return out.cpu(), ref
@@ -487,6 +494,52 @@ def test_qattention(cuda, B, heads, d, Tq, Tk, sym, sm_bits):
     assert err.max().item() < 2e-3 * scale + 1e-5, (err.max().item(), scale)
     mse = (err ** 2).mean().item()
     assert mse < 1e-7 * scale * scale + 1e-12, (mse, scale)
+
+
+@pytest.mark.parametrize("B,heads,d,Tq,Tk,sym,sm_bits", [
+    (2, 8, 40, 256, 256, False, 16),   # SD self-attention head shape
+    (1, 2, 40, 384, 1100, False, 16),  # ragged last key tile, Tq != Tk
+    (1, 3, 32, 640, 640, True, 8),     # symmetric codes, 8-bit softmax, two CTAs per SM
+    (1, 3, 24, 200, 136, False, 8),    # church head dim 24
+    (1, 2, 64, 300, 300, False, 16),   # the largest head dim of this path
+    (2, 2, 16, 160, 160, False, 16),   # 32-byte rows
+])
+def test_qattention_f16_operands(cuda, B, heads, d, Tq, Tk, sym, sm_bits):
+    """qd_attention_desc.qk_f16: Q / K as fp16 centred codes, QK^T on tcgen05 kind::f16 - the same integers as the code path,
+    so the result must agree with the fake-quant oracle to the same tolerance AND with the code path closely."""
+    out, ref = _run_attention(cuda, B, heads, d, Tq, Tk, sym, sm_bits, seed=B * 1000 + d, f16=True)
+    base, _ = _run_attention(cuda, B, heads, d, Tq, Tk, sym, sm_bits, seed=B * 1000 + d, f16=False)
+    err = (out.double() - ref.double()).abs()
+    scale = ref.abs().max().item()
+    assert torch.isfinite(out).all()
+    assert err.max().item() < 2e-3 * scale + 1e-5, (err.max().item(), scale)
+    assert (err ** 2).mean().item() < 1e-7 * scale * scale + 1e-12
+    assert ((out - base).double() ** 2).mean().item() < 1e-7 * scale * scale + 1e-12
+
+
+def test_qgemm_out_q_f16(cuda):
+    """qd_gemm_desc.out_q_f16: the requantising epilogue writes fp16 (code - zero_point) into the per-head padded layout."""
+    ops, fold = _ops()
+    gen = torch.Generator().manual_seed(5)
+    M, C, heads, d, Ph = 300, 64, 4, 40, 64
+    N = heads * d
+    L = _make_layer(N, C, 1, 4, gen, True)
+    a = torch.randint(0, 256, (M, C), generator=gen)
+    y = O.int_linear(a, L["zx"], L["ws"], L["scale"], L["bias"]).float()
+    q = ops.act_qparams(0.05, 117, 8, False)
+    ref = O.uaq_codes(y, q.delta, q.zero_point, 8, False).long() - 117
+    corr = (L["zx"] * L["ws"].double().sum(dim=1)).to(torch.int32).contiguous().to(cuda)
+    for prescale in (True, False):
+        out_q = torch.zeros(M, heads * Ph, dtype=torch.float16, device=cuda)
+        dsc = ops.gemm_desc(a.to(torch.uint8).to(cuda), L["ws"].to(torch.int8).contiguous().to(cuda), L["scale"].to(cuda), M=M, N=N,
+                            C=C, a_signed=False, bias=L["bias"].to(cuda), corr=corr, out_q=out_q, ldq=heads * Ph, oq=q,
+                            out_q_head=(d, Ph), out_q_f16=True, prescale=prescale)
+        ops.qgemm(dsc)
+        torch.cuda.synchronize()
+        got = out_q.cpu().reshape(M, heads, Ph)
+        assert (got[..., d:] == 0).all()
+        diff = (got[..., :d].reshape(M, N).long() - ref).abs()
+        assert diff.max().item() <= 1 and (diff != 0).float().mean().item() < 1e-3, (diff.max().item(), (diff != 0).float().mean().item())
 
 
 def test_timestep_embedding(cuda):

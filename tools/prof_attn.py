@@ -16,10 +16,18 @@ T = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 Tk = int(sys.argv[2]) if len(sys.argv) > 2 else T
 Tkp = (Tk + 15) // 16 * 16
 P = 64
-q = torch.zeros(B, T, heads, P, dtype=torch.uint8, device=dev)
-q[..., :d] = torch.randint(0, 256, (B, T, heads, d), dtype=torch.uint8, device=dev)
-k = torch.zeros(B, Tk, heads, P, dtype=torch.uint8, device=dev)
-k[..., :d] = torch.randint(0, 256, (B, Tk, heads, d), dtype=torch.uint8, device=dev)
+F16 = os.environ.get("ATTN_F16", "1") != "0"      # Q / K as fp16 centred codes (qd_attention_desc.qk_f16), the engine's default
+if F16:
+    P = 128
+    q = torch.zeros(B, T, heads, P // 2, dtype=torch.float16, device=dev)
+    q[..., :d] = (torch.randint(0, 256, (B, T, heads, d), device=dev) - 120).to(torch.float16)
+    k = torch.zeros(B, Tk, heads, P // 2, dtype=torch.float16, device=dev)
+    k[..., :d] = (torch.randint(0, 256, (B, Tk, heads, d), device=dev) - 131).to(torch.float16)
+else:
+    q = torch.zeros(B, T, heads, P, dtype=torch.uint8, device=dev)
+    q[..., :d] = torch.randint(0, 256, (B, T, heads, d), dtype=torch.uint8, device=dev)
+    k = torch.zeros(B, Tk, heads, P, dtype=torch.uint8, device=dev)
+    k[..., :d] = torch.randint(0, 256, (B, Tk, heads, d), dtype=torch.uint8, device=dev)
 vt = torch.zeros(B, heads * d, Tkp, dtype=torch.uint8, device=dev)
 vt[..., :Tk] = torch.randint(0, 256, (B, heads * d, Tk), dtype=torch.uint8, device=dev)
 out = torch.empty(B, T, heads * d, device=dev)
@@ -38,6 +46,7 @@ a.out_scale = a.delta_w * 0.03
 a.out, a.ld_out = ptr(out), heads * d
 ws = torch.zeros(B * heads * ((Tk + 127) // 128 * 128), dtype=torch.int32, device=dev)
 a.ws = ptr(ws)
+a.qk_f16 = 1 if F16 else 0
 for _ in range(2):
     ops.attention(a)
 torch.cuda.synchronize()
@@ -61,5 +70,5 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / REPS
 scores = B * heads * T * Tk
-print(f"attention Tq={T} Tk={Tk} [{os.environ.get('QDIFF_ATTENTION', 'tc')}]: {ms * 1e3:.1f} us, {scores / ms / 1e6:.1f} Gscore/s")
+print(f"attention Tq={T} Tk={Tk} [{os.environ.get('QDIFF_ATTENTION', 'tc')}{', fp16 q/k' if F16 else ''}]: {ms * 1e3:.1f} us, {scores / ms / 1e6:.1f} Gscore/s")
 L.qd_engine_destroy(eng)
