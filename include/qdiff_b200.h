@@ -49,8 +49,9 @@ typedef struct qd_qparams {
  *       top/mid/bottom x left/mid/right) because the reference zero-pads after de-quantisation.
  * geglu: GEGLU projection fused with its consumer's quantizer: N counts x AND gate columns, interleaved in
  *       groups of 4 (w row 8b+i = x-feature 4b+i, row 8b+4+i = gate-feature 4b+i); out_q is [M, N/2].
- * w_int4_packed: the 4-bit weight codes stay packed in HBM (K3 of the survey): w is [n_rows][taps*C/2] bytes, byte j of a
- *       row = wq[2j] | wq[2j+1] << 4 with UNSIGNED codes wq in [0,15]; w_zero[n] in [0,15] is the row's zero point.  The
+ * w_int4_packed: the 4-bit weight codes stay packed in HBM (K3 of the survey): w is [n_rows][taps*C/2] bytes; the 8 codes
+ *       8g .. 8g+7 of a row occupy bytes 4g .. 4g+3, byte 4g+j = wq[8g+j] | wq[8g+4+j] << 4 (a masked 32-bit word is four
+ *       consecutive codes) with UNSIGNED codes wq in [0,15]; w_zero[n] in [0,15] is the row's zero point.  The
  *       kernel unpacks to wq - w_zero (s8) in shared memory between the TMA load and the MMA; everything else
  *       (scale, corr, epilogue) is unchanged.  Halves the weight bytes in HBM and through L2.
  * Output: fp32 `out` and/or re-quantised codes `out_q` with the consumer's quantizer `oq`
@@ -325,6 +326,11 @@ int qd_nchw_to_nhwc(const float* src, float* dst, int32_t B, int32_t C, int32_t 
 int qd_nhwc_to_nchw(const float* src, float* dst, int32_t B, int32_t C, int32_t HW, qd_stream_t s);
 int qd_avgpool2x(const float* src, float* dst, int32_t B, int32_t H, int32_t W, int32_t C, qd_stream_t s);
 int qd_upsample2x_f32(const float* src, float* dst, int32_t B, int32_t H, int32_t W, int32_t C, qd_stream_t s);
+/* qd_vq_lookup: the codebook step of VQModelInterface.decode (ldm/models/autoencoder.py:274-283 -> taming's
+ *      VectorQuantizer2.forward): for each of `rows` latent pixels z[r, 0..C) (NHWC fp32, row pitch ld_z) the nearest of
+ *      the n_e codebook rows by d = sum(z^2) + sum(e^2) - 2 z.e (fp32, lowest index on ties); out = z + (e - z).  C <= 16. */
+int qd_vq_lookup(const float* z, long long ld_z, const float* codebook, float* out, long long ld_out, int32_t rows, int32_t C,
+                 int32_t n_e, qd_stream_t s);
 
 /* ------------------------------------------------------------------------------------------
  * qd_sampler_step -- closed-form latent update of the denoising loop, fused with the
@@ -376,7 +382,8 @@ enum qd_op_kind {
   QD_OP_AVGPOOL2X = 11,
   QD_OP_UPSAMPLE2X = 12,
   QD_OP_SPLIT3 = 13,
-  QD_OP_ATTENTION_FP = 14
+  QD_OP_ATTENTION_FP = 14,
+  QD_OP_VQ_LOOKUP = 15
 };
 
 /* generic argument block for the small helpers when recorded into an engine */
@@ -385,7 +392,7 @@ typedef struct qd_misc_desc {
   float* dst;
   long long ld_src, ld_dst;
   int32_t a, b, c, d;   /* meaning per op: see qd_engine_add_op */
-  const float* aux;     /* QD_OP_TIMESTEP_EMB: frequency table */
+  const float* aux;     /* QD_OP_TIMESTEP_EMB: frequency table; QD_OP_VQ_LOOKUP: codebook [c][b] (a = rows, b = C, c = n_e) */
 } qd_misc_desc;
 
 int qd_engine_create(int device, qd_engine** out);

@@ -695,6 +695,54 @@ __global__ void upsample2x_f32_kernel(const float* __restrict__ src, float* __re
   }
 }
 
+// ------------------------------------------------------------------------------------ VQ first stage
+// Nearest codebook entry per latent pixel (VectorQuantizer2.forward of taming-transformers, the `quantize` step of
+// VQModelInterface.decode, ldm/models/autoencoder.py:274-283): d_j = sum(z^2) + sum(e_j^2) - 2 z.e_j in fp32 with the
+// reference's association, argmin with the lowest index on ties, output z + (e - z) (the straight-through form: it
+// rounds).  One warp per pixel, lanes stride over the codebook.
+constexpr int VQ_MAX_C = 16;
+__global__ void __launch_bounds__(256) vq_lookup_kernel(const float* __restrict__ z, long long ld_z, const float* __restrict__ cb,
+                                                        float* __restrict__ out, long long ld_out, int rows, int C, int n_e) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    float zv[VQ_MAX_C];
+    float zz = 0.f;
+#pragma unroll
+    for (int c = 0; c < VQ_MAX_C; ++c) {
+      zv[c] = c < C ? z[r * ld_z + c] : 0.f;
+      if (c < C) zz = __fadd_rn(zz, __fmul_rn(zv[c], zv[c]));
+    }
+    float best = INFINITY;
+    int bi = 0x7fffffff;
+    for (int j = lane; j < n_e; j += 32) {
+      const float* e = cb + (long long)j * C;
+      float ee = 0.f, dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < VQ_MAX_C; ++c) {
+        if (c < C) {
+          const float ev = __ldg(e + c);
+          ee = __fadd_rn(ee, __fmul_rn(ev, ev));
+          dot = fmaf(zv[c], ev, dot);
+        }
+      }
+      const float dj = __fsub_rn(__fadd_rn(zz, ee), __fmul_rn(2.0f, dot));
+      if (dj < best) { best = dj; bi = j; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane < C) {
+      const float zc = z[r * ld_z + lane];
+      out[r * ld_out + lane] = __fadd_rn(zc, __fsub_rn(__ldg(cb + (long long)bi * C + lane), zc));
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ sampler
 __global__ void lincomb3_kernel(float* __restrict__ out, float a, const float* __restrict__ x, float b,
                                 const float* __restrict__ y, float c, const float* __restrict__ z, long long n) {

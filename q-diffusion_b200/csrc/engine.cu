@@ -227,7 +227,11 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
     if (H <= 0 || W <= 0 || B <= 0 || (long long)B * H * W != d->M) return fail(QD_ERR_BAD_ARG, "gemm: conv geometry");
     const int hw = H * W;
     int bh, bn;
-    if (hw >= 128) {
+    int bw = W;
+    if (W > 128) {                 // first-stage decoder maps (256, 512 wide): a tile is a 128-pixel segment of one row
+      if (W % 128) return fail(QD_ERR_UNSUPPORTED, "gemm: conv W=%d must divide or be a multiple of 128", W);
+      bw = 128; bh = 1; bn = 1;
+    } else if (hw >= 128) {
       if (128 % W) return fail(QD_ERR_UNSUPPORTED, "gemm: conv W=%d must divide 128", W);
       bh = 128 / W; bn = 1;
       if (H % bh) return fail(QD_ERR_UNSUPPORTED, "gemm: conv H=%d not a multiple of %d", H, bh);
@@ -236,9 +240,13 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
       bh = H; bn = 128 / hw;
     }
     a.H = H; a.W = W; a.bh = bh; a.bn = bn;
+    // pixel pitch: lda when it exceeds C (a column range of a wider NHWC buffer: the leading bfloat16 planes of a split3
+    // activation), else the dense C
+    const cuuint64_t pitch = d->lda > d->C ? (cuuint64_t)d->lda : (cuuint64_t)d->C;
+    if (pitch % 16) return fail(QD_ERR_UNSUPPORTED, "gemm: conv pixel pitch %llu must be a multiple of 16", (unsigned long long)pitch);
     dims[0] = (cuuint64_t)d->C; dims[1] = (cuuint64_t)W; dims[2] = (cuuint64_t)H; dims[3] = (cuuint64_t)B;
-    strides[0] = (cuuint64_t)d->C; strides[1] = (cuuint64_t)d->C * W; strides[2] = (cuuint64_t)d->C * W * H;
-    box[0] = qd::GEMM_BK; box[1] = (cuuint32_t)W; box[2] = (cuuint32_t)bh; box[3] = (cuuint32_t)bn;
+    strides[0] = pitch; strides[1] = pitch * W; strides[2] = pitch * W * H;
+    box[0] = qd::GEMM_BK; box[1] = (cuuint32_t)bw; box[2] = (cuuint32_t)bh; box[3] = (cuuint32_t)bn;
   }
   int rc = encode_u8_map(&pl->tmA, d->a, 4, dims, strides, box);
   if (rc) return rc;
@@ -314,7 +322,8 @@ int launch_gemm_mode_w(const GemmPlan& pl, cudaStream_t s) {
   if (stages < 2) stages = 2;
   a.stages = stages;
   const int smem = qd::gemm_smem_layout(a.BN, stages, epi_warps, W4 ? 1 : 0, res_bytes).total;
-  launch_k(qd::gemm_i8_kernel<MODE, W4>, pl.grid, qd::gemm_threads(MODE), smem, s, pl.tmA, pl.tmB, pl.tmR, a);
+  if (smem > 232448) return fail(QD_ERR_UNSUPPORTED, "gemm: BN=%d needs %d bytes of shared memory for 2 stages (mode %d, w4 %d)", a.BN, smem, MODE, (int)W4);
+  launch_k(qd::gemm_i8_kernel<MODE, W4>, pl.grid, qd::gemm_threads(MODE, W4), smem, s, pl.tmA, pl.tmB, pl.tmR, a);
   return check_launch("gemm_i8_kernel");
 }
 
@@ -347,7 +356,8 @@ int gemm_mode(const qd::GemmArgs& a) {
   }
   static const int ring_kb = [] { const char* e = getenv("QDIFF_RES_RING_KB"); return e ? atoi(e) : 5; }();
   const int num_kb = ((a.C + qd::GEMM_BK - 1) / qd::GEMM_BK) * a.taps * a.kdup;
-  const bool ring = a.residual && a.taps == 1 && num_kb <= ring_kb && !(reinterpret_cast<uintptr_t>(a.residual) & 15);
+  const bool ring = a.residual && a.taps == 1 && num_kb <= ring_kb && !(reinterpret_cast<uintptr_t>(a.residual) & 15) &&
+                    !a.w4;    // packed INT4 stages already carry the staging area of the packed tile: no room for the ring
   return (a.corr ? qd::EPI_CORR : 0) | ((a.taps == 9) ? qd::EPI_CONV : 0) | (a.rowvec ? qd::EPI_ROWVEC : 0) |
          (a.residual ? qd::EPI_RESIDUAL : 0) | (f ? qd::EPI_OUT_F32 : qd::EPI_OUT_Q) | (ring ? qd::EPI_RESTMA : 0);
 }
@@ -771,6 +781,11 @@ int launch_misc(int kind, const qd_misc_desc& m, cudaStream_t s) {
       if (m.d % 4) return fail(QD_ERR_UNSUPPORTED, "upsample: C %% 4");
       launch_k(qd::upsample2x_f32_kernel, grid_for((long long)m.a * m.b * m.c * m.d, 256), 256, 0, s, m.src, m.dst, m.a, m.b, m.c, m.d);
       return check_launch("upsample2x_f32_kernel");
+    case QD_OP_VQ_LOOKUP:
+      if (!m.aux || m.a <= 0 || m.b <= 0 || m.b > qd::VQ_MAX_C || m.c <= 0 || m.ld_src < m.b || m.ld_dst < m.b)
+        return fail(QD_ERR_BAD_ARG, "vq_lookup: bad args (rows=%d, C=%d <= %d, n_e=%d)", m.a, m.b, qd::VQ_MAX_C, m.c);
+      launch_k(qd::vq_lookup_kernel, grid_for((long long)m.a * 32, 256), 256, 0, s, m.src, m.ld_src, m.aux, m.dst, m.ld_dst, m.a, m.b, m.c);
+      return check_launch("vq_lookup_kernel");
     default:
       return fail(QD_ERR_BAD_ARG, "misc: unknown kind %d", kind);
   }
@@ -890,6 +905,11 @@ int qd_upsample2x_f32(const float* src, float* dst, int32_t B, int32_t H, int32_
   qd_misc_desc m{src, dst, 0, 0, B, H, W, C, nullptr};
   return launch_misc(QD_OP_UPSAMPLE2X, m, (cudaStream_t)s);
 }
+int qd_vq_lookup(const float* z, long long ld_z, const float* codebook, float* out, long long ld_out, int32_t rows, int32_t C,
+                 int32_t n_e, qd_stream_t s) {
+  qd_misc_desc m{z, out, ld_z, ld_out, rows, C, n_e, 0, codebook};
+  return launch_misc(QD_OP_VQ_LOOKUP, m, (cudaStream_t)s);
+}
 int qd_sampler_step(const qd_sampler_desc* d, qd_stream_t s) {
   if (!d || !d->x || !d->eps || !d->x_prev || d->n <= 0) return fail(QD_ERR_BAD_ARG, "sampler: bad args");
   launch_k(qd::sampler_step_kernel, grid_for(d->n, 256), 256, 0, (cudaStream_t)s, *d);
@@ -931,7 +951,7 @@ int qd_engine_add_op(qd_engine* e, int kind, const void* desc) {
     case QD_OP_SPLIT3: op.split = *reinterpret_cast<const qd_split_desc*>(desc); break;
     case QD_OP_ATTENTION_FP: op.attfp = *reinterpret_cast<const qd_attention_fp_desc*>(desc); break;
     case QD_OP_TIMESTEP_EMB: case QD_OP_COPY2D: case QD_OP_NCHW_TO_NHWC: case QD_OP_NHWC_TO_NCHW:
-    case QD_OP_AVGPOOL2X: case QD_OP_UPSAMPLE2X:
+    case QD_OP_AVGPOOL2X: case QD_OP_UPSAMPLE2X: case QD_OP_VQ_LOOKUP:
       op.misc = *reinterpret_cast<const qd_misc_desc*>(desc);
       break;
     default: return fail(QD_ERR_BAD_ARG, "unknown op kind %d", kind);

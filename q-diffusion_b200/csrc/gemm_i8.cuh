@@ -10,7 +10,8 @@
 //   warp 0   : TMA producer  (A tile 128 x 128 B, B tile BN x 128 B, 128B swizzle, mbarrier ring)
 //   warp 1   : MMA issuer    (tcgen05.mma.kind::i8, M=128, N=BN, K=32 per instruction, int32 acc in TMEM)
 //   warp 2   : TMEM allocator (512 columns: two accumulator stages of up to 256 columns)
-//   warps 2-3: INT4 unpack   (W4 variant only: packed 4-bit weight codes staged by TMA -> swizzled s8 operand tile)
+//   warps 2-3 and the LAST two warps: INT4 unpack (W4 variant only: packed 4-bit weight codes staged by TMA -> swizzled
+//              s8 operand tile; four warps = one per scheduler)
 //   warps 4+ : epilogue, 8 or 16 warps by MODE (tcgen05.ld -> smem transpose -> zero-point correction / scale /
 //                             bias / adds / GEGLU -> coalesced fp32 or requantised stores)
 //
@@ -54,7 +55,8 @@ __host__ __device__ constexpr bool gemm_res_tma(int MODE) { return MODE >= 0 && 
 __host__ __device__ constexpr int gemm_res_bytes(int MODE) {
   return gemm_res_tma(MODE) ? gemm_epi_warps(MODE) * GEMM_RES_NBUF * 4096 : 0;
 }
-__host__ __device__ constexpr int gemm_threads(int MODE) { return (4 + gemm_epi_warps(MODE)) * 32; }
+// W4 (packed INT4 weights): two more warps behind the epilogue warps join warps 2-3 as unpack warps
+__host__ __device__ constexpr int gemm_threads(int MODE, bool W4 = false) { return (4 + gemm_epi_warps(MODE) + (W4 ? 2 : 0)) * 32; }
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK;
 constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_EPI_TILE_BYTES = 32 * 128;  // per-epilogue-warp staging tile (32 rows x 32 int32)
@@ -79,7 +81,8 @@ struct GemmArgs {
   int BN;              // N tile (multiple of 16, <= 256)
   int tiles_m, tiles_n;
   int stages;
-  // conv geometry (taps == 9): activations are NHWC, tile = bn images x bh rows x W columns = 128 pixels
+  // conv geometry (taps == 9): activations are NHWC, tile = bn images x bh rows x W columns = 128 pixels (W > 128: a
+  // 128-pixel segment of one row)
   int H, W, bh, bn;
   int a_signed, b_signed;
   // epilogue
@@ -343,7 +346,7 @@ __device__ __forceinline__ void gemm_finalise4(const GemmArgs& p, const QuantK& 
 // W4: packed-INT4 weight variant (compile-time, so the s8 kernels carry none of the unpack role's code: with a
 // run-time flag the register allocation of the epilogue changed and the default path lost 8 %).
 template <int MODE, bool W4 = false>
-__global__ void __launch_bounds__(gemm_threads(MODE), 1)
+__global__ void __launch_bounds__(gemm_threads(MODE, W4), 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmR, const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -379,7 +382,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
-      if constexpr (W4) mbar_init(&ready_bar[s], 2);    // one arrival per unpack warp
+      if constexpr (W4) mbar_init(&ready_bar[s], 4);    // one arrival per unpack warp
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -410,11 +413,12 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int tn = tile - tm * p.tiles_n;
         const int m0 = tm * GEMM_BM;
         const int n0 = tn * p.BN;
-        int b0 = 0, h0 = 0;
+        int b0 = 0, h0 = 0, w0 = 0;
         if (p.taps == 9) {
           const int hw = p.H * p.W;
           b0 = m0 / hw;
           h0 = (m0 - b0 * hw) / p.W;
+          w0 = m0 - b0 * hw - h0 * p.W;      // != 0 only for rows wider than a tile (W > 128: the tile is a 128-pixel row segment)
         }
         for (int seg = 0; seg < p.taps * p.kdup; ++seg) {
           const int tap = seg % p.taps;            // activation geometry of this segment; the weight column offset is seg * C
@@ -425,7 +429,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint8_t* sb = sa + GEMM_A_STAGE_BYTES;
             mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
             if (p.taps == 9)
-              tma_load_4d(sa, &tmA, &full_bar[stage], kc * GEMM_BK, kx - 1, h0 + ky - 1, b0);
+              tma_load_4d(sa, &tmA, &full_bar[stage], kc * GEMM_BK, w0 + kx - 1, h0 + ky - 1, b0);
             else
               tma_load_4d(sa, &tmA, &full_bar[stage], kc * GEMM_BK, m0, 0, 0);
             if constexpr (W4)
@@ -472,43 +476,44 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp < 4) {
-    // ===================== INT4 unpack (warps 2-3, packed-weight GEMMs only) =====================
-    // 64 threads = 16 rows x 4 sixteen-byte pieces per pass.  A piece holds 32 codes (k = 32j .. 32j+31 of the
+  } else if (warp < 4 || warp >= 4 + EPI_WARPS) {
+    // ===================== INT4 unpack (warps 2, 3 and the two warps behind the epilogue warps; W4 only) ==========
+    // 128 threads = 32 rows x 4 sixteen-byte pieces per pass.  A piece holds 32 codes (k = 32j .. 32j+31 of the
     // k-block) and becomes two 16-byte chunks of the row in the 128B-swizzled s8 tile the MMA descriptor expects
     // (chunk index XOR row&7, identical to what TMA SWIZZLE_128B writes on the unpacked path).
+    // Nibble order (ops.pack_int4): byte j of a 4-byte word holds code k0+j in its low and code k0+4+j in its high nibble,
+    // so the masked word IS four consecutive codes - no byte permutation.  code - zp per byte without borrows:
+    // (code + (0x80 - zp)) ^ 0x80, the constant 0x80808080 - zp*0x01010101 kept per row.  7 integer instructions per 8
+    // codes (round 1: 11, on two warps: 1.7 k cycles per k-block against 0.9 k for the main loop).
     if constexpr (W4) {
-      const int t = threadIdx.x - 64;
-      const int r16 = t >> 2, piece = t & 3;
+      const int t = warp < 4 ? (int)threadIdx.x - 64 : (int)threadIdx.x - (4 + EPI_WARPS) * 32 + 64;   // 0..127
+      const int r32 = t >> 2, piece = t & 3;
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int tn = tile % p.tiles_n;
         const int n0 = tn * p.BN;
-        uint32_t zp4[16];     // per-row zero point replicated into 4 bytes, rows r16 + 16*i
+        uint32_t kz[8];       // 0x80808080 - zero point replicated into 4 bytes, rows r32 + 32*i
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int n = n0 + r16 + 16 * i;
-          zp4[i] = (16 * i < p.BN && n < p.N) ? 0x01010101u * (uint32_t)(uint8_t)__ldg(p.wzero + n) : 0u;
+        for (int i = 0; i < 8; ++i) {
+          const int n = n0 + r32 + 32 * i;
+          kz[i] = 0x80808080u - ((r32 + 32 * i < p.BN && n < p.N) ? 0x01010101u * (uint32_t)(uint8_t)__ldg(p.wzero + n) : 0u);
         }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           const uint8_t* sp = smem + lay.pack_off + (size_t)stage * p.BN * (GEMM_BK / 2);
           uint8_t* sb = smem + (size_t)stage * lay.stage_bytes + GEMM_A_STAGE_BYTES;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int row = r16 + 16 * i;
-            if (16 * i < p.BN) {
+          for (int i = 0; i < 8; ++i) {
+            const int row = r32 + 32 * i;
+            if (row < p.BN) {
               const uint4 w = *reinterpret_cast<const uint4*>(sp + row * (GEMM_BK / 2) + piece * 16);
               const uint32_t in[4] = {w.x, w.y, w.z, w.w};
               uint32_t o[8];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                // (code | 0x80) - zp never borrows across bytes; ^0x80 then yields the signed byte code - zp
-                const uint32_t lo = ((in[q] & 0x0F0F0F0Fu) | 0x80808080u) - zp4[i];
-                const uint32_t hi = (((in[q] >> 4) & 0x0F0F0F0Fu) | 0x80808080u) - zp4[i];
-                o[2 * q] = __byte_perm(lo, hi, 0x5140) ^ 0x80808080u;        // k = 8q+0..3: lo0 hi0 lo1 hi1
-                o[2 * q + 1] = __byte_perm(lo, hi, 0x7362) ^ 0x80808080u;    // k = 8q+4..7: lo2 hi2 lo3 hi3
+                o[2 * q] = ((in[q] & 0x0F0F0F0Fu) + kz[i]) ^ 0x80808080u;             // k = 8q+0..3
+                o[2 * q + 1] = (((in[q] >> 4) & 0x0F0F0F0Fu) + kz[i]) ^ 0x80808080u;  // k = 8q+4..7
               }
               uint8_t* dst = sb + row * GEMM_BK;
               *reinterpret_cast<uint4*>(dst + (((2 * piece) ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);

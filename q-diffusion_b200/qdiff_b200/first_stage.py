@@ -1,0 +1,377 @@
+"""First-stage DECODE on the engine: the step right after the sampling loop.
+
+Reference being replaced:
+  LatentDiffusion.decode_first_stage  ldm/models/diffusion/ddpm.py:710-767  (z = 1/scale_factor * z, then .decode)
+  AutoencoderKL.decode                ldm/models/autoencoder.py:330-333     (SD v1, LSUN-church kl-f8)
+  VQModelInterface.decode             ldm/models/autoencoder.py:274-283     (LSUN-bedroom vq-f4; codebook lookup first)
+  Decoder.forward                     ldm/modules/diffusionmodules/model.py:465-571 (ResnetBlock :85-144, AttnBlock
+                                      :153-205, Upsample :45-61)
+
+The containers below carry parameters only, with the reference's constructor keywords and state_dict keys
+(`decoder.*`, `post_quant_conv.*`, `quantize.embedding.weight`): a first-stage checkpoint of the reference loads with
+load_state_dict(strict=False).  `.decode()` lowers the graph once per latent shape to an engine program (CUDA graph) and
+replays it; there is no torch / CPU path.
+
+Arithmetic.  The first stage is NOT quantised by q-diffusion: weights and activations are floating point.  Every conv /
+1x1 conv is a tcgen05 kind::f16 contraction with fp32 accumulation (the same kernel as the weight-only UNet path) on
+bfloat16 PLANES of both operands: x = x_hi + x_mid + x_lo and w = w_hi + w_mid + w_lo, each plane a bfloat16 rounding of
+the remainder.  `precision` picks the plane products that are formed:
+    1  x_hi w_hi                                            (plain bfloat16: relative 2^-9 per product)
+    3  + x_mid w_hi + x_hi w_mid                            (default; error terms 2^-16: finer than fp16's 2^-11)
+    6  + x_lo w_hi + x_mid w_mid + x_hi w_lo                (fp32-faithful: 2^-24)
+as 1 / 2 / 3 accumulating launches over the leading 1 / 2 / 3 activation planes (qd_gemm_desc.lda = plane pitch).
+GroupNorm + swish, the attention softmax and all accumulations are fp32.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib, graph, ops
+from ._lib import check, lib
+from .unet import AttnBlock, _NoForward, _gn
+
+_PASSES = {1: ((0, 1),), 3: ((0, 2), (1, 1)), 6: ((0, 3), (1, 2), (2, 1))}      # (weight plane, leading activation planes)
+
+
+# ------------------------------------------------------------------------------- parameter containers
+class ResnetBlock(_NoForward):
+    """model.py:85-121 with temb_channels = 0 (the decoder passes temb=None: no temb_proj)."""
+
+    def __init__(self, in_channels, out_channels, conv_shortcut=False):
+        super().__init__()
+        self.in_channels, self.out_channels, self.use_conv_shortcut = in_channels, out_channels, conv_shortcut
+        self.norm1 = _gn(in_channels, 1e-6)
+        self.conv1 = nn.Conv2d(in_channels, out_channels, 3, 1, 1)
+        self.norm2 = _gn(out_channels, 1e-6)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, 3, 1, 1)
+        if in_channels != out_channels:
+            if conv_shortcut:
+                self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 3, 1, 1)
+            else:
+                self.nin_shortcut = nn.Conv2d(in_channels, out_channels, 1, 1, 0)
+
+
+class Upsample(_NoForward):
+    def __init__(self, in_channels, with_conv):
+        super().__init__()
+        self.with_conv = with_conv
+        if with_conv:
+            self.conv = nn.Conv2d(in_channels, in_channels, 3, 1, 1)
+
+
+class Decoder(_NoForward):
+    """Same keywords as ldm.modules.diffusionmodules.model.Decoder (model.py:466-469)."""
+
+    def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, dropout=0.0,
+                 resamp_with_conv=True, in_channels, resolution, z_channels, give_pre_end=False, tanh_out=False,
+                 use_linear_attn=False, attn_type="vanilla", **ignorekwargs):
+        super().__init__()
+        if use_linear_attn or attn_type != "vanilla":
+            raise NotImplementedError("only attn_type='vanilla' (every first stage the reference's configs use)")
+        if give_pre_end or tanh_out:
+            raise NotImplementedError("give_pre_end / tanh_out are not used by the reference's first-stage configs")
+        self.ch, self.num_resolutions, self.num_res_blocks = ch, len(ch_mult), num_res_blocks
+        self.resolution, self.in_channels, self.z_channels = resolution, in_channels, z_channels
+        block_in = ch * ch_mult[self.num_resolutions - 1]
+        curr_res = resolution // 2 ** (self.num_resolutions - 1)
+        self.z_shape = (1, z_channels, curr_res, curr_res)
+        self.conv_in = nn.Conv2d(z_channels, block_in, 3, 1, 1)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(block_in, block_in)
+        self.mid.attn_1 = AttnBlock(block_in)
+        self.mid.block_2 = ResnetBlock(block_in, block_in)
+        ups = []
+        for lv in reversed(range(self.num_resolutions)):
+            stage = nn.Module()
+            stage.block, stage.attn = nn.ModuleList(), nn.ModuleList()
+            block_out = ch * ch_mult[lv]
+            for _ in range(num_res_blocks + 1):
+                stage.block.append(ResnetBlock(block_in, block_out))
+                block_in = block_out
+                if curr_res in attn_resolutions:
+                    stage.attn.append(AttnBlock(block_in))
+            if lv != 0:
+                stage.upsample = Upsample(block_in, resamp_with_conv)
+                curr_res *= 2
+            ups.insert(0, stage)
+        self.up = nn.ModuleList(ups)
+        self.norm_out = _gn(block_in, 1e-6)
+        self.conv_out = nn.Conv2d(block_in, out_ch, 3, 1, 1)
+
+
+class _FirstStage(_NoForward):
+    """Shared engine plumbing: program cache, decode()."""
+    act_quant_params = {}
+    weight_quant_params = {"n_bits": 32}
+
+    def _init_engine_state(self, precision, cuda_graph):
+        if precision not in _PASSES:
+            raise ValueError(f"precision must be one of {sorted(_PASSES)} (bfloat16 plane products per MAC)")
+        self.precision, self.cuda_graph = precision, cuda_graph
+        self._programs, self._wcache = {}, {}
+
+    def load_state_dict(self, state_dict, strict=False, **kw):
+        """Encoder / loss / EMA keys of a full first-stage checkpoint are ignored (decode only)."""
+        own = set(self.state_dict().keys())
+        res = super().load_state_dict({k: v for k, v in state_dict.items() if k in own}, strict=False, **kw)
+        missing = [k for k in own if k not in state_dict]
+        if strict and missing:
+            raise KeyError(f"first-stage checkpoint lacks {missing[:4]} ...")
+        self._programs, self._wcache = {}, {}
+        return res
+
+    def _decode(self, z, quantize):
+        if not z.is_cuda:
+            raise RuntimeError("qdiff_b200 first stage: CUDA tensors only (the engine has no CPU fallback)")
+        key = (tuple(z.shape), z.device.index, bool(quantize), self.precision)
+        prog = self._programs.get(key)
+        if prog is None:
+            prog = compile_decoder(self, tuple(z.shape), z.device, quantize=quantize, precision=self.precision,
+                                   use_cuda_graph=self.cuda_graph)
+            self._programs = {key: prog}         # one resident program: decode shapes rarely change, buffers are large
+        return prog.run(z, torch.zeros(z.shape[0], device=z.device))
+
+
+class AutoencoderKL(_FirstStage):
+    """ldm.models.autoencoder.AutoencoderKL, decode side (autoencoder.py:285-333)."""
+
+    def __init__(self, ddconfig, embed_dim, lossconfig=None, precision=3, cuda_graph=True, **ignorekwargs):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.decoder = Decoder(**ddconfig)
+        self.post_quant_conv = nn.Conv2d(embed_dim, ddconfig["z_channels"], 1)
+        self._init_engine_state(precision, cuda_graph)
+
+    def decode(self, z):
+        return self._decode(z, False)
+
+
+class VectorQuantizer(_NoForward):
+    def __init__(self, n_e, e_dim):
+        super().__init__()
+        self.n_e, self.e_dim = n_e, e_dim
+        self.embedding = nn.Embedding(n_e, e_dim)
+
+
+class VQModelInterface(_FirstStage):
+    """ldm.models.autoencoder.VQModelInterface, decode side (autoencoder.py:14-61, 255-283)."""
+
+    def __init__(self, embed_dim, ddconfig, n_embed, lossconfig=None, precision=3, cuda_graph=True, **ignorekwargs):
+        super().__init__()
+        self.embed_dim, self.n_embed = embed_dim, n_embed
+        self.decoder = Decoder(**ddconfig)
+        self.quantize = VectorQuantizer(n_embed, embed_dim)
+        self.post_quant_conv = nn.Conv2d(embed_dim, ddconfig["z_channels"], 1)
+        self._init_engine_state(precision, cuda_graph)
+
+    def decode(self, h, force_not_quantize=False):
+        return self._decode(h, not force_not_quantize)
+
+
+def decode_first_stage(first_stage, z, scale_factor=1.0, force_not_quantize=False):
+    """LatentDiffusion.decode_first_stage (ddpm.py:710-767), plain branch: z = 1. / scale_factor * z, then decode."""
+    z = 1. / scale_factor * z
+    if isinstance(first_stage, VQModelInterface):
+        return first_stage.decode(z, force_not_quantize=force_not_quantize)
+    return first_stage.decode(z)
+
+
+# ------------------------------------------------------------------------------- lowering
+class FirstStageBuilder(graph.WeightOnlyBuilder):
+    """Decoder.forward as engine ops: fp32 GroupNorm+swish, bfloat16-plane GEMMs, fp32 attention."""
+
+    def __init__(self, fs, device, batch, precision):
+        super().__init__(fs, device, batch)
+        self.passes = _PASSES[precision]
+
+    def _planes(self, conv, label, Cp, im2col):
+        """bfloat16 planes of a conv weight as GEMM operands, one tile per pass: [Np, taps, planes, Cp] with the pass's
+        weight plane repeated over the activation planes it multiplies (im2col inputs interleave the planes per tap, so
+        they always carry three plane slots, the unused ones zero)."""
+        key = (self.dev.index or 0, "fs", label, Cp, self.passes, bool(im2col))
+        ent = self.wcache.get(key)
+        if ent is not None:
+            return ent
+        w = conv.weight.detach().to(self.dev, torch.float32)
+        N, Cin = w.shape[0], w.shape[1]
+        taps = 9 if (w.dim() == 4 and w.shape[-1] == 3) else 1
+        w3 = w.reshape(N, Cin, taps).permute(0, 2, 1).contiguous()                 # [N, taps, C]
+        hi = w3.to(torch.bfloat16)
+        r1 = w3 - hi.float()
+        mid = r1.to(torch.bfloat16)
+        lo = (r1 - mid.float()).to(torch.bfloat16)
+        planes = (hi, mid, lo)
+        Np = (N + 3) // 4 * 4              # the specialised epilogues store 4 columns at a time (conv_out: 3 channels)
+        tiles = []
+        for wp, nact in self.passes:
+            slots = 3 if im2col else nact
+            wk = torch.zeros((Np, taps, slots, Cp), dtype=torch.bfloat16, device=self.dev)
+            wk[:N, :, :nact, :Cin] = planes[wp][:, :, None, :]
+            tiles.append((wk.reshape(Np, -1).contiguous(), slots))
+        bias = torch.zeros(Np, dtype=torch.float32, device=self.dev)
+        if conv.bias is not None:
+            bias[:N] = conv.bias.detach().to(self.dev, torch.float32)
+        ent = dict(tiles=tiles, N=Np, N_real=N, taps=taps, bias=bias, ones=torch.ones(Np, dtype=torch.float32, device=self.dev))
+        self.wcache[key] = ent
+        return ent
+
+    def gemm_fp(self, conv, a, label, *, hw=None, residual=None, im2col=None):
+        """One floating-point conv / 1x1 conv: len(self.passes) accumulating GEMM launches.  a: split3 planes of the input.
+        hw: 3x3 stride-1 conv on an (H, W) map (implicit GEMM); im2col = (hw, stride, pad_tl, out_hw): explicit patches."""
+        W = self._planes(conv, label, a.Cp, im2col is not None)
+        N, taps = W["N"], W["taps"]
+        self.keep += [W["bias"], W["ones"]] + [t for t, _ in W["tiles"]]
+        src, conv_bhw, rows_pb = a, None, 0
+        if im2col is not None:
+            (H, Wd), stride, pad_tl, (Ho, Wo) = im2col
+            cbytes = 6 * a.Cp
+            patches = torch.zeros((self.B * Ho * Wo, 9 * cbytes), dtype=torch.uint8, device=self.dev)
+            self.keep.append(patches)
+            di = ops.im2col_desc(a.t, patches, B=self.B, H=H, W=Wd, C_=cbytes, Ho=Ho, Wo=Wo, stride=stride,
+                                 pad_top=pad_tl[0], pad_left=pad_tl[1], pad_code=0, ld_dst=9 * cbytes)
+            src = graph.Act(patches, self.B * Ho * Wo, 9 * cbytes)
+            self.add(_lib.QD_OP_IM2COL, di, label + ".im2col")
+        elif taps == 9:
+            conv_bhw, rows_pb = (self.B, hw[0], hw[1]), hw[0] * hw[1]
+        M = src.rows
+        o = self.new_f32(M, N)
+        for i, (tile, slots) in enumerate(W["tiles"]):
+            if im2col is not None:
+                g_taps, g_c, lda = 1, 9 * 6 * a.Cp, 9 * 6 * a.Cp
+            else:
+                g_taps, g_c, lda = taps, 2 * slots * a.Cp, 6 * a.Cp            # bytes: leading `slots` planes of 3
+            res = residual if i == 0 else o
+            d = ops.gemm_desc(src.t, tile, W["ones"], M=M, N=N, C=g_c, taps=g_taps, lda=lda, conv_bhw=conv_bhw,
+                              a_signed=False, bias=W["bias"] if i == 0 else None, rows_per_batch=rows_pb,
+                              residual=res.t if res is not None else None, ldr=res.ld if res is not None else 0,
+                              out=o.t, ldo=o.ld)
+            d.a_bf16 = 1
+            d.a = src.ptr
+            if res is not None:
+                d.residual = res.ptr
+            d.out = o.ptr
+            Cin = int(conv.weight.shape[1])
+            self.add(_lib.QD_OP_GEMM, d, label + (f".pass{i}" if i else ""),
+                     flops=2 * M * W["N_real"] * Cin * taps if i == 0 else 0)
+        self.layer_traces[label] = o
+        return o
+
+    def conv(self, conv, x_f32, label, hw, residual=None, upsample=None):
+        a = self.split3(x_f32, label + ".split", upsample=upsample)
+        return self.gemm_fp(conv, a, label, hw=hw, residual=residual)
+
+    def resnet(self, blk, x, hw):
+        """ResnetBlock.forward (model.py:122-144), temb None."""
+        k = self.key(blk)
+        T = hw[0] * hw[1]
+        h1 = self.gn_f32(x, blk.norm1, T, True, k + ".norm1")
+        h = self.conv(blk.conv1, h1, k + ".conv1", hw)
+        h2 = self.gn_f32(h, blk.norm2, T, True, k + ".norm2")
+        s = x
+        if blk.in_channels != blk.out_channels:
+            if getattr(blk, "use_conv_shortcut", False):
+                s = self.conv(blk.conv_shortcut, x, k + ".conv_shortcut", hw)
+            else:
+                s = self.conv(blk.nin_shortcut, x, k + ".nin_shortcut", hw)
+        return self.conv(blk.conv2, h2, k + ".conv2", hw, residual=s)
+
+    def attn(self, blk, x, hw):
+        """AttnBlock.forward (model.py:179-205): single head, d = C, softmax(q k^T C^-1/2) v, fp32."""
+        k = self.key(blk)
+        T, C_ = hw[0] * hw[1], x.cols
+        hn = self.gn_f32(x, blk.norm, T, False, k + ".norm")
+        a = self.split3(hn, k + ".qkv.split")
+        q = self.gemm_fp(blk.q, a, k + ".q")
+        kk = self.gemm_fp(blk.k, a, k + ".k")
+        v = self.gemm_fp(blk.v, a, k + ".v")
+        o = self.attention_fp(q, kk, v, heads=1, d=C_, Tq=T, Tk=T, q_layout=(0, C_), k_layout=(0, C_), v_layout=(0, C_),
+                              scale=float(int(C_) ** (-0.5)), label=k + ".attn")
+        return self.conv(blk.proj_out, o, k + ".proj_out", hw, residual=x)
+
+    def lower(self, fs, z_shape, quantize):
+        B, zc, H, W = z_shape
+        dec = fs.decoder
+        x_in = torch.zeros(z_shape, dtype=torch.float32, device=self.dev)
+        t_in = torch.zeros(B, dtype=torch.float32, device=self.dev)
+        self.keep += [x_in, t_in]
+        zh = self.new_f32(B * H * W, zc)
+        self.misc(_lib.QD_OP_NCHW_TO_NHWC, x_in.data_ptr(), zh.ptr, B, zc, H * W, label="z.nhwc")
+        if quantize:
+            cb = fs.quantize.embedding.weight.detach().to(self.dev, torch.float32).contiguous()
+            if cb.shape[1] != zc:
+                raise ValueError(f"codebook dim {cb.shape[1]} != latent channels {zc}")
+            zq = self.new_f32(B * H * W, zc)
+            self.misc(_lib.QD_OP_VQ_LOOKUP, zh.ptr, zq.ptr, B * H * W, zc, cb.shape[0], ld_src=zh.ld, ld_dst=zq.ld,
+                      label="quantize", aux=cb)
+            zh = zq
+        hw = (H, W)
+        h = self.conv(fs.post_quant_conv, zh, "post_quant_conv", hw)
+        h = h.view(0, int(fs.post_quant_conv.weight.shape[0]))              # drop the padding columns (N rounded up to 4)
+        h = self.gemm_fp(dec.conv_in, self.split3(h, "decoder.conv_in.split"), "decoder.conv_in", im2col=(hw, 1, (1, 1), hw))
+        h = self.resnet(dec.mid.block_1, h, hw)
+        h = self.attn(dec.mid.attn_1, h, hw)
+        h = self.resnet(dec.mid.block_2, h, hw)
+        self.traces["mid"] = (h, hw)
+        for lv in reversed(range(dec.num_resolutions)):
+            st = dec.up[lv]
+            for ib in range(dec.num_res_blocks + 1):
+                h = self.resnet(st.block[ib], h, hw)
+                if len(st.attn) > 0:
+                    h = self.attn(st.attn[ib], h, hw)
+            if lv != 0:
+                up = st.upsample
+                if up.with_conv:
+                    a = self.split3(h, self.key(up.conv) + ".split", upsample=(B, hw[0], hw[1]))
+                    hw = (2 * hw[0], 2 * hw[1])
+                    h = self.gemm_fp(up.conv, a, self.key(up.conv), hw=hw)
+                else:
+                    big = self.new_f32(4 * h.rows, h.cols)
+                    self.misc(_lib.QD_OP_UPSAMPLE2X, self.contig(h, "up").ptr, big.ptr, B, hw[0], hw[1], h.cols,
+                              label=self.key(up) + ".nearest")
+                    h, hw = big, (2 * hw[0], 2 * hw[1])
+            self.traces[f"up.{lv}"] = (h, hw)
+        hn = self.gn_f32(h, dec.norm_out, hw[0] * hw[1], True, "decoder.norm_out")
+        o = self.conv(dec.conv_out, hn, "decoder.conv_out", hw)
+        out = torch.zeros((B, o.cols, hw[0], hw[1]), dtype=torch.float32, device=self.dev)     # o.cols: out_ch padded to 4
+        self.keep.append(out)
+        self.misc(_lib.QD_OP_NHWC_TO_NCHW, o.ptr, out.data_ptr(), B, o.cols, hw[0] * hw[1], label="image.nchw")
+        return x_in, t_in, out[:, :int(dec.conv_out.weight.shape[0])]
+
+
+def compile_decoder(fs, z_shape, device, quantize=False, precision=3, use_cuda_graph=True):
+    """Lower the decode step of `fs` (AutoencoderKL / VQModelInterface container) for a fixed latent shape."""
+    lib()       # fail loudly if the CUDA library is missing
+    if not torch.cuda.is_available():
+        raise RuntimeError("qdiff_b200: no CUDA device; the engine has no CPU fallback")
+    b = FirstStageBuilder(fs, device, z_shape[0], precision)
+    with torch.no_grad():
+        x_in, t_in, out = b.lower(fs, z_shape, quantize)
+    b.flush()
+    check(lib().qd_engine_finalize(b.engine), "qd_engine_finalize")
+    prog = graph.Program(b.engine, b.keep, x_in, t_in, None, out, b.nops, b.traces, use_cuda_graph)
+    prog.op_names, prog.op_kinds, prog.op_flops = b.op_names, b.op_kinds, b.op_flops
+    prog.layer_traces = b.layer_traces
+    return prog
+
+
+# first-stage hyper-parameters of the reference's configs (configs/stable-diffusion/v1-inference.yaml:46-67,
+# models/first_stage_models/{vq-f4,kl-f8}/config.yaml as referenced by configs/latent-diffusion/*.yaml)
+CONFIGS = {
+    "sd_v1": dict(kind="kl", embed_dim=4, scale_factor=0.18215,
+                  ddconfig=dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128,
+                                ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0)),
+    "lsun_church": dict(kind="kl", embed_dim=4, scale_factor=1.0,
+                        ddconfig=dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128,
+                                      ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0)),
+    "lsun_bedroom": dict(kind="vq", embed_dim=3, n_embed=8192, scale_factor=1.0,
+                         ddconfig=dict(double_z=False, z_channels=3, resolution=256, in_channels=3, out_ch=3, ch=128,
+                                       ch_mult=[1, 2, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0)),
+}
+
+
+def build_first_stage(name_or_cfg, precision=3, cuda_graph=True):
+    cfg = CONFIGS[name_or_cfg] if isinstance(name_or_cfg, str) else name_or_cfg
+    if cfg["kind"] == "kl":
+        return AutoencoderKL(cfg["ddconfig"], cfg["embed_dim"], precision=precision, cuda_graph=cuda_graph)
+    return VQModelInterface(cfg["embed_dim"], cfg["ddconfig"], cfg["n_embed"], precision=precision, cuda_graph=cuda_graph)

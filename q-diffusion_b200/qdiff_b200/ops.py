@@ -69,20 +69,33 @@ def gemm_desc(a, w, scale, *, M, N, C, taps=1, lda=None, conv_bhw=None, a_signed
 
 
 def pack_int4(ws):
-    """s8 zero-point-free weight codes [rows, K] (each row spanning at most 15) -> (packed u8 [rows, K/2], zero int8 [rows]),
-    with ws == unpacked - zero[:, None].  Returns None when a row does not fit 4 bits."""
+    """s8 zero-point-free weight codes [rows, K] (each row spanning at most 15, K % 8 == 0) -> (packed u8 [rows, K/2],
+    zero int8 [rows]) with ws == unpack_int4(packed, zero).  Returns None when a row does not fit 4 bits.
+
+    Nibble order: the 8 codes k0 .. k0+7 of a group occupy 4 bytes, byte j = code[k0+j] | code[k0+4+j] << 4, so a masked
+    32-bit word (w & 0x0F0F0F0F, (w >> 4) & 0x0F0F0F0F) is four CONSECUTIVE codes: the GEMM's unpack warps need no byte
+    permutation (csrc/gemm_i8.cuh)."""
     import torch
     ws = ws.to(torch.int16)
     lo, hi = ws.amin(dim=1), ws.amax(dim=1)
-    if int((hi - lo).max()) > 15 or ws.shape[1] % 2:
+    if int((hi - lo).max()) > 15 or ws.shape[1] % 8:
         return None
     zero = (-lo).clamp(0, 15)
     zero = torch.where(hi + zero > 15, 15 - hi, zero)        # keep wq = ws + zero inside [0, 15]
     wq = ws + zero[:, None]
     if int(wq.min()) < 0 or int(wq.max()) > 15 or int(zero.min()) < 0:
         return None
-    packed = (wq[:, 0::2] | (wq[:, 1::2] << 4)).to(torch.uint8).contiguous()
+    g = wq.reshape(wq.shape[0], -1, 2, 4)                     # [rows, groups of 8, low/high nibble, byte]
+    packed = (g[:, :, 0, :] | (g[:, :, 1, :] << 4)).reshape(wq.shape[0], -1).to(torch.uint8).contiguous()
     return packed, zero.to(torch.int8).contiguous()
+
+
+def unpack_int4(packed, zero):
+    """Inverse of pack_int4: int16 codes [rows, K] (zero point removed)."""
+    import torch
+    g = packed.reshape(packed.shape[0], -1, 4).to(torch.int16)
+    codes = torch.stack([g & 15, g >> 4], dim=2).reshape(packed.shape[0], -1)
+    return codes - zero.to(codes.device, torch.int16)[:, None]
 
 
 def qgemm(desc):

@@ -26,7 +26,7 @@ from .quant_layer import QuantModule, UniformAffineQuantizer
 from .quant_model import QuantModel
 
 FORMAT = "qdiff_b200.packed"
-VERSION = 1
+VERSION = 2      # 2: nibble order of the 4-bit layers (ops.pack_int4: byte j of a word = code[j] | code[4+j] << 4)
 
 
 def _arch_of(model):
@@ -180,11 +180,7 @@ def load_packed(path, device="cuda", cuda_graph=True):
         if rec["packed"] and want_packed:
             w_dev, w_zero = rec["w"].to(dev), rec["w_zero"].to(dev)
         elif rec["packed"]:
-            pk = rec["w"].to(dev)
-            lo = (pk & 0x0F).to(torch.int16)
-            hi = (pk >> 4).to(torch.int16)
-            codes = torch.stack([lo, hi], dim=-1).reshape(pk.shape[0], -1) - rec["w_zero"].to(dev, torch.int16)[:, None]
-            w_dev = codes.to(torch.int8).contiguous()
+            w_dev = ops.unpack_int4(rec["w"].to(dev), rec["w_zero"].to(dev)).to(torch.int8).contiguous()
         else:
             w_dev = rec["w"].to(dev)
         cache[key] = dict(w8=False, w_dev=w_dev, w_zero=w_zero, delta_w=rec["delta_w"].to(dev), N=rec["N"],

@@ -137,10 +137,12 @@ def test_pack_int4_roundtrip_and_limits():
     packed, zero = ops.pack_int4(ws)
     assert packed.dtype == torch.uint8 and packed.shape == (37, 48) and zero.dtype == torch.int8
     assert int(zero.min()) >= 0 and int(zero.max()) <= 15
-    un = torch.stack([packed & 15, packed >> 4], dim=2).reshape(37, 96).to(torch.int16) - zero[:, None].to(torch.int16)
-    assert torch.equal(un, ws.to(torch.int16))
+    assert torch.equal(ops.unpack_int4(packed, zero), ws.to(torch.int16))
+    # nibble order: byte j of a 4-byte word = code[j] | code[4 + j] << 4 (what the unpack warps of the GEMM assume)
+    wq0 = (ws[0, :8] + zero[0]).to(torch.int64)
+    assert [int(b) for b in packed[0, :4]] == [int(wq0[j] | (wq0[4 + j] << 4)) for j in range(4)]
     assert ops.pack_int4(torch.randint(-128, 128, (4, 32), generator=gen)) is None     # 8-bit rows
-    assert ops.pack_int4(torch.zeros(4, 33, dtype=torch.int64)) is None                 # odd K
+    assert ops.pack_int4(torch.zeros(4, 36, dtype=torch.int64)) is None                 # K not a multiple of 8
 
 
 def test_groupnorm_workspace_rule_is_owned_by_the_library():

@@ -21,7 +21,7 @@ def _run(args, timeout=600):
 def test_txt2img_plms_synthetic(cuda, tmp_path):
     out = str(tmp_path / "z.pt")
     log = _run(["scripts/txt2img.py", "--plms", "--cond", "--ptq", "--quant_mode", "qdiff", "--quant_act", "--weight_bit", "4",
-                "--act_bit", "8", "--sm_abit", "16", "--split", "--n_samples", "2", "--n_iter", "1", "--ddim_steps", "3",
+                "--act_bit", "8", "--sm_abit", "16", "--split", "--n_samples", "2", "--n_iter", "1", "--ddim_steps", "4",
                 "--b200_synthetic", "sd_v1", "--b200_out", out])
     z = torch.load(out)["samples"]
     assert z.shape == (2, 4, 64, 64) and torch.isfinite(z).all(), log[-500:]

@@ -32,6 +32,7 @@ SHAPES = [
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--packed", action="store_true", help="also time every shape with packed INT4 weights (K3)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -45,23 +46,37 @@ def main():
         out = torch.empty(M, N, device=dev)
         d = ops.gemm_desc(a, w, scale, M=M, N=N, C=C, taps=taps, conv_bhw=(B, H, W) if taps == 9 else None,
                           a_signed=False, bias=bias, out=out, ldo=N)
-        for _ in range(3):
-            ops.qgemm(d)
-        torch.cuda.synchronize()
-        times = []
-        for _ in range(args.iters):
-            flush.zero_()   # evict L2 between timed launches
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            ops.qgemm(d)
-            e1.record()
+        def timed(desc):
+            for _ in range(3):
+                ops.qgemm(desc)
             torch.cuda.synchronize()
-            times.append(e0.elapsed_time(e1))
-        times.sort()
-        ms = times[len(times) // 2]
+            times = []
+            for _ in range(args.iters):
+                flush.zero_()   # evict L2 between timed launches
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ops.qgemm(desc)
+                e1.record()
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1))
+            times.sort()
+            return times[len(times) // 2]
+        ms = timed(d)
         tops = 2.0 * M * N * C * taps / (ms * 1e-3) / 1e12
-        rows.append(dict(shape=name, M=M, N=N, K=C * taps, ms=round(ms, 4), tops=round(tops, 1)))
-        print(f"{name:32s} M={M:6d} N={N:5d} K={C * taps:6d}  {ms:8.4f} ms  {tops:8.1f} TOP/s", flush=True)
+        row = dict(shape=name, M=M, N=N, K=C * taps, ms=round(ms, 4), tops=round(tops, 1))
+        extra = ""
+        if args.packed:
+            pk, zero = ops.pack_int4(w)
+            pk, zero = pk.to(dev), zero.to(dev)
+            out2 = torch.empty(M, N, device=dev)
+            d2 = ops.gemm_desc(a, pk, scale, M=M, N=N, C=C, taps=taps, conv_bhw=(B, H, W) if taps == 9 else None,
+                               a_signed=False, bias=bias, out=out2, ldo=N, w_zero=zero, w_rows=N)
+            ms2 = timed(d2)
+            assert torch.equal(out, out2), f"{name}: packed INT4 result differs from the s8 path"
+            row.update(ms_packed=round(ms2, 4), packed_over_s8=round(ms2 / ms, 3))
+            extra = f"   packed {ms2:8.4f} ms ({ms2 / ms:5.2f}x, bit-identical)"
+        rows.append(row)
+        print(f"{name:32s} M={M:6d} N={N:5d} K={C * taps:6d}  {ms:8.4f} ms  {tops:8.1f} TOP/s{extra}", flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "bench_gemm.json"), "w"), indent=1)
 
