@@ -190,6 +190,80 @@ __global__ void __launch_bounds__(128) attention_fp32_kernel(const qd_attention_
   }
 }
 
+// The same attention for long sequences (first-stage decoder mid block: T = 4096, d = 512; LDM / SD weight-only levels):
+// AFP_R query rows per block share every K and V row that is read, so K/V cross L2 T / AFP_R times instead of T times
+// (T = 4096, d = 512: 8 GB instead of 64 GB per image).  Phase 1: a warp per key, lanes over d, AFP_R dot products per K row;
+// phase 2: a warp per query row (max, exp, sum in shared memory); phase 3: a thread per output column, AFP_R accumulators.
+constexpr int AFP_R = 8;
+__global__ void __launch_bounds__(256) attention_fp32_rows_kernel(const qd_attention_fp_desc p) {
+  extern __shared__ float afp_sh[];
+  float* qs = afp_sh;                        // [AFP_R][d]
+  float* sc = afp_sh + AFP_R * p.d;          // [AFP_R][Tk]
+  __shared__ float inv_s[AFP_R];
+  const int bh = blockIdx.y, b = bh / p.heads, h = bh - b * p.heads;
+  const int r0 = blockIdx.x * AFP_R;
+  const int nr = min(AFP_R, p.Tq - r0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < AFP_R * p.d; i += blockDim.x) {
+    const int r = i / p.d, c = i - r * p.d;
+    qs[i] = r < nr ? p.q[((long long)b * p.Tq + r0 + r) * p.ld_q + p.q_off + h * p.head_stride_q + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = warp; j < p.Tk; j += 8) {
+    const float* k = p.k + ((long long)b * p.Tk + j) * p.ld_k + p.k_off + h * p.head_stride_k;
+    float acc[AFP_R];
+#pragma unroll
+    for (int r = 0; r < AFP_R; ++r) acc[r] = 0.f;
+    for (int i = lane; i < p.d; i += 32) {
+      const float kv = k[i];
+#pragma unroll
+      for (int r = 0; r < AFP_R; ++r) acc[r] = fmaf(qs[r * p.d + i], kv, acc[r]);
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int r = 0; r < AFP_R; ++r) {
+      float a = acc[r];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+      if (lane == r) mine = a;
+    }
+    if (lane < AFP_R) sc[lane * p.Tk + j] = mine * p.scale;
+  }
+  __syncthreads();
+  if (warp < AFP_R) {
+    float* row = sc + warp * p.Tk;
+    float mx = -INFINITY;
+    for (int j = lane; j < p.Tk; j += 32) mx = fmaxf(mx, row[j]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    float sum = 0.f;
+    for (int j = lane; j < p.Tk; j += 32) {
+      const float e = expf(row[j] - mx);
+      row[j] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    if (lane == 0) inv_s[warp] = 1.0f / sum;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.d; c += blockDim.x) {
+    const float* v = p.v + (long long)b * p.Tk * p.ld_v + p.v_off + h * p.head_stride_v + c;
+    float acc[AFP_R];
+#pragma unroll
+    for (int r = 0; r < AFP_R; ++r) acc[r] = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < p.Tk; ++j) {
+      const float vv = v[(long long)j * p.ld_v];
+#pragma unroll
+      for (int r = 0; r < AFP_R; ++r) acc[r] = fmaf(sc[r * p.Tk + j], vv, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < AFP_R; ++r)
+      if (r < nr) p.out[((long long)b * p.Tq + r0 + r) * p.ld_out + h * p.d + c] = acc[r] * inv_s[r];
+  }
+}
+
 // ------------------------------------------------------------------------------------ groupnorm
 // Three-kernel path (large feature maps).  Pass 1: a block reduces `slab` pixels x all channels to per-GROUP
 // partial sums (fp32 per thread over the slab, then double, in a fixed order: results are run-to-run

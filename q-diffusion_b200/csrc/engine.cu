@@ -559,6 +559,14 @@ int launch_split3(const qd_split_desc& d, cudaStream_t s) {
 int launch_attention_fp(const qd_attention_fp_desc& d, cudaStream_t s) {
   if (!d.q || !d.k || !d.v || !d.out || d.B <= 0 || d.heads <= 0 || d.d <= 0 || d.Tq <= 0 || d.Tk <= 0)
     return fail(QD_ERR_BAD_ARG, "attention_fp32: bad args");
+  // long sequences: AFP_R query rows per block share the K / V rows they read (K/V traffic / AFP_R)
+  const size_t smem_rows = (size_t)qd::AFP_R * (d.d + d.Tk) * sizeof(float);
+  if (d.Tq >= 256 && smem_rows <= 200 * 1024) {
+    static std::atomic<unsigned long long> optin{0};
+    if (int rc = ensure_smem_optin(qd::attention_fp32_rows_kernel, 200 * 1024, optin, "attention_fp32_rows")) return rc;
+    launch_k(qd::attention_fp32_rows_kernel, dim3((d.Tq + qd::AFP_R - 1) / qd::AFP_R, d.B * d.heads), 256, smem_rows, s, d);
+    return check_launch("attention_fp32_rows_kernel");
+  }
   const size_t smem = (size_t)(d.d + d.Tk) * sizeof(float);
   if (smem > 48 * 1024) return fail(QD_ERR_UNSUPPORTED, "attention_fp32: d + Tk = %d exceeds 12288 floats of shared memory", d.d + d.Tk);
   launch_k(qd::attention_fp32_kernel, dim3(d.Tq, d.B * d.heads), 128, smem, s, d);

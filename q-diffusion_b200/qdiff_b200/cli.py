@@ -7,7 +7,7 @@
 Same flags, same meaning; what runs underneath is the engine.  Scope: the denoising loop on a
 calibrated checkpoint -- `--ptq --resume --cali_ckpt ckpt.pth` (the checkpoint the reference's calibration wrote; it
 carries the FP weights, the AdaRound parameters and the activation quantizers, SURVEY Appendix C, so no base checkpoint
-is needed).  Calibration itself (`--ptq` without `--resume`), `--resume_w`, the text encoder and the first-stage decoder
+is needed).  Calibration itself (`--ptq` without `--resume`), `--resume_w` and the text encoder
 are outside the hot path: those flags parse, and the run stops with a message naming what to do instead.
 
 Extra flags of this implementation (all prefixed so they cannot collide with future reference flags):
@@ -15,6 +15,11 @@ Extra flags of this implementation (all prefixed so they cannot collide with fut
     --b200_context FILE       txt2img: pre-computed prompt embeddings {"c": [B,77,768], "uc": [1|B,77,768]} (torch.save);
                               without it a seeded N(0,1) context is used, like the reference's own dummy calibration input
     --b200_out FILE           where to save the latents / images tensor (default: <logdir or outdir>/samples.pt)
+    --b200_decode             LDM / txt2img: decode the final latents with the first stage ON THE ENGINE (qdiff_b200.first_stage;
+                              ddpm.py:710-767) and save the images in [0, 1] next to the latents.  Weights: --b200_first_stage
+                              FILE (a first-stage or full LDM / SD checkpoint: keys `decoder.*`, `post_quant_conv.*`,
+                              `quantize.embedding.weight`, optionally prefixed `first_stage_model.`), or seeded synthetic
+                              weights with --b200_synthetic.  --b200_decode_precision 1|3|6: bfloat16 plane products per MAC.
 Multi-GPU: run under `python -m torch.distributed.run`; the batch is sharded by images, every rank draws the full-batch
 noise from the seed and keeps its slice, rank 0 gathers and saves (qdiff_b200/dist.py).
 """
@@ -51,6 +56,9 @@ _TAIL = [
 _B200 = [
     (("--b200_synthetic",), dict(type=str, default=None, help="seeded synthetic workload (cifar10 | lsun_bedroom | lsun_church | sd_v1)")),
     (("--b200_out",), dict(type=str, default=None, help="output tensor file")),
+    (("--b200_decode",), dict(action="store_true", help="decode the latents with the first stage on the engine (LDM / txt2img)")),
+    (("--b200_first_stage",), dict(type=str, default=None, help="first-stage checkpoint for --b200_decode")),
+    (("--b200_decode_precision",), dict(type=int, default=3, choices=[1, 3, 6], help="bfloat16 plane products per MAC of the decoder")),
 ]
 
 
@@ -236,6 +244,50 @@ def _save(args, default_dir, tensor, meta, rank):
     return path
 
 
+def _first_stage(args, name, cfg_params, dev):
+    """(container on `dev`, scale_factor) for --b200_decode, or (None, 1.0).  name: synthetic workload; cfg_params: the
+    `model.params` block of an LDM / SD yaml (first_stage_config, scale_factor)."""
+    import torch
+    from . import first_stage as FS
+    from .unet import randomize_
+    if not args.b200_decode:
+        return None, 1.0
+    if name is not None:
+        if name not in FS.CONFIGS:
+            raise SystemExit(f"--b200_decode: no first stage is defined for the synthetic workload {name!r}")
+        cfg = FS.CONFIGS[name]
+    else:
+        fsc = cfg_params["first_stage_config"]
+        p = fsc["params"]
+        kind = "vq" if fsc["target"].endswith("VQModelInterface") else "kl" if fsc["target"].endswith("AutoencoderKL") else None
+        if kind is None:
+            raise SystemExit(f"--b200_decode: first stage {fsc['target']} is not AutoencoderKL / VQModelInterface")
+        cfg = dict(kind=kind, embed_dim=p["embed_dim"], n_embed=p.get("n_embed"), ddconfig=dict(p["ddconfig"]),
+                   scale_factor=float(cfg_params.get("scale_factor", 1.0)))
+    fs = FS.build_first_stage(cfg, precision=args.b200_decode_precision)
+    if args.b200_first_stage:
+        sd = torch.load(args.b200_first_stage, map_location="cpu", weights_only=False)
+        sd = sd.get("state_dict", sd)
+        sd = {(k[len("first_stage_model."):] if k.startswith("first_stage_model.") else k): v for k, v in sd.items()}
+        fs.load_state_dict(sd, strict=True)
+    elif name is not None:
+        randomize_(fs, seed=7)
+    else:
+        raise SystemExit("--b200_decode needs --b200_first_stage CKPT (or a --b200_synthetic workload)")
+    return fs.to(dev), cfg["scale_factor"]
+
+
+def _decode_images(fs, scale_factor, z, dev, chunk=4):
+    """decode_first_stage in chunks, then the scripts' image range: clamp((x + 1) / 2, 0, 1) (txt2img.py:527)."""
+    import torch
+    from .first_stage import decode_first_stage
+    outs = []
+    for i in range(0, z.shape[0], chunk):
+        x = decode_first_stage(fs, z[i:i + chunk].to(dev), scale_factor)
+        outs.append(torch.clamp((x + 1.0) / 2.0, min=0.0, max=1.0).cpu())
+    return torch.cat(outs)
+
+
 def _shard(n_total, world):
     if n_total % world:
         raise SystemExit(f"batch size {n_total} is not divisible by the {world} ranks")
@@ -361,7 +413,14 @@ def run_ldm(args):
     dt = time.time() - t0
     if rank == 0:
         print(f"{z.shape[0]} latents, {args.custom_steps} DDIM steps (eta {args.eta}), {dt:.2f} s -> {z.shape[0] / dt:.2f} /s on {world} GPU(s)")
-    return _save(args, args.logdir if args.logdir != "none" else ".", z, dict(kind="latents", steps=args.custom_steps, eta=args.eta), rank)
+    meta = dict(kind="latents", steps=args.custom_steps, eta=args.eta)
+    if args.b200_decode and rank == 0:
+        fs, sf = _first_stage(args, args.b200_synthetic, None if args.b200_synthetic else cfg, dev)
+        t1 = time.time()
+        meta["images"] = _decode_images(fs, sf, z, dev)
+        torch.cuda.synchronize()
+        print(f"decoded {tuple(meta['images'].shape)} in {time.time() - t1:.2f} s (first stage on the engine, precision {args.b200_decode_precision})")
+    return _save(args, args.logdir if args.logdir != "none" else ".", z, meta, rank)
 
 
 # ---------------------------------------------------------------------------------------------- txt2img
@@ -427,4 +486,11 @@ def run_txt2img(args):
     if rank == 0:
         print(f"{z.shape[0]} latents {tuple(z.shape[1:])}, {args.ddim_steps} {'PLMS' if args.plms else 'DDIM'} steps, "
               f"scale {args.scale}: {dt:.2f} s -> {z.shape[0] / dt:.3f} images/s on {world} GPU(s)")
-    return _save(args, args.outdir, z, dict(kind="latents", steps=args.ddim_steps, scale=args.scale, prompt=args.prompt), rank)
+    meta = dict(kind="latents", steps=args.ddim_steps, scale=args.scale, prompt=args.prompt)
+    if args.b200_decode and rank == 0:
+        fs, sf = _first_stage(args, args.b200_synthetic, None if args.b200_synthetic else cfg, dev)
+        t1 = time.time()
+        meta["images"] = _decode_images(fs, sf, z, dev, chunk=2)
+        torch.cuda.synchronize()
+        print(f"decoded {tuple(meta['images'].shape)} in {time.time() - t1:.2f} s (first stage on the engine, precision {args.b200_decode_precision})")
+    return _save(args, args.outdir, z, meta, rank)

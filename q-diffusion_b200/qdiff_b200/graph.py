@@ -1111,15 +1111,18 @@ class Builder:
 
 # ====================================================================== weight-only lowering (quant_act False)
 class WeightOnlyBuilder(Builder):
-    """set_quant_state(True, False): quantised weights, fp32 activations (BASELINE configs[0], qdiff/utils.py:407).
+    """set_quant_state(True, False): quantised weights, fp32 activations (BASELINE configs[0], qdiff/utils.py:407), and
+    set_quant_state(False, False): the full-precision state the reference uses for FP baselines and calibration data.
 
     Every QuantModule becomes  y = delta_w[n] * sum_k x[m,k] * ws[n,k] + bias  with the fp32 activation split into three
     bfloat16 planes (qd_split_bf16x3) and the integer weight codes held exactly in bfloat16: a tcgen05 kind::f16
-    contraction with fp32 accumulation, i.e. the reference's fp32 conv up to summation order.  Norms emit fp32 (+SiLU),
-    attention runs in fp32 (qd_attention_fp32).  Families: ddim (CIFAR) and LDM UNets without SpatialTransformer."""
+    contraction with fp32 accumulation, i.e. the reference's fp32 conv up to summation order.  With use_weight_quant
+    False the fp32 weight is split into three bfloat16 planes as well and the six plane products down to 2^-24 are formed
+    in three accumulating launches (x_{hi,mid,lo} w_hi, x_{hi,mid} w_mid, x_hi w_lo: qd_gemm_desc.lda = plane pitch).
+    Norms emit fp32 (+SiLU), attention runs in fp32 (qd_attention_fp32).  Families: ddim (CIFAR), LDM and SD UNets."""
 
-    def split3(self, src, label, act=0, upsample=None):
-        C_ = src.cols
+    def split3(self, src, label, act=0, upsample=None, cols=None):
+        C_ = src.cols if cols is None else cols
         Cp = (C_ + 15) // 16 * 16
         rows = src.rows * (4 if upsample is not None else 1)
         t = torch.zeros((rows, 3 * Cp), dtype=torch.bfloat16, device=self.dev)
@@ -1136,6 +1139,10 @@ class WeightOnlyBuilder(Builder):
         """One weight-only GEMM.  a: bfloat16 plane Act from split3.  im2col = (hw, stride, pad_tl, out_hw): explicit patch
         gather first (strided convs, conv_in)."""
         cols = tuple(cols) if cols is not None else None
+        if not getattr(qm, "use_weight_quant", True):
+            return self._gemm_fp_weights(qm, a, label, conv_bhw=conv_bhw, rowvec=rowvec, residual=residual, out=out,
+                                         rows_per_batch=rows_per_batch, cols=cols, accumulate_into=accumulate_into,
+                                         use_bias=use_bias, im2col=im2col)
         key = (self.dev.index or 0, "wo", label, cols, suffix, conv_bhw is not None or im2col is not None)
         ent = self.wcache.get(key)
         if ent is None or (self.want_specs and "ws_cpu" not in ent):
@@ -1204,8 +1211,92 @@ class WeightOnlyBuilder(Builder):
         self.layer_traces[label] = o
         return o
 
+    def _gemm_fp_weights(self, qm, a, label, *, conv_bhw, rowvec, residual, out, rows_per_batch, cols, accumulate_into,
+                         use_bias, im2col):
+        """use_weight_quant False: the layer's fp32 weight as three bfloat16 planes; launches (weight plane, leading
+        activation planes) = (hi, 3), (mid, 2), (lo, 1), each accumulating into the first one's output."""
+        key = (self.dev.index or 0, "wofp", label, cols, im2col is not None)
+        ent = self.wcache.get(key)
+        if ent is None:
+            w = qm.weight.detach().to(self.dev, torch.float32)
+            if cols is not None:
+                w = w[:, cols[0]:cols[1], ...]
+            N, Cin = w.shape[0], w.shape[1]
+            taps = 9 if (w.dim() == 4 and w.shape[-1] == 3) else 1
+            w3 = w.reshape(N, Cin, taps).permute(0, 2, 1).contiguous()
+            hi = w3.to(torch.bfloat16)
+            r1 = w3 - hi.float()
+            mid = r1.to(torch.bfloat16)
+            lo = (r1 - mid.float()).to(torch.bfloat16)
+            Np = (N + 3) // 4 * 4
+            tiles = []
+            for plane, nact in ((hi, 3), (mid, 2), (lo, 1)):
+                slots = 3 if im2col is not None else nact       # im2col patches interleave the planes per tap
+                wk = torch.zeros((Np, taps, slots, a.Cp), dtype=torch.bfloat16, device=self.dev)
+                wk[:N, :, :nact, :Cin] = plane[:, :, None, :]
+                tiles.append((wk.reshape(Np, -1).contiguous(), slots))
+            ent = dict(tiles=tiles, N=Np, N_real=N, taps=taps, ones=torch.ones(Np, dtype=torch.float32, device=self.dev))
+            self.wcache[key] = ent
+        N, taps = ent["N"], ent["taps"]
+        self.keep += [ent["ones"]] + [t for t, _ in ent["tiles"]]
+        bias = None
+        if use_bias and qm.bias is not None:
+            bias = torch.zeros(N, dtype=torch.float32, device=self.dev)
+            bias[:ent["N_real"]] = qm.bias.detach().to(self.dev, torch.float32)
+            self.keep.append(bias)
+        src_act = a
+        if im2col is not None:
+            (H, W), stride, pad_tl, (Ho, Wo) = im2col
+            cbytes = 6 * a.Cp
+            patches = torch.zeros((self.B * Ho * Wo, 9 * cbytes), dtype=torch.uint8, device=self.dev)
+            self.keep.append(patches)
+            di = ops.im2col_desc(a.t, patches, B=self.B, H=H, W=W, C_=cbytes, Ho=Ho, Wo=Wo, stride=stride,
+                                 pad_top=pad_tl[0], pad_left=pad_tl[1], pad_code=0, ld_dst=9 * cbytes)
+            src_act = Act(patches, self.B * Ho * Wo, 9 * cbytes)
+            src_act.bf16, src_act.C, src_act.Cp = True, a.C, a.Cp
+            self.add(_lib.QD_OP_IM2COL, di, label + ".im2col")
+            conv_bhw = None
+        M = src_act.rows
+        o = accumulate_into if accumulate_into is not None else (out if out is not None else self.new_f32(M, N))
+        first_res = accumulate_into if accumulate_into is not None else residual
+        for i, (tile, slots) in enumerate(ent["tiles"]):
+            if im2col is not None:
+                g_taps, g_c, lda = 1, 9 * 6 * a.Cp, 9 * 6 * a.Cp
+            else:
+                g_taps, g_c, lda = taps, 2 * slots * a.Cp, src_act.ld * src_act.t.element_size()
+            res = first_res if i == 0 else o
+            rv = rowvec if i == 0 else None
+            d = ops.gemm_desc(src_act.t, tile, ent["ones"], M=M, N=N, C=g_c, taps=g_taps, lda=lda, conv_bhw=conv_bhw,
+                              a_signed=False, bias=bias if i == 0 else None,
+                              rowvec=rv.t if rv is not None else None, ld_rowvec=rv.ld if rv is not None else 0,
+                              rows_per_batch=rows_per_batch, residual=res.t if res is not None else None,
+                              ldr=res.ld if res is not None else 0, out=o.t, ldo=o.ld)
+            d.a_bf16 = 1
+            d.a = src_act.ptr
+            if rv is not None:
+                d.rowvec = rv.ptr
+            if res is not None:
+                d.residual = res.ptr
+            d.out = o.ptr
+            Cin = int(qm.weight.shape[1]) if cols is None else cols[1] - cols[0]
+            self.add(_lib.QD_OP_GEMM, d, label + (f".pass{i}" if i else ""), flops=2 * M * ent["N_real"] * Cin * taps if i == 0 else 0)
+        self.layer_traces[label] = o
+        return o
+
     def lin(self, qm, x_f32, label, act=0, **kw):
-        return self.gemm_wo(qm, self.split3(x_f32, label + ".split", act=act), label, **kw)
+        cols = x_f32.cols // 2 if act == 2 else None
+        return self.gemm_wo(qm, self.split3(x_f32, label + ".split", act=act, cols=cols), label, **kw)
+
+    def ln_f32(self, x, norm, label):
+        """nn.LayerNorm with fp32 output (qd_layernorm_quant, n_out = 0)."""
+        out = self.new_f32(x.rows, x.cols)
+        d = ops.layernorm_desc(x.t, self.dev_t(norm.weight, torch.float32), self.dev_t(norm.bias, torch.float32),
+                               M=x.rows, C_=x.cols, ld_x=x.ld, eps=norm.eps, outs=[], out_f=out.t, ld_f=out.ld)
+        d.x = x.ptr
+        self.add(_lib.QD_OP_LAYERNORM, d, label,
+                 spec=dict(kind="layernorm", x=x, eps=norm.eps, gamma=norm.weight.detach().float().cpu(),
+                           beta=norm.bias.detach().float().cpu(), outs=[], out_f=out))
+        return out
 
     def gn_f32(self, x, norm, hw, silu, label, ss=None, ss_src=None):
         _, out_f = self.groupnorm(x, norm, hw, [], silu, label, ss=ss, want_f32=True, ss_src=ss_src)
@@ -1229,7 +1320,7 @@ class WeightOnlyBuilder(Builder):
 
     # ------------------------------------------------------------------ shortcut convs (with or without split)
     def shortcut(self, qm, x, label, split):
-        if split:
+        if split and getattr(qm, "use_weight_quant", True):     # full precision: the split only affects quantizers
             if qm.split == 0:
                 raise RuntimeError(f"{label}: split is set but the checkpoint has no split quantizers")
             s = self.gemm_wo(qm, self.split3(x.view(0, split), label + ".split0"), label + ".half0", cols=(0, split))
@@ -1331,9 +1422,170 @@ class WeightOnlyBuilder(Builder):
                   spec=dict(kind="nhwc_to_nchw", src=o, dst=out))
         return x_in, t_in, None, out[:, :int(model.conv_out.weight.shape[0])]
 
+    # ================================================================== LDM / SD family
+    def wo_resblock(self, blk, x, emb, hw, split):
+        """QuantResBlock._forward (qdiff/quant_block.py:83-111) with fp32 activations."""
+        k = self.key(blk)
+        H, W = hw
+        norm1, conv1 = blk.in_layers[0], blk.in_layers[2]
+        norm2, conv2 = blk.out_layers[0], blk.out_layers[3]
+        h1 = self.gn_f32(x, norm1, H * W, True, k + ".in_layers.0")
+        x_res, oh, ow = x, H, W
+        if getattr(blk, "updown", False):
+            x = self.contig(x, k)
+            if _name(blk.h_upd) == "Upsample":
+                oh, ow = 2 * H, 2 * W
+                a1 = self.split3(h1, k + ".h_upd.split", upsample=(self.B, H, W))
+                x_res = self.new_f32(self.B * oh * ow, x.cols)
+                self.misc(_lib.QD_OP_UPSAMPLE2X, x.ptr, x_res.ptr, self.B, H, W, x.cols, label=k + ".x_upd",
+                          spec=dict(kind="upsample2x", src=x, dst=x_res, B=self.B, H=H, W=W))
+            else:
+                oh, ow = H // 2, W // 2
+                hp = self.new_f32(self.B * oh * ow, x.cols)
+                self.misc(_lib.QD_OP_AVGPOOL2X, h1.ptr, hp.ptr, self.B, H, W, x.cols, label=k + ".h_upd",
+                          spec=dict(kind="avgpool2x", src=h1, dst=hp, B=self.B, H=H, W=W))
+                a1 = self.split3(hp, k + ".h_upd.split")
+                x_res = self.new_f32(self.B * oh * ow, x.cols)
+                self.misc(_lib.QD_OP_AVGPOOL2X, x.ptr, x_res.ptr, self.B, H, W, x.cols, label=k + ".x_upd",
+                          spec=dict(kind="avgpool2x", src=x, dst=x_res, B=self.B, H=H, W=W))
+        else:
+            a1 = self.split3(h1, k + ".in_layers.2.split")
+        emb_out = self.lin(blk.emb_layers[1], emb, k + ".emb_layers.1", act=1)
+        oc = int(conv2.weight.shape[0])
+        cb = (self.B, oh, ow)
+        if getattr(blk, "use_scale_shift_norm", False):
+            h = self.gemm_wo(conv1, a1, k + ".in_layers.2", conv_bhw=cb, rows_per_batch=oh * ow)
+            ss = (emb_out.t, _Offset(emb_out.t, 4 * oc), emb_out.ld)
+            h2 = self.gn_f32(h, norm2, oh * ow, True, k + ".out_layers.0", ss=ss, ss_src=(emb_out, oc))
+        else:
+            h = self.gemm_wo(conv1, a1, k + ".in_layers.2", conv_bhw=cb, rows_per_batch=oh * ow, rowvec=emb_out)
+            h2 = self.gn_f32(h, norm2, oh * ow, True, k + ".out_layers.0")
+        skip = blk.skip_connection
+        s_ = x_res
+        if _name(skip) == "QuantModule":
+            if skip.weight.shape[-1] != 1:
+                raise NotImplementedError("3x3 skip_connection (use_conv=True) is not used by any reference config")
+            s_ = self.shortcut(skip, x_res, k + ".skip_connection", split)
+        out = self.gemm_wo(conv2, self.split3(h2, k + ".out_layers.3.split"), k + ".out_layers.3", conv_bhw=cb,
+                           rows_per_batch=oh * ow, residual=s_)
+        return out, (oh, ow)
+
+    def wo_cross_attention(self, attn, xq, xkv, h_res, Tq, Tk, label):
+        """cross_attn_forward (qdiff/quant_block.py:190-221) with use_act_quant False: plain fp32 attention."""
+        heads = attn.heads
+        inner = int(attn.to_q.weight.shape[0])
+        d = inner // heads
+        q = self.lin(attn.to_q, xq, label + ".to_q")
+        a_kv = self.split3(xkv, label + ".kv.split")
+        kk = self.gemm_wo(attn.to_k, a_kv, label + ".to_k")
+        v = self.gemm_wo(attn.to_v, a_kv, label + ".to_v")
+        o = self.attention_fp(q, kk, v, heads=heads, d=d, Tq=Tq, Tk=Tk, q_layout=(0, d), k_layout=(0, d), v_layout=(0, d),
+                              scale=float(attn.scale), label=label + ".attn")
+        return self.lin(attn.to_out[0], o, label + ".to_out.0", residual=h_res)
+
+    def wo_spatial_transformer(self, st, x, ctx, hw):
+        """SpatialTransformer.forward (ldm/modules/attention.py:276-287) + QuantBasicTransformerBlock._forward
+        (qdiff/quant_block.py:263-271), fp32 activations."""
+        k = self.key(st)
+        T = hw[0] * hw[1]
+        hn = self.gn_f32(x, st.norm, T, False, k + ".norm")
+        h = self.lin(st.proj_in, hn, k + ".proj_in")
+        if ctx is None:
+            raise ValueError("SpatialTransformer needs a context tensor")
+        ctx_act, Tk = ctx
+        for i, blk in enumerate(st.transformer_blocks):
+            bk = f"{k}.transformer_blocks.{i}"
+            n1 = self.ln_f32(h, blk.norm1, bk + ".norm1")
+            h = self.wo_cross_attention(blk.attn1, n1, n1, h, T, T, bk + ".attn1")
+            n2 = self.ln_f32(h, blk.norm2, bk + ".norm2")
+            h = self.wo_cross_attention(blk.attn2, n2, ctx_act, h, T, Tk, bk + ".attn2")
+            n3 = self.ln_f32(h, blk.norm3, bk + ".norm3")
+            f = self.lin(blk.ff.net[0].proj, n3, bk + ".ff.net.0.proj")
+            h = self.lin(blk.ff.net[2], f, bk + ".ff.net.2", act=2, residual=h)      # GEGLU inside the plane split
+        return self.lin(st.proj_out, h, k + ".proj_out", residual=x)
+
+    def wo_attention_block(self, blk, x, hw):
+        """AttentionBlock._forward + QKVAttentionLegacy (openaimodel.py:321-327,384-406) in fp32: the qkv conv output
+        [B*T, heads * 3 * ch] is addressed in place (head h: q at 3*ch*h, k at +ch, v at +2*ch); (q s)(k s) = q k / sqrt(ch)."""
+        k = self.key(blk)
+        T, C_ = hw[0] * hw[1], x.cols
+        heads = blk.attention.n_heads
+        ch = C_ // heads
+        hn = self.gn_f32(x, blk.norm, T, False, k + ".norm")
+        qkv = self.lin(blk.qkv, hn, k + ".qkv")
+        o = self.attention_fp(qkv, qkv, qkv, heads=heads, d=ch, Tq=T, Tk=T, q_layout=(0, 3 * ch), k_layout=(ch, 3 * ch),
+                              v_layout=(2 * ch, 3 * ch), scale=1.0 / math.sqrt(ch), label=k + ".attention")
+        return self.lin(blk.proj_out, o, k + ".proj_out", residual=x)
+
     def lower_ldm(self, model, x_shape, ctx_shape):
-        raise NotImplementedError("weight-only sampling is lowered for the DDIM (CIFAR) family (BASELINE configs[0]); the "
-                                  "LDM / Stable Diffusion UNets run with --quant_act (W4A8 / W8A8) on this engine")
+        """UNetModel.forward (openaimodel.py:745-782) with fp32 activations (weight-only and full-precision states)."""
+        B, Cin, H, W = x_shape
+        x_in = torch.zeros(x_shape, dtype=torch.float32, device=self.dev)
+        t_in = torch.zeros(B, dtype=torch.float32, device=self.dev)
+        ctx_in = torch.zeros(ctx_shape, dtype=torch.float32, device=self.dev) if ctx_shape is not None else None
+        self.keep += [x_in, t_in] + ([ctx_in] if ctx_in is not None else [])
+        mc = model.model_channels
+        temb = self.new_f32(B, mc)
+        self.misc(_lib.QD_OP_TIMESTEP_EMB, t_in.data_ptr(), temb.ptr, B, mc, 0, label="timestep_embedding",
+                  aux=ops.timestep_freqs(mc, 0).to(self.dev), spec=dict(kind="timestep_emb", t=t_in, dst=temb, mode=0))
+        e = self.lin(model.time_embed[0], temb, "time_embed.0")
+        emb = self.lin(model.time_embed[2], e, "time_embed.2", act=1)
+        ctx = None
+        if ctx_in is not None:
+            ctx = (Act(ctx_in, ctx_shape[0] * ctx_shape[1], ctx_shape[2]), ctx_shape[1])
+        xh = self.new_f32(B * H * W, Cin)
+        self.misc(_lib.QD_OP_NCHW_TO_NHWC, x_in.data_ptr(), xh.ptr, B, Cin, H * W, label="x.nhwc",
+                  spec=dict(kind="nchw_to_nhwc", src=x_in, dst=xh))
+
+        def run(seq, h, hw, split):
+            for layer in seq:
+                n = _name(layer)
+                if n == "QuantModule":                       # conv_in
+                    h = self.gemm_wo(layer, self.split3(h, self.key(layer) + ".split"), self.key(layer),
+                                     im2col=(hw, 1, (1, 1), hw))
+                elif n in _RES:
+                    h, hw = self.wo_resblock(layer, h, emb, hw, split)
+                elif n in _ST:
+                    h = self.wo_spatial_transformer(layer, h, ctx, hw)
+                elif n in _ATTN:
+                    h = self.wo_attention_block(layer, h, hw)
+                elif n == "Downsample":
+                    op = layer.op
+                    if _name(op) != "QuantModule":
+                        raise NotImplementedError("Downsample without conv")
+                    ohw = (hw[0] // 2, hw[1] // 2)
+                    h = self.gemm_wo(op, self.split3(h, self.key(op) + ".split"), self.key(op), im2col=(hw, 2, (1, 1), ohw))
+                    hw = ohw
+                elif n == "Upsample":
+                    conv = layer.conv
+                    a = self.split3(h, self.key(conv) + ".split", upsample=(self.B, hw[0], hw[1]))
+                    hw = (2 * hw[0], 2 * hw[1])
+                    h = self.gemm_wo(conv, a, self.key(conv), conv_bhw=(self.B, hw[0], hw[1]), rows_per_batch=hw[0] * hw[1])
+                else:
+                    raise NotImplementedError(f"unhandled layer type {n} at {self.key(layer)}")
+            return h, hw
+
+        h, hw, hs = xh, (H, W), []
+        for i, blk in enumerate(model.input_blocks):
+            h, hw = run(blk, h, hw, 0)
+            hs.append((h, hw))
+            self.traces[f"input_blocks.{i}"] = (h, hw)
+        h, hw = run(model.middle_block, h, hw, 0)
+        self.traces["middle_block"] = (h, hw)
+        for i, blk in enumerate(model.output_blocks):
+            skip_t, _ = hs.pop()
+            split = h.cols if getattr(model, "split", False) else 0
+            h = self.concat(h, skip_t, f"output_blocks.{i}")
+            h, hw = run(blk, h, hw, split)
+            self.traces[f"output_blocks.{i}"] = (h, hw)
+        hn = self.gn_f32(h, model.out[0], hw[0] * hw[1], True, "out.0")
+        o = self.gemm_wo(model.out[2], self.split3(hn, "out.2.split"), "out.2", conv_bhw=(B, hw[0], hw[1]),
+                         rows_per_batch=hw[0] * hw[1])
+        out = torch.zeros((B, o.cols, hw[0], hw[1]), dtype=torch.float32, device=self.dev)   # o.cols: out channels padded to 4
+        self.keep.append(out)
+        self.misc(_lib.QD_OP_NHWC_TO_NCHW, o.ptr, out.data_ptr(), B, o.cols, hw[0] * hw[1], label="eps.nchw",
+                  spec=dict(kind="nhwc_to_nchw", src=o, dst=out))
+        return x_in, t_in, ctx_in, out[:, :int(model.out[2].weight.shape[0])]
 
 
 class _RowView:
@@ -1392,12 +1644,14 @@ def compile_unet(qnn, x_shape, ctx_shape, device, use_cuda_graph=True, cfg_dedup
     states = {(m.use_weight_quant, m.use_act_quant) for m in qnn.model.modules() if _name(m) == "QuantModule"}
     if states == {(True, True)}:
         b = Builder(qnn, device, x_shape[0])
-    elif states == {(True, False)}:
-        b = WeightOnlyBuilder(qnn, device, x_shape[0])      # quant_act False: fp32 activations, integer weights
+    elif states in ({(True, False)}, {(False, False)}):
+        # quant_act False: fp32 activations against integer weight codes, or - full-precision state - against the fp32
+        # weights themselves (three bfloat16 planes each)
+        b = WeightOnlyBuilder(qnn, device, x_shape[0])
     else:
         raise NotImplementedError(
-            f"the engine realises set_quant_state(True, True) and (True, False); got states {states}. The full-precision "
-            "state (False, False) is the reference's own path (calibration data / FP baselines).")
+            f"the engine realises set_quant_state(True, True), (True, False) and (False, False) applied to the whole model; "
+            f"got mixed states {states}")
     model = qnn.model
     with torch.no_grad():
         if cfg_dedup and (_name(model) != "UNetModel" or type(b) is not Builder):

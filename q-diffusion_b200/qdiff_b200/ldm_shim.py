@@ -6,7 +6,8 @@
 and scripts reach the UNet as model.model.diffusion_model (txt2img.py:367-383, DiffusionWrapper ddpm.py:1419-1445).
 LatentDiffusionShim provides exactly that surface, so the reference's own sampler classes run unchanged on top of a
 qdiff_b200.QuantModel (tests/test_ldm_shim_cpu.py drives the reference's PLMSSampler / DDIMSampler over it), and so
-do this repo's samplers (qdiff_b200/samplers.py).  No first stage / cond stage: those are outside the hot path.
+do this repo's samplers (qdiff_b200/samplers.py).  The first stage is optional (qdiff_b200.first_stage container:
+decode_first_stage runs on the engine); the cond stage (text encoder) is outside the scope.
 """
 import numpy as np
 import torch
@@ -34,8 +35,9 @@ class DiffusionWrapper:
 
 class LatentDiffusionShim:
     def __init__(self, unet, conditioning_key=None, timesteps=1000, linear_start=1e-4, linear_end=2e-2,
-                 beta_schedule="linear", device=None, parameterization="eps"):
+                 beta_schedule="linear", device=None, parameterization="eps", first_stage_model=None, scale_factor=1.0):
         self.model = DiffusionWrapper(unet, conditioning_key)
+        self.first_stage_model, self.scale_factor = first_stage_model, scale_factor
         self.parameterization = parameterization
         self.device = torch.device(device) if device is not None else torch.device(
             "cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
@@ -72,5 +74,12 @@ class LatentDiffusionShim:
     def get_learned_conditioning(self, c):
         raise NotImplementedError("the text encoder (cond stage) is outside the hot path: pass pre-computed embeddings")
 
-    def decode_first_stage(self, z):
-        raise NotImplementedError("the first-stage decoder is outside the hot path (SURVEY section 8 f2): save latents")
+    def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):
+        """ddpm.py:710-767, plain branch (no patch splitting): z / scale_factor -> first_stage_model.decode, on the engine."""
+        if self.first_stage_model is None:
+            raise NotImplementedError("no first stage attached: pass first_stage_model=qdiff_b200.first_stage.build_first_stage(...) "
+                                      "or save the latents")
+        if predict_cids:
+            raise NotImplementedError("predict_cids (codebook-index latents) is not used by the sampling scripts")
+        from .first_stage import decode_first_stage
+        return decode_first_stage(self.first_stage_model, z, self.scale_factor, force_not_quantize=force_not_quantize)

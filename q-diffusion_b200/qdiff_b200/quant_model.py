@@ -13,6 +13,7 @@ in place exactly like the reference (layers -> QuantModule, blocks -> Quant*Bloc
 keys match `ckpt.pth`; `forward(x, timesteps, context)` lowers the tree once per input shape to an
 engine program (qdiff_b200/graph.py) and replays it on the current CUDA stream.
 """
+import torch
 import torch.nn as nn
 
 from .quant_block import (BaseQuantBlock, QuantAttnBlock, QuantBasicTransformerBlock, QuantQKMatMul, QuantSMVMatMul,
@@ -122,6 +123,9 @@ class QuantModel(nn.Module):
             raise RuntimeError("qdiff_b200.QuantModel.forward_cfg needs CUDA tensors: the engine has no CPU fallback")
         if context is None or context.shape[0] != 2 * x.shape[0]:
             raise ValueError("forward_cfg: context must hold [uncond; cond] rows for the batch (2 x batch rows)")
+        if any(not (m.use_weight_quant and m.use_act_quant) for m in self.model.modules() if isinstance(m, QuantModule)):
+            # weight-only / full-precision states: the prefix dedup lives in the INT8 lowering; run the doubled batch
+            return self.forward(torch.cat([x, x]), torch.cat([timesteps, timesteps]), context)
         return self.program(x, context, cfg_dedup=True).run(x, timesteps, context)
 
     def forward(self, x, timesteps=None, context=None):

@@ -13,6 +13,8 @@ CASES = ["ddim_w4a8_split", "ldm_legacy_w4a8", "ldm_updown_w4a8", "sd_tiny_w4a8_
 # BASELINE configs[0] (weight-only W8, the reference's own CPU-runnable case): kept in a separate list because the name
 # says what it pins first - the oracle against the reference; the GPU tests run the engine's weight-only lowering on it too
 ORACLE_ONLY = ["ddim_w8_weightonly"]
+# weight-only LDM / SD fixtures; they also carry the reference's full-precision output (set_quant_state(False, False))
+WEIGHT_ONLY_LDM = ["sd_tiny_w4_weightonly", "ldm_updown_w8_weightonly", "ldm_legacy_w4_weightonly"]
 
 
 def load_case(name):
@@ -21,12 +23,13 @@ def load_case(name):
     return g
 
 
-def oracle_forward(g, trace=None, dtype=torch.float32):
+def oracle_forward(g, trace=None, dtype=torch.float32, weight_quant=True):
     """dtype=float64 evaluates the SAME algorithm with (almost) no rounding noise: the distance between that
     and the fp32 result is the reference's intrinsic noise band (fake-quant networks amplify ulp-level
     perturbations up to quantisation-noise level within a few layers; see DESIGN.md, Parity)."""
     q = g["qcfg"]
-    qc = U.QuantCfg(q["weight_bit"], q["act_bit"], q["a_sym"], q["sm_abit"], q["quant_act"], adaround=True)
+    qc = U.QuantCfg(q["weight_bit"], q["act_bit"], q["a_sym"], q["sm_abit"], q["quant_act"] and weight_quant, adaround=True,
+                    weight_quant=weight_quant)
     te = (O.timestep_embedding_ldm, O.timestep_embedding_ddim)
     U.set_dtype(dtype)
     if dtype != torch.float32:   # keep the fp32 sinusoid table, widen afterwards
@@ -71,7 +74,17 @@ def test_quantizer_known_answers():
     assert torch.equal(O.uaq_weight_fake_quant(w["w"], d, z, 4), w["y"])
 
 
-@pytest.mark.parametrize("name", CASES + ORACLE_ONLY)
+@pytest.mark.parametrize("name", WEIGHT_ONLY_LDM)
+def test_oracle_full_precision_state_matches_reference(name):
+    """set_quant_state(False, False) of the reference (FP baselines / calibration data) vs the oracle without quantizers."""
+    g = load_case(name)
+    out = oracle_forward(g, weight_quant=False)
+    ref = g["out_fp"]
+    assert (out - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
+    assert (ref - g["out"]).abs().max().item() > 1e-3        # and it is a different function than the weight-only state
+
+
+@pytest.mark.parametrize("name", CASES + ORACLE_ONLY + WEIGHT_ONLY_LDM)
 def test_oracle_matches_reference(name):
     g = load_case(name)
     trace = {}

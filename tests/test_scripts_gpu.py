@@ -36,6 +36,19 @@ def test_sample_diffusion_ldm_ddim_and_dpm_synthetic(cuda, tmp_path):
         assert z.shape == (2, 4, 32, 32) and torch.isfinite(z).all()
 
 
+def test_sample_diffusion_ldm_decodes_images_on_the_engine(cuda, tmp_path):
+    """--b200_decode: the first stage (kl-f8 decoder, seeded weights) runs on the engine after the loop: 32x32x4 latents ->
+    256x256x3 images in [0, 1], saved next to the latents."""
+    out = str(tmp_path / "img.pt")
+    log = _run(["scripts/sample_diffusion_ldm.py", "--seed", "41", "-c", "4", "-e", "0.0", "--batch_size", "2", "-n", "2", "--ptq",
+                "--quant_act", "--weight_bit", "8", "--b200_synthetic", "lsun_church", "--b200_decode", "--b200_out", out])
+    blob = torch.load(out)
+    img = blob["images"]
+    assert blob["samples"].shape == (2, 4, 32, 32)
+    assert img.shape == (2, 3, 256, 256) and torch.isfinite(img).all(), log[-500:]
+    assert float(img.min()) >= 0.0 and float(img.max()) <= 1.0 and float(img.std()) > 1e-3
+
+
 def test_sample_diffusion_ddim_from_reference_format_checkpoint(cuda, tmp_path):
     """--resume --cali_ckpt with a ckpt.pth in the reference's key format (the golden DDIM fixture's checkpoint) and a
     cifar10.yml-style config written next to it: the route a user of the reference takes."""

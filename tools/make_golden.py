@@ -152,10 +152,15 @@ def make_case(name, family, params, qcfg, batch, ctx_dim=None, seed=0):
     out = fwd(x, t, c)
     for h in hooks:
         h.remove()
+    extra = {}
+    if qcfg.get("save_fp"):                     # the reference's full-precision state on the same inputs
+        qnn.set_quant_state(False, False)
+        extra["out_fp"] = fwd(x, t, c)
+        qnn.set_quant_state(True, qcfg["quant_act"])
     os.makedirs(OUT, exist_ok=True)
     # fp16-exact storage is not acceptable for a parity oracle: keep fp32
     torch.save(dict(name=name, family=family, params=params, qcfg=qcfg, ckpt=ckpt, x=x, t=t, context=c, out=out,
-                    traces=traces, torch_version=torch.__version__), os.path.join(OUT, name + ".pt"))
+                    traces=traces, torch_version=torch.__version__, **extra), os.path.join(OUT, name + ".pt"))
     nq = sum(1 for k in ckpt if k.endswith("act_quantizer.delta"))
     print(f"{name}: {len(ckpt)} ckpt keys, {nq} act quantizers, out std {out.std().item():.4f}, "
           f"file {os.path.getsize(os.path.join(OUT, name + '.pt')) / 1e6:.2f} MB")
@@ -195,6 +200,22 @@ CASES = [
                     num_res_blocks=1, channel_mult=[1, 2], num_heads=2, use_spatial_transformer=True,
                     transformer_depth=1, context_dim=64, legacy=False), res=16, split=True),
      dict(weight_bit=4, act_bit=8, a_sym=False, sm_abit=16, quant_act=True), 64),
+    # weight-only (quant_act off) and full-precision states of the LDM / SD families: what `--ptq` without `--quant_act`
+    # runs (qdiff/utils.py:407), plus set_quant_state(False, False) on the same inputs (out_fp)
+    ("sd_tiny_w4_weightonly", "ldm",
+     dict(unet=dict(image_size=16, in_channels=4, out_channels=4, model_channels=32, attention_resolutions=[2, 1],
+                    num_res_blocks=1, channel_mult=[1, 2], num_heads=2, use_spatial_transformer=True,
+                    transformer_depth=1, context_dim=64, legacy=False), res=16, split=True),
+     dict(weight_bit=4, act_bit=8, a_sym=False, sm_abit=16, quant_act=False, save_fp=True), 64),
+    ("ldm_updown_w8_weightonly", "ldm",
+     dict(unet=dict(image_size=16, in_channels=4, out_channels=4, model_channels=32, attention_resolutions=[1, 2],
+                    num_res_blocks=1, channel_mult=[1, 2], num_heads=2, use_scale_shift_norm=True,
+                    resblock_updown=True), res=16),
+     dict(weight_bit=8, act_bit=8, a_sym=False, sm_abit=8, quant_act=False, save_fp=True), None),
+    ("ldm_legacy_w4_weightonly", "ldm",
+     dict(unet=dict(image_size=16, in_channels=3, out_channels=3, model_channels=32, attention_resolutions=[2, 1],
+                    num_res_blocks=1, channel_mult=[1, 2], num_head_channels=32), res=16),
+     dict(weight_bit=4, act_bit=8, a_sym=True, sm_abit=8, quant_act=False, save_fp=True), None),
 ]
 
 
@@ -232,7 +253,8 @@ if __name__ == "__main__":
     if not only:
         make_quantizer_kats()
     seeds = {"ddim_w4a8_split": 100, "ldm_legacy_w4a8": 101, "ldm_updown_w4a8": 102, "sd_tiny_w4a8_sm16": 103,
-             "ldm_updown_w8a8": 104, "ddim_w8_weightonly": 105}
+             "ldm_updown_w8a8": 104, "ddim_w8_weightonly": 105, "sd_tiny_w4_weightonly": 106,
+             "ldm_updown_w8_weightonly": 107, "ldm_legacy_w4_weightonly": 108}
     for (name, family, params, qcfg, ctx) in CASES:
         if only and name not in only:
             continue
