@@ -454,7 +454,13 @@ int launch_groupnorm(const qd_groupnorm_desc& d, cudaStream_t s) {
       return !e ? 0 : (!strcmp(e, "fused") ? 1 : (!strcmp(e, "split") ? 2 : 0));
     }();
     const long long limit = force == 1 ? 512LL * qd::GN_NU : (force == 2 ? 0 : 256LL * qd::GN_NU);
-    if (ok && units <= limit) {
+    // The one-block-per-(image, group) kernel reads cpg * 4 bytes per pixel out of every C * 4 (sector-inefficient for
+    // narrow groups) and launches B * groups blocks: it only pays in the launch-latency regime.  Measured per op on the
+    // four UNets (profiles/r02_gn_fused_vs_split.txt): the three-kernel path (statistics from the producing GEMMs'
+    // slab sums, then a coalesced apply pass) wins everywhere except maps below ~2 M elements with <= 2048 blocks
+    // (church / SD 4x4 and 8x8 levels: 10 vs 17 us); CIFAR at batch 256 (8192 blocks of 64-256 threads): 6.3 -> 1.7 ms.
+    const bool small_problem = (long long)d.B * d.HW * d.C <= (2LL << 20) && (long long)d.B * d.groups <= 2048;
+    if (ok && units <= limit && (force == 1 || small_problem)) {
       int threads = units <= 256LL * qd::GN_NU ? 256 : 512;
       if (units < 256) threads = (int)((units + 31) / 32 * 32);
       if (threads < cpg / 2) threads = (cpg / 2 + 31) / 32 * 32;

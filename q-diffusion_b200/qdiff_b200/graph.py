@@ -1007,8 +1007,8 @@ class Builder:
         return x_in, t_in, ctx_in, out
 
     # ================================================================== DDIM (CIFAR) family
-    def ddim_resnet(self, blk, x, temb, hw, split):
-        """QuantResnetBlock.forward, qdiff/quant_block.py:307-330."""
+    def ddim_resnet(self, blk, x, temb, hw, split, out=None):
+        """QuantResnetBlock.forward, qdiff/quant_block.py:307-330.  out: view the block's result is written into."""
         k = self.key(blk)
         H, W = hw
         (a1,), _ = self.groupnorm(x, blk.norm1, H * W, [blk.conv1.act_quantizer], True, k + ".norm1")
@@ -1029,9 +1029,9 @@ class Builder:
                           accumulate_into=s, use_bias=False)
             else:
                 s = self.qlinear(nin, x, k + ".nin_shortcut")
-        return self.conv3x3_s1(blk.conv2, a2, hw, k + ".conv2", residual=s)
+        return self.conv3x3_s1(blk.conv2, a2, hw, k + ".conv2", residual=s, out=out)
 
-    def ddim_attn(self, blk, x, hw):
+    def ddim_attn(self, blk, x, hw, out=None):
         """QuantAttnBlock.forward, qdiff/quant_block.py:354-386 (single head, d = C, scale C^-1/2 after QK^T)."""
         k = self.key(blk)
         T = hw[0] * hw[1]
@@ -1045,7 +1045,7 @@ class Builder:
         o = self.attention(qc, kc, vt, heads=1, d=C_, Tq=T, Tk=T, q_layout=(0, Pq), k_layout=(0, Pq), v_layout=(0, C_),
                            sim_scale_extra=float(int(C_) ** (-0.5)), qw=blk.act_quantizer_w, label=k + ".attn",
                            consumer=blk.proj_out)
-        return self.gemm(blk.proj_out, o, k + ".proj_out", residual=x)
+        return self.gemm(blk.proj_out, o, k + ".proj_out", residual=x, out=out)
 
     def lower_ddim(self, model, x_shape):
         B, Cin, H, W = x_shape
@@ -1061,45 +1061,89 @@ class Builder:
         xh = self.new_f32(B * H * W, Cin)
         self.misc(_lib.QD_OP_NCHW_TO_NHWC, x_in.data_ptr(), xh.ptr, B, Cin, H * W, label="x.nhwc",
                   spec=dict(kind="nchw_to_nhwc", src=x_in, dst=xh))
+        nres = model.num_resolutions
+        # torch.cat([h, hs.pop()], dim=1) without copies (ddim/models/diffusion.py:346): decoder block u (in execution order)
+        # consumes the u-th last skip.  Its concat buffer is allocated when that skip is produced - the producer's last GEMM
+        # writes the right-hand columns - and whatever produces h for block u (mid.block_2, the previous decoder block, an
+        # upsample conv) writes the left-hand ones.  QDIFF_DDIM_CAT=copy restores the two copies per block (A/B switch).
+        up_blocks = [model.up[lv].block[ib] for lv in reversed(range(nres)) for ib in range(model.num_res_blocks + 1)]
+        n_hs = len(up_blocks)
+        cat_buf = [None] * n_hs
+        in_place = os.environ.get("QDIFF_DDIM_CAT", "inplace") != "copy"
+
+        def skip_view(i_hs, cs, rows):
+            """Right-hand columns of the concat buffer of the decoder block that will pop skip number i_hs."""
+            u = n_hs - 1 - i_hs
+            total = int(up_blocks[u].in_channels) if in_place and 0 <= u < n_hs else 0
+            if total <= cs or total % 4 or cs % 4:
+                return None
+            cat_buf[u] = self.new_f32(rows, total)
+            return cat_buf[u].view(total - cs, cs)
+
+        def h_view(u, ch, rows):
+            """Left-hand columns of decoder block u's concat buffer (None: the buffer does not exist or does not fit)."""
+            buf = cat_buf[u] if 0 <= u < n_hs else None
+            if buf is None or buf.rows != rows or ch >= buf.cols or ch % 4:
+                return None
+            return buf.view(0, ch)
+
         a = self.quantize(xh, model.conv_in.act_quantizer, "conv_in.q")
         hw = (H, W)
-        h = self.conv_im2col(model.conv_in, a, hw, "conv_in", 1, (1, 1), hw, (9 * Cin + 31) // 32 * 32)
+        h = self.conv_im2col(model.conv_in, a, hw, "conv_in", 1, (1, 1), hw, (9 * Cin + 31) // 32 * 32,
+                             out=skip_view(0, int(model.conv_in.weight.shape[0]), B * H * W))
         hs = [(h, hw)]
-        nres = model.num_resolutions
         for lv in range(nres):
             st = model.down[lv]
             for ib in range(model.num_res_blocks):
-                h = self.ddim_resnet(st.block[ib], hs[-1][0], temb, hw, 0)
-                if len(st.attn) > 0:
-                    h = self.ddim_attn(st.attn[ib], h, hw)
+                blk = st.block[ib]
+                dest = skip_view(len(hs), int(blk.out_channels), B * hw[0] * hw[1])
+                has_attn = len(st.attn) > 0
+                h = self.ddim_resnet(blk, hs[-1][0], temb, hw, 0, out=None if has_attn else dest)
+                if has_attn:
+                    h = self.ddim_attn(st.attn[ib], h, hw, out=dest)
                 hs.append((h, hw))
             if lv != nres - 1:
                 conv = st.downsample.conv
                 a = self.quantize(hs[-1][0], conv.act_quantizer, self.key(conv) + ".q")
                 ohw = (hw[0] // 2, hw[1] // 2)
                 # F.pad (0,1,0,1) then 3x3 stride 2, padding 0 (ddim/models/diffusion.py:67-71)
-                h = self.conv_im2col(conv, a, hw, self.key(conv), 2, (0, 0), ohw, 9 * a.cols)
+                h = self.conv_im2col(conv, a, hw, self.key(conv), 2, (0, 0), ohw, 9 * a.cols,
+                                     out=skip_view(len(hs), int(conv.weight.shape[0]), B * ohw[0] * ohw[1]))
                 hw = ohw
                 hs.append((h, hw))
         h = hs[-1][0]
         h = self.ddim_resnet(model.mid.block_1, h, temb, hw, 0)
         h = self.ddim_attn(model.mid.attn_1, h, hw)
-        h = self.ddim_resnet(model.mid.block_2, h, temb, hw, 0)
+        h = self.ddim_resnet(model.mid.block_2, h, temb, hw, 0,
+                             out=h_view(0, int(model.mid.block_2.out_channels), B * hw[0] * hw[1]))
         self.traces["mid"] = (h, hw)
+        u = 0
         for lv in reversed(range(nres)):
             st = model.up[lv]
             for ib in range(model.num_res_blocks + 1):
                 split = h.cols if (lv < 4 and split_on) else 0
                 skip_t, _ = hs.pop()
-                cat = self.concat(h, skip_t, f"up.{lv}.block.{ib}")
-                h = self.ddim_resnet(st.block[ib], cat, temb, hw, split)
-                if len(st.attn) > 0:
-                    h = self.ddim_attn(st.attn[ib], h, hw)
+                buf = cat_buf[u]
+                if (buf is not None and h.t is buf.t and skip_t.t is buf.t and h.col0 == 0 and skip_t.col0 == h.cols
+                        and h.cols + skip_t.cols == buf.cols):
+                    cat = buf                                   # both halves were produced in place
+                else:
+                    cat = self.concat(h, skip_t, f"up.{lv}.block.{ib}")
+                blk = st.block[ib]
+                last_of_level = ib == model.num_res_blocks
+                # who produces h for decoder block u + 1: this block (or its attention), unless an upsample conv follows
+                dest = None if (last_of_level and lv != 0) else h_view(u + 1, int(blk.out_channels), B * hw[0] * hw[1])
+                has_attn = len(st.attn) > 0
+                h = self.ddim_resnet(blk, cat, temb, hw, split, out=None if has_attn else dest)
+                if has_attn:
+                    h = self.ddim_attn(st.attn[ib], h, hw, out=dest)
+                u += 1
             if lv != 0:
                 conv = st.upsample.conv
                 a = self.quantize(h, conv.act_quantizer, self.key(conv) + ".q", upsample=(B, hw[0], hw[1]))
                 hw = (2 * hw[0], 2 * hw[1])
-                h = self.conv3x3_s1(conv, a, hw, self.key(conv))
+                h = self.conv3x3_s1(conv, a, hw, self.key(conv),
+                                    out=h_view(u, int(conv.weight.shape[0]), B * hw[0] * hw[1]))
         (a,), _ = self.groupnorm(h, model.norm_out, hw[0] * hw[1], [model.conv_out.act_quantizer], True, "norm_out")
         o = self.conv3x3_s1(model.conv_out, a, hw, "conv_out")
         out = torch.zeros((B, o.cols, hw[0], hw[1]), dtype=torch.float32, device=self.dev)

@@ -75,6 +75,18 @@ def main():
                     b.lower_ldm(qnn.model, tuple(g["x"].shape), None if g["context"] is None else tuple(g["context"].shape))
             b.flush()
             print(f"{name} state {state}: {len(fake.ops) - n0} ops")
+    # ---- INT8 lowering of the DDIM family (concat-free decoder): op counts with and without the in-place concat
+    g = load_case("ddim_w4a8_split")
+    qnn = build_qnn(g, dev)
+    for mode in ("inplace", "copy"):
+        os.environ["QDIFF_DDIM_CAT"] = mode
+        b = graph.Builder(qnn, dev, g["x"].shape[0])
+        with torch.no_grad():
+            b.lower_ddim(qnn.model, tuple(g["x"].shape))
+        b.flush()
+        ncopy = sum(1 for k in b.op_kinds if k == _lib.QD_OP_COPY2D)
+        print(f"ddim_w4a8_split INT8, QDIFF_DDIM_CAT={mode}: {b.nops} ops, {ncopy} copy2d")
+    os.environ.pop("QDIFF_DDIM_CAT", None)
 
 
 if __name__ == "__main__":
