@@ -195,10 +195,12 @@ __global__ void __launch_bounds__(128) attention_fp32_kernel(const qd_attention_
 // (T = 4096, d = 512: 8 GB instead of 64 GB per image).  Phase 1: a warp per key, lanes over d, AFP_R dot products per K row;
 // phase 2: a warp per query row (max, exp, sum in shared memory); phase 3: a thread per output column, AFP_R accumulators.
 constexpr int AFP_R = 8;
+__host__ __device__ inline int afp_tk_pitch(int Tk) { return (Tk + 3) & ~3; }     // score row pitch (16-byte aligned rows)
 __global__ void __launch_bounds__(256) attention_fp32_rows_kernel(const qd_attention_fp_desc p) {
   extern __shared__ float afp_sh[];
+  const int tkp = afp_tk_pitch(p.Tk);
   float* qs = afp_sh;                        // [AFP_R][d]
-  float* sc = afp_sh + AFP_R * p.d;          // [AFP_R][Tk]
+  float* sc = afp_sh + AFP_R * p.d;          // [AFP_R][tkp]
   __shared__ float inv_s[AFP_R];
   const int bh = blockIdx.y, b = bh / p.heads, h = bh - b * p.heads;
   const int r0 = blockIdx.x * AFP_R;
@@ -209,15 +211,21 @@ __global__ void __launch_bounds__(256) attention_fp32_rows_kernel(const qd_atten
     qs[i] = r < nr ? p.q[((long long)b * p.Tq + r0 + r) * p.ld_q + p.q_off + h * p.head_stride_q + c] : 0.f;
   }
   __syncthreads();
+  // phase 1: a lane owns 4 consecutive channels per step: one 16-byte K load and AFP_R 16-byte shared loads of q feed
+  // 4 * AFP_R FMAs (the scalar form issued one shared load per FMA and was LSU-bound).  d % 4 == 0 (checked by the launcher).
   for (int j = warp; j < p.Tk; j += 8) {
     const float* k = p.k + ((long long)b * p.Tk + j) * p.ld_k + p.k_off + h * p.head_stride_k;
     float acc[AFP_R];
 #pragma unroll
     for (int r = 0; r < AFP_R; ++r) acc[r] = 0.f;
-    for (int i = lane; i < p.d; i += 32) {
-      const float kv = k[i];
+    for (int i = 4 * lane; i < p.d; i += 128) {
+      const float4 kv = *reinterpret_cast<const float4*>(k + i);
 #pragma unroll
-      for (int r = 0; r < AFP_R; ++r) acc[r] = fmaf(qs[r * p.d + i], kv, acc[r]);
+      for (int r = 0; r < AFP_R; ++r) {
+        const float4 qv = *reinterpret_cast<const float4*>(qs + r * p.d + i);
+        acc[r] = fmaf(qv.x, kv.x, acc[r]); acc[r] = fmaf(qv.y, kv.y, acc[r]);
+        acc[r] = fmaf(qv.z, kv.z, acc[r]); acc[r] = fmaf(qv.w, kv.w, acc[r]);
+      }
     }
     float mine = 0.f;
 #pragma unroll
@@ -227,18 +235,18 @@ __global__ void __launch_bounds__(256) attention_fp32_rows_kernel(const qd_atten
       for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
       if (lane == r) mine = a;
     }
-    if (lane < AFP_R) sc[lane * p.Tk + j] = mine * p.scale;
+    if (lane < AFP_R) sc[lane * tkp + j] = mine * p.scale;
   }
   __syncthreads();
   if (warp < AFP_R) {
-    float* row = sc + warp * p.Tk;
+    float* row = sc + warp * tkp;
     float mx = -INFINITY;
     for (int j = lane; j < p.Tk; j += 32) mx = fmaxf(mx, row[j]);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
     float sum = 0.f;
-    for (int j = lane; j < p.Tk; j += 32) {
-      const float e = expf(row[j] - mx);
+    for (int j = lane; j < tkp; j += 32) {
+      const float e = j < p.Tk ? expf(row[j] - mx) : 0.f;     // the pitch padding takes part in phase 3 as zeros
       row[j] = e;
       sum += e;
     }
@@ -247,16 +255,29 @@ __global__ void __launch_bounds__(256) attention_fp32_rows_kernel(const qd_atten
     if (lane == 0) inv_s[warp] = 1.0f / sum;
   }
   __syncthreads();
+  // phase 3: a thread owns an output column; 4 keys per step: AFP_R 16-byte shared loads of the probabilities (broadcast)
+  // and 4 V loads feed 4 * AFP_R FMAs
   for (int c = threadIdx.x; c < p.d; c += blockDim.x) {
     const float* v = p.v + (long long)b * p.Tk * p.ld_v + p.v_off + h * p.head_stride_v + c;
     float acc[AFP_R];
 #pragma unroll
     for (int r = 0; r < AFP_R; ++r) acc[r] = 0.f;
-#pragma unroll 4
-    for (int j = 0; j < p.Tk; ++j) {
+    const int t4 = p.Tk & ~3;
+#pragma unroll 2
+    for (int j = 0; j < t4; j += 4) {
+      const float v0 = v[(long long)j * p.ld_v], v1 = v[(long long)(j + 1) * p.ld_v];
+      const float v2 = v[(long long)(j + 2) * p.ld_v], v3 = v[(long long)(j + 3) * p.ld_v];
+#pragma unroll
+      for (int r = 0; r < AFP_R; ++r) {
+        const float4 pr = *reinterpret_cast<const float4*>(sc + r * tkp + j);
+        acc[r] = fmaf(pr.x, v0, acc[r]); acc[r] = fmaf(pr.y, v1, acc[r]);
+        acc[r] = fmaf(pr.z, v2, acc[r]); acc[r] = fmaf(pr.w, v3, acc[r]);
+      }
+    }
+    for (int j = t4; j < p.Tk; ++j) {
       const float vv = v[(long long)j * p.ld_v];
 #pragma unroll
-      for (int r = 0; r < AFP_R; ++r) acc[r] = fmaf(sc[r * p.Tk + j], vv, acc[r]);
+      for (int r = 0; r < AFP_R; ++r) acc[r] = fmaf(sc[r * tkp + j], vv, acc[r]);
     }
 #pragma unroll
     for (int r = 0; r < AFP_R; ++r)

@@ -183,6 +183,19 @@ int pick_bn(int N, int tiles_m, int sms, int hint, int step, long long K) {
 
 int gemm_mode(const qd::GemmArgs& a);
 
+// Split-K workspace: ONE fixed-size buffer per device, allocated at the first plan that needs it and never moved (recorded
+// programs and captured CUDA graphs hold the pointer).  Ops of a device run one after the other, so they can share it.
+constexpr size_t kSplitWsBytes = 64u << 20;
+int32_t* splitk_workspace() {
+  static void* ws[kMaxDevices] = {};
+  static std::mutex mu;
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!ws[dev] && cudaMalloc(&ws[dev], kSplitWsBytes) != cudaSuccess) { ws[dev] = nullptr; cudaGetLastError(); }
+  return reinterpret_cast<int32_t*>(ws[dev]);
+}
+
 int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
   if (!d || !d->a || !d->w || !d->scale) return fail(QD_ERR_BAD_ARG, "gemm: null operand");
   if (d->taps != 1 && d->taps != 9) return fail(QD_ERR_UNSUPPORTED, "gemm: taps must be 1 or 9 (got %d)", d->taps);
@@ -207,6 +220,16 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
       return fail(QD_ERR_BAD_ARG, "gemm: geglu needs N %% 8 == 0, out_q only, plain GEMM");
   }
   a.BN = pick_bn(d->N, a.tiles_m, sms, d->bn_hint, d->geglu ? 32 : 16, (long long)d->C * d->taps * a.kdup);
+  // split-K candidates (see below) take the widest N tile: few tiles remain, and what is shared among the SMs is the K loop
+  static const int splitk_enabled = [] { const char* e = getenv("QDIFF_SPLITK"); return (e && !strcmp(e, "0")) ? 0 : 1; }();
+  const int num_kb_all = ((d->C + qd::GEMM_BK - 1) / qd::GEMM_BK) * d->taps * a.kdup;
+  const bool splitk_candidate = splitk_enabled && !d->bn_hint && !d->a_bf16 && !d->w_int4_packed && d->out && !d->out_q && !d->geglu &&
+                                !(d->N & 3) && !(d->ldo & 3) && (!d->residual || !(d->ldr & 3)) && (!d->rowvec || !(d->ld_rowvec & 3)) &&
+                                num_kb_all >= 16;
+  if (splitk_candidate) {
+    const int bn_wide = d->N >= 256 ? 256 : (d->N + 15) / 16 * 16;
+    if (2 * a.tiles_m * ((d->N + bn_wide - 1) / bn_wide) <= sms) a.BN = bn_wide;
+  }
   if (a.BN % 16 || a.BN < 16 || a.BN > 256) return fail(QD_ERR_BAD_ARG, "gemm: bad BN %d", a.BN);
   a.tiles_n = (d->N + a.BN - 1) / a.BN;
   a.a_signed = d->a_signed; a.b_signed = 1;
@@ -296,6 +319,28 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
   const int tiles = a.tiles_m * a.tiles_n;
   pl->grid = tiles < sms ? tiles : sms;
   pl->mode = gemm_mode(a);
+  // ---- split-K: short-M, long-K layers (the 4x4 / 8x8 levels: 4-48 output tiles, 90-220 k-blocks each).  A CTA's main loop
+  // runs at ~0.5 us per k-block whatever the N tile (profiles/r02_sweep_bn_small_m.txt: 50 us for BN = 32 ... 256), so the only
+  // lever is to share a tile's K loop among idle SMs.  fp32-output layers without GroupNorm slab statistics only.
+  {
+    const int num_kb = num_kb_all;
+    const bool eligible = splitk_candidate && pl->mode >= 0 && 2 * tiles <= sms &&
+                          (!a.gn_stats || (!(a.M & 31) && !(a.ld_stats & 1)));
+    if (eligible) {
+      int splits = sms / tiles;
+      if (splits > 16) splits = 16;
+      if (splits > num_kb / 4) splits = num_kb / 4;
+      if (splits >= 2 && (size_t)splits * a.M * a.N * 4 <= kSplitWsBytes) {
+        const int per = (num_kb + splits - 1) / splits;
+        splits = (num_kb + per - 1) / per;
+        int32_t* ws = splitk_workspace();
+        if (ws && splits >= 2) {
+          a.splits = splits; a.kb_per_split = per; a.ws = ws;
+          pl->grid = tiles * splits < sms ? tiles * splits : sms;
+        }
+      }
+    }
+  }
   if (a.bf16 && pl->mode < 0)
     return fail(QD_ERR_UNSUPPORTED, "gemm: weight-only (a_bf16) layer needs a specialised epilogue (N %% 4 == 0, aligned leading dimensions)");
   memset(&pl->tmR, 0, sizeof(pl->tmR));
@@ -364,6 +409,12 @@ int gemm_mode(const qd::GemmArgs& a) {
 
 int launch_gemm(const GemmPlan& pl, cudaStream_t s) {
   using namespace qd;
+  if (pl.args.splits > 1) {     // K slices -> workspace, then the epilogue pass
+    if (int rc = launch_gemm_mode<EPI_SPLITK>(pl, s)) return rc;
+    const long long units = (long long)((pl.args.M + 31) / 32) * (pl.args.N >> 2);      // (32-row slab, column quad) per thread
+    launch_k(qd::splitk_finish_kernel, grid_for(units, 256), 256, 0, s, pl.args);
+    return check_launch("splitk_finish_kernel");
+  }
   switch (pl.mode) {
     case EPI_OUT_F32: return launch_gemm_mode<EPI_OUT_F32>(pl, s);
     case EPI_OUT_F32 | EPI_CORR: return launch_gemm_mode<EPI_OUT_F32 | EPI_CORR>(pl, s);
@@ -436,6 +487,11 @@ long long gn_workspace_floats(int B, int HW, int C, int groups) {
   return (long long)B * nslab * groups * 2 * 2 + (long long)B * groups * 2 + 16;   // doubles count as 2 floats
 }
 
+int use_stats_env() {
+  static const int v = [] { const char* e = getenv("QDIFF_GN_STATS"); return (e && !strcmp(e, "0")) ? 0 : 1; }();
+  return v;
+}
+
 int launch_groupnorm(const qd_groupnorm_desc& d, cudaStream_t s) {
   if (!d.x || !d.gamma || !d.beta) return fail(QD_ERR_BAD_ARG, "groupnorm: null arg");
   if (d.groups <= 0 || d.groups > qd::GN_MAX_GROUPS || d.C % 4 || d.C % d.groups || d.ld_x % 4)
@@ -459,7 +515,10 @@ int launch_groupnorm(const qd_groupnorm_desc& d, cudaStream_t s) {
     // four UNets (profiles/r02_gn_fused_vs_split.txt): the three-kernel path (statistics from the producing GEMMs'
     // slab sums, then a coalesced apply pass) wins everywhere except maps below ~2 M elements with <= 2048 blocks
     // (church / SD 4x4 and 8x8 levels: 10 vs 17 us); CIFAR at batch 256 (8192 blocks of 64-256 threads): 6.3 -> 1.7 ms.
-    const bool small_problem = (long long)d.B * d.HW * d.C <= (2LL << 20) && (long long)d.B * d.groups <= 2048;
+    // ... and, when the producing GEMMs left slab statistics, only below ~0.5 M elements (church 8x8 level, 1.5 M elements:
+    // 25 us fused vs 13 us for finalize-from-statistics + apply)
+    const long long elems = (long long)d.B * d.HW * d.C;
+    const bool small_problem = elems <= ((d.stats_in && use_stats_env()) ? (512LL << 10) : (2LL << 20)) && (long long)d.B * d.groups <= 2048;
     if (ok && units <= limit && (force == 1 || small_problem)) {
       int threads = units <= 256LL * qd::GN_NU ? 256 : 512;
       if (units < 256) threads = (int)((units + 31) / 32 * 32);
@@ -479,7 +538,7 @@ int launch_groupnorm(const qd_groupnorm_desc& d, cudaStream_t s) {
   if (threads > 256) threads = 256;
   if (threads < 2 * d.groups) threads = (2 * d.groups + 31) / 32 * 32;
   int rc;
-  static const int use_stats = [] { const char* e = getenv("QDIFF_GN_STATS"); return (e && !strcmp(e, "0")) ? 0 : 1; }();
+  const int use_stats = use_stats_env();
   if (d.stats_in && use_stats) {
     // the producing GEMMs left per-slab column sums: no pass over x for the statistics
     if (d.HW % 32) return fail(QD_ERR_BAD_ARG, "groupnorm: stats_in needs HW %% 32 == 0");
@@ -566,8 +625,10 @@ int launch_attention_fp(const qd_attention_fp_desc& d, cudaStream_t s) {
   if (!d.q || !d.k || !d.v || !d.out || d.B <= 0 || d.heads <= 0 || d.d <= 0 || d.Tq <= 0 || d.Tk <= 0)
     return fail(QD_ERR_BAD_ARG, "attention_fp32: bad args");
   // long sequences: AFP_R query rows per block share the K / V rows they read (K/V traffic / AFP_R)
-  const size_t smem_rows = (size_t)qd::AFP_R * (d.d + d.Tk) * sizeof(float);
-  if (d.Tq >= 256 && smem_rows <= 200 * 1024) {
+  const size_t smem_rows = (size_t)qd::AFP_R * (d.d + qd::afp_tk_pitch(d.Tk)) * sizeof(float);
+  const bool aligned = !(d.d & 3) && !(d.ld_q & 3) && !(d.ld_k & 3) && !(d.q_off & 3) && !(d.k_off & 3) && !(d.head_stride_q & 3) &&
+                       !(d.head_stride_k & 3) && !((uintptr_t)d.q & 15) && !((uintptr_t)d.k & 15);
+  if (d.Tq >= 256 && smem_rows <= 200 * 1024 && aligned) {
     static std::atomic<unsigned long long> optin{0};
     if (int rc = ensure_smem_optin(qd::attention_fp32_rows_kernel, 200 * 1024, optin, "attention_fp32_rows")) return rc;
     launch_k(qd::attention_fp32_rows_kernel, dim3((d.Tq + qd::AFP_R - 1) / qd::AFP_R, d.B * d.heads), 256, smem_rows, s, d);

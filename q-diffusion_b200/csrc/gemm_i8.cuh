@@ -72,6 +72,7 @@ constexpr int EPI_TRANS = 64;     // requantised code output, transposed [img][n
 constexpr int EPI_CONV = 128;     // 3x3 conv (taps == 9); with EPI_CORR the correction table is indexed by border class
 constexpr int EPI_RESTMA = 256;   // with EPI_RESIDUAL: residual sub-tiles arrive through the per-warp TMA ring (short-K GEMMs)
 constexpr int EPI_BF16 = 512;     // weight-only layers: bfloat16 x3 activation planes x bfloat16 weight codes, fp32 accumulators
+constexpr int EPI_SPLITK = 1024;  // split-K partial: raw int32 accumulators of one K slice -> ws[split][M][N] (splitk_finish_kernel applies the epilogue)
 
 struct GemmArgs {
   int M, N;            // logical output rows / columns (columns >= N are masked)
@@ -115,6 +116,11 @@ struct GemmArgs {
   float2* gn_stats;
   long long ld_stats;
   int bf16;            // weight-only layer: bfloat16 operands, fp32 accumulators (EPI_BF16 modes)
+  // split-K (short-M, long-K layers: few output tiles, the K loop of a tile is shared by `splits` CTAs): work item =
+  // (tile, split); split z reduces k-blocks [z * kb_per_split, (z + 1) * kb_per_split) and stores its raw accumulators to
+  // ws[z][M][N]; splitk_finish_kernel sums the slices (integers: exact, order-free) and applies the epilogue
+  int splits, kb_per_split;
+  int32_t* ws;
 };
 // Specialised requantising modes take the pre-divided constants (one FFMA per element: quant_math.cuh quant_bits_pre)
 __host__ __device__ constexpr bool gemm_qpre(int MODE) { return MODE >= 0 && (MODE & 16) != 0 && (MODE & 32) == 0; }
@@ -369,9 +375,11 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int splits = p.splits > 1 ? p.splits : 1;
+  const int num_tiles = p.tiles_m * p.tiles_n * splits;       // work items: (tile, K slice)
   const int kb_per_tap = (p.C + GEMM_BK - 1) / GEMM_BK;
-  const int num_kb = kb_per_tap * p.taps * p.kdup;
+  const int num_kb_all = kb_per_tap * p.taps * p.kdup;
+  const int kb_slice = splits > 1 ? p.kb_per_split : num_kb_all;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -408,7 +416,10 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = (uint32_t)(GEMM_A_STAGE_BYTES + (W4 ? p.BN * (GEMM_BK / 2) : p.BN * GEMM_BK));
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+        const int tile = item / splits;
+        const int kb0 = (item - tile * splits) * kb_slice;
+        const int kb1 = min(num_kb_all, kb0 + kb_slice);
         const int tm = tile / p.tiles_n;
         const int tn = tile - tm * p.tiles_n;
         const int m0 = tm * GEMM_BM;
@@ -420,10 +431,11 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           h0 = (m0 - b0 * hw) / p.W;
           w0 = m0 - b0 * hw - h0 * p.W;      // != 0 only for rows wider than a tile (W > 128: the tile is a 128-pixel row segment)
         }
-        for (int seg = 0; seg < p.taps * p.kdup; ++seg) {
+        int seg = kb0 / kb_per_tap, kc = kb0 - seg * kb_per_tap;
+        for (int kb = kb0; kb < kb1; ++kb) {
           const int tap = seg % p.taps;            // activation geometry of this segment; the weight column offset is seg * C
           const int ky = tap / 3, kx = tap - ky * 3;
-          for (int kc = 0; kc < kb_per_tap; ++kc) {
+          {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + (size_t)stage * lay.stage_bytes;
             uint8_t* sb = sa + GEMM_A_STAGE_BYTES;
@@ -439,6 +451,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_2d(sb, &tmB, &full_bar[stage], seg * p.C + kc * GEMM_BK, n0);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
+          if (++kc == kb_per_tap) { kc = 0; ++seg; }
         }
       }
     }
@@ -451,11 +464,13 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+        const int kb0 = (item % splits) * kb_slice;
+        const int kb1 = min(num_kb_all, kb0 + kb_slice);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           const int kc = kb % kb_per_tap;
           const int rem = p.C - kc * GEMM_BK;
           const int nmma = rem >= GEMM_BK ? 4 : (rem >> 5);
@@ -466,8 +481,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t db = make_smem_desc_sw128(sa + GEMM_A_STAGE_BYTES);
           for (int j = 0; j < nmma; ++j) {
             // advance 32 bytes (one K=32 slice) inside the 128B swizzle row: +2 in 16-byte units
-            if constexpr (BF16) umma_bf16(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (kb | j) ? 1u : 0u);
-            else umma_i8(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (kb | j) ? 1u : 0u);
+            if constexpr (BF16) umma_bf16(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, ((kb - kb0) | j) ? 1u : 0u);
+            else umma_i8(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, ((kb - kb0) | j) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -490,7 +505,10 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int r32 = t >> 2, piece = t & 3;
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+        const int tile = item / splits;
+        const int kb0 = (item - tile * splits) * kb_slice;
+        const int num_kb = min(num_kb_all, kb0 + kb_slice) - kb0;
         const int tn = tile % p.tiles_n;
         const int n0 = tn * p.BN;
         uint32_t kz[8];       // 0x80808080 - zero point replicated into 4 bytes, rows r32 + 32*i
@@ -569,7 +587,9 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
       for (int i = 0; i < GEMM_RES_NBUF - 1; ++i) res_issue();
     }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+      const int tile = item / splits;
+      [[maybe_unused]] const int zsplit = item - tile * splits;
       const int tm = tile / p.tiles_n;
       const int tn = tile - tm * p.tiles_n;
       const int n_base = tn * p.BN;
@@ -584,7 +604,43 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
-      if constexpr (kTrans) {
+      if constexpr (MODE >= 0 && (MODE & EPI_SPLITK) != 0) {
+        // raw accumulators of this K slice -> ws[zsplit][M][N], 16-byte stores through the staging tile (row-major, coalesced)
+        int32_t* wz = p.ws + (long long)zsplit * p.M * p.N;
+        for (int c = half * 32; c < p.BN; c += CSTEP) {
+          const int ncols = (p.BN - c) >= 32 ? 32 : 16;
+          if (ncols == 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + (uint32_t)c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint32_t v[16];
+            tmem_ld_32x16(t_row + (uint32_t)c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          __syncwarp();
+          const int n = n_base + c + cq * 4;
+          if (cq * 4 < ncols && n < p.N) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int row = it * 4 + rsub;
+              const int m = m_warp + row;
+              if (m < p.M)
+                *reinterpret_cast<uint4*>(wz + (long long)m * p.N + n) =
+                    *reinterpret_cast<const uint4*>(stg + row * 128 + ((cq ^ (row & 7)) << 4));
+            }
+          }
+          __syncwarp();
+        }
+      } else if constexpr (kTrans) {
         // V^T code output [img][n][token'] (token' = att_vt_perm order inside each group of 16).  The warp's
         // 32 tokens x 32 channels go through the staging tile; each lane then owns ONE channel and emits whole
         // 16-token groups as 16 B stores (the thread-per-row form below needs 32 byte stores per lane and chunk).
@@ -843,6 +899,58 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// Second half of a split-K GEMM: sum the K slices (int32: exact in any order) and apply the fp32 epilogue of the plain
+// kernel - zero-point correction (per border class for convs), scale, bias, per-image vector, residual - in the same
+// operation order, plus the GroupNorm slab statistics when the consumer wants them.  A thread owns 4 output columns of
+// one 32-row slab (consecutive threads = consecutive column quads: every row access of a warp is one contiguous 512 B).
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const GemmArgs p) {
+  const int nq4 = p.N >> 2;
+  const int nslab = (p.M + 31) >> 5;
+  const long long total = (long long)nslab * nq4;
+  const long long slice = (long long)p.M * p.N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int sl = (int)(i / nq4);
+    const int n = (int)(i - (long long)sl * nq4) << 2;
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n));
+    float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) bi = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+    int4 c1 = make_int4(0, 0, 0, 0);
+    if (p.corr && p.taps != 9) c1 = __ldg(reinterpret_cast<const int4*>(p.corr + n));
+    float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
+    const int m1 = min(p.M, (sl << 5) + 32);
+    for (int m = sl << 5; m < m1; ++m) {
+      const int32_t* w = p.ws + (long long)m * p.N + n;
+      int4 a = *reinterpret_cast<const int4*>(w);
+      for (int z = 1; z < p.splits; ++z) {
+        const int4 v = *reinterpret_cast<const int4*>(w + z * slice);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+      int cls, img;
+      gemm_row_meta(p, m, cls, img);
+      int4 c = c1;
+      if (p.corr && p.taps == 9) c = __ldg(reinterpret_cast<const int4*>(p.corr + (long long)cls * p.N + n));
+      a.x -= c.x; a.y -= c.y; a.z -= c.z; a.w -= c.w;
+      float4 y = make_float4((float)a.x * sc.x + bi.x, (float)a.y * sc.y + bi.y, (float)a.z * sc.z + bi.z, (float)a.w * sc.w + bi.w);
+      if (p.rowvec) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(p.rowvec + (long long)img * p.ld_rowvec + n));
+        y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+      }
+      if (p.residual) {
+        const float4 r = *reinterpret_cast<const float4*>(p.residual + (long long)m * p.ldr + n);
+        y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+      }
+      *reinterpret_cast<float4*>(p.out + (long long)m * p.ldo + n) = y;
+      gs[0] += y.x; gs[1] += y.y; gs[2] += y.z; gs[3] += y.w;
+      gq[0] += y.x * y.x; gq[1] += y.y * y.y; gq[2] += y.z * y.z; gq[3] += y.w * y.w;
+    }
+    if (p.gn_stats) {
+      float2* st = p.gn_stats + (long long)sl * p.ld_stats + n;
+      *reinterpret_cast<float4*>(st) = make_float4(gs[0], gq[0], gs[1], gq[1]);
+      *reinterpret_cast<float4*>(st + 2) = make_float4(gs[2], gq[2], gs[3], gq[3]);
+    }
+  }
 }
 
 }  // namespace qd

@@ -1011,22 +1011,35 @@ class Builder:
         """QuantResnetBlock.forward, qdiff/quant_block.py:307-330.  out: view the block's result is written into."""
         k = self.key(blk)
         H, W = hw
-        (a1,), _ = self.groupnorm(x, blk.norm1, H * W, [blk.conv1.act_quantizer], True, k + ".norm1")
+        has_nin = blk.in_channels != blk.out_channels
+        if has_nin and getattr(blk, "use_conv_shortcut", False):
+            raise NotImplementedError("conv_shortcut=True is not used by the reference configs")
+        a_skip = None
+        if has_nin and split % 4 == 0 and os.environ.get("QDIFF_DDIM_NINQ", "fused") != "separate":
+            # nin_shortcut's (split) input quantizer reads the tensor norm1 reads: emitted by the same GroupNorm pass
+            nin = blk.nin_shortcut
+            if split and nin.split == 0:
+                raise RuntimeError(f"{k}.nin_shortcut: split_shortcut is set but the checkpoint has no split quantizers")
+            raw = (nin.act_quantizer, nin.act_quantizer_0 if split else None, split)
+            (a1,), _, a_skip = self.groupnorm(x, blk.norm1, H * W, [blk.conv1.act_quantizer], True, k + ".norm1", raw=raw)
+        else:
+            (a1,), _ = self.groupnorm(x, blk.norm1, H * W, [blk.conv1.act_quantizer], True, k + ".norm1")
         tp = self.qlinear(blk.temb_proj, temb, k + ".temb_proj", act=1)
         h = self.conv3x3_s1(blk.conv1, a1, hw, k + ".conv1", rowvec=tp)
         (a2,), _ = self.groupnorm(h, blk.norm2, H * W, [blk.conv2.act_quantizer], True, k + ".norm2")
         s = x
-        if blk.in_channels != blk.out_channels:
-            if getattr(blk, "use_conv_shortcut", False):
-                raise NotImplementedError("conv_shortcut=True is not used by the reference configs")
+        if has_nin:
             nin = blk.nin_shortcut
             if split:
                 if nin.split == 0:
                     raise RuntimeError(f"{k}.nin_shortcut: split_shortcut is set but the checkpoint has no split quantizers")
-                a = self.quantize(x, nin.act_quantizer, k + ".nin.q", split=split, q1=nin.act_quantizer_0)
+                a = a_skip if a_skip is not None else \
+                    self.quantize(x, nin.act_quantizer, k + ".nin.q", split=split, q1=nin.act_quantizer_0)
                 s = self.gemm(nin, a, k + ".nin_shortcut.half0", cols=(0, split), suffix="", zx=a.zp[0], dx=a.delta[0])
                 self.gemm(nin, a, k + ".nin_shortcut", cols=(split, a.cols), suffix="_0", zx=a.zp[1], dx=a.delta[1],
                           accumulate_into=s, use_bias=False)
+            elif a_skip is not None:
+                s = self.gemm(nin, a_skip, k + ".nin_shortcut")
             else:
                 s = self.qlinear(nin, x, k + ".nin_shortcut")
         return self.conv3x3_s1(blk.conv2, a2, hw, k + ".conv2", residual=s, out=out)

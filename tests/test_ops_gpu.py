@@ -100,6 +100,57 @@ def test_qconv3x3(cuda, B, H, W, C, N, asym):
     _report(f"qconv3x3 B{B} {H}x{W} C{C} N{N}", out, ref, atol=1e-4, rtol=2e-6)
 
 
+@pytest.mark.parametrize("B,H,W,C,N,mode", [
+    (8, 4, 4, 768, 768, "rowvec"),      # church 4x4 level: 1 M tile x 3 N tiles, 54 k-blocks -> 13 K slices
+    (8, 8, 8, 512, 256, "residual"),    # 4 M tiles, in-place residual
+    (3, 8, 8, 1280, 320, "plain"),      # ragged batch: the last M tile is partly empty
+    (16, 8, 8, 1280, 1280, "residual"), # SD 8x8 level
+    (32, 8, 8, 768, 768, "stats"),      # church 8x8 level: 2048 rows, residual + GroupNorm slab statistics from the finish pass
+])
+def test_qconv3x3_split_k(cuda, B, H, W, C, N, mode):
+    """Short-M, long-K convs run split-K (engine.cu plan_gemm): K slices as raw int32 partial tiles, then
+    splitk_finish_kernel with the plain kernel's epilogue (correction per border class, scale, bias, per-image vector,
+    residual).  Checked against the exact integer oracle like every other conv; the launch counter proves the two-kernel
+    path was taken."""
+    ops, fold = _ops()
+    from qdiff_b200 import _lib
+    gen = torch.Generator().manual_seed(5 + B + C)
+    L = _make_layer(N, C, 9, 4, gen, True)
+    a = torch.randint(0, 256, (B, C, H, W), generator=gen)
+    ref = O.int_conv3x3(a, L["zx"], L["ws"], L["scale"], L["bias"]).permute(0, 2, 3, 1).reshape(B * H * W, N)
+    M = B * H * W
+    a_dev = a.permute(0, 2, 3, 1).contiguous().to(torch.uint8).to(cuda)
+    w_dev = fold.to_k_major(L["ws"]).to(torch.int8).to(cuda)
+    corr = fold.border_corr(L["ws"], L["zx"]).to(cuda)
+    kw = {}
+    out = torch.full((M, N), float("nan"), device=cuda)
+    if mode == "rowvec":
+        rv = torch.randn(B, N, generator=gen)
+        ref = ref + rv.repeat_interleave(H * W, dim=0)
+        kw = dict(rowvec=rv.to(cuda), ld_rowvec=N, rows_per_batch=H * W)
+    elif mode in ("residual", "stats"):
+        res = torch.randn(M, N, generator=gen)
+        ref = ref + res
+        out = res.to(cuda).clone()
+        kw = dict(residual=out, ldr=N)
+    slabs = None
+    if mode == "stats":
+        slabs = torch.full((M // 32, N, 2), float("nan"), device=cuda)
+        kw.update(gn_stats=slabs, ld_stats=N)
+    d = ops.gemm_desc(a_dev, w_dev, L["scale"].to(cuda), M=M, N=N, C=C, taps=9, conv_bhw=(B, H, W), a_signed=False,
+                      bias=L["bias"].to(cuda), corr=corr, out=out, ldo=N, **kw)
+    n0 = _lib.lib().qd_launch_count()
+    ops.qgemm(d)
+    torch.cuda.synchronize()
+    assert _lib.lib().qd_launch_count() - n0 == 2, "expected the split-K pair of launches (GEMM slices + finish)"
+    _report(f"qconv3x3 split-K B{B} {H}x{W} C{C} N{N} {mode}", out, ref, atol=1e-4, rtol=2e-6)
+    if slabs is not None:
+        o64 = out.double().cpu().reshape(M // 32, 32, N)
+        got = slabs.double().cpu()
+        for k, want in enumerate((o64.sum(dim=1), (o64 * o64).sum(dim=1))):
+            assert (got[..., k] - want).abs().max() <= 1e-5 * max(1.0, want.abs().max().item())
+
+
 @pytest.mark.parametrize("taps,M_or_bhw,N,C", [
     (1, 300, 320, 320),            # partial last k-block, ragged M
     (1, 4096, 640, 1280),          # multi-tile persistent loop, pipeline wrap-around
