@@ -411,8 +411,7 @@ int launch_gemm(const GemmPlan& pl, cudaStream_t s) {
   using namespace qd;
   if (pl.args.splits > 1) {     // K slices -> workspace, then the epilogue pass
     if (int rc = launch_gemm_mode<EPI_SPLITK>(pl, s)) return rc;
-    const long long units = (long long)((pl.args.M + 31) / 32) * (pl.args.N >> 2);      // (32-row slab, column quad) per thread
-    launch_k(qd::splitk_finish_kernel, grid_for(units, 256), 256, 0, s, pl.args);
+    launch_k(qd::splitk_finish_kernel, dim3((pl.args.N + 31) / 32, (pl.args.M + 31) / 32), 256, 0, s, pl.args);
     return check_launch("splitk_finish_kernel");
   }
   switch (pl.mode) {

@@ -903,52 +903,56 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // Second half of a split-K GEMM: sum the K slices (int32: exact in any order) and apply the fp32 epilogue of the plain
 // kernel - zero-point correction (per border class for convs), scale, bias, per-image vector, residual - in the same
-// operation order, plus the GroupNorm slab statistics when the consumer wants them.  A thread owns 4 output columns of
-// one 32-row slab (consecutive threads = consecutive column quads: every row access of a warp is one contiguous 512 B).
+// operation order, plus the GroupNorm slab statistics when the consumer wants them.  Block = one 32-row slab x 32 columns:
+// thread (row, column quad); a warp touches 4 rows x 128 contiguous bytes per access.  grid = (N / 32, M / 32).
 __global__ void __launch_bounds__(256) splitk_finish_kernel(const GemmArgs p) {
-  const int nq4 = p.N >> 2;
-  const int nslab = (p.M + 31) >> 5;
-  const long long total = (long long)nslab * nq4;
-  const long long slice = (long long)p.M * p.N;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int sl = (int)(i / nq4);
-    const int n = (int)(i - (long long)sl * nq4) << 2;
+  __shared__ float sy[32][33], sq[32][33];
+  const int r = threadIdx.x >> 3, q = threadIdx.x & 7;
+  const int m = blockIdx.y * 32 + r;
+  const int n = blockIdx.x * 32 + q * 4;
+  const bool ok = m < p.M && n < p.N;
+  float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ok) {
+    const long long slice = (long long)p.M * p.N;
+    const int32_t* w = p.ws + (long long)m * p.N + n;
+    int4 a = *reinterpret_cast<const int4*>(w);
+#pragma unroll 4
+    for (int z = 1; z < p.splits; ++z) {
+      const int4 v = *reinterpret_cast<const int4*>(w + z * slice);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    int cls, img;
+    gemm_row_meta(p, m, cls, img);
+    if (p.corr) {
+      const int4 c = __ldg(reinterpret_cast<const int4*>(p.corr + (p.taps == 9 ? (long long)cls * p.N : 0) + n));
+      a.x -= c.x; a.y -= c.y; a.z -= c.z; a.w -= c.w;
+    }
     const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n));
     float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.bias) bi = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-    int4 c1 = make_int4(0, 0, 0, 0);
-    if (p.corr && p.taps != 9) c1 = __ldg(reinterpret_cast<const int4*>(p.corr + n));
-    float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
-    const int m1 = min(p.M, (sl << 5) + 32);
-    for (int m = sl << 5; m < m1; ++m) {
-      const int32_t* w = p.ws + (long long)m * p.N + n;
-      int4 a = *reinterpret_cast<const int4*>(w);
-      for (int z = 1; z < p.splits; ++z) {
-        const int4 v = *reinterpret_cast<const int4*>(w + z * slice);
-        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-      }
-      int cls, img;
-      gemm_row_meta(p, m, cls, img);
-      int4 c = c1;
-      if (p.corr && p.taps == 9) c = __ldg(reinterpret_cast<const int4*>(p.corr + (long long)cls * p.N + n));
-      a.x -= c.x; a.y -= c.y; a.z -= c.z; a.w -= c.w;
-      float4 y = make_float4((float)a.x * sc.x + bi.x, (float)a.y * sc.y + bi.y, (float)a.z * sc.z + bi.z, (float)a.w * sc.w + bi.w);
-      if (p.rowvec) {
-        const float4 r = __ldg(reinterpret_cast<const float4*>(p.rowvec + (long long)img * p.ld_rowvec + n));
-        y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
-      }
-      if (p.residual) {
-        const float4 r = *reinterpret_cast<const float4*>(p.residual + (long long)m * p.ldr + n);
-        y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
-      }
-      *reinterpret_cast<float4*>(p.out + (long long)m * p.ldo + n) = y;
-      gs[0] += y.x; gs[1] += y.y; gs[2] += y.z; gs[3] += y.w;
-      gq[0] += y.x * y.x; gq[1] += y.y * y.y; gq[2] += y.z * y.z; gq[3] += y.w * y.w;
+    y = make_float4((float)a.x * sc.x + bi.x, (float)a.y * sc.y + bi.y, (float)a.z * sc.z + bi.z, (float)a.w * sc.w + bi.w);
+    if (p.rowvec) {
+      const float4 rv = __ldg(reinterpret_cast<const float4*>(p.rowvec + (long long)img * p.ld_rowvec + n));
+      y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w;
     }
-    if (p.gn_stats) {
-      float2* st = p.gn_stats + (long long)sl * p.ld_stats + n;
-      *reinterpret_cast<float4*>(st) = make_float4(gs[0], gq[0], gs[1], gq[1]);
-      *reinterpret_cast<float4*>(st + 2) = make_float4(gs[2], gq[2], gs[3], gq[3]);
+    if (p.residual) {
+      const float4 rs = *reinterpret_cast<const float4*>(p.residual + (long long)m * p.ldr + n);
+      y.x += rs.x; y.y += rs.y; y.z += rs.z; y.w += rs.w;
+    }
+    *reinterpret_cast<float4*>(p.out + (long long)m * p.ldo + n) = y;
+  }
+  if (p.gn_stats) {        // column sums of the slab's 32 rows (host: M % 32 == 0), fixed order
+    sy[r][4 * q] = y.x; sy[r][4 * q + 1] = y.y; sy[r][4 * q + 2] = y.z; sy[r][4 * q + 3] = y.w;
+    sq[r][4 * q] = y.x * y.x; sq[r][4 * q + 1] = y.y * y.y; sq[r][4 * q + 2] = y.z * y.z; sq[r][4 * q + 3] = y.w * y.w;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int col = blockIdx.x * 32 + threadIdx.x;
+      if (col < p.N) {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { s0 += sy[i][threadIdx.x]; s1 += sq[i][threadIdx.x]; }
+        p.gn_stats[(long long)blockIdx.y * p.ld_stats + col] = make_float2(s0, s1);
+      }
     }
   }
 }
