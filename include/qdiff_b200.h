@@ -329,6 +329,9 @@ int qd_upsample2x_f32(const float* src, float* dst, int32_t B, int32_t H, int32_
 /* qd_vq_lookup: the codebook step of VQModelInterface.decode (ldm/models/autoencoder.py:274-283 -> taming's
  *      VectorQuantizer2.forward): for each of `rows` latent pixels z[r, 0..C) (NHWC fp32, row pitch ld_z) the nearest of
  *      the n_e codebook rows by d = sum(z^2) + sum(e^2) - 2 z.e (fp32, lowest index on ties); out = z + (e - z).  C <= 16. */
+/* qd_softmax_rows: in-place softmax over each row of an fp32 [rows, cols] matrix with row pitch ld (the softmax of the
+ *      first-stage AttnBlock, model.py:190-192, between its two tensor-core products). */
+int qd_softmax_rows(float* x, long long ld, int32_t rows, int32_t cols, qd_stream_t s);
 int qd_vq_lookup(const float* z, long long ld_z, const float* codebook, float* out, long long ld_out, int32_t rows, int32_t C,
                  int32_t n_e, qd_stream_t s);
 
@@ -383,7 +386,8 @@ enum qd_op_kind {
   QD_OP_UPSAMPLE2X = 12,
   QD_OP_SPLIT3 = 13,
   QD_OP_ATTENTION_FP = 14,
-  QD_OP_VQ_LOOKUP = 15
+  QD_OP_VQ_LOOKUP = 15,
+  QD_OP_SOFTMAX_ROWS = 16
 };
 
 /* generic argument block for the small helpers when recorded into an engine */
@@ -392,7 +396,8 @@ typedef struct qd_misc_desc {
   float* dst;
   long long ld_src, ld_dst;
   int32_t a, b, c, d;   /* meaning per op: see qd_engine_add_op */
-  const float* aux;     /* QD_OP_TIMESTEP_EMB: frequency table; QD_OP_VQ_LOOKUP: codebook [c][b] (a = rows, b = C, c = n_e) */
+  const float* aux;     /* QD_OP_TIMESTEP_EMB: frequency table; QD_OP_VQ_LOOKUP: codebook [c][b] (a = rows, b = C, c = n_e);
+                           QD_OP_SOFTMAX_ROWS: src == dst, a = rows, b = cols, ld_src = row pitch */
 } qd_misc_desc;
 
 int qd_engine_create(int device, qd_engine** out);

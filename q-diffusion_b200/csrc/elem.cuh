@@ -790,6 +790,39 @@ __global__ void upsample2x_f32_kernel(const float* __restrict__ src, float* __re
   }
 }
 
+// In-place softmax over the rows of an fp32 matrix (first-stage AttnBlock on the tensor cores: scores from the plane GEMM,
+// probabilities into the next plane split; model.py:190-192).  One block per row, exact expf, fixed reduction order.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x, long long ld, int cols) {
+  __shared__ float red[8];
+  float* row = x + (long long)blockIdx.x * ld;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < cols; j += blockDim.x) mx = fmaxf(mx, row[j]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < cols; j += blockDim.x) {
+    const float e = expf(row[j] - mx);
+    row[j] = e;
+    sum += e;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float inv = 1.0f / tot;
+  for (int j = threadIdx.x; j < cols; j += blockDim.x) row[j] *= inv;
+}
+
 // ------------------------------------------------------------------------------------ VQ first stage
 // Nearest codebook entry per latent pixel (VectorQuantizer2.forward of taming-transformers, the `quantize` step of
 // VQModelInterface.decode, ldm/models/autoencoder.py:274-283): d_j = sum(z^2) + sum(e_j^2) - 2 z.e_j in fp32 with the

@@ -855,6 +855,10 @@ int launch_misc(int kind, const qd_misc_desc& m, cudaStream_t s) {
       if (m.d % 4) return fail(QD_ERR_UNSUPPORTED, "upsample: C %% 4");
       launch_k(qd::upsample2x_f32_kernel, grid_for((long long)m.a * m.b * m.c * m.d, 256), 256, 0, s, m.src, m.dst, m.a, m.b, m.c, m.d);
       return check_launch("upsample2x_f32_kernel");
+    case QD_OP_SOFTMAX_ROWS:
+      if (m.a <= 0 || m.b <= 0 || m.ld_src < m.b || m.src != m.dst) return fail(QD_ERR_BAD_ARG, "softmax_rows: in place, rows=%d cols=%d", m.a, m.b);
+      launch_k(qd::softmax_rows_kernel, dim3(m.a), 256, 0, s, m.dst, m.ld_src, m.b);
+      return check_launch("softmax_rows_kernel");
     case QD_OP_VQ_LOOKUP:
       if (!m.aux || m.a <= 0 || m.b <= 0 || m.b > qd::VQ_MAX_C || m.c <= 0 || m.ld_src < m.b || m.ld_dst < m.b)
         return fail(QD_ERR_BAD_ARG, "vq_lookup: bad args (rows=%d, C=%d <= %d, n_e=%d)", m.a, m.b, qd::VQ_MAX_C, m.c);
@@ -979,6 +983,10 @@ int qd_upsample2x_f32(const float* src, float* dst, int32_t B, int32_t H, int32_
   qd_misc_desc m{src, dst, 0, 0, B, H, W, C, nullptr};
   return launch_misc(QD_OP_UPSAMPLE2X, m, (cudaStream_t)s);
 }
+int qd_softmax_rows(float* x, long long ld, int32_t rows, int32_t cols, qd_stream_t s) {
+  qd_misc_desc m{x, x, ld, ld, rows, cols, 0, 0, nullptr};
+  return launch_misc(QD_OP_SOFTMAX_ROWS, m, (cudaStream_t)s);
+}
 int qd_vq_lookup(const float* z, long long ld_z, const float* codebook, float* out, long long ld_out, int32_t rows, int32_t C,
                  int32_t n_e, qd_stream_t s) {
   qd_misc_desc m{z, out, ld_z, ld_out, rows, C, n_e, 0, codebook};
@@ -1025,7 +1033,7 @@ int qd_engine_add_op(qd_engine* e, int kind, const void* desc) {
     case QD_OP_SPLIT3: op.split = *reinterpret_cast<const qd_split_desc*>(desc); break;
     case QD_OP_ATTENTION_FP: op.attfp = *reinterpret_cast<const qd_attention_fp_desc*>(desc); break;
     case QD_OP_TIMESTEP_EMB: case QD_OP_COPY2D: case QD_OP_NCHW_TO_NHWC: case QD_OP_NHWC_TO_NCHW:
-    case QD_OP_AVGPOOL2X: case QD_OP_UPSAMPLE2X: case QD_OP_VQ_LOOKUP:
+    case QD_OP_AVGPOOL2X: case QD_OP_UPSAMPLE2X: case QD_OP_VQ_LOOKUP: case QD_OP_SOFTMAX_ROWS:
       op.misc = *reinterpret_cast<const qd_misc_desc*>(desc);
       break;
     default: return fail(QD_ERR_BAD_ARG, "unknown op kind %d", kind);

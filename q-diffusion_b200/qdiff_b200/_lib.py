@@ -18,7 +18,7 @@ c_vp = C.c_void_p
 
 QD_OP_GEMM, QD_OP_QUANTIZE, QD_OP_GROUPNORM, QD_OP_LAYERNORM, QD_OP_IM2COL, QD_OP_ATTENTION = 1, 2, 3, 4, 5, 6
 QD_OP_TIMESTEP_EMB, QD_OP_COPY2D, QD_OP_NCHW_TO_NHWC, QD_OP_NHWC_TO_NCHW, QD_OP_AVGPOOL2X, QD_OP_UPSAMPLE2X = 7, 8, 9, 10, 11, 12
-QD_OP_SPLIT3, QD_OP_ATTENTION_FP, QD_OP_VQ_LOOKUP = 13, 14, 15
+QD_OP_SPLIT3, QD_OP_ATTENTION_FP, QD_OP_VQ_LOOKUP, QD_OP_SOFTMAX_ROWS = 13, 14, 15, 16
 
 
 class QParams(C.Structure):
@@ -134,7 +134,7 @@ class SamplerDesc(C.Structure):
 
 EXPORTS = [
     "qd_qgemm_i8", "qd_quantize", "qd_groupnorm_quant", "qd_groupnorm_workspace_floats", "qd_layernorm_quant",
-    "qd_im2col_i8", "qd_qattention", "qd_split_bf16x3", "qd_attention_fp32", "qd_lincomb3", "qd_timestep_embedding", "qd_copy2d", "qd_nchw_to_nhwc", "qd_nhwc_to_nchw", "qd_avgpool2x", "qd_upsample2x_f32", "qd_vq_lookup",
+    "qd_im2col_i8", "qd_qattention", "qd_split_bf16x3", "qd_attention_fp32", "qd_lincomb3", "qd_timestep_embedding", "qd_copy2d", "qd_nchw_to_nhwc", "qd_nhwc_to_nchw", "qd_avgpool2x", "qd_upsample2x_f32", "qd_vq_lookup", "qd_softmax_rows",
     "qd_sampler_step", "qd_engine_create", "qd_engine_add_op", "qd_engine_num_ops", "qd_engine_finalize",
     "qd_engine_run", "qd_engine_run_range", "qd_engine_destroy", "qd_last_error", "qd_num_sms", "qd_launch_count",
 ]
@@ -167,6 +167,7 @@ def lib():
     L.qd_nhwc_to_nchw.argtypes = [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]
     L.qd_avgpool2x.argtypes = [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]
     L.qd_upsample2x_f32.argtypes = [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]
+    L.qd_softmax_rows.argtypes = [c_vp, c_ll, c_i32, c_i32, c_vp]
     L.qd_vq_lookup.argtypes = [c_vp, c_ll, c_vp, c_vp, c_ll, c_i32, c_i32, c_i32, c_vp]
     L.qd_groupnorm_workspace_floats.argtypes = [c_i32, c_i32, c_i32, c_i32]
     L.qd_groupnorm_workspace_floats.restype = c_ll

@@ -40,6 +40,35 @@ def test_decode_matches_reference(cuda, name, precision):
     assert torch.equal(out, out2)
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_decode_with_tensor_core_attention(cuda, name, monkeypatch):
+    """QDIFF_FS_ATTN=tc: the AttnBlock products of the decoder as bfloat16-plane GEMMs + qd_softmax_rows (the path long
+    sequences take by default) on the tiny fixtures; same tolerance as the fp32-kernel path."""
+    from qdiff_b200 import first_stage as FS
+    monkeypatch.setenv("QDIFF_FS_ATTN", "tc")
+    g = load(name)
+    fs = _build(g, 3, cuda)
+    out = FS.decode_first_stage(fs, g["z"].to(cuda), g["scale_factor"]).cpu()
+    err = float((out - g["out"]).abs().max()) / float(g["out"].abs().max())
+    print(f"{name} precision 3, tensor-core attention: max err / max|ref| = {err:.3e}")
+    assert err <= TOL[3]
+    prog = next(iter(fs._programs.values()))
+    assert any(n.endswith(".softmax") for n in prog.op_names), "the tensor-core attention path was not taken"
+
+
+def test_softmax_rows(cuda):
+    from qdiff_b200 import _lib
+    x = torch.randn(37, 1000, generator=torch.Generator().manual_seed(2)) * 4.0
+    buf = torch.zeros(37, 1024)
+    buf[:, :1000] = x
+    d = buf.to(cuda)
+    _lib.check(_lib.lib().qd_softmax_rows(_lib.ptr(d), 1024, 37, 1000, _lib.stream_ptr()), "qd_softmax_rows")
+    got = d.cpu()
+    ref = torch.softmax(x.double(), dim=1)
+    assert float((got[:, :1000].double() - ref).abs().max()) <= 2e-7
+    assert torch.equal(got[:, 1000:], torch.zeros(37, 24))           # the pitch padding is not touched
+
+
 def test_vq_lookup_matches_oracle(cuda):
     """qd_vq_lookup vs VectorQuantizer2's published algorithm (oracle): indices on an 8192-entry codebook."""
     import ctypes as C

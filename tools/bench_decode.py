@@ -13,7 +13,8 @@ for p in (ROOT, os.path.join(ROOT, "q-diffusion_b200")):
 from qdiff_b200 import first_stage as FS  # noqa: E402
 from qdiff_b200.unet import randomize_  # noqa: E402
 
-KIND = {1: "gemm", 3: "groupnorm", 5: "im2col", 9: "nchw2nhwc", 10: "nhwc2nchw", 13: "split3", 14: "attention_fp", 15: "vq_lookup"}
+KIND = {1: "gemm", 3: "groupnorm", 5: "im2col", 8: "copy2d", 9: "nchw2nhwc", 10: "nhwc2nchw", 13: "split3", 14: "attention_fp", 15: "vq_lookup",
+        16: "softmax_rows"}
 
 
 def main(name="sd_v1", batch=2, precision=3):
