@@ -220,6 +220,8 @@ class FirstStageBuilder(graph.WeightOnlyBuilder):
     def gemm_fp(self, conv, a, label, *, hw=None, residual=None, im2col=None):
         """One floating-point conv / 1x1 conv: len(self.passes) accumulating GEMM launches.  a: split3 planes of the input.
         hw: 3x3 stride-1 conv on an (H, W) map (implicit GEMM); im2col = (hw, stride, pad_tl, out_hw): explicit patches."""
+        if im2col is None and hw is not None and int(conv.weight.shape[-1]) == 3 and not self.implicit_conv_ok(hw[0], hw[1]):
+            im2col = (hw, 1, (1, 1), hw)          # feature-map sizes the implicit-GEMM tiling does not cover
         W = self._planes(conv, label, a.Cp, im2col is not None)
         N, taps = W["N"], W["taps"]
         self.keep += [W["bias"], W["ones"]] + [t for t, _ in W["tiles"]]

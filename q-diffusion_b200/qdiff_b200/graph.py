@@ -611,8 +611,20 @@ class Builder:
         a = self.quantize(x_f32, qm.act_quantizer, label + ".q", act=act, out_cols=cols)
         return self.gemm(qm, a, label, **kw)
 
+    @staticmethod
+    def implicit_conv_ok(H, W):
+        """Feature-map shapes the implicit-GEMM conv tiles (a 128-pixel tile = whole rows, whole small images, or a
+        128-pixel segment of a wide row): plan_gemm's rule.  Every other shape takes the explicit patch gather."""
+        if W > 128:
+            return W % 128 == 0
+        if H * W >= 128:
+            return 128 % W == 0 and H % (128 // W) == 0
+        return 128 % (H * W) == 0
+
     def conv3x3_s1(self, qm, a, hw, label, **kw):
         H, W = hw
+        if not self.implicit_conv_ok(H, W):      # e.g. 96x96 or 24x24 latents: correct for any size, 9x the operand bytes
+            return self.conv_im2col(qm, a, hw, label, 1, (1, 1), hw, 9 * a.cols, rows_per_batch=H * W, **kw)
         return self.gemm(qm, a, label, conv_bhw=(self.B, H, W), rows_per_batch=H * W, **kw)
 
     def conv_im2col(self, qm, a, hw, label, stride, pad_tl, out_hw, k_to, **kw):
@@ -1196,6 +1208,9 @@ class WeightOnlyBuilder(Builder):
         """One weight-only GEMM.  a: bfloat16 plane Act from split3.  im2col = (hw, stride, pad_tl, out_hw): explicit patch
         gather first (strided convs, conv_in)."""
         cols = tuple(cols) if cols is not None else None
+        if conv_bhw is not None and im2col is None and not self.implicit_conv_ok(conv_bhw[1], conv_bhw[2]):
+            hw_ = (conv_bhw[1], conv_bhw[2])
+            conv_bhw, im2col = None, (hw_, 1, (1, 1), hw_)          # any feature-map size: explicit patch gather
         if not getattr(qm, "use_weight_quant", True):
             return self._gemm_fp_weights(qm, a, label, conv_bhw=conv_bhw, rowvec=rowvec, residual=residual, out=out,
                                          rows_per_batch=rows_per_batch, cols=cols, accumulate_into=accumulate_into,
