@@ -13,6 +13,9 @@ from qdiff_b200 import _lib, ops  # noqa: E402
 dev = torch.device("cuda:0")
 B = 16
 SHAPES = [(320, 4096), (640, 4096), (960, 4096), (640, 1024), (1920, 1024), (1280, 256), (2560, 256), (1280, 64)]
+if "--shape" in sys.argv:          # --shape B C HW: one shape (e.g. CIFAR top level: 256 128 1024)
+    i = sys.argv.index("--shape")
+    B, SHAPES = int(sys.argv[i + 1]), [(int(sys.argv[i + 2]), int(sys.argv[i + 3]))]
 L = _lib.lib()
 for Cc, HW in SHAPES:
     x = torch.randn(B * HW, Cc, device=dev)
