@@ -273,7 +273,7 @@ int plan_gemm(const qd_gemm_desc* d, GemmPlan* pl) {
   }
   int rc = encode_u8_map(&pl->tmA, d->a, 4, dims, strides, box);
   if (rc) return rc;
-  // ---- B map: [w_rows][taps*C] s8, or [w_rows][taps*C/2] packed 4-bit codes (unswizzled: warps 2-3 re-lay it out)
+  // ---- B map: [w_rows][taps*C] s8, or [w_rows][taps*C/2] packed 4-bit codes (unswizzled: the unpack warps re-lay it out)
   {
     const int w_rows = d->w_rows > 0 ? d->w_rows : d->N;
     if (d->w_int4_packed) {

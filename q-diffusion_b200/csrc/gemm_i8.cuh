@@ -105,7 +105,7 @@ struct GemmArgs {
   int geglu;
   int oq_d, oq_pitch;      // > 0: per-head padded code layout for row-major out_q
   int oq_f16;              // out_q receives fp16 (code - zero_point) instead of 8-bit codes (ldq / oq_pitch in fp16 elements)
-  // packed INT4 weights (K3): the B tile arrives as BN x 64 packed bytes and warps 2-3 expand it to the s8
+  // packed INT4 weights (K3): the B tile arrives as BN x 64 packed bytes and the four unpack warps expand it to the s8
   // 128B-swizzled operand tile in shared memory (wq - wzero[n]) before the MMA consumes the stage
   int w4;
   const int8_t* wzero;     // [w_rows]

@@ -370,7 +370,7 @@ def _ldm_config(args):
 
 def run_ldm(args):
     """run / make_convolutional_sample / convsample_ddim of the reference script (:85-163) on the engine.  Saves the
-    LATENTS (the first-stage decoder is outside the hot path)."""
+    LATENTS; with --b200_decode also the images, decoded by the first stage on the engine (qdiff_b200.first_stage)."""
     import torch
     from . import dist as qdist, samplers, unet
     _require_resume(args)
@@ -426,7 +426,8 @@ def run_ldm(args):
 # ---------------------------------------------------------------------------------------------- txt2img
 def run_txt2img(args):
     """The sampling loop of the reference's main() (:505-541) on the engine: PLMS / DDIM with classifier-free guidance.
-    Prompt embeddings come from --b200_context (the CLIP text encoder is outside the hot path); saves the latents."""
+    Prompt embeddings come from --b200_context (the CLIP text encoder is outside the scope); saves the latents,
+    with --b200_decode also the decoded images."""
     import torch
     from . import dist as qdist, samplers, unet
     _require_resume(args)

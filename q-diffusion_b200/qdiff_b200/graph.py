@@ -856,7 +856,8 @@ class Builder:
         ch = C_ // heads
         qk, smv = blk.attention.qkv_matmul, blk.attention.smv_matmul
         if _name(qk) != "QuantQKMatMul":
-            raise NotImplementedError("weight-only (quant_act=False) LDM attention is not lowered yet")
+            raise NotImplementedError("the INT8 lowering needs the quantised attention wrappers (QuantQKMatMul): build the QuantModel with "
+                                      "act_quant_params['leaf_param'] = True, or run the weight-only state (WeightOnlyBuilder)")
         (a,), _ = self.groupnorm(x, blk.norm, T, [blk.qkv.act_quantizer], False, k + ".norm")
         s = 1.0 / math.sqrt(math.sqrt(ch))
         idx = torch.arange(3 * C_, device=self.dev).reshape(heads, 3, ch)

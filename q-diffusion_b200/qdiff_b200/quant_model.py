@@ -69,6 +69,7 @@ class QuantModel(nn.Module):
             if isinstance(m, (QuantModule, BaseQuantBlock)):
                 m.set_quant_state(weight_quant, act_quant)
         self._programs = {}     # programs depend on the state; the folded weights (self._wcache) do not
+        self._int8_state = None
 
     def set_running_stat(self, running_stat: bool, sm_only=False):
         for m in self.model.modules():
@@ -91,6 +92,7 @@ class QuantModel(nn.Module):
         """Drop compiled engine programs AND the folded weights (call after changing quantizer parameters or weights)."""
         self._programs = {}
         self._wcache = {}
+        self._int8_state = None
 
     def program(self, x, context=None, cfg_dedup=False):
         from . import graph
@@ -115,6 +117,14 @@ class QuantModel(nn.Module):
         self._programs[key] = prog      # (re)insert at the most-recently-used end
         return prog
 
+    def _is_int8_state(self):
+        """All QuantModules in (weight_quant, act_quant) = (True, True)?  Cached: this sits on the per-step path (walking the
+        module tree of the SD UNet costs ~1 ms of host time); set_quant_state / invalidate reset it."""
+        if getattr(self, "_int8_state", None) is None:
+            self._int8_state = all(m.use_weight_quant and m.use_act_quant for m in self.model.modules()
+                                   if isinstance(m, QuantModule))
+        return self._int8_state
+
     def forward_cfg(self, x, timesteps, context):
         """eps of the classifier-free-guidance batch [x; x] with timesteps [t; t] and context [uncond; cond] (what
         p_sample_plms / p_sample_ddim build, plms.py:185-189) from ONE copy of x and t: the guidance-invariant prefix of the
@@ -123,7 +133,7 @@ class QuantModel(nn.Module):
             raise RuntimeError("qdiff_b200.QuantModel.forward_cfg needs CUDA tensors: the engine has no CPU fallback")
         if context is None or context.shape[0] != 2 * x.shape[0]:
             raise ValueError("forward_cfg: context must hold [uncond; cond] rows for the batch (2 x batch rows)")
-        if any(not (m.use_weight_quant and m.use_act_quant) for m in self.model.modules() if isinstance(m, QuantModule)):
+        if not self._is_int8_state():
             # weight-only / full-precision states: the prefix dedup lives in the INT8 lowering; run the doubled batch
             return self.forward(torch.cat([x, x]), torch.cat([timesteps, timesteps]), context)
         return self.program(x, context, cfg_dedup=True).run(x, timesteps, context)
