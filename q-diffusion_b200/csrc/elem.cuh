@@ -394,10 +394,16 @@ __global__ void __launch_bounds__(128) gn_finalize_from_stats_kernel(const float
 // 32 rows, up to 4 quads per thread) needed 118 registers and ran 96-thread blocks at 21 % occupancy: every warp sat
 // on its first FFMA waiting for DRAM (profiles/r02_gn_apply_before.txt: 1.8-3 TB/s).  The consumer count and the raw
 // output are template parameters so that the common single-consumer case carries one quantizer's constants only.
-constexpr int GN_BATCH = 8;
+// Occupancy (round 2, profiles/r02_gn_apply_variants.txt): the single-consumer kernel waited on DRAM with 24 of 64 warps
+// resident (79 registers, 8-row load batches).  4-row batches under a 64-register cap (4 blocks = 32 warps per SM) are 6-10 %
+// faster on every UNet's shapes; 6 blocks per SM spill and lose 30 %.  The multi-consumer / raw-output variants keep 8 rows.
+constexpr int GN_BATCH = 8;                                   // host: rows per block are multiples of GN_BATCH * TY
+__host__ __device__ constexpr int gn_apply_batch(int NOUT, bool RAW) { return (NOUT <= 1 && !RAW) ? 4 : 8; }
+__host__ __device__ constexpr int gn_apply_minblocks(int NOUT, bool RAW) { return (NOUT <= 1 && !RAW) ? 4 : 1; }
 template <int NOUT, bool RAW>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const qd_groupnorm_desc p, const float* __restrict__ stats,
+__global__ void __launch_bounds__(256, gn_apply_minblocks(NOUT, RAW)) gn_apply_kernel(const qd_groupnorm_desc p, const float* __restrict__ stats,
                                                        int rows_per_block, int TX) {
+  constexpr int NB = gn_apply_batch(NOUT, RAW);      // rows per thread and load batch
   const int b = blockIdx.z;
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int TY = blockDim.x / TX;
@@ -431,14 +437,14 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const qd_groupnorm_desc p
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(p.HW, r0 + rows_per_block);
   const long long step = (long long)TY * p.ld_x;
-  for (int rb = r0 + ty; rb < r1; rb += GN_BATCH * TY) {
+  for (int rb = r0 + ty; rb < r1; rb += NB * TY) {
     const float* xp = p.x + ((long long)b * p.HW + rb) * p.ld_x + c;
-    float4 vv[GN_BATCH];
+    float4 vv[NB];
 #pragma unroll
-    for (int i = 0; i < GN_BATCH; ++i)
+    for (int i = 0; i < NB; ++i)
       if (rb + i * TY < r1) vv[i] = *reinterpret_cast<const float4*>(xp + i * step);
 #pragma unroll
-    for (int i = 0; i < GN_BATCH; ++i) {
+    for (int i = 0; i < NB; ++i) {
       const int r = rb + i * TY;
       if (r >= r1) break;
       const float4 v = vv[i];
